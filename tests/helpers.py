@@ -1,0 +1,55 @@
+"""Shared helpers for the parity tests (fixtures -> oracle State / HyperParams)."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from oracle import alpine_oracle as orc
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# model kwargs of every golden case (must mirror oracle/gen_golden.py CASES)
+CASE_KW = {
+    "kl_basic": dict(n_components=6, n_covariate_components=[3], lam=[1e3]),
+    "kl_reg_nan": dict(n_components=9, n_covariate_components=[4, 3], lam=[1e3, 5e2],
+                       orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
+    "frob_reg": dict(n_components=9, n_covariate_components=[4, 3], lam=[1e3, 5e2],
+                     orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, loss_type="frobenius"),
+    "kl_lam0": dict(n_components=5, n_covariate_components=[2], lam=[0.0], alpha_W=1.5, l1_ratio_W=1.0),
+    "als_reg": dict(n_components=6, n_covariate_components=[3, 2], lam=[1e2, 1e3],
+                    orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, use_als=True),
+    "kl_long200": dict(n_components=9, n_covariate_components=[3], lam=[1e3],
+                       orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
+}
+
+
+def golden_names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load_golden(name):
+    return dict(np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=False))
+
+
+def hp_of(name) -> orc.HyperParams:
+    kw = dict(CASE_KW[name])
+    kw.pop("use_als", None)
+    return orc.HyperParams(**kw)
+
+
+def inputs_of(g):
+    """X (genes x cells, the reference's F-order view), Ys (c_i x n), initial State."""
+    n_cov = int(g["n_cov"])
+    X = np.asarray(g["X_cells_by_genes"]).astype(np.float32).T
+    Ys = [np.ascontiguousarray(g[f"Y{i}_cells_by_cat"].T) for i in range(n_cov)]
+    st = orc.State(g["W0"].copy(), g["H0"].copy(), [g[f"B0_{i}"].copy() for i in range(n_cov)],
+                   [int(b) for b in g["blocks"]])
+    return X, Ys, st
+
+
+def rel_fro(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))

@@ -1,0 +1,95 @@
+"""Pin the NumPy oracle against trajectories produced by the unmodified reference.
+
+The fixtures under tests/golden/ were written by oracle/gen_golden.py, which
+runs the reference's own _initialize_matrices/_fit/_scale_matrices.  Tolerances:
+the oracle and the reference (torch/MKL) differ only in fp32 summation order.
+"""
+import numpy as np
+import pytest
+
+from oracle import alpine_oracle as orc
+from tests.helpers import CASE_KW, golden_names, hp_of, inputs_of, load_golden, rel_fro
+
+TRAJ_TOL = 2e-6  # Frobenius-relative, per kept iteration (<= 10 iterations)
+LONG_TOL = 5e-5  # 200 iterations of drift
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_step_trajectory_matches_reference(name):
+    g = load_golden(name)
+    hp = hp_of(name)
+    X, Ys, st = inputs_of(g)
+    use_als = CASE_KW[name].get("use_als", False)
+    kept = set(int(i) for i in g["kept_iters"])
+    n_iter = int(max(kept))
+    tol = LONG_TOL if n_iter > 20 else TRAJ_TOL
+    for it in range(1, n_iter + 1):
+        (orc.als_step if use_als else orc.mu_step)(X, Ys, st, hp)
+        if it in kept:
+            assert rel_fro(st.W, g[f"W_it{it}"]) < tol, (name, it, "W")
+            assert rel_fro(st.H, g[f"H_it{it}"]) < tol, (name, it, "H")
+            for i in range(len(Ys)):
+                assert rel_fro(st.Bs[i], g[f"B{i}_it{it}"]) < tol, (name, it, f"B{i}")
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n != "kl_long200"])
+def test_loss_matches_reference(name):
+    g = load_golden(name)
+    hp = hp_of(name)
+    X, Ys, st = inputs_of(g)
+    it = int(g["kept_iters"][-1])
+    st.W, st.H = g[f"W_it{it}"].copy(), g[f"H_it{it}"].copy()
+    st.Bs = [g[f"B{i}_it{it}"].copy() for i in range(len(Ys))]
+    ref = g["loss_history_ref_fp32"][it - 1]
+    got32 = orc.compute_loss(X, Ys, st, hp)
+    got64 = orc.compute_loss(X, Ys, st, hp, dtype=np.float64)
+    np.testing.assert_allclose(got32, ref, rtol=2e-5)
+    np.testing.assert_allclose(got64[1], float(g["final_recon_fp64"]), rtol=1e-10)
+    np.testing.assert_allclose(got64[:2], ref[:2], rtol=1e-4)
+    # the KL terms y*log(y/yhat) - y + yhat cancel; fp32 leaves an absolute error ~ eps32 * sum(y)
+    np.testing.assert_allclose(got64[2:], ref[2:], rtol=1e-4, atol=1e-6 * X.shape[1])
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_scale_transform_scores_match_reference(name):
+    g = load_golden(name)
+    hp = hp_of(name)
+    X, Ys, st = inputs_of(g)
+    it = int(g["kept_iters"][-1])
+    st.W, st.H = g[f"W_it{it}"].copy(), g[f"H_it{it}"].copy()
+    st.Bs = [g[f"B{i}_it{it}"].copy() for i in range(len(Ys))]
+    orc.scale_matrices(st, hp)
+    assert rel_fro(st.W, g["W_scaled"]) < 1e-6
+    assert rel_fro(st.H, g["H_scaled"]) < 1e-6
+    for i in range(len(Ys)):
+        assert rel_fro(st.Bs[i], g[f"B{i}_scaled"]) < 1e-6
+    scores = orc.covariate_gene_scores(st.Ws(), st.Hs(), Ys)
+    for i, s in enumerate(scores):
+        assert rel_fro(s, g[f"gene_scores{i}"]) < 1e-6
+    Ht = orc.transform_loop(X, g["W_scaled"], g["Ht0"], 5, hp.eps)
+    assert rel_fro(Ht, g["Ht_5"]) < 2e-6
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names()])
+def test_one_hot_matches_reference_encoder(name):
+    g = load_golden(name)
+    for i in range(int(g["n_cov"])):
+        labels = [np.nan if na else str(v) for v, na in zip(g[f"labels{i}"], g[f"labels{i}_isna"])]
+        Y, cats = orc.one_hot(labels)
+        np.testing.assert_array_equal(Y, g[f"Y{i}_cells_by_cat"])
+        # sklearn names the columns "<key>_<category>"
+        assert [c.split("_", 1)[1] for c in g[f"cats{i}"]] == cats
+
+
+def test_long_run_top100_rankings_match_reference():
+    """Gene rankings per component after 200 iterations (north_star parity criterion)."""
+    g = load_golden("kl_long200")
+    hp = hp_of("kl_long200")
+    X, Ys, st = inputs_of(g)
+    for _ in range(200):
+        orc.mu_step(X, Ys, st, hp)
+    Wref = g["W_it200"]
+    for k in range(st.W.shape[1]):
+        top_ref = np.argsort(-Wref[:, k], kind="stable")[:100]
+        top_got = np.argsort(-st.W[:, k], kind="stable")[:100]
+        np.testing.assert_array_equal(top_got, top_ref)
