@@ -1,0 +1,233 @@
+"""ctypes binding of ``libalpine_b200.so`` (the C ABI declared in ``include/alpine_b200.h``).
+
+PyTorch owns every tensor; this module only passes raw device pointers and the
+current CUDA stream across the boundary.  There is no CPU fallback: if the
+shared library is missing or no sm_100 GPU is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import List, Optional, Sequence
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libalpine_b200.so")
+
+LOSS_KL = 0
+LOSS_FROBENIUS = 1
+LOSS_TYPES = {"kl-divergence": LOSS_KL, "frobenius": LOSS_FROBENIUS}
+
+_lib = None
+
+# name -> (restype, argtypes); mirrors include/alpine_b200.h one to one
+_c_ctx = ctypes.c_void_p
+_f32p = ctypes.c_void_p
+SIGNATURES = {
+    "alpine_abi_version": (ctypes.c_int, []),
+    "alpine_last_error": (ctypes.c_char_p, []),
+    "alpine_launch_count": (ctypes.c_longlong, []),
+    "alpine_create": (ctypes.c_int, [ctypes.POINTER(_c_ctx), ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                     ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                     ctypes.c_int]),
+    "alpine_destroy": (ctypes.c_int, [_c_ctx]),
+    "alpine_bind_dense": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64]),
+    "alpine_bind_labels": (ctypes.c_int, [_c_ctx, ctypes.c_int, _f32p]),
+    "alpine_bind_factors": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, _f32p, ctypes.c_int64,
+                                           ctypes.POINTER(ctypes.c_void_p)]),
+    "alpine_set_hparams": (ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_double), ctypes.c_double, ctypes.c_double,
+                                          ctypes.c_double, ctypes.c_double]),
+    "alpine_reduce_buffer_size": (ctypes.c_int64, [_c_ctx]),
+    "alpine_bind_reduce_buffer": (ctypes.c_int, [_c_ctx, _f32p]),
+    "alpine_fit_begin": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_mu_partials": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+    "alpine_mu_apply": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_fit_losses": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]),
+    "alpine_scale": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+    "alpine_transform": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_xh_product": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "alpine_wx_product": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "alpine_query": (ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
+                                    ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+}
+
+
+class AlpineNativeError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the C-ABI library and declare every prototype of the header."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or os.environ.get("ALPINE_B200_LIB", LIB_PATH)
+    if not os.path.isfile(p):
+        raise AlpineNativeError(
+            f"{p} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(there is no CPU fallback for the MU loop)"
+        )
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _check(lib, status: int) -> None:
+    if status != 0:
+        msg = lib.alpine_last_error()
+        raise AlpineNativeError(f"alpine_b200 native call failed (status {status}): {msg.decode() if msg else '?'}")
+
+
+def launch_count() -> int:
+    return int(load_library().alpine_launch_count())
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return int(torch.cuda.current_stream(device).cuda_stream)
+
+
+def padded_rows(rows: int, cols: int, device, dtype=torch.float32, fill: Optional[float] = None) -> torch.Tensor:
+    """(rows, cols) fp32 view whose row pitch is a multiple of 4 floats (TMA needs 16-byte pitches)."""
+    ld = (cols + 3) // 4 * 4
+    buf = torch.empty((rows, ld), dtype=dtype, device=device) if fill is None else torch.full(
+        (rows, ld), fill, dtype=dtype, device=device)
+    return buf[:, :cols]
+
+
+class Solver:
+    """One device-resident shard of cells: X (cells-major), Y_i, and the factors W, H, B_i it updates in place."""
+
+    def __init__(self, device, n_genes: int, n_cells: int, k_blocks: Sequence[int], c_cov: Sequence[int],
+                 loss_type: str = "kl-divergence"):
+        if not torch.cuda.is_available():
+            raise AlpineNativeError("alpine_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise AlpineNativeError(f"device must be a CUDA device, got {device!r}")
+        self.dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device("cuda", self.dev_index)
+        self.G, self.n = int(n_genes), int(n_cells)
+        self.k_blocks = [int(k) for k in k_blocks]
+        self.c_cov = [int(c) for c in c_cov]
+        self.K = sum(self.k_blocks)
+        self.n_cov = len(self.c_cov)
+        if loss_type not in LOSS_TYPES:
+            raise ValueError("loss_type must be either 'kl-divergence' or 'frobenius'.")
+        kb = (ctypes.c_int * len(self.k_blocks))(*self.k_blocks)
+        cc = (ctypes.c_int * max(1, self.n_cov))(*(self.c_cov or [0]))
+        self._ctx = _c_ctx()
+        _check(self.lib, self.lib.alpine_create(ctypes.byref(self._ctx), self.dev_index, self.G, self.n,
+                                                len(self.k_blocks), kb, self.n_cov, cc, LOSS_TYPES[loss_type]))
+        self._keep: dict = {}
+
+    # -- lifetime ----------------------------------------------------------------------------------------
+    def close(self) -> None:
+        if getattr(self, "_ctx", None):
+            self.lib.alpine_destroy(self._ctx)
+            self._ctx = None
+            self._keep.clear()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _stream(self) -> int:
+        return _stream_ptr(self.device)
+
+    # -- binding -----------------------------------------------------------------------------------------
+    def bind_dense(self, X_cells_major: torch.Tensor) -> None:
+        """X as (n_cells, n_genes) fp32 with unit column stride and a row pitch divisible by 4."""
+        X = X_cells_major
+        assert X.is_cuda and X.dtype == torch.float32 and X.shape == (self.n, self.G) and X.stride(1) == 1
+        self._keep["X"] = X
+        _check(self.lib, self.lib.alpine_bind_dense(self._ctx, X.data_ptr(), X.stride(0) if self.n > 1 else max(X.stride(0), self.G)))
+
+    def bind_labels(self, Ys: List[torch.Tensor]) -> None:
+        assert len(Ys) == self.n_cov
+        for i, Y in enumerate(Ys):
+            assert Y.is_cuda and Y.dtype == torch.float32 and Y.shape == (self.c_cov[i], self.n) and Y.is_contiguous()
+            _check(self.lib, self.lib.alpine_bind_labels(self._ctx, i, Y.data_ptr()))
+        self._keep["Ys"] = list(Ys)
+
+    def bind_factors(self, W: torch.Tensor, H: torch.Tensor, Bs: List[torch.Tensor]) -> None:
+        assert W.is_cuda and W.dtype == torch.float32 and W.shape == (self.G, self.K) and W.stride(1) == 1
+        assert H.is_cuda and H.dtype == torch.float32 and H.shape == (self.K, self.n) and H.stride(1) == 1
+        assert len(Bs) == self.n_cov
+        for i, B in enumerate(Bs):
+            assert B.is_cuda and B.dtype == torch.float32 and B.is_contiguous()
+            assert B.shape == (self.c_cov[i], self.k_blocks[i])
+        arr = (ctypes.c_void_p * max(1, self.n_cov))(*([B.data_ptr() for B in Bs] or [None]))
+        self._keep.update(W=W, H=H, Bs=list(Bs))
+        ldH = H.stride(0) if self.K > 1 else max(H.stride(0), self.n)
+        ldW = W.stride(0) if self.G > 1 else max(W.stride(0), self.K)
+        _check(self.lib, self.lib.alpine_bind_factors(self._ctx, W.data_ptr(), ldW, H.data_ptr(), ldH, arr))
+
+    def set_hparams(self, lam: Sequence[float], alpha_W: float, l1_ratio_W: float, orth_W: float, eps: float) -> None:
+        arr = (ctypes.c_double * max(1, self.n_cov))(*([float(v) for v in lam] or [0.0]))
+        _check(self.lib, self.lib.alpine_set_hparams(self._ctx, arr, float(alpha_W), float(l1_ratio_W), float(orth_W),
+                                                     float(eps)))
+
+    def reduce_buffer(self) -> torch.Tensor:
+        """Allocate and bind the per-iteration all-reduce payload [X H^T | H H^T | rowsum(H) | B statistics]."""
+        if "reduce" not in self._keep:
+            size = int(self.lib.alpine_reduce_buffer_size(self._ctx))
+            buf = torch.zeros(size, dtype=torch.float32, device=self.device)
+            _check(self.lib, self.lib.alpine_bind_reduce_buffer(self._ctx, buf.data_ptr()))
+            self._keep["reduce"] = buf
+        return self._keep["reduce"]
+
+    # -- the loop ----------------------------------------------------------------------------------------
+    def fit_begin(self, max_iter: int) -> None:
+        _check(self.lib, self.lib.alpine_fit_begin(self._ctx, int(max_iter), self._stream()))
+
+    def mu_partials(self) -> None:
+        _check(self.lib, self.lib.alpine_mu_partials(self._ctx, self._stream()))
+
+    def mu_apply(self, it: int) -> None:
+        _check(self.lib, self.lib.alpine_mu_apply(self._ctx, int(it), self._stream()))
+
+    def losses(self, n_iter: int):
+        """(||X||_F^2, rows[n_iter][2 + n_cov]) of this shard; synchronises the stream."""
+        import numpy as np
+
+        xn = ctypes.c_double(0.0)
+        rows = np.zeros((max(n_iter, 1), 2 + self.n_cov), dtype=np.float64)
+        _check(self.lib, self.lib.alpine_fit_losses(self._ctx, int(n_iter), ctypes.byref(xn),
+                                                    rows.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                    self._stream()))
+        return float(xn.value), rows[:n_iter]
+
+    def scale(self) -> None:
+        _check(self.lib, self.lib.alpine_scale(self._ctx, self._stream()))
+
+    def transform(self, n_iter: int) -> None:
+        _check(self.lib, self.lib.alpine_transform(self._ctx, int(n_iter), self._stream()))
+
+    # -- the two contractions on their own -----------------------------------------------------------------
+    def xh_product(self) -> torch.Tensor:
+        """(K, G): sum_j X[g][j] H[k][j] with the bound X and H."""
+        out = padded_rows(self.K, self.G, self.device)
+        _check(self.lib, self.lib.alpine_xh_product(self._ctx, out.data_ptr(), out.stride(0), self._stream()))
+        return out
+
+    def wx_product(self) -> torch.Tensor:
+        """(K, n): sum_g W[g][k] X[g][j] with the bound X and W."""
+        out = padded_rows(self.K, self.n, self.device)
+        _check(self.lib, self.lib.alpine_wx_product(self._ctx, out.data_ptr(), out.stride(0), self._stream()))
+        return out
+
+    def query(self) -> dict:
+        a, b, c, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        _check(self.lib, self.lib.alpine_query(self._ctx, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c),
+                                               ctypes.byref(d)))
+        return {"num_sms": a.value, "gemm_grid": b.value, "smem_stages": c.value, "k_padded": d.value}

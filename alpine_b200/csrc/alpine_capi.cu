@@ -1,0 +1,789 @@
+// C ABI of the B200-native MU-NMF path (see include/alpine_b200.h for the contract and the reference lines each
+// entry point replaces).  Host side only: context bookkeeping, TMA descriptors, workspace and kernel launches.
+#include "../../include/alpine_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mu_gemm_sm100.cuh"
+#include "mu_small_kernels.cuh"
+
+using namespace alpine;
+
+namespace {
+
+thread_local std::string g_last_error;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                        \
+  do {                                                                                                      \
+    cudaError_t e__ = (expr);                                                                               \
+    if (e__ != cudaSuccess)                                                                                 \
+      return fail(ALPINE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+#define AL_TRY(expr)          \
+  do {                        \
+    int r__ = (expr);         \
+    if (r__ != ALPINE_OK) return r__; \
+  } while (0)
+#define LAUNCH_CHECK()                                                                                      \
+  do {                                                                                                      \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                                     \
+    cudaError_t e__ = cudaGetLastError();                                                                   \
+    if (e__ != cudaSuccess)                                                                                 \
+      return fail(ALPINE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor map: dims {inner, outer}, row pitch ld (floats), box {box_inner, box_outer}
+int make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner,
+             uint32_t box_outer, bool swizzle128) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(ALPINE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld & 3) != 0)
+    return fail(ALPINE_ERR_ARG, "TMA operand must be 16-byte aligned with a leading dimension divisible by 4");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ALPINE_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ALPINE_OK;
+}
+
+inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
+
+struct GemmPlan {
+  bool valid = false;
+  int mt = 2;
+  CUtensorMap tmX, tmB;
+  GemmParams p{};
+  ReduceParams r{};
+  int grid = 0;
+  size_t smem = 0;
+};
+
+}  // namespace
+
+struct alpine_ctx {
+  int device = 0;
+  long long G = 0, n = 0;
+  int K = 0, Kp = 0, n_blocks = 0, n_cov = 0, Kg = 0, q_total = 0;
+  int kblk[kMaxCov + 1] = {0};
+  int ccov[kMaxCov] = {0};
+  int loss_type = LOSS_KL;
+  int num_sms = 0;
+  bool simt = false;
+  int mt = 2;
+
+  const float* X = nullptr;
+  long long ldX = 0;
+  const float* Y[kMaxCov] = {nullptr};
+  float* W = nullptr;
+  long long ldW = 0;
+  float* H = nullptr;
+  long long ldH = 0;
+  float* B[kMaxCov] = {nullptr};
+
+  double lam[kMaxCov] = {0};
+  double alpha = 0, l1 = 0, orth = 0, eps = 1e-6;
+  bool hparams_set = false;
+
+  // workspaces (device)
+  long long ldG = 0, ldN = 0;
+  float* WT = nullptr;     // [K][ldG]
+  float* A = nullptr;      // [K][ldN]   W^T X
+  float* numG = nullptr;   // [Kg][ldN]
+  float* denG = nullptr;
+  float* T = nullptr;      // [K][K]     W^T W
+  float* colsum = nullptr; // [K]
+  float* gram_partial = nullptr;
+  float* gram_rs_partial = nullptr;
+  int gram_blocks_max = 0;
+  float* q_partial = nullptr;
+  double* pred_partial = nullptr;
+  int stat_blocks = 0;
+  double* t1_partial = nullptr;
+  int sl_blocks_n = 0;
+  double* sumsq_partial = nullptr;
+  double* xnorm2 = nullptr;
+  double* loss_hist = nullptr;
+  int loss_cap = 0;
+  int* err = nullptr;
+  float* partial = nullptr;
+  size_t partial_floats = 0;
+  float* own_reduce = nullptr;
+  float* reduce = nullptr;  // [Pt K*ldG | S K*K | hsum K | Q q_total]
+
+  GemmPlan plan_xh, plan_wx;
+  bool ws_ready = false;
+  bool fit_active = false;
+
+  float* red_Pt() const { return reduce; }
+  float* red_S() const { return reduce + static_cast<size_t>(K) * ldG; }
+  float* red_hsum() const { return red_S() + static_cast<size_t>(K) * K; }
+  float* red_Q() const { return red_hsum() + K; }
+  long long reduce_floats() const { return static_cast<long long>(K) * ldG + static_cast<long long>(K) * K + K + q_total; }
+};
+
+namespace {
+
+CovTable make_cov_table(const alpine_ctx* c) {
+  CovTable t;
+  t.n_cov = c->n_cov;
+  int row = 0, q = 0;
+  for (int i = 0; i < c->n_cov; ++i) {
+    t.d[i].row0 = row;
+    t.d[i].k = c->kblk[i];
+    t.d[i].c = c->ccov[i];
+    t.d[i].Y = c->Y[i];
+    t.d[i].B = c->B[i];
+    t.d[i].q_off = q;
+    t.d[i].lam = static_cast<float>(c->lam[i]);
+    row += c->kblk[i];
+    q += c->ccov[i] * c->kblk[i];
+  }
+  return t;
+}
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+  if (*p != nullptr) return ALPINE_OK;
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(p), (count > 0 ? count : 1) * sizeof(T)));
+  return ALPINE_OK;
+}
+
+int gram_blocks_for(const alpine_ctx* c, long long L, long long* chunk) {
+  const int want = 2 * c->num_sms;
+  long long ch = round_up((L + want - 1) / want, 32);
+  if (ch < 256) ch = 256;
+  *chunk = ch;
+  return ceil_div(L, ch);
+}
+
+int set_kernel_attrs();
+
+int ensure_workspace(alpine_ctx* c) {
+  if (c->ws_ready) return ALPINE_OK;
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(set_kernel_attrs());
+  const size_t K = c->K;
+  AL_TRY(dev_alloc(&c->WT, K * c->ldG));
+  AL_TRY(dev_alloc(&c->A, K * c->ldN));
+  AL_TRY(dev_alloc(&c->numG, static_cast<size_t>(c->Kg) * c->ldN));
+  AL_TRY(dev_alloc(&c->denG, static_cast<size_t>(c->Kg) * c->ldN));
+  AL_TRY(dev_alloc(&c->T, K * K));
+  AL_TRY(dev_alloc(&c->colsum, K));
+  long long chunk;
+  int gb = gram_blocks_for(c, c->n, &chunk);
+  int gb2 = gram_blocks_for(c, c->G, &chunk);
+  c->gram_blocks_max = gb > gb2 ? gb : gb2;
+  AL_TRY(dev_alloc(&c->gram_partial, static_cast<size_t>(c->gram_blocks_max) * K * K));
+  AL_TRY(dev_alloc(&c->gram_rs_partial, static_cast<size_t>(c->gram_blocks_max) * K));
+  c->stat_blocks = ceil_div(c->n, kStatCells);
+  AL_TRY(dev_alloc(&c->q_partial, static_cast<size_t>(c->stat_blocks) * (c->q_total > 0 ? c->q_total : 1)));
+  AL_TRY(dev_alloc(&c->pred_partial, static_cast<size_t>(c->stat_blocks) * (c->n_cov > 0 ? c->n_cov : 1)));
+  c->sl_blocks_n = ceil_div(c->n, kSLCols);
+  AL_TRY(dev_alloc(&c->t1_partial, static_cast<size_t>(c->sl_blocks_n)));
+  AL_TRY(dev_alloc(&c->sumsq_partial, 1024));
+  AL_TRY(dev_alloc(&c->xnorm2, 1));
+  AL_TRY(dev_alloc(&c->err, 8));
+  CU_TRY(cudaMemset(c->err, 0, 8 * sizeof(int)));
+  CU_TRY(cudaMemset(c->t1_partial, 0, sizeof(double) * c->sl_blocks_n));
+  if (c->reduce == nullptr) {
+    AL_TRY(dev_alloc(&c->own_reduce, static_cast<size_t>(c->reduce_floats())));
+    c->reduce = c->own_reduce;
+  }
+  c->ws_ready = true;
+  return ALPINE_OK;
+}
+
+int set_kernel_attrs() {
+  const int big = 227 * 1024;
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_XH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_XH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_WX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_WX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  const int sl8 = static_cast<int>(sym_long_smem_bytes<8>(128)), sl16 = static_cast<int>(sym_long_smem_bytes<16>(256));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<16, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl16));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<16, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl16));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<16, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl16));
+  CU_TRY(cudaFuncSetAttribute(cov_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  CU_TRY(cudaFuncSetAttribute(guided_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return ALPINE_OK;
+}
+
+template <int ORIENT, int MT>
+int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
+  auto kern = mu_gemm_kernel<ORIENT, MT>;
+  kern<<<pl.grid, GemmCfg<MT>::kThreads, pl.smem, st>>>(pl.tmX, pl.tmB, pl.p);
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+// Build the plan of one contraction.  M rows of D, reduction R, B operand [K][ldB] with R columns.
+int build_plan(alpine_ctx* c, GemmPlan* pl, int orient, const float* Bop, long long ldB) {
+  const int mt = c->mt;
+  const int rows = mt * kBM;
+  const long long M = (orient == ORIENT_XH) ? c->G : c->n;
+  const long long R = (orient == ORIENT_XH) ? c->n : c->G;
+  pl->mt = mt;
+  GemmParams& p = pl->p;
+  p.M = static_cast<int>(M);
+  p.R = static_cast<int>(R);
+  p.K = c->K;
+  p.Kp = c->Kp;
+  p.num_tiles = ceil_div(M, rows);
+  p.kb_per_tile = ceil_div(R, kBK);
+  const long long total = static_cast<long long>(p.num_tiles) * p.kb_per_tile;
+  pl->grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
+  const long long per_cta = (total + pl->grid - 1) / pl->grid;
+  p.max_segs = ceil_div(per_cta, p.kb_per_tile) + 1;
+  // pipeline depths from the shared-memory budget
+  const size_t budget = 227 * 1024 - 1024;
+  const int x_tile = rows * kBK * 4;
+  int sb = 3, sx = 0;
+  for (; sb >= 2; --sb) {
+    sx = kMaxXStages;
+    while (sx >= 2 && gemm_smem_layout(x_tile, p.Kp, sx, sb).total > budget) --sx;
+    if (sx >= 3 || sb == 2) break;
+  }
+  if (sx < 2) return fail(ALPINE_ERR_ARG, "K=%d does not fit the shared-memory pipeline", c->K);
+  if (const char* e = getenv("ALPINE_B200_SX")) sx = atoi(e) < sx ? (atoi(e) < 1 ? 1 : atoi(e)) : sx;
+  p.sx = sx;
+  p.sb = sb;
+  pl->smem = gemm_smem_layout(x_tile, p.Kp, sx, sb).total + 1024;
+  // partial-sum slots
+  const size_t need = static_cast<size_t>(pl->grid) * p.max_segs * p.K * rows;
+  if (need > c->partial_floats) {
+    if (c->partial) cudaFree(c->partial);
+    c->partial = nullptr;
+    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c->partial), need * sizeof(float)));
+    c->partial_floats = need;
+    c->plan_xh.valid = false;
+    c->plan_wx.valid = false;
+  }
+  p.partial = c->partial;
+  p.err = c->err;
+  // tensor maps: X is [n cells][G genes] (inner = genes)
+  if (orient == ORIENT_XH)
+    AL_TRY(make_map(&pl->tmX, c->X, c->G, c->n, c->ldX, rows, kBK, false));
+  else
+    AL_TRY(make_map(&pl->tmX, c->X, c->G, c->n, c->ldX, kBK, rows, true));
+  AL_TRY(make_map(&pl->tmB, Bop, R, c->K, ldB, kBK, p.Kp, true));
+  ReduceParams& r = pl->r;
+  r.partial = c->partial;
+  r.rows = rows;
+  r.M = p.M;
+  r.K = p.K;
+  r.num_tiles = p.num_tiles;
+  r.kb_per_tile = p.kb_per_tile;
+  r.grid = pl->grid;
+  r.max_segs = p.max_segs;
+  pl->valid = true;
+  return ALPINE_OK;
+}
+
+// out[k][m] (ld_out) = contraction of the bound X with B operand [K][ldB]
+int run_gemm(alpine_ctx* c, int orient, const float* Bop, long long ldB, float* out, long long ld_out,
+             cudaStream_t st) {
+  const long long M = (orient == ORIENT_XH) ? c->G : c->n;
+  const long long R = (orient == ORIENT_XH) ? c->n : c->G;
+  if (c->simt) {
+    dim3 grid(ceil_div(M, 128), c->K);
+    if (orient == ORIENT_XH)
+      simt_gemm_kernel<ORIENT_XH><<<grid, 128, 0, st>>>(c->X, c->ldX, Bop, ldB, (int)M, (int)R, c->K, out, ld_out);
+    else
+      simt_gemm_kernel<ORIENT_WX><<<grid, 128, 0, st>>>(c->X, c->ldX, Bop, ldB, (int)M, (int)R, c->K, out, ld_out);
+    LAUNCH_CHECK();
+    return ALPINE_OK;
+  }
+  GemmPlan* pl = (orient == ORIENT_XH) ? &c->plan_xh : &c->plan_wx;
+  if (!pl->valid) {
+    AL_TRY(build_plan(c, pl, orient, Bop, ldB));
+    // building one plan may have re-allocated the shared partial buffer
+    GemmPlan* other = (orient == ORIENT_XH) ? &c->plan_wx : &c->plan_xh;
+    if (other->valid) {
+      other->p.partial = c->partial;
+      other->r.partial = c->partial;
+    }
+  }
+  if (orient == ORIENT_XH) {
+    if (pl->mt == 2) AL_TRY((launch_gemm_t<ORIENT_XH, 2>(*pl, st)));
+    else AL_TRY((launch_gemm_t<ORIENT_XH, 1>(*pl, st)));
+  } else {
+    if (pl->mt == 2) AL_TRY((launch_gemm_t<ORIENT_WX, 2>(*pl, st)));
+    else AL_TRY((launch_gemm_t<ORIENT_WX, 1>(*pl, st)));
+  }
+  ReduceParams r = pl->r;
+  r.out = out;
+  r.ld = ld_out;
+  dim3 rgrid(r.num_tiles, c->K < 16 ? c->K : 16);
+  reduce_partials_kernel<<<rgrid, 256, 0, st>>>(r);
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+int run_gram(alpine_ctx* c, const float* A, long long ld, long long L, float* C, int ldC, float* rowsum,
+             cudaStream_t st) {
+  GramParams g;
+  g.A = A;
+  g.ld = ld;
+  g.K = c->K;
+  g.L = L;
+  const int blocks = gram_blocks_for(c, L, &g.chunk);
+  g.partial = c->gram_partial;
+  g.rs_partial = rowsum ? c->gram_rs_partial : nullptr;
+  const int tiles = ceil_div(c->K, 128);
+  gram_partial_kernel<<<dim3(blocks, tiles * tiles), 256, 0, st>>>(g);
+  LAUNCH_CHECK();
+  gram_finish_kernel<<<ceil_div(static_cast<long long>(c->K) * c->K, 256), 256, 0, st>>>(
+      c->gram_partial, c->gram_rs_partial, blocks, c->K, C, ldC, rowsum);
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+template <int EPI>
+int run_sym_long(alpine_ctx* c, const SymLongParams& p, cudaStream_t st) {
+  const int blocks = ceil_div(p.L, kSLCols);
+  if (c->K <= 128) {
+    auto kern = sym_long_kernel<8, EPI>;
+    const size_t smem = sym_long_smem_bytes<8>(c->K);
+    kern<<<blocks, 256, smem, st>>>(p);
+  } else {
+    auto kern = sym_long_kernel<16, EPI>;
+    const size_t smem = sym_long_smem_bytes<16>(c->K);
+    kern<<<blocks, 256, smem, st>>>(p);
+  }
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+// statistics of the current (H, B): S = H H^T, hsum, Q_i (and the prediction-loss partials)
+int run_stats(alpine_ctx* c, double* loss_row, cudaStream_t st) {
+  const CovTable tab = make_cov_table(c);
+  if (c->n_cov > 0) {
+    int kmax = 0, cmax = 0;
+    for (int i = 0; i < c->n_cov; ++i) {
+      kmax = c->kblk[i] > kmax ? c->kblk[i] : kmax;
+      cmax = c->ccov[i] > cmax ? c->ccov[i] : cmax;
+    }
+    const size_t smem = (static_cast<size_t>(cmax) * kmax + static_cast<size_t>(kmax + cmax) * (kStatCells + 1)) * 4;
+    if (smem > 200 * 1024) return fail(ALPINE_ERR_ARG, "covariate block too large for the statistics kernel");
+    cov_stats_kernel<<<dim3(c->stat_blocks, c->n_cov), kStatCells, smem, st>>>(
+        tab, c->loss_type, c->H, c->ldH, (int)c->n, (float)c->eps, c->q_total, c->q_partial, c->pred_partial);
+    LAUNCH_CHECK();
+  }
+  AL_TRY(run_gram(c, c->H, c->ldH, c->n, c->red_S(), c->K, c->red_hsum(), st));
+  StatsFinishParams f;
+  f.q_partial = c->q_partial;
+  f.q_blocks = c->stat_blocks;
+  f.q_total = c->q_total;
+  f.stats_q = c->red_Q();
+  f.pred_partial = c->pred_partial;
+  f.n_cov = c->n_cov;
+  f.t1_partial = c->t1_partial;
+  f.t1_n = c->sl_blocks_n;
+  f.T = c->T;
+  f.ldT = c->K;
+  f.S = c->red_S();
+  f.ldS = c->K;
+  f.K = c->K;
+  f.loss_row = loss_row;
+  stats_finish_kernel<<<1, 256, 0, st>>>(f);
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+int check_bound(const alpine_ctx* c, bool need_labels) {
+  if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
+  if (c->X == nullptr) return fail(ALPINE_ERR_STATE, "alpine_bind_dense has not been called");
+  if (c->W == nullptr || c->H == nullptr) return fail(ALPINE_ERR_STATE, "alpine_bind_factors has not been called");
+  if (need_labels) {
+    for (int i = 0; i < c->n_cov; ++i)
+      if (c->Y[i] == nullptr || c->B[i] == nullptr)
+        return fail(ALPINE_ERR_STATE, "covariate %d has no labels / B bound", i);
+    if (!c->hparams_set) return fail(ALPINE_ERR_STATE, "alpine_set_hparams has not been called");
+  }
+  return ALPINE_OK;
+}
+
+int check_kernel_error(alpine_ctx* c) {
+  int h[8];
+  CU_TRY(cudaMemcpy(h, c->err, sizeof(h), cudaMemcpyDeviceToHost));
+  if (h[0] != 0) {
+    cudaMemset(c->err, 0, sizeof(h));
+    return fail(ALPINE_ERR_KERNEL, "contraction kernel pipeline timeout: code %d block %d thread %d aux %d %d", h[0],
+                h[1], h[2], h[3], h[4]);
+  }
+  return ALPINE_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int alpine_abi_version(void) { return 2; }
+const char* alpine_last_error(void) { return g_last_error.c_str(); }
+long long alpine_launch_count(void) { return g_launches.load(); }
+
+int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells, int n_blocks, const int* k_blocks,
+                  int n_cov, const int* c_cov, int loss_type) {
+  if (out == nullptr || k_blocks == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
+  if (n_genes <= 0 || n_cells <= 0) return fail(ALPINE_ERR_ARG, "empty matrix: %lld genes x %lld cells", (long long)n_genes, (long long)n_cells);
+  if (n_genes > 0x7fffffffLL || n_cells > 0x7fffffffLL) return fail(ALPINE_ERR_ARG, "dimension exceeds int32");
+  if (n_blocks != n_cov + 1 || n_cov < 0 || n_cov > kMaxCov)
+    return fail(ALPINE_ERR_ARG, "n_blocks must be n_cov + 1 with n_cov <= %d", kMaxCov);
+  if (loss_type != ALPINE_LOSS_KL && loss_type != ALPINE_LOSS_FROBENIUS) return fail(ALPINE_ERR_ARG, "unknown loss_type");
+  int dev_count = 0;
+  CU_TRY(cudaGetDeviceCount(&dev_count));
+  if (device < 0 || device >= dev_count) return fail(ALPINE_ERR_ARG, "device %d not present (%d devices)", device, dev_count);
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(ALPINE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  alpine_ctx* c = new alpine_ctx();
+  c->device = device;
+  c->G = n_genes;
+  c->n = n_cells;
+  c->n_blocks = n_blocks;
+  c->n_cov = n_cov;
+  c->loss_type = loss_type;
+  c->num_sms = prop.multiProcessorCount;
+  int K = 0, Kg = 0, q = 0;
+  for (int i = 0; i < n_blocks; ++i) {
+    if (k_blocks[i] <= 0) {
+      delete c;
+      return fail(ALPINE_ERR_ARG, "block %d has %d components", i, k_blocks[i]);
+    }
+    c->kblk[i] = k_blocks[i];
+    K += k_blocks[i];
+    if (i < n_cov) {
+      if (c_cov == nullptr || c_cov[i] <= 0) {
+        delete c;
+        return fail(ALPINE_ERR_ARG, "covariate %d has no categories", i);
+      }
+      c->ccov[i] = c_cov[i];
+      Kg += k_blocks[i];
+      q += c_cov[i] * k_blocks[i];
+    }
+  }
+  if (K > 256) {
+    delete c;
+    return fail(ALPINE_ERR_ARG, "total components %d > 256 is not supported", K);
+  }
+  c->K = K;
+  c->Kp = static_cast<int>(round_up(K, 16));
+  c->Kg = Kg;
+  c->q_total = q;
+  c->mt = (c->Kp <= 128) ? 2 : 1;
+  if (const char* e = getenv("ALPINE_B200_MT"))
+    if (atoi(e) == 1) c->mt = 1;
+  if (const char* e = getenv("ALPINE_B200_GEMM")) c->simt = (strcmp(e, "simt") == 0);
+  c->ldG = round_up(n_genes, 4);
+  c->ldN = round_up(n_cells, 4);
+  *out = c;
+  return ALPINE_OK;
+}
+
+int alpine_destroy(alpine_ctx* c) {
+  if (c == nullptr) return ALPINE_OK;
+  cudaSetDevice(c->device);
+  void* ptrs[] = {c->WT, c->A, c->numG, c->denG, c->T, c->colsum, c->gram_partial, c->gram_rs_partial, c->q_partial,
+                  c->pred_partial, c->t1_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
+                  c->own_reduce};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  delete c;
+  return ALPINE_OK;
+}
+
+int alpine_bind_dense(alpine_ctx* c, const float* X, int64_t ldX) {
+  if (c == nullptr || X == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
+  if (ldX < c->G || (ldX & 3) != 0 || (reinterpret_cast<uintptr_t>(X) & 15) != 0)
+    return fail(ALPINE_ERR_ARG, "X needs ldX >= n_genes, ldX %% 4 == 0 and a 16-byte aligned base");
+  c->X = X;
+  c->ldX = ldX;
+  c->plan_xh.valid = c->plan_wx.valid = false;
+  return ALPINE_OK;
+}
+
+int alpine_bind_labels(alpine_ctx* c, int i, const float* Y) {
+  if (c == nullptr || Y == nullptr || i < 0 || i >= c->n_cov) return fail(ALPINE_ERR_ARG, "bad covariate index %d", i);
+  c->Y[i] = Y;
+  return ALPINE_OK;
+}
+
+int alpine_bind_factors(alpine_ctx* c, float* W, int64_t ldW, float* H, int64_t ldH, float* const* Bs) {
+  if (c == nullptr || W == nullptr || H == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
+  if (ldW < c->K) return fail(ALPINE_ERR_ARG, "ldW < K");
+  if (ldH < c->n || (ldH & 3) != 0 || (reinterpret_cast<uintptr_t>(H) & 15) != 0)
+    return fail(ALPINE_ERR_ARG, "H needs ldH >= n_cells, ldH %% 4 == 0 and a 16-byte aligned base");
+  if (c->n_cov > 0 && Bs == nullptr) return fail(ALPINE_ERR_ARG, "Bs is null");
+  c->W = W;
+  c->ldW = ldW;
+  c->H = H;
+  c->ldH = ldH;
+  for (int i = 0; i < c->n_cov; ++i) c->B[i] = Bs[i];
+  c->plan_xh.valid = c->plan_wx.valid = false;
+  return ALPINE_OK;
+}
+
+int alpine_set_hparams(alpine_ctx* c, const double* lam, double alpha_W, double l1_ratio_W, double orth_W, double eps) {
+  if (c == nullptr || (c->n_cov > 0 && lam == nullptr)) return fail(ALPINE_ERR_ARG, "null argument");
+  for (int i = 0; i < c->n_cov; ++i) c->lam[i] = lam[i];
+  c->alpha = alpha_W;
+  c->l1 = l1_ratio_W;
+  c->orth = orth_W;
+  c->eps = eps;
+  c->hparams_set = true;
+  return ALPINE_OK;
+}
+
+int64_t alpine_reduce_buffer_size(const alpine_ctx* c) { return c ? c->reduce_floats() : 0; }
+
+int alpine_bind_reduce_buffer(alpine_ctx* c, float* buf) {
+  if (c == nullptr || buf == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
+  if ((reinterpret_cast<uintptr_t>(buf) & 15) != 0) return fail(ALPINE_ERR_ARG, "reduce buffer must be 16-byte aligned");
+  c->reduce = buf;
+  return ALPINE_OK;
+}
+
+int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
+  AL_TRY(check_bound(c, true));
+  if (max_iter <= 0) return fail(ALPINE_ERR_ARG, "max_iter must be positive");
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(ensure_workspace(c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (max_iter > c->loss_cap) {
+    if (c->loss_hist) cudaFree(c->loss_hist);
+    c->loss_hist = nullptr;
+    AL_TRY(dev_alloc(&c->loss_hist, static_cast<size_t>(max_iter) * (2 + c->n_cov)));
+    c->loss_cap = max_iter;
+  }
+  // ||X||_F^2 (first term of the trace identity that replaces main.py:736)
+  const int sb = 1024;
+  sumsq_partial_kernel<<<sb, 256, 0, st>>>(c->X, c->ldX, c->n, (int)c->G, c->sumsq_partial);
+  LAUNCH_CHECK();
+  sum_double_kernel<<<1, 32, 0, st>>>(c->sumsq_partial, sb, c->xnorm2);
+  LAUNCH_CHECK();
+  // W^T master copy for the gene-side kernels
+  transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
+                                                                                       c->WT, c->ldG);
+  LAUNCH_CHECK();
+  AL_TRY(run_stats(c, nullptr, st));
+  c->fit_active = true;
+  return ALPINE_OK;
+}
+
+int alpine_mu_partials(alpine_ctx* c, void* stream) {
+  AL_TRY(check_bound(c, true));
+  if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
+  CU_TRY(cudaSetDevice(c->device));
+  return run_gemm(c, ORIENT_XH, c->H, c->ldH, c->red_Pt(), c->ldG, static_cast<cudaStream_t>(stream));
+}
+
+int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
+  AL_TRY(check_bound(c, true));
+  if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
+  if (iter < 0 || iter >= c->loss_cap) return fail(ALPINE_ERR_ARG, "iteration %d outside [0, %d)", iter, c->loss_cap);
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  // ---- W update (main.py:592-612) on W^T, then refresh the caller's row-major W
+  SymLongParams w{};
+  w.Sym = c->red_S();
+  w.ldS = c->K;
+  w.Mat = c->WT;
+  w.ldM = c->ldG;
+  w.K = c->K;
+  w.L = c->G;
+  w.Num = c->red_Pt();
+  w.ldNum = c->ldG;
+  w.c1 = static_cast<float>((1.0 - c->l1) * c->alpha);
+  w.c2 = static_cast<float>(c->l1 * c->alpha);
+  w.orth = static_cast<float>(c->orth);
+  w.eps = static_cast<float>(c->eps);
+  AL_TRY(run_sym_long<EPI_W>(c, w, st));
+  transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
+                                                                                       c->W, c->ldW);
+  LAUNCH_CHECK();
+  // ---- B updates (main.py:615-628) from the statistics of the old H / old B
+  const CovTable tab = make_cov_table(c);
+  if (c->n_cov > 0) {
+    int ckmax = 0;
+    for (int i = 0; i < c->n_cov; ++i) ckmax = c->ccov[i] * c->kblk[i] > ckmax ? c->ccov[i] * c->kblk[i] : ckmax;
+    b_update_kernel<<<c->n_cov, 128, ckmax * sizeof(float), st>>>(tab, c->loss_type, c->red_Q(), c->red_hsum(),
+                                                                  c->red_S(), c->K, (float)c->eps);
+    LAUNCH_CHECK();
+  }
+  // ---- T = W^T W of the new W
+  AL_TRY(run_gram(c, c->WT, c->ldG, c->G, c->T, c->K, nullptr, st));
+  // ---- A = W^T X (main.py:653)
+  AL_TRY(run_gemm(c, ORIENT_WX, c->WT, c->ldG, c->A, c->ldN, st));
+  // ---- guided terms (main.py:637-650) with the old H and the new B
+  if (c->n_cov > 0) {
+    int kmax = 0, ckmax = 0;
+    for (int i = 0; i < c->n_cov; ++i) {
+      kmax = c->kblk[i] > kmax ? c->kblk[i] : kmax;
+      ckmax = c->ccov[i] * c->kblk[i] > ckmax ? c->ccov[i] * c->kblk[i] : ckmax;
+    }
+    const size_t smem = (static_cast<size_t>(ckmax) + 3ull * kmax * 128) * sizeof(float);
+    if (smem > 200 * 1024) return fail(ALPINE_ERR_ARG, "covariate block too large for the guided-terms kernel");
+    guided_terms_kernel<<<dim3(ceil_div(c->n, 128), c->n_cov), 128, smem, st>>>(tab, c->loss_type, c->H, c->ldH, (int)c->n,
+                                                                               (float)c->eps, c->numG, c->denG, c->ldN);
+    LAUNCH_CHECK();
+  }
+  // ---- H update (main.py:652-663)
+  SymLongParams h{};
+  h.Sym = c->T;
+  h.ldS = c->K;
+  h.Mat = c->H;
+  h.ldM = c->ldH;
+  h.K = c->K;
+  h.L = c->n;
+  h.Num = c->A;
+  h.ldNum = c->ldN;
+  h.numG = c->numG;
+  h.denG = c->denG;
+  h.ldD = c->ldN;
+  h.Kg = c->Kg;
+  h.eps = static_cast<float>(c->eps);
+  h.t1_partial = c->t1_partial;
+  AL_TRY(run_sym_long<EPI_H>(c, h, st));
+  // ---- statistics of the new H for the next iteration + loss terms of this one (main.py:666, 726-753)
+  AL_TRY(run_stats(c, c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov), st));
+  return ALPINE_OK;
+}
+
+int alpine_fit_losses(alpine_ctx* c, int n_iter, double* xnorm2, double* rows, void* stream) {
+  if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
+  if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
+  if (n_iter < 0 || n_iter > c->loss_cap) return fail(ALPINE_ERR_ARG, "n_iter outside the loss history");
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CU_TRY(cudaStreamSynchronize(st));
+  AL_TRY(check_kernel_error(c));
+  if (xnorm2) CU_TRY(cudaMemcpy(xnorm2, c->xnorm2, sizeof(double), cudaMemcpyDeviceToHost));
+  if (rows && n_iter > 0)
+    CU_TRY(cudaMemcpy(rows, c->loss_hist, sizeof(double) * n_iter * (2 + c->n_cov), cudaMemcpyDeviceToHost));
+  return ALPINE_OK;
+}
+
+int alpine_scale(alpine_ctx* c, void* stream) {
+  AL_TRY(check_bound(c, false));
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(ensure_workspace(c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
+                                                                                       c->WT, c->ldG);
+  LAUNCH_CHECK();
+  rowsum_kernel<<<c->K, 256, 0, st>>>(c->WT, c->ldG, c->G, c->colsum);  // s = W.sum(0), main.py:776
+  LAUNCH_CHECK();
+  scale_w_kernel<<<2 * c->num_sms, 256, 0, st>>>(c->W, c->ldW, (int)c->G, c->K, c->colsum);
+  LAUNCH_CHECK();
+  scale_h_kernel<<<4 * c->num_sms, 256, 0, st>>>(c->H, c->ldH, c->K, (int)c->n, c->colsum);
+  LAUNCH_CHECK();
+  if (c->n_cov > 0) {
+    for (int i = 0; i < c->n_cov; ++i)
+      if (c->B[i] == nullptr) return fail(ALPINE_ERR_STATE, "covariate %d has no B bound", i);
+    scale_b_kernel<<<c->n_cov, 128, 0, st>>>(make_cov_table(c), c->colsum);
+    LAUNCH_CHECK();
+  }
+  return ALPINE_OK;
+}
+
+int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
+  AL_TRY(check_bound(c, false));
+  if (n_iter < 0) return fail(ALPINE_ERR_ARG, "n_iter must be >= 0");
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(ensure_workspace(c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
+                                                                                       c->WT, c->ldG);
+  LAUNCH_CHECK();
+  AL_TRY(run_gram(c, c->WT, c->ldG, c->G, c->T, c->K, nullptr, st));       // T = W^T W, loop-invariant
+  AL_TRY(run_gemm(c, ORIENT_WX, c->WT, c->ldG, c->A, c->ldN, st));           // A = W^T X, loop-invariant (main.py:706)
+  SymLongParams h{};
+  h.Sym = c->T;
+  h.ldS = c->K;
+  h.Mat = c->H;
+  h.ldM = c->ldH;
+  h.K = c->K;
+  h.L = c->n;
+  h.Num = c->A;
+  h.ldNum = c->ldN;
+  h.eps = static_cast<float>(c->eps);
+  for (int it = 0; it < n_iter; ++it) AL_TRY(run_sym_long<EPI_TRANSFORM>(c, h, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return check_kernel_error(c);
+}
+
+int alpine_xh_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
+  AL_TRY(check_bound(c, false));
+  if (out == nullptr || ld_out < c->G) return fail(ALPINE_ERR_ARG, "bad output");
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(ensure_workspace(c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AL_TRY(run_gemm(c, ORIENT_XH, c->H, c->ldH, out, ld_out, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return check_kernel_error(c);
+}
+
+int alpine_wx_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
+  AL_TRY(check_bound(c, false));
+  if (out == nullptr || ld_out < c->n) return fail(ALPINE_ERR_ARG, "bad output");
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(ensure_workspace(c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
+                                                                                       c->WT, c->ldG);
+  LAUNCH_CHECK();
+  AL_TRY(run_gemm(c, ORIENT_WX, c->WT, c->ldG, out, ld_out, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return check_kernel_error(c);
+}
+
+int alpine_query(const alpine_ctx* c, int* num_sms, int* gemm_grid, int* smem_stages, int* k_padded) {
+  if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
+  if (num_sms) *num_sms = c->num_sms;
+  if (gemm_grid) *gemm_grid = c->plan_xh.valid ? c->plan_xh.grid : 0;
+  if (smem_stages) *smem_stages = c->plan_xh.valid ? c->plan_xh.p.sx : 0;
+  if (k_padded) *k_padded = c->Kp;
+  return ALPINE_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,456 @@
+// The two dense contractions of ALPINE's multiplicative-update step over the gene x cell matrix X, as one
+// warp-specialised, persistent, stream-K tcgen05 kernel for sm_100a (3xTF32 split precision, fp32 accumulate):
+//
+//   ORIENT_XH:  D[g][k] = sum_j X[g][j] * H[k][j]     (reference main.py:596,  (2*X_batch) @ H^T)
+//   ORIENT_WX:  D[j][k] = sum_g X[g][j] * W[g][k]     (reference main.py:653,  (2*W^T) @ X_batch)
+//
+// X lives in HBM exactly as the reference holds it: cells-major, X_phys[j][g] (main.py:104, 445).  Both
+// contractions stream that single copy once through TMA; the 128-row (M) side of the MMA is genes (XH) or
+// cells (WX), the N side is the K components (padded to a multiple of 16), the reduction runs over the other
+// axis of X in blocks of 32.
+//
+//  * A operand (X super-tile, MT*128 rows x 32 reduction elements, fp32): TMA -> shared memory ring -> 4*MT
+//    converter warps split every value into tf32 hi + lo and write both to TENSOR MEMORY (tcgen05.st), so the
+//    tensor core reads A from TMEM and the memory orientation of X does not matter (XH reads the tile
+//    transposed out of shared memory, WX reads 128B-swizzled rows).
+//  * B operand (H or W^T tile, Kp x 32 fp32, K-major): TMA (SWIZZLE_128B, rows >= K zero-filled) -> shared memory
+//    ring; the converter warps split it in place (hi) and into a second buffer (lo); the MMA reads both through
+//    UMMA shared-memory descriptors.  One B tile serves MT*128 rows of X, which keeps L2->SM traffic of the
+//    small operand below that of X itself.
+//  * D accumulates in TMEM (fp32, MT accumulators of Kp columns): per 8-deep k-step three MMAs
+//    Alo*Bhi + Ahi*Blo + Ahi*Bhi (small terms first).
+//  * Work split: the (super-tile, k-block) space is cut into gridDim.x equal contiguous ranges (stream-K).  Every
+//    contiguous piece of one tile ("segment") is stored to a partial-sum slot; reduce_partials_kernel adds the
+//    slots of a tile in a fixed order, so results are deterministic and no CTA ever waits for another.
+//  * Every mbarrier wait is bounded (clock64): a protocol bug reports an error code instead of hanging the GPU.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace alpine {
+
+constexpr int kBM = 128;         // rows per MMA tile == TMEM lanes
+constexpr int kBK = 32;          // reduction elements per pipeline stage (128 bytes of fp32)
+constexpr int kUmmaK = 8;        // tf32: 32 bytes per MMA k-step
+constexpr int kTmemCols = 512;
+constexpr int kTmemAOff = 256;   // A staging starts here; accumulators occupy [0, 256)
+constexpr int kMaxXStages = 8;
+constexpr int kMaxBStages = 4;
+constexpr int kMaxAStages = 4;
+constexpr long long kTimeoutCycles = 1ll << 30;  // ~0.5 s: a wait that long is a bug, never a hang
+
+enum { ORIENT_XH = 0, ORIENT_WX = 1 };
+
+// error codes written to GemmParams::err[0]; err[1..4] = blockIdx, threadIdx, k-block counter, aux
+enum { ERR_NONE = 0, ERR_XPROD_EMPTY = 1, ERR_BPROD_EMPTY = 2, ERR_CONV_XFULL = 3, ERR_CONV_BFULL = 4,
+       ERR_CONV_AEMPTY = 5, ERR_MMA_CFULL = 6, ERR_MMA_ACCEMPTY = 7, ERR_EPI_ACCFULL = 8 };
+
+struct GemmParams {
+  int M;            // rows of D (genes for XH, cells for WX)
+  int R;            // reduction length
+  int K;            // real component count
+  int Kp;           // MMA N: K padded to a multiple of 16 (<= 256 / MT)
+  int num_tiles;    // ceil(M / (MT*128))
+  int kb_per_tile;  // ceil(R / 32)
+  int sx;           // X ring depth
+  int sb;           // B ring depth
+  int max_segs;     // partial slots per CTA
+  float* partial;   // [gridDim.x * max_segs][K][MT*128]
+  int* err;         // [8]
+};
+
+__host__ __device__ inline long long gemm_range_begin(long long total, int grid, int cta) {
+  return total * cta / grid;
+}
+
+struct AbortCtx {
+  volatile int* flag;  // shared
+  int* err;            // global
+};
+
+__device__ __noinline__ void report_timeout(const AbortCtx& a, int code, int aux0, int aux1) {
+  if (atomicCAS(a.err, 0, code) == 0) {
+    a.err[1] = blockIdx.x;
+    a.err[2] = threadIdx.x;
+    a.err[3] = aux0;
+    a.err[4] = aux1;
+    __threadfence();
+  }
+  *a.flag = 1;
+}
+
+// bounded mbarrier wait (single thread)
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, const AbortCtx& a, int code, int aux0,
+                                         int aux1) {
+  if (ptx::mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (true) {
+    if (ptx::mbar_try_wait(bar, parity)) return true;
+    if (*a.flag) return false;
+    if (clock64() - t0 > kTimeoutCycles) {
+      report_timeout(a, code, aux0, aux1);
+      return false;
+    }
+  }
+}
+// warp-uniform bounded wait: lane 0 polls with the timeout, then every lane acquires the completed phase itself
+__device__ __forceinline__ bool warp_wait_bar(uint64_t* bar, uint32_t parity, const AbortCtx& a, int code, int aux0,
+                                              int aux1) {
+  int ok = 1;
+  if ((threadIdx.x & 31) == 0) ok = wait_bar(bar, parity, a, code, aux0, aux1) ? 1 : 0;
+  ok = __shfl_sync(0xffffffffu, ok, 0);
+  if (!ok) return false;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+  }
+  return true;
+}
+
+template <int MT>
+struct GemmCfg {
+  static constexpr int kRows = MT * kBM;            // rows of X per super-tile
+  static constexpr int kConvWarps = 4 * MT;         // one converter/epilogue thread per row
+  static constexpr int kThreads = (kConvWarps + 3) * 32;
+  static constexpr int kXTileBytes = kRows * kBK * 4;
+  static constexpr int kAStageCols = MT * 64;       // per tile: 32 hi + 32 lo columns
+  static constexpr int kAStages = (kTmemCols - kTmemAOff) / kAStageCols;
+  static constexpr int kAccStride = kTmemAOff / MT;  // column distance between the MT accumulators
+  static constexpr int kMaxKp = kAccStride;
+};
+
+struct GemmSmemLayout {
+  size_t x_off, b_off, bar_off, total;
+};
+__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int x_tile_bytes, int Kp, int sx, int sb) {
+  GemmSmemLayout l;
+  l.x_off = 0;
+  l.b_off = static_cast<size_t>(sx) * x_tile_bytes;
+  l.bar_off = l.b_off + static_cast<size_t>(sb) * 2 * Kp * kBK * 4;
+  l.total = l.bar_off + (2 * kMaxXStages + 2 * kMaxBStages + 2 * kMaxAStages + 2) * 8 + 16;
+  return l;
+}
+
+template <int ORIENT, int MT>
+__global__ void __launch_bounds__(GemmCfg<MT>::kThreads, 1)
+mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
+               const GemmParams p) {
+  using Cfg = GemmCfg<MT>;
+  constexpr int kRows = Cfg::kRows;
+  constexpr int kConvWarps = Cfg::kConvWarps;
+  constexpr int kXTileBytes = Cfg::kXTileBytes;
+  constexpr int kAStages = Cfg::kAStages;
+  constexpr int kAStageCols = Cfg::kAStageCols;
+  constexpr int kWarpXProd = kConvWarps, kWarpMma = kConvWarps + 1, kWarpBProd = kConvWarps + 2;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int SX = p.sx, SB = p.sb;
+  const int b_tile_bytes = p.Kp * kBK * 4;
+  const GemmSmemLayout lay = gemm_smem_layout(kXTileBytes, p.Kp, SX, SB);
+  uint8_t* smem_x = smem + lay.x_off;
+  uint8_t* smem_b = smem + lay.b_off;
+
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + lay.bar_off);
+  uint64_t* xfull_bar = bars;                           // [SX]  TMA -> converters
+  uint64_t* xempty_bar = xfull_bar + kMaxXStages;       // [SX]  converters -> X producer
+  uint64_t* bfull_bar = xempty_bar + kMaxXStages;       // [SB]  TMA -> converters
+  uint64_t* bempty_bar = bfull_bar + kMaxBStages;       // [SB]  MMA commit -> B producer
+  uint64_t* cfull_bar = bempty_bar + kMaxBStages;       // [kAStages]  converters -> MMA (A in TMEM + B split)
+  uint64_t* aempty_bar = cfull_bar + kMaxAStages;       // [kAStages]  MMA commit -> converters
+  uint64_t* accfull_bar = aempty_bar + kMaxAStages;     // MMA commit -> epilogue
+  uint64_t* accempty_bar = accfull_bar + 1;             // epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty_bar + 1);
+  volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+
+  AbortCtx actx{abort_flag, p.err};
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SX; ++i) {
+      ptx::mbar_init(&xfull_bar[i], 1);
+      ptx::mbar_init(&xempty_bar[i], kConvWarps);
+    }
+    for (int i = 0; i < SB; ++i) {
+      ptx::mbar_init(&bfull_bar[i], 1);
+      ptx::mbar_init(&bempty_bar[i], 1);
+    }
+    for (int i = 0; i < kAStages; ++i) {
+      ptx::mbar_init(&cfull_bar[i], kConvWarps);
+      ptx::mbar_init(&aempty_bar[i], 1);
+    }
+    ptx::mbar_init(accfull_bar, 1);
+    ptx::mbar_init(accempty_bar, kConvWarps);
+    *abort_flag = 0;
+    ptx::fence_barrier_init();
+  }
+  if (warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
+  if (warp == kWarpBProd && lane == 0) ptx::prefetch_tensormap(&tmB);
+  if (warp == kWarpMma) {
+    ptx::tmem_alloc(tmem_slot, kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long long kbT = p.kb_per_tile;
+  const long long total = static_cast<long long>(p.num_tiles) * kbT;
+  const int cta = blockIdx.x;
+  const long long range_begin = gemm_range_begin(total, gridDim.x, cta);
+  const long long range_end = gemm_range_begin(total, gridDim.x, cta + 1);
+
+  if (warp == kWarpXProd) {
+    // ===================================================== TMA producer of the X ring
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long pos = range_begin; pos < range_end; ++pos, ++it) {
+        const int tile = static_cast<int>(pos / kbT);
+        const int kb = static_cast<int>(pos - tile * kbT);
+        const int s = it % SX;
+        if (!wait_bar(&xempty_bar[s], ((it / SX) & 1) ^ 1, actx, ERR_XPROD_EMPTY, it, s)) break;
+        uint8_t* dst = smem_x + static_cast<size_t>(s) * kXTileBytes;
+        ptx::mbar_arrive_expect_tx(&xfull_bar[s], kXTileBytes);
+        if (ORIENT == ORIENT_XH)  // box {kRows genes, 32 cells} at (gene0, cell0): smem [32 cells][kRows genes]
+          ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], tile * kRows, kb * kBK, ptx::kEvictFirst);
+        else  // box {32 genes, kRows cells} at (gene0, cell0): smem [kRows cells][32 genes], 128B swizzle
+          ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], kb * kBK, tile * kRows, ptx::kEvictFirst);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpBProd) {
+    // ===================================================== TMA producer of the B ring
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long pos = range_begin; pos < range_end; ++pos, ++it) {
+        const int kb = static_cast<int>(pos % kbT);
+        const int s = it % SB;
+        if (!wait_bar(&bempty_bar[s], ((it / SB) & 1) ^ 1, actx, ERR_BPROD_EMPTY, it, s)) break;
+        uint8_t* dst = smem_b + static_cast<size_t>(s) * 2 * b_tile_bytes;
+        ptx::mbar_arrive_expect_tx(&bfull_bar[s], b_tile_bytes);
+        ptx::tma_load_2d(dst, &tmB, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+      }
+    }
+    __syncwarp();
+  } else if (warp == kWarpMma) {
+    // ===================================================== MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = ptx::make_idesc_tf32(kBM, p.Kp);
+      uint32_t it = 0, seg = 0;
+      bool ok = true;
+      for (long long pos = range_begin; pos < range_end && ok; ++seg) {
+        const int kb0 = static_cast<int>(pos % kbT);
+        const long long left = range_end - pos;
+        const int kb1 = static_cast<int>((kbT - kb0) < left ? kbT : kb0 + left);
+        if (seg > 0) {
+          if (!wait_bar(accempty_bar, (seg - 1) & 1, actx, ERR_MMA_ACCEMPTY, seg, 0)) break;
+          ptx::tc_fence_after();
+        }
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int t = it % kAStages;
+          const int sbi = it % SB;
+          if (!wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
+            ok = false;
+            break;
+          }
+          ptx::tc_fence_after();
+          const uint32_t sb_addr = ptx::smem_u32(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes);
+          const uint64_t dhi = ptx::make_kmajor_sw128_desc(sb_addr);
+          const uint64_t dlo = ptx::make_kmajor_sw128_desc(sb_addr + b_tile_bytes);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint32_t d_acc = tmem_base + mt * Cfg::kAccStride;
+            const uint32_t a_hi = tmem_base + kTmemAOff + t * kAStageCols + mt * 64;
+            const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+            for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
+              // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+              const uint64_t bh = dhi + static_cast<uint64_t>(2 * ks);
+              const uint64_t bl = dlo + static_cast<uint64_t>(2 * ks);
+              ptx::mma_tf32_ts(d_acc, a_lo + ks * kUmmaK, bh, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+              ptx::mma_tf32_ts(d_acc, a_hi + ks * kUmmaK, bl, idesc, 1u);
+              ptx::mma_tf32_ts(d_acc, a_hi + ks * kUmmaK, bh, idesc, 1u);
+            }
+          }
+          ptx::tc_commit(&aempty_bar[t]);
+          ptx::tc_commit(&bempty_bar[sbi]);
+        }
+        if (ok) ptx::tc_commit(accfull_bar);
+        pos += kb1 - kb0;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================== converter + epilogue warps (one thread per X row)
+    const int row = warp * 32 + lane;          // row inside the super-tile
+    const int mt = warp >> 2;                  // which 128-row MMA tile
+    const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
+    const int conv_threads = kConvWarps * 32;
+    uint32_t it = 0, seg = 0;
+    bool ok = true;
+    for (long long pos = range_begin; pos < range_end && ok; ++seg) {
+      const int tile = static_cast<int>(pos / kbT);
+      const int kb0 = static_cast<int>(pos % kbT);
+      const long long left = range_end - pos;
+      const int kb1 = static_cast<int>((kbT - kb0) < left ? kbT : kb0 + left);
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int s = it % SX;
+        const int sbi = it % SB;
+        const int t = it % kAStages;
+        // ---- X tile: shared memory fp32 -> registers (hi, lo)
+        if (!warp_wait_bar(&xfull_bar[s], (it / SX) & 1, actx, ERR_CONV_XFULL, it, s)) {
+          ok = false;
+          break;
+        }
+        const float* sX = reinterpret_cast<const float*>(smem_x + static_cast<size_t>(s) * kXTileBytes);
+        uint32_t hi[32], lo[32];
+        if (ORIENT == ORIENT_XH) {
+          // tile is [32 cells][kRows genes]; this thread owns gene `row`
+#pragma unroll
+          for (int kk = 0; kk < 32; ++kk) ptx::split_tf32(sX[kk * kRows + row], hi[kk], lo[kk]);
+        } else {
+          // tile is [kRows cells][32 genes] with the TMA 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+          const float4* rp = reinterpret_cast<const float4*>(sX + row * kBK);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 q = rp[c ^ (row & 7)];
+            ptx::split_tf32(q.x, hi[4 * c + 0], lo[4 * c + 0]);
+            ptx::split_tf32(q.y, hi[4 * c + 1], lo[4 * c + 1]);
+            ptx::split_tf32(q.z, hi[4 * c + 2], lo[4 * c + 2]);
+            ptx::split_tf32(q.w, hi[4 * c + 3], lo[4 * c + 3]);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&xempty_bar[s]);  // the X slot can be refilled
+        // ---- B tile: split in place (hi) and into the second buffer (lo); all converter threads share the work
+        if (!warp_wait_bar(&bfull_bar[sbi], (it / SB) & 1, actx, ERR_CONV_BFULL, it, sbi)) {
+          ok = false;
+          break;
+        }
+        {
+          float4* bh = reinterpret_cast<float4*>(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes);
+          float4* bl = reinterpret_cast<float4*>(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes + b_tile_bytes);
+          const int n4 = p.Kp * (kBK / 4);
+          for (int i = threadIdx.x; i < n4; i += conv_threads) {
+            const float4 v = bh[i];
+            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+            ptx::split_tf32(v.x, h0, l0);
+            ptx::split_tf32(v.y, h1, l1);
+            ptx::split_tf32(v.z, h2, l2);
+            ptx::split_tf32(v.w, h3, l3);
+            bh[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+            bl[i] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+          }
+          ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+        }
+        // ---- A tile: registers -> tensor memory stage t (once the MMAs that read it two stages ago are done)
+        if (!warp_wait_bar(&aempty_bar[t], ((it / kAStages) & 1) ^ 1, actx, ERR_CONV_AEMPTY, it, t)) {
+          ok = false;
+          break;
+        }
+        ptx::tc_fence_after();
+        const uint32_t a_addr = tmem_base + lane_sel + kTmemAOff + t * kAStageCols + mt * 64;
+        ptx::tmem_st_x32(a_addr, hi);
+        ptx::tmem_st_x32(a_addr + 32, lo);
+        ptx::tc_wait_st();
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&cfull_bar[t]);
+      }
+      if (!ok) break;
+
+      // ---- epilogue of this segment: accumulator -> partial-sum slot [K][kRows]
+      if (!warp_wait_bar(accfull_bar, seg & 1, actx, ERR_EPI_ACCFULL, seg, 0)) {
+        ok = false;
+        break;
+      }
+      ptx::tc_fence_after();
+      (void)tile;
+      float* dst = p.partial + (static_cast<size_t>(cta) * p.max_segs + seg) * p.K * kRows + row;
+      const uint32_t acc_addr = tmem_base + lane_sel + mt * Cfg::kAccStride;
+      for (int c0 = 0; c0 < p.Kp; c0 += 16) {
+        uint32_t v[16];
+        ptx::tmem_ld_x16(acc_addr + c0, v);
+        ptx::tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.K) dst[static_cast<size_t>(c0 + i) * kRows] = __uint_as_float(v[i]);
+      }
+      // accumulator drained: hand TMEM back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(accempty_bar);
+      pos += kb1 - kb0;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == kWarpMma) ptx::tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out[k][m] = sum over the segments of m's tile, in stream-K order (fixed => deterministic).
+// grid = (num_tiles, ceil(K / rows_per_block)); block = kRows threads is not required: threads stride over rows.
+struct ReduceParams {
+  const float* partial;
+  int rows;  // MT*128
+  int M, K;
+  int num_tiles, kb_per_tile, grid, max_segs;
+  float* out;
+  long long ld;
+};
+__global__ void reduce_partials_kernel(const ReduceParams p) {
+  const int tile = blockIdx.x;
+  const long long kbT = p.kb_per_tile;
+  const long long total = static_cast<long long>(p.num_tiles) * kbT;
+  const long long t_begin = tile * kbT, t_end = t_begin + kbT;
+  // first CTA whose (non-empty) range contains t_begin
+  int c = static_cast<int>(t_begin * p.grid / total);
+  while (c + 1 < p.grid && gemm_range_begin(total, p.grid, c + 1) <= t_begin) ++c;
+  while (c > 0 && gemm_range_begin(total, p.grid, c) > t_begin) --c;
+  __shared__ int s_slots[512];
+  __shared__ int s_n;
+  if (threadIdx.x == 0) {
+    int cnt = 0;
+    for (int q = c; q < p.grid && gemm_range_begin(total, p.grid, q) < t_end; ++q) {
+      const long long b = gemm_range_begin(total, p.grid, q), e = gemm_range_begin(total, p.grid, q + 1);
+      if (e <= b) continue;
+      const int first_tile = static_cast<int>(b / kbT);
+      if (cnt < 512) s_slots[cnt++] = q * p.max_segs + (tile - first_tile);
+    }
+    s_n = cnt;
+  }
+  __syncthreads();
+  const int ns = s_n;
+  const int m0 = tile * p.rows;
+  for (int k = blockIdx.y; k < p.K; k += gridDim.y) {
+    for (int r = threadIdx.x; r < p.rows; r += blockDim.x) {
+      if (m0 + r >= p.M) break;
+      float acc = 0.f;
+      for (int q = 0; q < ns; ++q)
+        acc += __ldcg(p.partial + (static_cast<size_t>(s_slots[q]) * p.K + k) * p.rows + r);
+      p.out[static_cast<long long>(k) * p.ld + m0 + r] = acc;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Plain fp32 CUDA-core version of the same contractions (debug / A-B checking only: ALPINE_B200_GEMM=simt).
+// out[k][m] = sum_r A(m, r) * B[k][r];  XH: A(m, r) = X[r * ldX + m];  WX: A(m, r) = X[m * ldX + r].
+template <int ORIENT>
+__global__ void simt_gemm_kernel(const float* __restrict__ X, long long ldX, const float* __restrict__ B,
+                                 long long ldB, int M, int R, int K, float* __restrict__ out, long long ld_out) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = blockIdx.y;
+  if (m >= M || k >= K) return;
+  float acc = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const float a = (ORIENT == ORIENT_XH) ? X[static_cast<long long>(r) * ldX + m] : X[static_cast<long long>(m) * ldX + r];
+    acc = fmaf(a, __ldg(B + static_cast<long long>(k) * ldB + r), acc);
+  }
+  out[static_cast<long long>(k) * ld_out + m] = acc;
+}
+
+}  // namespace alpine

@@ -1,0 +1,556 @@
+// Element-wise and reduction kernels around the tcgen05 contractions: 3xTF32 operand splitting, the W / B
+// multiplicative updates, guided (covariate) terms of the H update, per-iteration statistics and loss terms,
+// post-fit scaling and the transform update.  All are HBM-bound streaming kernels: coalesced along the
+// contiguous dimension, fp64 only in the loss accumulators, partial sums reduced in a fixed order.
+#pragma once
+#include "ptx_sm100.cuh"
+
+namespace alpine {
+
+enum { LOSS_KL = 0, LOSS_FROB = 1 };
+constexpr int kMaxCov = 8;
+
+struct CovDesc {
+  int row0;         // first row of the block in H / first column in W
+  int k;            // components of the block
+  int c;            // categories
+  const float* Y;   // [c][n] one-hot (zero column = missing label)
+  float* B;         // [c][k]
+  int q_off;        // offset (floats) of this block's Q / YH matrix inside the stats area
+  float lam;
+};
+struct CovTable {
+  int n_cov;
+  CovDesc d[kMaxCov];
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// sum of squares of a pitched matrix in fp64 (||X||_F^2), two-stage deterministic reduction
+__global__ void sumsq_partial_kernel(const float* __restrict__ X, long long ld, long long rows, int cols,
+                                     double* __restrict__ partial) {
+  double acc = 0.0;
+  const int cols4 = cols >> 2;  // ld % 4 == 0 and base 16B aligned => float4 loads are aligned per row
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float4* p4 = reinterpret_cast<const float4*>(X + r * ld);
+    float s = 0.f;
+    for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
+      const float4 v = __ldg(p4 + c);
+      s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    for (int c = (cols4 << 2) + threadIdx.x; c < cols; c += blockDim.x) {
+      const float v = X[r * ld + c];
+      s += v * v;
+    }
+    acc += static_cast<double>(s);
+  }
+  __shared__ double red[32];
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) t += red[w];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void sum_double_kernel(const double* __restrict__ partial, int n, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double t = 0.0;
+    for (int i = 0; i < n; ++i) t += partial[i];
+    *out = t;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// B update (reference main.py:615-628) from cell-reduced statistics; one block per covariate.
+//   KL  : B *= (lam * Q) / max(lam * hsum, eps),  Q = (Y / max(B H_i, eps)) H_i^T
+//   Frob: B *= (2 * YH) / max(2 * B (H_i H_i^T), eps)
+__global__ void b_update_kernel(const CovTable tab, int loss_type, const float* __restrict__ stats_q,
+                                const float* __restrict__ hsum, const float* __restrict__ S, int ldS, float eps) {
+  const CovDesc d = tab.d[blockIdx.x];
+  extern __shared__ float bs[];  // old B copy [c][k]
+  for (int e = threadIdx.x; e < d.c * d.k; e += blockDim.x) bs[e] = d.B[e];
+  __syncthreads();
+  const float* Q = stats_q + d.q_off;
+  for (int e = threadIdx.x; e < d.c * d.k; e += blockDim.x) {
+    const int c = e / d.k, k = e - c * d.k;
+    float num, den;
+    if (loss_type == LOSS_KL) {
+      num = d.lam * Q[e];
+      den = d.lam * hsum[d.row0 + k];
+    } else {
+      num = 2.0f * Q[e];
+      float acc = 0.f;
+      for (int k2 = 0; k2 < d.k; ++k2) acc += (2.0f * bs[c * d.k + k2]) * S[(d.row0 + k2) * ldS + d.row0 + k];
+      den = acc;
+    }
+    den = fmaxf(den, eps);
+    d.B[e] = bs[e] * (num / den);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Guided terms of the H update for the covariate rows (reference main.py:637-650), per cell, old H, new B:
+//   KL  : numG = (lam B^T) (Y / max(B H_i, eps)) ;  denG = (lam B^T) 1
+//   Frob: numG = (2 lam B^T) Y                   ;  denG = (2 lam B^T) (B H_i)
+// One thread per cell; B in shared memory; per-thread row accumulators in shared memory [k][tid].
+__global__ void __launch_bounds__(128) guided_terms_kernel(const CovTable tab, int loss_type,
+                                                           const float* __restrict__ H, long long ldH, int n,
+                                                           float eps, float* __restrict__ numG,
+                                                           float* __restrict__ denG, long long ldD) {
+  extern __shared__ float sm[];
+  const CovDesc d = tab.d[blockIdx.y];
+  float* Bs = sm;                    // [c][k]
+  float* acc_n = sm + d.c * d.k;     // [k][128]
+  float* acc_d = acc_n + d.k * 128;  // [k][128]
+  float* hcol = acc_d + d.k * 128;   // [k][128]
+  for (int e = threadIdx.x; e < d.c * d.k; e += blockDim.x) Bs[e] = d.B[e];
+  __syncthreads();
+  const long long j = blockIdx.x * 128ll + threadIdx.x;
+  if (j >= n) return;
+  const int t = threadIdx.x;
+  for (int k = 0; k < d.k; ++k) {
+    hcol[k * 128 + t] = H[(d.row0 + k) * ldH + j];
+    acc_n[k * 128 + t] = 0.f;
+    acc_d[k * 128 + t] = 0.f;
+  }
+  const float scale = (loss_type == LOSS_KL) ? d.lam : 2.0f * d.lam;
+  for (int c = 0; c < d.c; ++c) {
+    float yhat = 0.f;
+    for (int k = 0; k < d.k; ++k) yhat += Bs[c * d.k + k] * hcol[k * 128 + t];
+    const float y = __ldg(d.Y + static_cast<long long>(c) * n + j);
+    const float rn = (loss_type == LOSS_KL) ? y / fmaxf(yhat, eps) : y;
+    const float rd = (loss_type == LOSS_KL) ? 1.0f : yhat;
+    for (int k = 0; k < d.k; ++k) {
+      const float lb = scale * Bs[c * d.k + k];
+      acc_n[k * 128 + t] += lb * rn;
+      acc_d[k * 128 + t] += lb * rd;
+    }
+  }
+  for (int k = 0; k < d.k; ++k) {
+    numG[(d.row0 + k) * ldD + j] = acc_n[k * 128 + t];
+    denG[(d.row0 + k) * ldD + j] = acc_d[k * 128 + t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Per-covariate cell statistics from the NEW H and NEW B (inputs of the next B update and the prediction loss,
+// reference main.py:618-626 and 727-748): per block of 256 cells
+//   KL  : Qp[c][k] = sum_j rho[c][j] H_i[k][j], rho = Y / max(B H_i, eps);  pred = sum y log(max(y/yh,eps)) - y + yh
+//   Frob: Qp[c][k] = sum_j Y[c][j] H_i[k][j];                               pred = sum (y - B H_i)^2
+constexpr int kStatCells = 256;
+__global__ void __launch_bounds__(kStatCells) cov_stats_kernel(const CovTable tab, int loss_type,
+                                                               const float* __restrict__ H, long long ldH, int n,
+                                                               float eps, int q_total,
+                                                               float* __restrict__ q_partial,     // [blocks][q_total]
+                                                               double* __restrict__ pred_partial  // [blocks][n_cov]
+) {
+  extern __shared__ float sm[];
+  const CovDesc d = tab.d[blockIdx.y];
+  constexpr int P = kStatCells + 1;
+  float* Bs = sm;                // [c][k]
+  float* hs = sm + d.c * d.k;    // [k][P]
+  float* rs = hs + d.k * P;      // [c][P]
+  __shared__ double red[kStatCells / 32];
+  for (int e = threadIdx.x; e < d.c * d.k; e += blockDim.x) Bs[e] = d.B[e];
+  const int t = threadIdx.x;
+  const long long j = blockIdx.x * static_cast<long long>(kStatCells) + t;
+  const bool live = j < n;
+  for (int k = 0; k < d.k; ++k) hs[k * P + t] = live ? H[(d.row0 + k) * ldH + j] : 0.f;
+  __syncthreads();
+  double pl = 0.0;
+  for (int c = 0; c < d.c; ++c) {
+    float yhat = 0.f;
+    for (int k = 0; k < d.k; ++k) yhat += Bs[c * d.k + k] * hs[k * P + t];
+    const float y = live ? __ldg(d.Y + static_cast<long long>(c) * n + j) : 0.f;
+    float r;
+    if (loss_type == LOSS_KL) {
+      const float yh = fmaxf(yhat, eps);
+      r = y / yh;
+      if (live) pl += static_cast<double>(y * logf(fmaxf(y / yh, eps)) - y + yh);
+    } else {
+      r = y;
+      const float dlt = y - yhat;
+      if (live) pl += static_cast<double>(dlt * dlt);
+    }
+    rs[c * P + t] = live ? r : 0.f;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < d.c * d.k; e += blockDim.x) {
+    const int c = e / d.k, k = e - c * d.k;
+    float acc = 0.f;
+    for (int u = 0; u < kStatCells; ++u) acc += rs[c * P + u] * hs[k * P + u];
+    q_partial[static_cast<size_t>(blockIdx.x) * q_total + d.q_off + e] = acc;
+  }
+  for (int o = 16; o > 0; o >>= 1) pl += __shfl_down_sync(0xffffffffu, pl, o);
+  if ((t & 31) == 0) red[t >> 5] = pl;
+  __syncthreads();
+  if (t == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kStatCells / 32; ++w) s += red[w];
+    pred_partial[static_cast<size_t>(blockIdx.x) * tab.n_cov + blockIdx.y] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Post-fit scaling (reference main.py:772-781): column sums of W, then W /= s, H *= s, B /= s.
+__global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int ldP, int K,
+                                     float* __restrict__ s) {
+  for (int k = threadIdx.x + blockIdx.x * blockDim.x; k < K; k += blockDim.x * gridDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < chunks; ++c) acc += partial[c * ldP + k];
+    s[k] = acc;
+  }
+}
+__global__ void scale_w_kernel(float* __restrict__ W, long long ldW, int G, int K, const float* __restrict__ s) {
+  const long long total = static_cast<long long>(G) * K;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long g = i / K;
+    const int k = static_cast<int>(i - g * K);
+    W[g * ldW + k] = W[g * ldW + k] / s[k];
+  }
+}
+__global__ void scale_h_kernel(float* __restrict__ H, long long ldH, int K, int n, const float* __restrict__ s) {
+  const long long total = static_cast<long long>(K) * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i / n);
+    const long long j = i - static_cast<long long>(k) * n;
+    H[k * ldH + j] = H[k * ldH + j] * s[k];
+  }
+}
+__global__ void scale_b_kernel(const CovTable tab, const float* __restrict__ s) {
+  const CovDesc d = tab.d[blockIdx.x];
+  for (int e = threadIdx.x; e < d.c * d.k; e += blockDim.x) d.B[e] = d.B[e] / s[d.row0 + (e % d.k)];
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// out[c][r] = in[r][c]  (W <-> W^T), 32x32 tiles through shared memory, both sides coalesced
+__global__ void transpose_kernel(const float* __restrict__ in, long long ld_in, int rows, int cols,
+                                 float* __restrict__ out, long long ld_out) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int rr = r0 + r, cc = c0 + threadIdx.x;
+    tile[r][threadIdx.x] = (rr < rows && cc < cols) ? in[static_cast<long long>(rr) * ld_in + cc] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int cc = c0 + r, rr = r0 + threadIdx.x;
+    if (cc < cols && rr < rows) out[static_cast<long long>(cc) * ld_out + rr] = tile[threadIdx.x][r];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Z = Sym (K x K, symmetric) * Mat (K x L, L long), fused with the multiplicative update that consumes Z.
+// This is the Gram reformulation of the reference's G x n sized products:
+//   EPI_W : Mat = W^T [K][G], Sym = S = H H^T :  Z^T = W (H H^T)  replaces ((2W) @ H) @ H^T   (main.py:599)
+//           den = 2 Z + (1-l1) alpha W + orth (rowsum_k(W) - W) + l1 alpha ; W *= 2 P / max(den, eps)   (main.py:596-605)
+//   EPI_H : Mat = H [K][n],   Sym = T = W^T W :  Z = (W^T W) H    replaces (2W^T) @ (W @ H)      (main.py:654)
+//           H *= (numG + 2 A) / max(denG + 2 Z, eps)                                            (main.py:648-656)
+//   EPI_TRANSFORM: H *= 2 A / max(2 Z, eps)                                                     (main.py:706-709)
+// One block = all K rows x 64 columns; 16 x 16 threads, each KI rows (ty + 16 i) x 4 consecutive columns.
+enum { EPI_W = 0, EPI_H = 1, EPI_TRANSFORM = 2 };
+constexpr int kSLCols = 64;
+struct SymLongParams {
+  const float* Sym;
+  int ldS;
+  float* Mat;  // updated in place
+  long long ldM;
+  int K;
+  long long L;
+  const float* Num;  // EPI_W: P^T [K][ldNum];  EPI_H / EPI_TRANSFORM: A = W^T X [K][ldNum]
+  long long ldNum;
+  const float* numG;  // EPI_H: guided rows [Kg][ldD]
+  const float* denG;
+  long long ldD;
+  int Kg;
+  float c1, c2, orth, eps;
+  double* t1_partial;  // EPI_H: [gridDim.x]  sum A .* Hnew
+};
+template <int KI>
+inline size_t sym_long_smem_bytes(int K) {
+  return (static_cast<size_t>(K) * kSLCols + 32 * KI * 16) * sizeof(float) + kSLCols * sizeof(double);
+}
+template <int KI, int EPI>
+__global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
+  constexpr int KW = KI * 16;
+  extern __shared__ __align__(16) uint8_t sl_smem[];
+  double* cs = reinterpret_cast<double*>(sl_smem);                // [64] column sums (EPI_W)
+  float* Ms = reinterpret_cast<float*>(sl_smem + kSLCols * 8);    // [K][64]
+  float* Ss = Ms + static_cast<size_t>(p.K) * kSLCols;            // [32][KW]
+  __shared__ double red[8];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long c0 = static_cast<long long>(blockIdx.x) * kSLCols;
+  const bool full = c0 + kSLCols <= p.L;
+
+  for (int e = tid; e < p.K * 16; e += 256) {
+    const int k = e >> 4, c4 = e & 15;
+    const long long col = c0 + 4 * c4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* src = p.Mat + static_cast<long long>(k) * p.ldM + col;
+    if (full) {
+      v = *reinterpret_cast<const float4*>(src);
+    } else {
+      if (col + 0 < p.L) v.x = src[0];
+      if (col + 1 < p.L) v.y = src[1];
+      if (col + 2 < p.L) v.z = src[2];
+      if (col + 3 < p.L) v.w = src[3];
+    }
+    reinterpret_cast<float4*>(Ms)[e] = v;
+  }
+  float4 acc[KI];
+#pragma unroll
+  for (int i = 0; i < KI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int k0 = 0; k0 < p.K; k0 += 32) {
+    __syncthreads();
+    for (int e = tid; e < 32 * KW; e += 256) {
+      const int kk = e / KW, r = e - kk * KW;
+      Ss[e] = (k0 + kk < p.K && r < p.K) ? __ldg(p.Sym + static_cast<long long>(k0 + kk) * p.ldS + r) : 0.f;
+    }
+    __syncthreads();
+    const int kmax = min(32, p.K - k0);
+    for (int kk = 0; kk < kmax; ++kk) {
+      const float4 m = reinterpret_cast<const float4*>(Ms)[(k0 + kk) * 16 + tx];
+#pragma unroll
+      for (int i = 0; i < KI; ++i) {
+        const float sv = Ss[kk * KW + ty + 16 * i];
+        acc[i].x = fmaf(sv, m.x, acc[i].x);
+        acc[i].y = fmaf(sv, m.y, acc[i].y);
+        acc[i].z = fmaf(sv, m.z, acc[i].z);
+        acc[i].w = fmaf(sv, m.w, acc[i].w);
+      }
+    }
+  }
+  if (EPI == EPI_W) {
+    // rowsum_k W[g][:] in fp64 so that (rowsum - w) does not cancel (the reference sums the other K-1 entries)
+    if (tid < kSLCols) {
+      double sacc = 0.0;
+      for (int k = 0; k < p.K; ++k) sacc += static_cast<double>(Ms[k * kSLCols + tid]);
+      cs[tid] = sacc;
+    }
+    __syncthreads();
+  }
+  double t1 = 0.0;
+  const long long col = c0 + 4 * tx;
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const int k = ty + 16 * i;
+    if (k >= p.K || col >= p.L) continue;
+    const float4 old4 = reinterpret_cast<const float4*>(Ms)[k * 16 + tx];
+    const float oldv[4] = {old4.x, old4.y, old4.z, old4.w};
+    const float zv[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
+    float nv[4] = {0.f, 0.f, 0.f, 0.f}, gn[4] = {0.f, 0.f, 0.f, 0.f}, gd[4] = {0.f, 0.f, 0.f, 0.f};
+    const float* nsrc = p.Num + static_cast<long long>(k) * p.ldNum + col;
+    const bool g_on = (EPI == EPI_H) && (k < p.Kg);
+    if (full) {
+      const float4 t = *reinterpret_cast<const float4*>(nsrc);
+      nv[0] = t.x, nv[1] = t.y, nv[2] = t.z, nv[3] = t.w;
+      if (g_on) {
+        const float4 a = *reinterpret_cast<const float4*>(p.numG + static_cast<long long>(k) * p.ldD + col);
+        const float4 b = *reinterpret_cast<const float4*>(p.denG + static_cast<long long>(k) * p.ldD + col);
+        gn[0] = a.x, gn[1] = a.y, gn[2] = a.z, gn[3] = a.w;
+        gd[0] = b.x, gd[1] = b.y, gd[2] = b.z, gd[3] = b.w;
+      }
+    } else {
+      for (int x = 0; x < 4; ++x)
+        if (col + x < p.L) {
+          nv[x] = nsrc[x];
+          if (g_on) {
+            gn[x] = p.numG[static_cast<long long>(k) * p.ldD + col + x];
+            gd[x] = p.denG[static_cast<long long>(k) * p.ldD + col + x];
+          }
+        }
+    }
+    float outv[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) {
+      float num, den;
+      if (EPI == EPI_W) {
+        const float others = static_cast<float>(cs[4 * tx + x] - static_cast<double>(oldv[x]));
+        den = (2.0f * zv[x] + p.c1 * oldv[x]) + p.orth * others;  // main.py:599-601
+        den += p.c2;                                              // main.py:603
+        num = 2.0f * nv[x];                                       // main.py:596
+      } else if (EPI == EPI_H) {
+        num = gn[x] + 2.0f * nv[x];   // main.py:648, 653
+        den = gd[x] + 2.0f * zv[x];   // main.py:649, 654
+      } else {
+        num = 2.0f * nv[x];  // main.py:706
+        den = 2.0f * zv[x];  // main.py:707
+      }
+      den = fmaxf(den, p.eps);             // main.py:604, 655, 708
+      outv[x] = oldv[x] * (num / den);     // main.py:605, 656, 709
+      if (EPI == EPI_H && col + x < p.L) t1 += static_cast<double>(nv[x]) * static_cast<double>(outv[x]);
+    }
+    float* dst = p.Mat + static_cast<long long>(k) * p.ldM + col;
+    if (full) {
+      *reinterpret_cast<float4*>(dst) = make_float4(outv[0], outv[1], outv[2], outv[3]);
+    } else {
+      for (int x = 0; x < 4; ++x)
+        if (col + x < p.L) dst[x] = outv[x];
+    }
+  }
+  if (EPI == EPI_H) {
+    for (int o = 16; o > 0; o >>= 1) t1 += __shfl_down_sync(0xffffffffu, t1, o);
+    if ((tid & 31) == 0) red[tid >> 5] = t1;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < 8; ++w) s += red[w];
+      p.t1_partial[blockIdx.x] = s;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Gram matrix of a K x L matrix with a long L:  C = A A^T  (H H^T, main.py:599 / W^T W, main.py:654 after the
+// reformulation), plus row sums of A.  Block (x = column chunk, y = 128x128 output tile); partials are summed
+// in a fixed order by gram_finish_kernel.
+struct GramParams {
+  const float* A;
+  long long ld;
+  int K;
+  long long L;
+  long long chunk;     // columns per block (multiple of 32)
+  float* partial;      // [gridDim.x][K*K]
+  float* rs_partial;   // [gridDim.x][K] or nullptr
+};
+__global__ void __launch_bounds__(256) gram_partial_kernel(const GramParams p) {
+  constexpr int KW = 128, KI = 8;
+  __shared__ float Aa[32][KW + 1];
+  __shared__ float Ab[32][KW + 1];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tiles = (p.K + KW - 1) / KW;
+  const int ra = (blockIdx.y / tiles) * KW, cb = (blockIdx.y % tiles) * KW;
+  const long long j_begin = blockIdx.x * p.chunk;
+  const long long j_end = min(p.L, j_begin + p.chunk);
+  float acc[KI][KI];
+  float rs[KI];
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    rs[i] = 0.f;
+#pragma unroll
+    for (int j = 0; j < KI; ++j) acc[i][j] = 0.f;
+  }
+  for (long long j0 = j_begin; j0 < j_end; j0 += 32) {
+    __syncthreads();
+    for (int e = tid; e < KW * 32; e += 256) {
+      const int k = e >> 5, jj = e & 31;
+      const bool jin = j0 + jj < j_end;
+      Aa[jj][k] = (jin && ra + k < p.K) ? p.A[static_cast<long long>(ra + k) * p.ld + j0 + jj] : 0.f;
+      Ab[jj][k] = (jin && cb + k < p.K) ? p.A[static_cast<long long>(cb + k) * p.ld + j0 + jj] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int jj = 0; jj < 32; ++jj) {
+      float a[KI], b[KI];
+#pragma unroll
+      for (int i = 0; i < KI; ++i) {
+        a[i] = Aa[jj][ty + 16 * i];
+        b[i] = Ab[jj][tx + 16 * i];
+      }
+#pragma unroll
+      for (int i = 0; i < KI; ++i) {
+        rs[i] += a[i];
+#pragma unroll
+        for (int j = 0; j < KI; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+    }
+  }
+  float* dst = p.partial + static_cast<size_t>(blockIdx.x) * p.K * p.K;
+#pragma unroll
+  for (int i = 0; i < KI; ++i) {
+    const int r = ra + ty + 16 * i;
+    if (r >= p.K) continue;
+#pragma unroll
+    for (int j = 0; j < KI; ++j) {
+      const int c = cb + tx + 16 * j;
+      if (c < p.K) dst[r * p.K + c] = acc[i][j];
+    }
+    if (p.rs_partial != nullptr && cb == 0 && tx == 0) p.rs_partial[static_cast<size_t>(blockIdx.x) * p.K + r] = rs[i];
+  }
+}
+__global__ void gram_finish_kernel(const float* __restrict__ partial, const float* __restrict__ rs_partial,
+                                   int blocks, int K, float* __restrict__ C, int ldC, float* __restrict__ rowsum) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < K * K) {
+    float acc = 0.f;
+    for (int b = 0; b < blocks; ++b) acc += partial[static_cast<size_t>(b) * K * K + e];
+    C[(e / K) * ldC + (e % K)] = acc;
+  }
+  if (rowsum != nullptr && e < K) {
+    float acc = 0.f;
+    for (int b = 0; b < blocks; ++b) acc += rs_partial[static_cast<size_t>(b) * K + e];
+    rowsum[e] = acc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Finish the per-iteration statistics on one block (fixed summation order):
+//   stats_q  <- sum over cell blocks of q_partial                (input of the next B update)
+//   loss_row <- [ t1 = sum A .* Hnew, t2 = sum T .* S, pred_0.. ] (fp64; recon = ||X||^2 - 2 t1 + t2)
+struct StatsFinishParams {
+  const float* q_partial;
+  int q_blocks, q_total;
+  float* stats_q;
+  const double* pred_partial;
+  int n_cov;
+  const double* t1_partial;
+  int t1_n;
+  const float* T;
+  int ldT;
+  const float* S;
+  int ldS;
+  int K;
+  double* loss_row;  // [2 + n_cov] or nullptr
+};
+__global__ void stats_finish_kernel(const StatsFinishParams p) {
+  for (int e = threadIdx.x; e < p.q_total; e += blockDim.x) {
+    float acc = 0.f;
+    for (int b = 0; b < p.q_blocks; ++b) acc += p.q_partial[static_cast<size_t>(b) * p.q_total + e];
+    p.stats_q[e] = acc;
+  }
+  if (p.loss_row == nullptr) return;
+  __shared__ double red[32];
+  double t2 = 0.0;
+  for (int e = threadIdx.x; e < p.K * p.K; e += blockDim.x) {
+    const int a = e / p.K, b = e - a * p.K;
+    t2 += static_cast<double>(p.T[a * p.ldT + b]) * static_cast<double>(p.S[a * p.ldS + b]);
+  }
+  for (int o = 16; o > 0; o >>= 1) t2 += __shfl_down_sync(0xffffffffu, t2, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) s += red[w];
+    double t1 = 0.0;
+    for (int i = 0; i < p.t1_n; ++i) t1 += p.t1_partial[i];
+    p.loss_row[0] = t1;
+    p.loss_row[1] = s;
+    for (int i = 0; i < p.n_cov; ++i) {
+      double a = 0.0;
+      for (int b = 0; b < p.q_blocks; ++b) a += p.pred_partial[static_cast<size_t>(b) * p.n_cov + i];
+      p.loss_row[2 + i] = a;
+    }
+  }
+}
+
+// column sums of W (main.py:776) = row sums of W^T, one block per component, fp64 accumulation, fixed order
+__global__ void __launch_bounds__(256) rowsum_kernel(const float* __restrict__ A, long long ld, long long L,
+                                                     float* __restrict__ out) {
+  __shared__ double red[256];
+  const float* row = A + static_cast<long long>(blockIdx.x) * ld;
+  double acc = 0.0;
+  for (long long j = threadIdx.x; j < L; j += 256) acc += static_cast<double>(row[j]);
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = static_cast<float>(red[0]);
+}
+
+}  // namespace alpine

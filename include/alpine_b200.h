@@ -1,0 +1,100 @@
+/* alpine_b200 -- C ABI of the B200-native multiplicative-update NMF path of ALPINE.
+ *
+ * This is the drop-in boundary: the reference has no FFI of its own (it is pure
+ * Python over torch), so each entry point below cites the reference code it replaces.  A host binding
+ * (ctypes, see INTEGRATION.md and alpine_b200/_native.py) passes raw device pointers obtained from
+ * torch tensors; the library never owns X, Y, W, H or B.  Every function returns 0 on success and a
+ * non-zero status otherwise; alpine_last_error() returns a thread-local message for the last failure.
+ * No C++ types, exceptions or torch types cross this boundary.
+ *
+ * Layout conventions (all float32):
+ *   X  cells-major:  X[j * ldX + g], j < n cells, g < G genes, ldX % 4 == 0, 16-byte aligned base
+ *      (this is what the reference holds on the device: main.py:104, 445 keep adata.X's memory order)
+ *   W  G x K row-major with leading dimension ldW (ldW % 4 == 0); column blocks in covariate order,
+ *      unguided block last (main.py:79)
+ *   H  K x n row-major with leading dimension ldH (ldH % 4 == 0)
+ *   Y_i  c_i x n row-major one-hot, all-zero column for a missing label (encoder.py:32-37, main.py:447)
+ *   B_i  c_i x k_i row-major contiguous
+ */
+#ifndef ALPINE_B200_H
+#define ALPINE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct alpine_ctx alpine_ctx;
+
+enum { ALPINE_LOSS_KL = 0, ALPINE_LOSS_FROBENIUS = 1 };
+enum { ALPINE_OK = 0, ALPINE_ERR_ARG = 1, ALPINE_ERR_CUDA = 2, ALPINE_ERR_KERNEL = 3, ALPINE_ERR_STATE = 4 };
+
+/* ABI version of this header (bumped on any signature change). */
+int alpine_abi_version(void);
+/* Message of the last failing call on this thread. */
+const char* alpine_last_error(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long alpine_launch_count(void);
+
+/* Create a solver context for one device-resident shard of cells.
+ * Replaces the per-fit setup the reference does implicitly in ALPINE.__init__/_fit (main.py:62-80, 486-496).
+ *   n_blocks  = n_cov + 1; k_blocks[i] = components of block i (covariates first, unguided last)
+ *   c_cov[i]  = number of categories of covariate i
+ *   loss_type = ALPINE_LOSS_KL | ALPINE_LOSS_FROBENIUS (main.py:57, 371)                                   */
+int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells, int n_blocks,
+                  const int* k_blocks, int n_cov, const int* c_cov, int loss_type);
+int alpine_destroy(alpine_ctx* ctx);
+
+/* Bind the expression matrix (AlpineMatrices.X, main.py:445). */
+int alpine_bind_dense(alpine_ctx* ctx, const float* X_cells_major, int64_t ldX);
+/* Bind the one-hot label matrix of covariate i (AlpineMatrices.Ys[i], main.py:446-449). */
+int alpine_bind_labels(alpine_ctx* ctx, int i, const float* Y);
+/* Bind the factor matrices that the updates mutate in place (AlpineMatrices.Ws/Hs/Bs, main.py:454-470). */
+int alpine_bind_factors(alpine_ctx* ctx, float* W, int64_t ldW, float* H, int64_t ldH, float* const* Bs);
+/* Hyper-parameters read by the loop (main.py:64-67, 72): lam[n_cov], alpha_W, l1_ratio_W, orth_W, eps. */
+int alpine_set_hparams(alpine_ctx* ctx, const double* lam, double alpha_W, double l1_ratio_W, double orth_W,
+                       double eps);
+
+/* The per-iteration all-reduce payload: [ (X H^T)^T | H H^T | rowsum(H) | per-covariate B statistics ].
+ * The caller owns the buffer (so that torch.distributed can all-reduce it); size in floats.               */
+int64_t alpine_reduce_buffer_size(const alpine_ctx* ctx);
+int alpine_bind_reduce_buffer(alpine_ctx* ctx, float* buf);
+
+/* Start a fit: ||X||_F^2, tf32 split of the initial H, initial statistics (H H^T, B statistics).
+ * max_iter sizes the device-side loss history.  Replaces the head of _fit (main.py:486-498).              */
+int alpine_fit_begin(alpine_ctx* ctx, int max_iter, void* stream);
+/* First half of one full-batch iteration: numerator X H^T of the W update (main.py:596) into the reduce
+ * buffer, next to the statistics written by the previous iteration.  No data-path collective inside.      */
+int alpine_mu_partials(alpine_ctx* ctx, void* stream);
+/* Second half, after the (optional) all-reduce of the reduce buffer: W update (main.py:597-612), B updates
+ * (main.py:615-628), H update (main.py:631-663), loss terms of iteration `iter` (main.py:666, 726-753) and
+ * the statistics for the next iteration.                                                                  */
+int alpine_mu_apply(alpine_ctx* ctx, int iter, void* stream);
+/* Synchronise and read back the loss terms: xnorm2 = ||X||_F^2 and, per iteration, 2 + n_cov doubles
+ * [ tr(W^T X H^T), tr(W^T W H H^T), pred_0, ... ] of THIS shard; all are additive across shards and
+ * recon = xnorm2 - 2*t1 + t2 (the trace identity that replaces main.py:736).  Also reports kernel faults. */
+int alpine_fit_losses(alpine_ctx* ctx, int n_iter, double* xnorm2, double* rows, void* stream);
+
+/* Post-fit scaling (_scale_matrices, main.py:772-781). */
+int alpine_scale(alpine_ctx* ctx, void* stream);
+
+/* H-only transform loop (_transform, main.py:705-709) on the bound X and H with the bound (fixed) W:
+ *   A = W^T X once, T = W^T W once, then n_iter times  H *= 2A / max(2 T H, eps).                        */
+int alpine_transform(alpine_ctx* ctx, int n_iter, void* stream);
+
+/* The two dense contractions on their own (used by tests and for roofline measurement):
+ *   alpine_xh_product: out[k * ld_out + g] = sum_j X[g][j] * H[k][j]      (main.py:596 without the factor 2)
+ *   alpine_wx_product: out[k * ld_out + j] = sum_g W[g][k] * X[g][j]      (main.py:653 without the factor 2)
+ * using the bound X and the bound H / W.  ld_out % 4 == 0.                                                */
+int alpine_xh_product(alpine_ctx* ctx, float* out, int64_t ld_out, void* stream);
+int alpine_wx_product(alpine_ctx* ctx, float* out, int64_t ld_out, void* stream);
+
+/* Introspection for bench.py: SM count, grid and pipeline depth used by the contraction kernels. */
+int alpine_query(const alpine_ctx* ctx, int* num_sms, int* gemm_grid, int* smem_stages, int* k_padded);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ALPINE_B200_H */

@@ -1,0 +1,57 @@
+"""Helpers for the `-m gpu` parity tests: golden fixture -> device-resident Solver (through the C ABI)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from alpine_b200 import _native
+from tests.helpers import CASE_KW
+
+
+def to_dev_padded(a: np.ndarray, device) -> torch.Tensor:
+    t = _native.padded_rows(a.shape[0], a.shape[1], device)
+    t.copy_(torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)))
+    return t
+
+
+class DeviceProblem:
+    """X (cells x genes), Ys (c_i x n), W0 (G x K), H0 (K x n), Bs0 on the GPU, bound to a native Solver."""
+
+    def __init__(self, X_cells_by_genes, Ys, W0, H0, Bs0, blocks, kw, device="cuda:0"):
+        self.device = torch.device(device)
+        n, G = X_cells_by_genes.shape
+        self.X = to_dev_padded(X_cells_by_genes, self.device)
+        self.Ys = [torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.device) for y in Ys]
+        self.W = torch.from_numpy(np.ascontiguousarray(W0, dtype=np.float32)).to(self.device)
+        self.H = to_dev_padded(H0, self.device)
+        self.Bs = [torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device) for b in Bs0]
+        self.solver = _native.Solver(self.device, G, n, blocks, [y.shape[0] for y in Ys],
+                                     kw.get("loss_type", "kl-divergence"))
+        self.solver.bind_dense(self.X)
+        self.solver.bind_labels(self.Ys)
+        self.solver.bind_factors(self.W, self.H, self.Bs)
+        self.solver.set_hparams(kw.get("lam", []), kw.get("alpha_W", 0.0), kw.get("l1_ratio_W", 0.0),
+                                kw.get("orth_W", 0.0), kw.get("eps", 1e-6))
+        self.solver.reduce_buffer()
+
+    def run(self, n_iter, on_iter=None):
+        s = self.solver
+        s.fit_begin(n_iter)
+        for it in range(n_iter):
+            s.mu_partials()
+            s.mu_apply(it)
+            if on_iter is not None:
+                on_iter(it + 1)
+        return s.losses(n_iter)
+
+    def host(self):
+        return self.W.cpu().numpy(), self.H.cpu().numpy(), [b.cpu().numpy() for b in self.Bs]
+
+
+def problem_from_golden(name, g, device="cuda:0") -> DeviceProblem:
+    n_cov = int(g["n_cov"])
+    Ys = [np.ascontiguousarray(g[f"Y{i}_cells_by_cat"].T) for i in range(n_cov)]
+    kw = dict(CASE_KW[name])
+    kw.pop("use_als", None)
+    return DeviceProblem(g["X_cells_by_genes"], Ys, g["W0"], g["H0"], [g[f"B0_{i}"] for i in range(n_cov)],
+                         [int(b) for b in g["blocks"]], kw, device)
