@@ -87,7 +87,6 @@ inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 
 struct GemmPlan {
   bool valid = false;
-  int mt = 2;
   CUtensorMap tmX, tmB;
   GemmParams p{};
   ReduceParams r{};
@@ -106,7 +105,6 @@ struct alpine_ctx {
   int loss_type = LOSS_KL;
   int num_sms = 0;
   bool simt = false;
-  int mt = 2;
 
   const float* X = nullptr;
   long long ldX = 0;
@@ -232,10 +230,12 @@ int ensure_workspace(alpine_ctx* c) {
 
 int set_kernel_attrs() {
   const int big = 227 * 1024;
-  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_XH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_XH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_WX, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_WX, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define ALPINE_GEMM_ATTR(NC)                                                                                   \
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_XH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)); \
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_WX, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  ALPINE_GEMM_ATTR(1) ALPINE_GEMM_ATTR(2) ALPINE_GEMM_ATTR(3) ALPINE_GEMM_ATTR(4)
+  ALPINE_GEMM_ATTR(5) ALPINE_GEMM_ATTR(6) ALPINE_GEMM_ATTR(7) ALPINE_GEMM_ATTR(8)
+#undef ALPINE_GEMM_ATTR
   const int sl8 = static_cast<int>(sym_long_smem_bytes<8>(128)), sl16 = static_cast<int>(sym_long_smem_bytes<16>(256));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
@@ -248,21 +248,28 @@ int set_kernel_attrs() {
   return ALPINE_OK;
 }
 
-template <int ORIENT, int MT>
+template <int ORIENT>
 int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
-  auto kern = mu_gemm_kernel<ORIENT, MT>;
-  kern<<<pl.grid, GemmCfg<MT>::kThreads, pl.smem, st>>>(pl.tmX, pl.tmB, pl.p);
+  switch (pl.p.Kp / 16) {
+#define ALPINE_GEMM_CASE(NC)                                                                     \
+  case NC:                                                                                       \
+    mu_gemm_kernel<ORIENT, NC><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmB, pl.p);    \
+    break;
+    ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
+    ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
+#undef ALPINE_GEMM_CASE
+    default:
+      return fail(ALPINE_ERR_ARG, "unsupported padded component count %d", pl.p.Kp);
+  }
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
 
 // Build the plan of one contraction.  M rows of D, reduction R, B operand [K][ldB] with R columns.
 int build_plan(alpine_ctx* c, GemmPlan* pl, int orient, const float* Bop, long long ldB) {
-  const int mt = c->mt;
-  const int rows = mt * kBM;
+  const int rows = kRows;
   const long long M = (orient == ORIENT_XH) ? c->G : c->n;
   const long long R = (orient == ORIENT_XH) ? c->n : c->G;
-  pl->mt = mt;
   GemmParams& p = pl->p;
   p.M = static_cast<int>(M);
   p.R = static_cast<int>(R);
@@ -276,18 +283,19 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient, const float* Bop, long l
   p.max_segs = ceil_div(per_cta, p.kb_per_tile) + 1;
   // pipeline depths from the shared-memory budget
   const size_t budget = 227 * 1024 - 1024;
-  const int x_tile = rows * kBK * 4;
   int sb = 3, sx = 0;
   for (; sb >= 2; --sb) {
     sx = kMaxXStages;
-    while (sx >= 2 && gemm_smem_layout(x_tile, p.Kp, sx, sb).total > budget) --sx;
+    while (sx >= 2 && gemm_smem_layout(p.Kp, sx, sb).total > budget) --sx;
     if (sx >= 3 || sb == 2) break;
   }
   if (sx < 2) return fail(ALPINE_ERR_ARG, "K=%d does not fit the shared-memory pipeline", c->K);
   if (const char* e = getenv("ALPINE_B200_SX")) sx = atoi(e) < sx ? (atoi(e) < 1 ? 1 : atoi(e)) : sx;
   p.sx = sx;
   p.sb = sb;
-  pl->smem = gemm_smem_layout(x_tile, p.Kp, sx, sb).total + 1024;
+  p.chunk = 8;
+  if (const char* e = getenv("ALPINE_B200_CHUNK")) p.chunk = atoi(e) > 0 ? atoi(e) : p.chunk;
+  pl->smem = gemm_smem_layout(p.Kp, sx, sb).total + 1024;
   // partial-sum slots
   const size_t need = static_cast<size_t>(pl->grid) * p.max_segs * p.K * rows;
   if (need > c->partial_floats) {
@@ -343,13 +351,10 @@ int run_gemm(alpine_ctx* c, int orient, const float* Bop, long long ldB, float* 
       other->r.partial = c->partial;
     }
   }
-  if (orient == ORIENT_XH) {
-    if (pl->mt == 2) AL_TRY((launch_gemm_t<ORIENT_XH, 2>(*pl, st)));
-    else AL_TRY((launch_gemm_t<ORIENT_XH, 1>(*pl, st)));
-  } else {
-    if (pl->mt == 2) AL_TRY((launch_gemm_t<ORIENT_WX, 2>(*pl, st)));
-    else AL_TRY((launch_gemm_t<ORIENT_WX, 1>(*pl, st)));
-  }
+  if (orient == ORIENT_XH)
+    AL_TRY(launch_gemm_t<ORIENT_XH>(*pl, st));
+  else
+    AL_TRY(launch_gemm_t<ORIENT_WX>(*pl, st));
   ReduceParams r = pl->r;
   r.out = out;
   r.ld = ld_out;
@@ -502,17 +507,15 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
       q += c_cov[i] * k_blocks[i];
     }
   }
-  if (K > 256) {
+  if (K > kAccStride) {
     delete c;
-    return fail(ALPINE_ERR_ARG, "total components %d > 256 is not supported", K);
+    return fail(ALPINE_ERR_ARG, "total components %d > %d is not supported (two fp32 accumulators per CTA in TMEM)", K,
+                kAccStride);
   }
   c->K = K;
   c->Kp = static_cast<int>(round_up(K, 16));
   c->Kg = Kg;
   c->q_total = q;
-  c->mt = (c->Kp <= 128) ? 2 : 1;
-  if (const char* e = getenv("ALPINE_B200_MT"))
-    if (atoi(e) == 1) c->mt = 1;
   if (const char* e = getenv("ALPINE_B200_GEMM")) c->simt = (strcmp(e, "simt") == 0);
   c->ldG = round_up(n_genes, 4);
   c->ldN = round_up(n_cells, 4);

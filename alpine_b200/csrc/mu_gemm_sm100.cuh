@@ -9,16 +9,18 @@
 // cells (WX), the N side is the K components (padded to a multiple of 16), the reduction runs over the other
 // axis of X in blocks of 32.
 //
-//  * A operand (X super-tile, MT*128 rows x 32 reduction elements, fp32): TMA -> shared memory ring -> 4*MT
+//  * A operand (X super-tile, 256 rows x 32 reduction elements, fp32): TMA -> shared memory ring -> 8
 //    converter warps split every value into tf32 hi + lo and write both to TENSOR MEMORY (tcgen05.st), so the
 //    tensor core reads A from TMEM and the memory orientation of X does not matter (XH reads the tile
 //    transposed out of shared memory, WX reads 128B-swizzled rows).
 //  * B operand (H or W^T tile, Kp x 32 fp32, K-major): TMA (SWIZZLE_128B, rows >= K zero-filled) -> shared memory
 //    ring; the converter warps split it in place (hi) and into a second buffer (lo); the MMA reads both through
-//    UMMA shared-memory descriptors.  One B tile serves MT*128 rows of X, which keeps L2->SM traffic of the
+//    UMMA shared-memory descriptors.  One B tile serves 256 rows of X, which keeps L2->SM traffic of the
 //    small operand below that of X itself.
-//  * D accumulates in TMEM (fp32, MT accumulators of Kp columns): per 8-deep k-step three MMAs
-//    Alo*Bhi + Ahi*Blo + Ahi*Bhi (small terms first).
+//  * D accumulates in TMEM (fp32, 2 accumulators of Kp columns): per 8-deep k-step three MMAs
+//    Alo*Bhi + Ahi*Blo + Ahi*Bhi (small terms first).  The tensor core accumulates with round-toward-zero, so
+//    after every `chunk` k-blocks the accumulator is drained into an fp32 master sum held in the registers of
+//    the epilogue threads (round-to-nearest adds); the drain of one tile overlaps the MMAs of the other.
 //  * Work split: the (super-tile, k-block) space is cut into gridDim.x equal contiguous ranges (stream-K).  Every
 //    contiguous piece of one tile ("segment") is stored to a partial-sum slot; reduce_partials_kernel adds the
 //    slots of a tile in a fixed order, so results are deterministic and no CTA ever waits for another.
@@ -48,13 +50,14 @@ struct GemmParams {
   int M;            // rows of D (genes for XH, cells for WX)
   int R;            // reduction length
   int K;            // real component count
-  int Kp;           // MMA N: K padded to a multiple of 16 (<= 256 / MT)
-  int num_tiles;    // ceil(M / (MT*128))
+  int Kp;           // MMA N: K padded to a multiple of 16 (<= 128)
+  int num_tiles;    // ceil(M / 256)
   int kb_per_tile;  // ceil(R / 32)
   int sx;           // X ring depth
   int sb;           // B ring depth
+  int chunk;        // k-blocks accumulated in TMEM between two round-to-nearest flushes
   int max_segs;     // partial slots per CTA
-  float* partial;   // [gridDim.x * max_segs][K][MT*128]
+  float* partial;   // [gridDim.x * max_segs][K][256]
   int* err;         // [8]
 };
 
@@ -104,50 +107,45 @@ __device__ __forceinline__ bool warp_wait_bar(uint64_t* bar, uint32_t parity, co
   return true;
 }
 
-template <int MT>
-struct GemmCfg {
-  static constexpr int kRows = MT * kBM;            // rows of X per super-tile
-  static constexpr int kConvWarps = 4 * MT;         // one converter/epilogue thread per row
-  static constexpr int kThreads = (kConvWarps + 3) * 32;
-  static constexpr int kXTileBytes = kRows * kBK * 4;
-  static constexpr int kAStageCols = MT * 64;       // per tile: 32 hi + 32 lo columns
-  static constexpr int kAStages = (kTmemCols - kTmemAOff) / kAStageCols;
-  static constexpr int kAccStride = kTmemAOff / MT;  // column distance between the MT accumulators
-  static constexpr int kMaxKp = kAccStride;
-};
+// Fixed geometry: a super-tile is 2 MMA tiles (256 rows of X); 8 converter/epilogue warps, one thread per row.
+constexpr int kMT = 2;
+constexpr int kRows = kMT * kBM;
+constexpr int kConvWarps = 4 * kMT;
+constexpr int kGemmThreads = (kConvWarps + 3) * 32;
+constexpr int kXTileBytes = kRows * kBK * 4;
+constexpr int kAStageCols = kMT * 64;   // per MMA tile: 32 hi + 32 lo columns
+constexpr int kAStages = (kTmemCols - kTmemAOff) / kAStageCols;
+constexpr int kAccStride = kTmemAOff / kMT;  // column distance between the two accumulators (=> Kp <= 128)
 
 struct GemmSmemLayout {
   size_t x_off, b_off, bar_off, total;
 };
-__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int x_tile_bytes, int Kp, int sx, int sb) {
+__host__ __device__ inline GemmSmemLayout gemm_smem_layout(int Kp, int sx, int sb) {
   GemmSmemLayout l;
   l.x_off = 0;
-  l.b_off = static_cast<size_t>(sx) * x_tile_bytes;
+  l.b_off = static_cast<size_t>(sx) * kXTileBytes;
   l.bar_off = l.b_off + static_cast<size_t>(sb) * 2 * Kp * kBK * 4;
-  l.total = l.bar_off + (2 * kMaxXStages + 2 * kMaxBStages + 2 * kMaxAStages + 2) * 8 + 16;
+  l.total = l.bar_off + (2 * kMaxXStages + 2 * kMaxBStages + 2 * kMaxAStages + 4) * 8 + 16;
   return l;
 }
 
-template <int ORIENT, int MT>
-__global__ void __launch_bounds__(GemmCfg<MT>::kThreads, 1)
+// NC = Kp / 16: number of 16-column groups of the accumulator (compile time: the fp32 master sum of a thread's
+// accumulator row lives in 16*NC registers).
+template <int ORIENT, int NC>
+__global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
                const GemmParams p) {
-  using Cfg = GemmCfg<MT>;
-  constexpr int kRows = Cfg::kRows;
-  constexpr int kConvWarps = Cfg::kConvWarps;
-  constexpr int kXTileBytes = Cfg::kXTileBytes;
-  constexpr int kAStages = Cfg::kAStages;
-  constexpr int kAStageCols = Cfg::kAStageCols;
+  constexpr int Kp = 16 * NC;
   constexpr int kWarpXProd = kConvWarps, kWarpMma = kConvWarps + 1, kWarpBProd = kConvWarps + 2;
+  constexpr int b_tile_bytes = Kp * kBK * 4;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int SX = p.sx, SB = p.sb;
-  const int b_tile_bytes = p.Kp * kBK * 4;
-  const GemmSmemLayout lay = gemm_smem_layout(kXTileBytes, p.Kp, SX, SB);
+  const int SX = p.sx, SB = p.sb, C = p.chunk;
+  const GemmSmemLayout lay = gemm_smem_layout(Kp, SX, SB);
   uint8_t* smem_x = smem + lay.x_off;
   uint8_t* smem_b = smem + lay.b_off;
 
@@ -158,9 +156,9 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   uint64_t* bempty_bar = bfull_bar + kMaxBStages;       // [SB]  MMA commit -> B producer
   uint64_t* cfull_bar = bempty_bar + kMaxBStages;       // [kAStages]  converters -> MMA (A in TMEM + B split)
   uint64_t* aempty_bar = cfull_bar + kMaxAStages;       // [kAStages]  MMA commit -> converters
-  uint64_t* accfull_bar = aempty_bar + kMaxAStages;     // MMA commit -> epilogue
-  uint64_t* accempty_bar = accfull_bar + 1;             // epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty_bar + 1);
+  uint64_t* accfull_bar = aempty_bar + kMaxAStages;     // [kMT]  MMA commit (end of a chunk) -> flush
+  uint64_t* accempty_bar = accfull_bar + kMT;           // [kMT]  flush -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accempty_bar + kMT);
   volatile int* abort_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   AbortCtx actx{abort_flag, p.err};
@@ -178,8 +176,10 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       ptx::mbar_init(&cfull_bar[i], kConvWarps);
       ptx::mbar_init(&aempty_bar[i], 1);
     }
-    ptx::mbar_init(accfull_bar, 1);
-    ptx::mbar_init(accempty_bar, kConvWarps);
+    for (int i = 0; i < kMT; ++i) {
+      ptx::mbar_init(&accfull_bar[i], 1);
+      ptx::mbar_init(&accempty_bar[i], 4);
+    }
     *abort_flag = 0;
     ptx::fence_barrier_init();
   }
@@ -211,9 +211,9 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         if (!wait_bar(&xempty_bar[s], ((it / SX) & 1) ^ 1, actx, ERR_XPROD_EMPTY, it, s)) break;
         uint8_t* dst = smem_x + static_cast<size_t>(s) * kXTileBytes;
         ptx::mbar_arrive_expect_tx(&xfull_bar[s], kXTileBytes);
-        if (ORIENT == ORIENT_XH)  // box {kRows genes, 32 cells} at (gene0, cell0): smem [32 cells][kRows genes]
+        if (ORIENT == ORIENT_XH)  // box {256 genes, 32 cells} at (gene0, cell0): smem [32 cells][256 genes]
           ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], tile * kRows, kb * kBK, ptx::kEvictFirst);
-        else  // box {32 genes, kRows cells} at (gene0, cell0): smem [kRows cells][32 genes], 128B swizzle
+        else  // box {32 genes, 256 cells} at (gene0, cell0): smem [256 cells][32 genes], 128B swizzle
           ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], kb * kBK, tile * kRows, ptx::kEvictFirst);
       }
     }
@@ -235,20 +235,18 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   } else if (warp == kWarpMma) {
     // ===================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(kBM, p.Kp);
-      uint32_t it = 0, seg = 0;
+      const uint32_t idesc = ptx::make_idesc_tf32(kBM, Kp);
+      uint32_t it = 0, mc = 0;  // k-block counter, chunk counter
       bool ok = true;
-      for (long long pos = range_begin; pos < range_end && ok; ++seg) {
+      for (long long pos = range_begin; pos < range_end && ok;) {
         const int kb0 = static_cast<int>(pos % kbT);
         const long long left = range_end - pos;
-        const int kb1 = static_cast<int>((kbT - kb0) < left ? kbT : kb0 + left);
-        if (seg > 0) {
-          if (!wait_bar(accempty_bar, (seg - 1) & 1, actx, ERR_MMA_ACCEMPTY, seg, 0)) break;
-          ptx::tc_fence_after();
-        }
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        const int len = static_cast<int>((kbT - kb0) < left ? (kbT - kb0) : left);
+        for (int li = 0; li < len && ok; ++li, ++it) {
           const int t = it % kAStages;
           const int sbi = it % SB;
+          const bool c_first = (li % C) == 0;
+          const bool c_last = (li % C) == C - 1 || li == len - 1;
           if (!wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
             ok = false;
             break;
@@ -258,8 +256,15 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const uint64_t dhi = ptx::make_kmajor_sw128_desc(sb_addr);
           const uint64_t dlo = ptx::make_kmajor_sw128_desc(sb_addr + b_tile_bytes);
 #pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint32_t d_acc = tmem_base + mt * Cfg::kAccStride;
+          for (int mt = 0; mt < kMT; ++mt) {
+            if (c_first && mc > 0) {  // the previous chunk of this accumulator must have been flushed
+              if (!wait_bar(&accempty_bar[mt], (mc - 1) & 1, actx, ERR_MMA_ACCEMPTY, mc, mt)) {
+                ok = false;
+                break;
+              }
+              ptx::tc_fence_after();
+            }
+            const uint32_t d_acc = tmem_base + mt * kAccStride;
             const uint32_t a_hi = tmem_base + kTmemAOff + t * kAStageCols + mt * 64;
             const uint32_t a_lo = a_hi + 32;
 #pragma unroll
@@ -267,61 +272,63 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
               // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
               const uint64_t bh = dhi + static_cast<uint64_t>(2 * ks);
               const uint64_t bl = dlo + static_cast<uint64_t>(2 * ks);
-              ptx::mma_tf32_ts(d_acc, a_lo + ks * kUmmaK, bh, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+              ptx::mma_tf32_ts(d_acc, a_lo + ks * kUmmaK, bh, idesc, (c_first && ks == 0) ? 0u : 1u);
               ptx::mma_tf32_ts(d_acc, a_hi + ks * kUmmaK, bl, idesc, 1u);
               ptx::mma_tf32_ts(d_acc, a_hi + ks * kUmmaK, bh, idesc, 1u);
             }
+            if (c_last) ptx::tc_commit(&accfull_bar[mt]);
           }
+          if (!ok) break;
           ptx::tc_commit(&aempty_bar[t]);
           ptx::tc_commit(&bempty_bar[sbi]);
+          if (c_last) ++mc;
         }
-        if (ok) ptx::tc_commit(accfull_bar);
-        pos += kb1 - kb0;
+        pos += len;
       }
     }
     __syncwarp();
   } else {
-    // ===================================================== converter + epilogue warps (one thread per X row)
+    // ===================================================== converter + flush/epilogue warps (one thread per X row)
     const int row = warp * 32 + lane;          // row inside the super-tile
     const int mt = warp >> 2;                  // which 128-row MMA tile
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
-    const int conv_threads = kConvWarps * 32;
-    uint32_t it = 0, seg = 0;
+    const uint32_t acc_addr = tmem_base + lane_sel + mt * kAccStride;
+    constexpr int conv_threads = kConvWarps * 32;
+    uint32_t it = 0, fc = 0, seg = 0;  // k-block counter, flushed-chunk counter, segment counter
     bool ok = true;
+    // fp32 master sum of this thread's accumulator row.  The tensor core adds into its accumulator with
+    // round-toward-zero, which biases long sums of positive terms low (~2.5e-8 per MMA); chunks of C k-blocks
+    // are therefore summed here with round-to-nearest.
+    float master[Kp];
+#pragma unroll
+    for (int i = 0; i < Kp; ++i) master[i] = 0.f;
+
+    auto flush = [&]() -> bool {
+      if (!warp_wait_bar(&accfull_bar[mt], fc & 1, actx, ERR_EPI_ACCFULL, fc, mt)) return false;
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        uint32_t v[16];
+        ptx::tmem_ld_x16(acc_addr + 16 * c, v);
+        ptx::tc_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) master[16 * c + i] += __uint_as_float(v[i]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&accempty_bar[mt]);
+      ++fc;
+      return true;
+    };
+
     for (long long pos = range_begin; pos < range_end && ok; ++seg) {
-      const int tile = static_cast<int>(pos / kbT);
       const int kb0 = static_cast<int>(pos % kbT);
       const long long left = range_end - pos;
-      const int kb1 = static_cast<int>((kbT - kb0) < left ? kbT : kb0 + left);
-      for (int kb = kb0; kb < kb1; ++kb, ++it) {
+      const int len = static_cast<int>((kbT - kb0) < left ? (kbT - kb0) : left);
+      for (int li = 0; li < len; ++li, ++it) {
         const int s = it % SX;
         const int sbi = it % SB;
         const int t = it % kAStages;
-        // ---- X tile: shared memory fp32 -> registers (hi, lo)
-        if (!warp_wait_bar(&xfull_bar[s], (it / SX) & 1, actx, ERR_CONV_XFULL, it, s)) {
-          ok = false;
-          break;
-        }
-        const float* sX = reinterpret_cast<const float*>(smem_x + static_cast<size_t>(s) * kXTileBytes);
-        uint32_t hi[32], lo[32];
-        if (ORIENT == ORIENT_XH) {
-          // tile is [32 cells][kRows genes]; this thread owns gene `row`
-#pragma unroll
-          for (int kk = 0; kk < 32; ++kk) ptx::split_tf32(sX[kk * kRows + row], hi[kk], lo[kk]);
-        } else {
-          // tile is [kRows cells][32 genes] with the TMA 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
-          const float4* rp = reinterpret_cast<const float4*>(sX + row * kBK);
-#pragma unroll
-          for (int c = 0; c < 8; ++c) {
-            const float4 q = rp[c ^ (row & 7)];
-            ptx::split_tf32(q.x, hi[4 * c + 0], lo[4 * c + 0]);
-            ptx::split_tf32(q.y, hi[4 * c + 1], lo[4 * c + 1]);
-            ptx::split_tf32(q.z, hi[4 * c + 2], lo[4 * c + 2]);
-            ptx::split_tf32(q.w, hi[4 * c + 3], lo[4 * c + 3]);
-          }
-        }
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&xempty_bar[s]);  // the X slot can be refilled
         // ---- B tile: split in place (hi) and into the second buffer (lo); all converter threads share the work
         if (!warp_wait_bar(&bfull_bar[sbi], (it / SB) & 1, actx, ERR_CONV_BFULL, it, sbi)) {
           ok = false;
@@ -330,7 +337,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         {
           float4* bh = reinterpret_cast<float4*>(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes);
           float4* bl = reinterpret_cast<float4*>(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes + b_tile_bytes);
-          const int n4 = p.Kp * (kBK / 4);
+          constexpr int n4 = Kp * (kBK / 4);
           for (int i = threadIdx.x; i < n4; i += conv_threads) {
             const float4 v = bh[i];
             uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
@@ -343,44 +350,66 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
           ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
         }
-        // ---- A tile: registers -> tensor memory stage t (once the MMAs that read it two stages ago are done)
-        if (!warp_wait_bar(&aempty_bar[t], ((it / kAStages) & 1) ^ 1, actx, ERR_CONV_AEMPTY, it, t)) {
+        // ---- lagged flush: the chunk that ended kAStages k-blocks ago (its MMAs are the ones the aempty wait
+        //      below waits for anyway), overlapped with the other tile's MMAs
+        if (li >= kAStages && ((li - kAStages) % C) == C - 1) {
+          if (!flush()) {
+            ok = false;
+            break;
+          }
+        }
+        // ---- X tile: shared memory fp32 -> (hi, lo) -> tensor memory stage t
+        if (!warp_wait_bar(&xfull_bar[s], (it / SX) & 1, actx, ERR_CONV_XFULL, it, s) ||
+            !warp_wait_bar(&aempty_bar[t], ((it / kAStages) & 1) ^ 1, actx, ERR_CONV_AEMPTY, it, t)) {
           ok = false;
           break;
         }
         ptx::tc_fence_after();
+        const float* sX = reinterpret_cast<const float*>(smem_x + static_cast<size_t>(s) * kXTileBytes);
         const uint32_t a_addr = tmem_base + lane_sel + kTmemAOff + t * kAStageCols + mt * 64;
-        ptx::tmem_st_x32(a_addr, hi);
-        ptx::tmem_st_x32(a_addr + 32, lo);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t hi[16], lo[16];
+          if (ORIENT == ORIENT_XH) {
+            // tile is [32 cells][256 genes]; this thread owns gene `row`
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk) ptx::split_tf32(sX[(16 * h + kk) * kRows + row], hi[kk], lo[kk]);
+          } else {
+            // tile is [256 cells][32 genes] with the TMA 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+            const float4* rp = reinterpret_cast<const float4*>(sX + row * kBK);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const float4 q = rp[(4 * h + c) ^ (row & 7)];
+              ptx::split_tf32(q.x, hi[4 * c + 0], lo[4 * c + 0]);
+              ptx::split_tf32(q.y, hi[4 * c + 1], lo[4 * c + 1]);
+              ptx::split_tf32(q.z, hi[4 * c + 2], lo[4 * c + 2]);
+              ptx::split_tf32(q.w, hi[4 * c + 3], lo[4 * c + 3]);
+            }
+          }
+          ptx::tmem_st_x16(a_addr + 16 * h, hi);
+          ptx::tmem_st_x16(a_addr + 32 + 16 * h, lo);
+        }
         ptx::tc_wait_st();
         ptx::tc_fence_before();
         __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(&cfull_bar[t]);
+        if (lane == 0) {
+          ptx::mbar_arrive(&xempty_bar[s]);  // the X slot can be refilled
+          ptx::mbar_arrive(&cfull_bar[t]);   // A (TMEM) and B (shared memory) of this k-block are ready
+        }
       }
       if (!ok) break;
-
-      // ---- epilogue of this segment: accumulator -> partial-sum slot [K][kRows]
-      if (!warp_wait_bar(accfull_bar, seg & 1, actx, ERR_EPI_ACCFULL, seg, 0)) {
-        ok = false;
-        break;
-      }
-      ptx::tc_fence_after();
-      (void)tile;
+      // ---- remaining chunks of this segment, then the segment's sum -> partial-sum slot [K][256]
+      const int n_chunks = (len + C - 1) / C;
+      const int flushed = (len >= kAStages) ? (len - kAStages) / C : 0;
+      for (int r = flushed; r < n_chunks && ok; ++r) ok = flush();
+      if (!ok) break;
       float* dst = p.partial + (static_cast<size_t>(cta) * p.max_segs + seg) * p.K * kRows + row;
-      const uint32_t acc_addr = tmem_base + lane_sel + mt * Cfg::kAccStride;
-      for (int c0 = 0; c0 < p.Kp; c0 += 16) {
-        uint32_t v[16];
-        ptx::tmem_ld_x16(acc_addr + c0, v);
-        ptx::tc_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (c0 + i < p.K) dst[static_cast<size_t>(c0 + i) * kRows] = __uint_as_float(v[i]);
+      for (int i = 0; i < Kp; ++i) {
+        if (i < p.K) dst[static_cast<size_t>(i) * kRows] = master[i];
+        master[i] = 0.f;
       }
-      // accumulator drained: hand TMEM back to the MMA warp
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(accempty_bar);
-      pos += kb1 - kb0;
+      pos += len;
     }
   }
 
@@ -395,7 +424,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 // grid = (num_tiles, ceil(K / rows_per_block)); block = kRows threads is not required: threads stride over rows.
 struct ReduceParams {
   const float* partial;
-  int rows;  // MT*128
+  int rows;  // 256
   int M, K;
   int num_tiles, kb_per_tile, grid, max_segs;
   float* out;

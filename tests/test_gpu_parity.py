@@ -34,16 +34,15 @@ PRODUCT_SHAPES = [
     (777, 1000, 100),
     (5000, 2000, 25),
     (3001, 2600, 100),
-    (1200, 640, 130),
+    (1200, 640, 128),
+    (40000, 512, 100),
 ]
 
 
-@pytest.mark.parametrize("mt", ["2", "1"])
 @pytest.mark.parametrize("shape", PRODUCT_SHAPES)
-def test_contractions_match_fp64(shape, mt, monkeypatch):
+def test_contractions_match_fp64(shape):
     """X H^T (main.py:596) and W^T X (main.py:653) as 3xTF32 tcgen05 GEMMs vs float64 matmul."""
     gu = _gpu_utils()
-    monkeypatch.setenv("ALPINE_B200_MT", mt)
     n, G, K = shape
     rng = np.random.default_rng(n + G + K)
     X = rng.gamma(0.3, 2.0, size=(n, G)).astype(np.float32)
@@ -193,7 +192,7 @@ def test_argument_errors_are_reported():
     from alpine_b200 import _native
 
     with pytest.raises(_native.AlpineNativeError):
-        _native.Solver("cuda:0", 10, 10, [300], [])  # K > 256
+        _native.Solver("cuda:0", 10, 10, [129], [])  # K > 128
     s = _native.Solver("cuda:0", 64, 64, [4], [])
     with pytest.raises(_native.AlpineNativeError):
         s.fit_begin(3)  # nothing bound
