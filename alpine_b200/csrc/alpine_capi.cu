@@ -87,7 +87,7 @@ inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b -
 
 struct GemmPlan {
   bool valid = false;
-  CUtensorMap tmX, tmB;
+  CUtensorMap tmX, tmBhi, tmBlo;
   GemmParams p{};
   ReduceParams r{};
   int grid = 0;
@@ -122,6 +122,8 @@ struct alpine_ctx {
   // workspaces (device)
   long long ldG = 0, ldN = 0;
   float* WT = nullptr;     // [K][ldG]
+  float* Hsplit = nullptr; // [2][K][ldN]  tf32 hi / lo copies of H   (B operand of X H^T)
+  float* Wsplit = nullptr; // [2][K][ldG]  tf32 hi / lo copies of W^T (B operand of W^T X)
   float* A = nullptr;      // [K][ldN]   W^T X
   float* numG = nullptr;   // [Kg][ldN]
   float* denG = nullptr;
@@ -200,6 +202,10 @@ int ensure_workspace(alpine_ctx* c) {
   const size_t K = c->K;
   AL_TRY(dev_alloc(&c->WT, K * c->ldG));
   AL_TRY(dev_alloc(&c->A, K * c->ldN));
+  AL_TRY(dev_alloc(&c->Hsplit, 2 * K * c->ldN));
+  AL_TRY(dev_alloc(&c->Wsplit, 2 * K * c->ldG));
+  CU_TRY(cudaMemset(c->Hsplit, 0, 2 * K * c->ldN * sizeof(float)));
+  CU_TRY(cudaMemset(c->Wsplit, 0, 2 * K * c->ldG * sizeof(float)));
   AL_TRY(dev_alloc(&c->numG, static_cast<size_t>(c->Kg) * c->ldN));
   AL_TRY(dev_alloc(&c->denG, static_cast<size_t>(c->Kg) * c->ldN));
   AL_TRY(dev_alloc(&c->T, K * K));
@@ -253,7 +259,7 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
   switch (pl.p.Kp / 16) {
 #define ALPINE_GEMM_CASE(NC)                                                                     \
   case NC:                                                                                       \
-    mu_gemm_kernel<ORIENT, NC><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmB, pl.p);    \
+    mu_gemm_kernel<ORIENT, NC><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmBhi, pl.tmBlo, pl.p); \
     break;
     ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
     ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
@@ -265,8 +271,8 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
   return ALPINE_OK;
 }
 
-// Build the plan of one contraction.  M rows of D, reduction R, B operand [K][ldB] with R columns.
-int build_plan(alpine_ctx* c, GemmPlan* pl, int orient, const float* Bop, long long ldB) {
+// Build the plan of one contraction.  M rows of D, reduction R; the B operand is read from the split workspace.
+int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
   const int rows = kRows;
   const long long M = (orient == ORIENT_XH) ? c->G : c->n;
   const long long R = (orient == ORIENT_XH) ? c->n : c->G;
@@ -313,7 +319,12 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient, const float* Bop, long l
     AL_TRY(make_map(&pl->tmX, c->X, c->G, c->n, c->ldX, rows, kBK, false));
   else
     AL_TRY(make_map(&pl->tmX, c->X, c->G, c->n, c->ldX, kBK, rows, true));
-  AL_TRY(make_map(&pl->tmB, Bop, R, c->K, ldB, kBK, p.Kp, true));
+  {
+    float* sp = (orient == ORIENT_XH) ? c->Hsplit : c->Wsplit;
+    const long long ldS = (orient == ORIENT_XH) ? c->ldN : c->ldG;
+    AL_TRY(make_map(&pl->tmBhi, sp, R, c->K, ldS, kBK, p.Kp, true));
+    AL_TRY(make_map(&pl->tmBlo, sp + static_cast<size_t>(c->K) * ldS, R, c->K, ldS, kBK, p.Kp, true));
+  }
   ReduceParams& r = pl->r;
   r.partial = c->partial;
   r.rows = rows;
@@ -342,8 +353,14 @@ int run_gemm(alpine_ctx* c, int orient, const float* Bop, long long ldB, float* 
     return ALPINE_OK;
   }
   GemmPlan* pl = (orient == ORIENT_XH) ? &c->plan_xh : &c->plan_wx;
+  {
+    float* sp = (orient == ORIENT_XH) ? c->Hsplit : c->Wsplit;
+    const long long ldS = (orient == ORIENT_XH) ? c->ldN : c->ldG;
+    split_operand_kernel<<<2 * c->num_sms, 256, 0, st>>>(Bop, ldB, c->K, R, sp, sp + static_cast<size_t>(c->K) * ldS, ldS);
+    LAUNCH_CHECK();
+  }
   if (!pl->valid) {
-    AL_TRY(build_plan(c, pl, orient, Bop, ldB));
+    AL_TRY(build_plan(c, pl, orient));
     // building one plan may have re-allocated the shared partial buffer
     GemmPlan* other = (orient == ORIENT_XH) ? &c->plan_wx : &c->plan_xh;
     if (other->valid) {
@@ -526,7 +543,7 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
 int alpine_destroy(alpine_ctx* c) {
   if (c == nullptr) return ALPINE_OK;
   cudaSetDevice(c->device);
-  void* ptrs[] = {c->WT, c->A, c->numG, c->denG, c->T, c->colsum, c->gram_partial, c->gram_rs_partial, c->q_partial,
+  void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->gram_partial, c->gram_rs_partial, c->q_partial,
                   c->pred_partial, c->t1_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
                   c->own_reduce};
   for (void* p : ptrs)

@@ -13,10 +13,10 @@
 //    converter warps split every value into tf32 hi + lo and write both to TENSOR MEMORY (tcgen05.st), so the
 //    tensor core reads A from TMEM and the memory orientation of X does not matter (XH reads the tile
 //    transposed out of shared memory, WX reads 128B-swizzled rows).
-//  * B operand (H or W^T tile, Kp x 32 fp32, K-major): TMA (SWIZZLE_128B, rows >= K zero-filled) -> shared memory
-//    ring; the converter warps split it in place (hi) and into a second buffer (lo); the MMA reads both through
-//    UMMA shared-memory descriptors.  One B tile serves 256 rows of X, which keeps L2->SM traffic of the
-//    small operand below that of X itself.
+//  * B operand (H or W^T, [K][R] K-major, pre-split into tf32 hi / lo copies by split_operand_kernel; 90 MB at
+//    most, L2 resident): two TMA loads (SWIZZLE_128B, rows >= K zero-filled) -> shared memory ring -> UMMA
+//    shared-memory descriptors.  One B tile pair serves 256 rows of X, which keeps L2->SM traffic of the small
+//    operand below that of X itself.
 //  * D accumulates in TMEM (fp32, 2 accumulators of Kp columns): per 8-deep k-step three MMAs
 //    Alo*Bhi + Ahi*Blo + Ahi*Bhi (small terms first).  The tensor core accumulates with round-toward-zero, so
 //    after every `chunk` k-blocks the accumulator is drained into an fp32 master sum held in the registers of
@@ -44,7 +44,7 @@ enum { ORIENT_XH = 0, ORIENT_WX = 1 };
 
 // error codes written to GemmParams::err[0]; err[1..4] = blockIdx, threadIdx, k-block counter, aux
 enum { ERR_NONE = 0, ERR_XPROD_EMPTY = 1, ERR_BPROD_EMPTY = 2, ERR_CONV_XFULL = 3, ERR_CONV_BFULL = 4,
-       ERR_CONV_AEMPTY = 5, ERR_MMA_CFULL = 6, ERR_MMA_ACCEMPTY = 7, ERR_EPI_ACCFULL = 8 };
+       ERR_CONV_AEMPTY = 5, ERR_MMA_CFULL = 6, ERR_MMA_ACCEMPTY = 7, ERR_EPI_ACCFULL = 8, ERR_MMA_BFULL = 9 };
 
 struct GemmParams {
   int M;            // rows of D (genes for XH, cells for WX)
@@ -81,30 +81,34 @@ __device__ __noinline__ void report_timeout(const AbortCtx& a, int code, int aux
   *a.flag = 1;
 }
 
-// bounded mbarrier wait (single thread)
-__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, const AbortCtx& a, int code, int aux0,
-                                         int aux1) {
-  if (ptx::mbar_try_wait(bar, parity)) return true;
+// Bounded mbarrier wait.  try_wait suspends in hardware; the clock and the abort flag are looked at only every
+// 256 polls.  The slow path is out of line so that the hot loops stay small.  Safe to call from one lane or from
+// a whole warp.
+__device__ __forceinline__ bool wait_bar_slow(uint64_t* bar, uint32_t parity, volatile int* flag, int* err, int code,
+                                           int aux0, int aux1) {
   const long long t0 = clock64();
+  uint32_t polls = 0;
   while (true) {
     if (ptx::mbar_try_wait(bar, parity)) return true;
-    if (*a.flag) return false;
-    if (clock64() - t0 > kTimeoutCycles) {
-      report_timeout(a, code, aux0, aux1);
-      return false;
+    if ((++polls & 255u) == 0) {
+      if (*flag) return false;
+      if (clock64() - t0 > kTimeoutCycles) {
+        report_timeout(AbortCtx{flag, err}, code, aux0, aux1);
+        return false;
+      }
     }
   }
 }
-// warp-uniform bounded wait: lane 0 polls with the timeout, then every lane acquires the completed phase itself
+__device__ __forceinline__ bool wait_bar(uint64_t* bar, uint32_t parity, const AbortCtx& a, int code, int aux0,
+                                         int aux1) {
+  if (ptx::mbar_try_wait(bar, parity)) return true;
+  return wait_bar_slow(bar, parity, a.flag, a.err, code, aux0, aux1);
+}
+// warp-uniform variant: every lane polls (the instruction is warp-wide anyway); the verdict is made uniform
 __device__ __forceinline__ bool warp_wait_bar(uint64_t* bar, uint32_t parity, const AbortCtx& a, int code, int aux0,
                                               int aux1) {
-  int ok = 1;
-  if ((threadIdx.x & 31) == 0) ok = wait_bar(bar, parity, a, code, aux0, aux1) ? 1 : 0;
-  ok = __shfl_sync(0xffffffffu, ok, 0);
-  if (!ok) return false;
-  while (!ptx::mbar_try_wait(bar, parity)) {
-  }
-  return true;
+  const bool ok = wait_bar(bar, parity, a, code, aux0, aux1);
+  return __all_sync(0xffffffffu, ok);
 }
 
 // Fixed geometry: a super-tile is 2 MMA tiles (256 rows of X); 8 converter/epilogue warps, one thread per row.
@@ -132,9 +136,9 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int Kp, int sx, int s
 // NC = Kp / 16: number of 16-column groups of the accumulator (compile time: the fp32 master sum of a thread's
 // accumulator row lives in 16*NC registers).
 template <int ORIENT, int NC>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB,
-               const GemmParams p) {
+__global__ void __maxnreg__(184)
+mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
+               const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
   constexpr int Kp = 16 * NC;
   constexpr int kWarpXProd = kConvWarps, kWarpMma = kConvWarps + 1, kWarpBProd = kConvWarps + 2;
   constexpr int b_tile_bytes = Kp * kBK * 4;
@@ -184,7 +188,10 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     ptx::fence_barrier_init();
   }
   if (warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
-  if (warp == kWarpBProd && lane == 0) ptx::prefetch_tensormap(&tmB);
+  if (warp == kWarpBProd && lane == 0) {
+    ptx::prefetch_tensormap(&tmBhi);
+    ptx::prefetch_tensormap(&tmBlo);
+  }
   if (warp == kWarpMma) {
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
@@ -227,8 +234,9 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int s = it % SB;
         if (!wait_bar(&bempty_bar[s], ((it / SB) & 1) ^ 1, actx, ERR_BPROD_EMPTY, it, s)) break;
         uint8_t* dst = smem_b + static_cast<size_t>(s) * 2 * b_tile_bytes;
-        ptx::mbar_arrive_expect_tx(&bfull_bar[s], b_tile_bytes);
-        ptx::tma_load_2d(dst, &tmB, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+        ptx::mbar_arrive_expect_tx(&bfull_bar[s], 2 * b_tile_bytes);
+        ptx::tma_load_2d(dst, &tmBhi, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+        ptx::tma_load_2d(dst + b_tile_bytes, &tmBlo, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
       }
     }
     __syncwarp();
@@ -247,7 +255,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const int sbi = it % SB;
           const bool c_first = (li % C) == 0;
           const bool c_last = (li % C) == C - 1 || li == len - 1;
-          if (!wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
+          if (!wait_bar(&bfull_bar[sbi], (it / SB) & 1, actx, ERR_MMA_BFULL, it, sbi) ||
+              !wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
             ok = false;
             break;
           }
@@ -293,7 +302,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int mt = warp >> 2;                  // which 128-row MMA tile
     const uint32_t lane_sel = static_cast<uint32_t>((warp & 3) * 32) << 16;  // this warp's TMEM lane quarter
     const uint32_t acc_addr = tmem_base + lane_sel + mt * kAccStride;
-    constexpr int conv_threads = kConvWarps * 32;
+    const uint32_t smem_x_u32 = ptx::smem_u32(smem_x);
     uint32_t it = 0, fc = 0, seg = 0;  // k-block counter, flushed-chunk counter, segment counter
     bool ok = true;
     // fp32 master sum of this thread's accumulator row.  The tensor core adds into its accumulator with
@@ -327,29 +336,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const int len = static_cast<int>((kbT - kb0) < left ? (kbT - kb0) : left);
       for (int li = 0; li < len; ++li, ++it) {
         const int s = it % SX;
-        const int sbi = it % SB;
         const int t = it % kAStages;
-        // ---- B tile: split in place (hi) and into the second buffer (lo); all converter threads share the work
-        if (!warp_wait_bar(&bfull_bar[sbi], (it / SB) & 1, actx, ERR_CONV_BFULL, it, sbi)) {
-          ok = false;
-          break;
-        }
-        {
-          float4* bh = reinterpret_cast<float4*>(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes);
-          float4* bl = reinterpret_cast<float4*>(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes + b_tile_bytes);
-          constexpr int n4 = Kp * (kBK / 4);
-          for (int i = threadIdx.x; i < n4; i += conv_threads) {
-            const float4 v = bh[i];
-            uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-            ptx::split_tf32(v.x, h0, l0);
-            ptx::split_tf32(v.y, h1, l1);
-            ptx::split_tf32(v.z, h2, l2);
-            ptx::split_tf32(v.w, h3, l3);
-            bh[i] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-            bl[i] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
-          }
-          ptx::fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-        }
         // ---- lagged flush: the chunk that ended kAStages k-blocks ago (its MMAs are the ones the aempty wait
         //      below waits for anyway), overlapped with the other tile's MMAs
         if (li >= kAStages && ((li - kAStages) % C) == C - 1) {
@@ -365,7 +352,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           break;
         }
         ptx::tc_fence_after();
-        const float* sX = reinterpret_cast<const float*>(smem_x + static_cast<size_t>(s) * kXTileBytes);
+        const uint32_t sX = smem_x_u32 + static_cast<uint32_t>(s) * kXTileBytes;
         const uint32_t a_addr = tmem_base + lane_sel + kTmemAOff + t * kAStageCols + mt * 64;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -373,17 +360,17 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           if (ORIENT == ORIENT_XH) {
             // tile is [32 cells][256 genes]; this thread owns gene `row`
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk) ptx::split_tf32(sX[(16 * h + kk) * kRows + row], hi[kk], lo[kk]);
+            for (int kk = 0; kk < 16; ++kk)
+              ptx::split_tf32_fast(ptx::lds_f32(sX + ((16 * h + kk) * kRows + row) * 4), hi[kk], lo[kk]);
           } else {
             // tile is [256 cells][32 genes] with the TMA 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
-            const float4* rp = reinterpret_cast<const float4*>(sX + row * kBK);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-              const float4 q = rp[(4 * h + c) ^ (row & 7)];
-              ptx::split_tf32(q.x, hi[4 * c + 0], lo[4 * c + 0]);
-              ptx::split_tf32(q.y, hi[4 * c + 1], lo[4 * c + 1]);
-              ptx::split_tf32(q.z, hi[4 * c + 2], lo[4 * c + 2]);
-              ptx::split_tf32(q.w, hi[4 * c + 3], lo[4 * c + 3]);
+              const float4 q = ptx::lds_v4(sX + row * (kBK * 4) + (((4 * h + c) ^ (row & 7)) << 4));
+              ptx::split_tf32_fast(q.x, hi[4 * c + 0], lo[4 * c + 0]);
+              ptx::split_tf32_fast(q.y, hi[4 * c + 1], lo[4 * c + 1]);
+              ptx::split_tf32_fast(q.z, hi[4 * c + 2], lo[4 * c + 2]);
+              ptx::split_tf32_fast(q.w, hi[4 * c + 3], lo[4 * c + 3]);
             }
           }
           ptx::tmem_st_x16(a_addr + 16 * h, hi);

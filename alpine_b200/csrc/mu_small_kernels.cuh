@@ -226,6 +226,29 @@ __global__ void scale_b_kernel(const CovTable tab, const float* __restrict__ s) 
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// 3xTF32 operand split of the small (K x R) operand of a contraction: hi / lo copies with the same pitch.
+// Pitches are multiples of 4 floats and bases 16-byte aligned, so whole float4 groups are always in bounds.
+__global__ void split_operand_kernel(const float* __restrict__ src, long long ld_src, int rows, long long cols,
+                                     float* __restrict__ hi, float* __restrict__ lo, long long ld_dst) {
+  const long long c4n = (cols + 3) >> 2;
+  const long long total = static_cast<long long>(rows) * c4n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / c4n, c = (i - r * c4n) << 2;
+    const float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    ptx::split_tf32(v.x, h0, l0);
+    ptx::split_tf32(v.y, h1, l1);
+    ptx::split_tf32(v.z, h2, l2);
+    ptx::split_tf32(v.w, h3, l3);
+    *reinterpret_cast<float4*>(hi + r * ld_dst + c) =
+        make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+    *reinterpret_cast<float4*>(lo + r * ld_dst + c) =
+        make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // out[c][r] = in[r][c]  (W <-> W^T), 32x32 tiles through shared memory, both sides coalesced
 __global__ void transpose_kernel(const float* __restrict__ in, long long ld_in, int rows, int cols,
                                  float* __restrict__ out, long long ld_out) {

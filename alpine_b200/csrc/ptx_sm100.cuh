@@ -43,6 +43,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 
+// shared-memory accesses through 32-bit shared-window addresses (generic pointers cost 64-bit address math)
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds_v4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
 // ---------------------------------------------------------------- TMA
 // L2 cache-policy descriptors (the encodings createpolicy.fractional produces).
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
@@ -139,6 +151,13 @@ __device__ __forceinline__ uint32_t round_tf32(float x) { return (__float_as_uin
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
   hi = round_tf32(x);
   lo = round_tf32(x - __uint_as_float(hi));
+}
+// Same split with lo left as the exact fp32 remainder: the tensor core reads only the tf32 bits of an operand
+// (the low 13 mantissa bits are ignored), i.e. it truncates lo; lo has a random sign, so this adds no bias and
+// |x - hi - trunc(lo)| <= 2^-21 |x|.  Three integer/float ops per element, used on the streamed X tiles.
+__device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = round_tf32(x);
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 // ---------------------------------------------------------------- descriptors

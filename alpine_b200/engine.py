@@ -1,0 +1,96 @@
+"""Host-side driver of the MU loop: one process per GPU, cells sharded across ranks.
+
+The reference runs the whole loop on one device (``ALPINE._fit``, main.py:486-676).  Here every rank owns a
+column block of X / H / Y (cells) and a replica of W / B; per iteration the only exchange is ONE all-reduce (sum)
+of the packed buffer ``[X H^T | H H^T | rowsum(H) | B statistics]``, issued through
+``torch.distributed`` (NCCL on the GPUs; gloo in the CPU tests of this logic).  After it every rank applies the
+identical W and B updates and updates its own H block; the loss terms are additive across ranks and are summed
+once, after the last iteration.
+
+``MUEngine`` is independent of the CUDA library: it drives any object with the ``ShardSolver`` methods, which is
+how the sharding logic is tested on CPU with world_size 2.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Protocol, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def shard_bounds(n_cells: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced column block [lo, hi) of rank ``rank``; blocks differ in size by at most one cell."""
+    if world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank {rank} / world_size {world_size}")
+    base, extra = divmod(int(n_cells), int(world_size))
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+class ShardSolver(Protocol):
+    n_cov: int
+
+    def reduce_buffer(self) -> torch.Tensor: ...
+    def fit_begin(self, max_iter: int) -> None: ...
+    def mu_partials(self) -> None: ...
+    def mu_apply(self, it: int) -> None: ...
+    def losses(self, n_iter: int) -> Tuple[float, np.ndarray]: ...
+
+
+def dist_info(group=None) -> Tuple[int, int]:
+    """(rank, world_size) of the active process group, (0, 1) when torch.distributed is not initialised."""
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+class MUEngine:
+    """Runs ``max_iter`` full-batch MU iterations on this rank's shard and returns the global loss history."""
+
+    def __init__(self, solver: ShardSolver, lam: Sequence[float], group=None):
+        self.solver = solver
+        self.lam = [float(v) for v in lam]
+        self.group = group
+        self.rank, self.world = dist_info(group)
+
+    def _all_reduce(self, t: torch.Tensor) -> None:
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+
+    def run(self, max_iter: int, on_iter: Optional[Callable[[int], None]] = None) -> np.ndarray:
+        """Returns rows ``[total, reconstruction, prediction_0, ...]`` per iteration (main.py:750-753)."""
+        s = self.solver
+        buf = s.reduce_buffer()
+        s.fit_begin(max_iter)      # leaves this shard's statistics of the initial H / B in the buffer
+        for it in range(max_iter):
+            s.mu_partials()        # X H^T of this shard into the reduce buffer (main.py:596)
+            # The iteration's only data-path collective.  The statistics part [H H^T | rowsum(H) | B statistics]
+            # still holds this shard's values (written by fit_begin / the previous mu_apply), so one message
+            # carries everything the W and B updates need.
+            self._all_reduce(buf)
+            s.mu_apply(it)         # W, B, H updates + loss terms (main.py:597-663, 726-753)
+            if on_iter is not None:
+                on_iter(it)
+        return self.collect_losses(max_iter)
+
+    def collect_losses(self, n_iter: int) -> np.ndarray:
+        xn, rows = self.solver.losses(n_iter)
+        n_cov = rows.shape[1] - 2
+        packed = np.concatenate([[xn], rows.reshape(-1)]).astype(np.float64)
+        if self.world > 1:
+            dev = self.solver.reduce_buffer().device
+            t = torch.from_numpy(packed).to(dev)
+            self._all_reduce(t)
+            packed = t.cpu().numpy()
+        xn = float(packed[0])
+        rows = packed[1:].reshape(n_iter, 2 + n_cov)
+        out = np.zeros((n_iter, 2 + n_cov), dtype=np.float64)
+        out[:, 1] = xn - 2.0 * rows[:, 0] + rows[:, 1]  # ||X||^2 - 2 tr(W^T X H^T) + tr(W^T W H H^T)
+        out[:, 2:] = rows[:, 2:]
+        out[:, 0] = out[:, 1] + sum(self.lam[i] * out[:, 2 + i] for i in range(n_cov))
+        return out

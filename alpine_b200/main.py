@@ -1,0 +1,470 @@
+"""Drop-in ``ALPINE`` model class over the B200-native MU loop.
+
+Public surface = the reference's ``alpine/main.py`` (class ``ALPINE`` main.py:46-320, ``AlpineMatrices``
+main.py:28-43): same constructor keywords, methods, attributes set by ``fit`` and AnnData slots written.  The
+arithmetic of the loop (``_fit`` main.py:486-676, ``_compute_loss`` 726-753, ``_scale_matrices`` 772-781, the
+``_transform`` loop 705-709) runs in ``libalpine_b200.so`` through ``alpine_b200._native``; host code here only
+prepares tensors (``_initialize_matrices`` keeps the reference's seeding and draw order, main.py:436-472, so the
+initial W/H/B are bit-identical to the reference on the same device type) and moves results back.
+
+There is no CPU path: ``device`` must be a CUDA device with an sm_100 GPU behind it.
+"""
+from __future__ import annotations
+
+import gc
+import warnings
+from contextlib import nullcontext
+from copy import copy, deepcopy
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Union
+
+import numpy as np
+import numpy.typing as npt
+import pandas as pd
+import torch
+
+from . import _native, validation
+from .engine import MUEngine, dist_info, shard_bounds
+from .utils.anndata_compat import AnnData
+from .utils.encoder import FeatureEncoders
+from .utils.kneedle import find_elbow
+
+Float32Array = npt.NDArray[np.float32]
+
+
+@dataclass
+class AlpineMatrices:
+    """Device-resident factor matrices (reference main.py:28-43).
+
+    ``X`` is the genes x cells *view* of the cells-major upload (same strides as the reference's tensor,
+    SURVEY.md 8 a1); ``Ws`` / ``Hs`` are column / row block views of the packed ``W`` (G x K) and ``H`` (K x n)
+    buffers the kernels update in place; blocks are ordered covariates first, unguided last (main.py:79).
+    Under cell sharding ``X``, ``Ys`` and ``Hs`` hold this rank's column block ``[lo, hi)``.
+    """
+
+    X: torch.Tensor
+    Ys: List[torch.Tensor]
+    Ws: List[torch.Tensor]
+    Hs: List[torch.Tensor]
+    Bs: List[torch.Tensor]
+    W: Optional[torch.Tensor] = field(default=None, repr=False)
+    H: Optional[torch.Tensor] = field(default=None, repr=False)
+    X_cells_major: Optional[torch.Tensor] = field(default=None, repr=False)
+    X_host: Optional[np.ndarray] = field(default=None, repr=False)
+    Ys_host: Optional[List[np.ndarray]] = field(default=None, repr=False)
+    shard: tuple = (0, 0)
+    n_total: int = 0
+
+    def to_numpy(self) -> Dict[str, Union[Float32Array, List[Float32Array]]]:
+        # the reference copies X back from the device (main.py:38); the host copy it came from is identical
+        X = self.X_host if self.X_host is not None else self.X.cpu().numpy().astype(np.float32)
+        Ys = self.Ys_host if self.Ys_host is not None else [y.cpu().numpy().astype(np.float32) for y in self.Ys]
+        return {
+            "X": X,
+            "Ys": Ys,
+            "Ws": [w.cpu().numpy().astype(np.float32) for w in self.Ws],
+            "Hs": [h.cpu().numpy().astype(np.float32) for h in _gather_cells(self.Hs, self.shard, self.n_total)],
+            "Bs": [b.cpu().numpy().astype(np.float32) for b in self.Bs],
+        }
+
+
+def _gather_cells(Hs: List[torch.Tensor], shard, n_total: int) -> List[torch.Tensor]:
+    """All ranks' column blocks of every H block, concatenated along cells (identity without sharding)."""
+    rank, world = dist_info()
+    if world == 1 or n_total == 0 or (shard[1] - shard[0]) == n_total:
+        return Hs
+    import torch.distributed as dist
+
+    out = []
+    for h in Hs:
+        full = torch.zeros((h.shape[0], n_total), dtype=h.dtype, device=h.device)
+        full[:, shard[0]:shard[1]] = h
+        dist.all_reduce(full)  # disjoint blocks: the sum is the concatenation
+        out.append(full)
+    return out
+
+
+class ALPINE:
+    def __init__(
+        self,
+        n_components: int,
+        n_covariate_components: List[int],
+        lam: List[float],
+        orth_W: float = 0.0,
+        alpha_W: float = 0.0,
+        l1_ratio_W: float = 0.0,
+        use_als: bool = False,
+        scale_needed: bool = True,
+        loss_type: str = "kl-divergence",
+        device: str = "cuda",
+        eps: float = 1e-6,
+        random_state: int = 42,
+        l1_ratio: Optional[float] = None,
+    ):
+        # `l1_ratio` is accepted as an alias of the reference's `l1_ratio_W` (BASELINE north_star spelling)
+        if l1_ratio is not None:
+            l1_ratio_W = l1_ratio
+        self.n_components = n_components
+        self.n_covariate_components = n_covariate_components
+        self.lam = lam
+        self.orth_W = orth_W
+        self.alpha_W = alpha_W
+        self.l1_ratio_W = l1_ratio_W
+        self.use_als = use_als
+        self.scale_needed = scale_needed
+        self.device = torch.device(device)
+        self.loss_type = loss_type
+        self.eps = eps
+        self.random_state = random_state
+        validation.check_model_args(self)
+        self.n_all_components = self.n_covariate_components + [self.n_components]  # main.py:79
+        self.total_components = sum(self.n_all_components)
+
+    # ------------------------------------------------------------------------------------------------ fit
+    def fit(
+        self,
+        adata: AnnData,
+        covariate_keys: List[str],
+        batch_size: Optional[int] = None,
+        max_iter: Optional[int] = None,
+        sampling_method: str = "random",
+        verbose: bool = False,
+    ) -> "ALPINE":
+        validation.check_fit_args(self, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose)
+        self.feature_names = adata.var_names.tolist()
+        self.n_features = adata.shape[1]
+        self.covariate_keys = covariate_keys
+        self.sampling_method = sampling_method
+        self.verbose = verbose
+
+        # The reference transposes to genes x cells (main.py:104); that view shares the cells-major buffer, which
+        # is the layout the kernels stream, so the "transpose" stays a view here as well.
+        X = np.ascontiguousarray(adata.X, dtype=np.float32).T
+        n_sample = X.shape[1]
+        self.fe = FeatureEncoders(covariate_keys)
+        Y = self.fe.fit_transform(adata.obs)
+        self.batch_size = batch_size if batch_size is not None else n_sample
+
+        if max_iter is None:
+            # warm-up run + Kneedle elbow on log10(reconstruction loss) (main.py:116-131, 755-770)
+            m_warmup = self._initialize_matrices(X, Y)
+            self.max_iter = 200
+            self._fit(m_warmup)
+            self.max_iter = self._compute_best_iter(self.loss_history["reconstruction loss"].values)
+            del m_warmup
+            gc.collect()
+            torch.cuda.empty_cache()
+        else:
+            self.max_iter = max_iter
+
+        m = self._initialize_matrices(X, Y)
+        self._fit(m)
+        if self.scale_needed:
+            self._scale_matrices(m)
+        self.matrices = m.to_numpy()
+        self.store_embeddings(adata)
+        return self
+
+    def fit_transform(
+        self,
+        adata: AnnData,
+        covariate_keys: List[str],
+        batch_size: Optional[int] = None,
+        max_iter: Optional[int] = None,
+        sampling_method: str = "random",
+        verbose: bool = False,
+    ) -> None:
+        self.fit(adata, covariate_keys, batch_size=batch_size, max_iter=max_iter, sampling_method=sampling_method,
+                 verbose=verbose).transform(adata)
+
+    # ------------------------------------------------------------------------------------------ transform
+    def transform(self, adata: AnnData, n_iter: Optional[int] = None) -> None:
+        validation.check_transform_args(self, adata, n_iter)
+        self._transform(adata, n_iter if n_iter is not None else self.max_iter)
+
+    def _transform(self, adata: AnnData, n_iter: int) -> None:
+        """H-only MU on new cells with the fitted (scaled) W (main.py:678-724).
+
+        The reference recomputes the loop-invariant ``2 W^T X`` every iteration; here ``A = W^T X`` (one sweep of X)
+        and ``T = W^T W`` are formed once and each iteration is ``H *= 2A / max(2 T H, eps)`` on K x n only.
+        """
+        Xcm = np.ascontiguousarray(adata.X, dtype=np.float32)
+        if not np.all(Xcm >= 0):
+            raise ValueError("All elements in adata.X must be non-negative.")
+        dev = self._cuda_device()
+        n_sample, G = Xcm.shape
+        K = self.total_components
+        Xd = _native.padded_rows(n_sample, G, dev)
+        Xd.copy_(torch.from_numpy(Xcm), non_blocking=False)
+        # un-reseeded draw from the device generator, as the reference (main.py:687-689)
+        H = _native.padded_rows(K, n_sample, dev)
+        H.copy_(torch.rand((K, n_sample), dtype=torch.float32, device=dev))
+        W = torch.cat([torch.tensor(w, dtype=torch.float32, device=dev) for w in self.matrices["Ws"]], dim=1).contiguous()
+        solver = _native.Solver(dev, G, n_sample, [K], [])
+        try:
+            solver.bind_dense(Xd)
+            solver.bind_factors(W, H, [])
+            solver.set_hparams([], 0.0, 0.0, 0.0, self.eps)
+            solver.transform(n_iter)
+            H_host = H.cpu().numpy()
+        finally:
+            solver.close()
+        start = 0
+        parts = []
+        for k in self.n_all_components:
+            parts.append(H_host[start:start + k])
+            start += k
+        for i, covariate in enumerate(self.covariate_keys):
+            adata.obsm[covariate] = parts[i].T
+            adata.varm[covariate] = deepcopy(self.matrices["Ws"][i])
+        adata.obsm["ALPINE_embedding"] = parts[-1].T
+        adata.varm["ALPINE_weights"] = deepcopy(self.matrices["Ws"][-1])
+
+    # -------------------------------------------------------------------------------------------- queries
+    def compute_loss(self, adata: AnnData):
+        """Host re-evaluation of the objective on (possibly new) data (main.py:187-236)."""
+        validation.check_trained(self)
+        validation.check_adata(adata)
+        if "ALPINE_embedding" not in adata.obsm:
+            raise ValueError("ALPINE_embedding not found in adata.obsm. Please transform the data first.")
+        X = np.asarray(adata.X).astype(np.float32).T
+        Hs = [np.asarray(adata.obsm[c]).T for c in self.covariate_keys] + [np.asarray(adata.obsm["ALPINE_embedding"]).T]
+        Ws = [np.asarray(adata.varm[c]) for c in self.covariate_keys] + [np.asarray(adata.varm["ALPINE_weights"])]
+        W, H = np.concatenate(Ws, axis=1), np.concatenate(Hs, axis=0)
+        recon_loss = np.linalg.norm(X - W @ H, ord="fro") ** 2
+        Ys = self.fe.transform(adata.obs)
+        Bs = self.matrices["Bs"]
+        pred_loss = []
+        for i in range(len(Ys)):
+            y, y_hat = Ys[i].T, Bs[i] @ Hs[i]
+            if self.loss_type == "kl-divergence":
+                y_hat = np.clip(y_hat, a_min=self.eps, a_max=None)
+                pred_loss.append(np.sum(y * np.log(np.clip(y / y_hat, a_min=self.eps, a_max=None)) - y + y_hat))
+            else:
+                pred_loss.append(np.linalg.norm(y - y_hat, ord="fro") ** 2)
+        return recon_loss + sum(self.lam[i] * pl for i, pl in enumerate(pred_loss))
+
+    def get_decomposed_matrices(self):
+        validation.check_trained(self)
+        return self.matrices
+
+    def get_covariate_gene_scores(self, adata: Optional[AnnData] = None) -> Union[Dict[str, pd.DataFrame], None]:
+        """Per-category mean embedding pushed through W_i (main.py:246-273)."""
+        validation.check_trained(self)
+        scores = {}
+        for i, covariate in enumerate(self.covariate_keys):
+            W, H, Y = self.matrices["Ws"][i], self.matrices["Hs"][i], self.matrices["Ys"][i]
+            per_category = H @ Y.T / Y.sum(axis=1)
+            scores[covariate] = pd.DataFrame(W @ per_category, index=self.feature_names,
+                                             columns=self.fe.encoded_labels[covariate])
+        if adata is None:
+            return scores
+        for condition, df in scores.items():
+            adata.varm[condition + "_gene_scores"] = df
+        return None
+
+    def get_normalized_expression(self, adata: AnnData, library_size: Optional[float] = None) -> None:
+        """Reconstruct counts from the unguided block and library-size normalise them (main.py:275-301).
+
+        ``scanpy.pp.normalize_total`` (absent here) is restated: every cell is scaled to ``target_sum``, which
+        defaults to the median of the per-cell totals; cells with a zero total are left untouched.
+        """
+        validation.check_trained(self)
+        validation.check_adata(adata)
+        if "ALPINE_embedding" not in adata.obsm:
+            raise ValueError("ALPINE_embedding not found in adata.obsm. Please transform the data first.")
+        if (library_size is not None) and (library_size <= 0):
+            raise ValueError("library_size must be a positive float.")
+        W = self.matrices["Ws"][-1]
+        H = np.asarray(adata.obsm["ALPINE_embedding"]).T
+        Xn = np.dot(W, H).astype(np.float32).T
+        totals = Xn.sum(axis=1)
+        target = float(np.median(totals[totals > 0])) if library_size is None else float(library_size)
+        scale = np.where(totals > 0, totals / target, 1.0).astype(np.float32)
+        adata.layers["normalized_expression"] = Xn / scale[:, None]
+
+    def store_embeddings(self, adata: AnnData) -> None:
+        """Write embeddings / weights into the AnnData slots of main.py:303-320."""
+        validation.check_trained(self)
+        validation.check_adata(adata)
+        adata.obsm["ALPINE_embedding"] = copy(self.matrices["Hs"][-1].T)
+        adata.varm["ALPINE_weights"] = copy(self.matrices["Ws"][-1])
+        dummy_matrices = self.fe.transform(adata.obs)
+        for i, covariate in enumerate(self.covariate_keys):
+            adata.obsm[covariate] = copy(self.matrices["Hs"][i].T)
+            adata.obsm[f"{covariate}_dummy_matrix"] = dummy_matrices[i]
+            adata.varm[covariate] = copy(self.matrices["Ws"][i])
+
+    # ------------------------------------------------------------------------------------- device helpers
+    def _cuda_device(self) -> torch.device:
+        if self.device.type != "cuda":
+            raise _native.AlpineNativeError(
+                f"alpine_b200 runs the MU loop on a B200 only (device={str(self.device)!r}); there is no CPU fallback")
+        if not torch.cuda.is_available():
+            raise _native.AlpineNativeError("no CUDA device is available; alpine_b200 has no CPU fallback")
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        return torch.device("cuda", idx)
+
+    def _initialize_matrices(self, X_array: Float32Array, Y_list_array: List[Float32Array]) -> AlpineMatrices:
+        """Seed, upload, draw W / H / B in the reference's order (main.py:436-472).
+
+        ``X_array`` is genes x cells (a view of the cells-major buffer).  With torch.distributed initialised and
+        world_size > 1, every rank draws the full W, H, B from the same seed (identical streams on identical
+        devices) and keeps its own column block of X, Y and H.
+        """
+        dev = self._cuda_device()
+        torch.manual_seed(self.random_state)
+        torch.cuda.manual_seed(self.random_state)
+        G, n = X_array.shape
+        rank, world = dist_info()
+        lo, hi = shard_bounds(n, world, rank)
+        n_loc = hi - lo
+        K = self.total_components
+
+        Xcm_host = X_array.T  # cells x genes; C-contiguous when X_array came from fit()
+        Xd = _native.padded_rows(n_loc, G, dev)
+        Xd.copy_(torch.from_numpy(np.ascontiguousarray(Xcm_host[lo:hi])))
+        Ys_host = [np.ascontiguousarray(y.T, dtype=np.float32) for y in Y_list_array]  # c_i x n (main.py:447)
+        Ys = [torch.from_numpy(np.ascontiguousarray(y[:, lo:hi])).to(dev) for y in Ys_host]
+
+        W = torch.empty((G, K), dtype=torch.float32, device=dev)
+        H = _native.padded_rows(K, n_loc, dev)
+        eps = self.eps
+        col = 0
+        Ws = []
+        for k in self.n_all_components:  # main.py:454-458
+            W[:, col:col + k] = torch.rand((G, k), dtype=torch.float32, device=dev).clamp(min=eps)
+            Ws.append(W[:, col:col + k])
+            col += k
+        row = 0
+        Hs = []
+        for k in self.n_all_components:  # main.py:460-464
+            full = torch.rand((k, n), dtype=torch.float32, device=dev).clamp(min=eps)
+            H[row:row + k, :] = full[:, lo:hi]
+            Hs.append(H[row:row + k, :])
+            row += k
+            del full
+        Bs = [torch.rand((y.shape[0], k), dtype=torch.float32, device=dev).clamp(min=eps).contiguous()
+              for (y, k) in zip(Ys_host, self.n_covariate_components)]  # main.py:466-470
+        return AlpineMatrices(X=Xd.T, Ys=Ys, Ws=Ws, Hs=Hs, Bs=Bs, W=W, H=H, X_cells_major=Xd, X_host=X_array,
+                              Ys_host=Ys_host, shard=(lo, hi), n_total=n)
+
+    def _make_solver(self, m: AlpineMatrices) -> "_native.Solver":
+        n_loc, G = m.X_cells_major.shape
+        solver = _native.Solver(m.W.device, G, n_loc, self.n_all_components, [y.shape[0] for y in m.Ys], self.loss_type)
+        solver.bind_dense(m.X_cells_major)
+        solver.bind_labels(m.Ys)
+        solver.bind_factors(m.W, m.H, m.Bs)
+        solver.set_hparams(self.lam, self.alpha_W, self.l1_ratio_W, self.orth_W, self.eps)
+        return solver
+
+    # ------------------------------------------------------------------------------------------- hot loop
+    def _fit(self, m: AlpineMatrices) -> None:
+        """``max_iter`` MU iterations, in place on ``m`` (main.py:486-676); leaves ``self.loss_history``."""
+        n_loc = m.X_cells_major.shape[0]
+        full_batch = self.batch_size >= m.n_total
+        if self.sampling_method not in ("random", "weighted"):
+            raise ValueError(f"Unknown sampling method: {self.sampling_method}. Only 'weighted', and 'random' are supported.")
+        if self.use_als or not full_batch or self.sampling_method == "weighted":
+            raise NotImplementedError(
+                "alpine_b200 implements the full-batch multiplicative-update path (use_als=False, batch_size=None, "
+                "sampling_method='random'); the ALS and mini-batch variants of the reference (main.py:509-588) are "
+                "listed as next steps in DESIGN.md")
+        solver = self._make_solver(m)
+        try:
+            engine = MUEngine(solver, self.lam)
+            pbar = None
+            if self.verbose:
+                from tqdm import tqdm
+
+                pbar = tqdm(total=self.max_iter, desc="Iteration", ncols=100)
+            with (pbar if pbar is not None else nullcontext()):
+                history = engine.run(self.max_iter, on_iter=(lambda it: pbar.update(1)) if pbar is not None else None)
+        finally:
+            solver.close()
+        colnames = ["total loss", "reconstruction loss"] + [f"prediction loss({k})" for k in self.covariate_keys]
+        self.loss_history = pd.DataFrame(history.tolist(), columns=colnames)
+        del n_loc
+
+    def _compute_loss(self, m: AlpineMatrices) -> List[float]:
+        """[total, reconstruction, prediction...] of the current factors (main.py:726-753).
+
+        Evaluated by the same device kernels the loop uses (trace identity for the reconstruction term); one MU
+        iteration is NOT applied: the statistics pass alone is run on a scratch copy of the factors.
+        """
+        scratch = AlpineMatrices(X=m.X, Ys=m.Ys, Ws=[], Hs=[], Bs=[b.clone() for b in m.Bs], W=m.W.clone(),
+                                 H=_clone_padded(m.H), X_cells_major=m.X_cells_major, shard=m.shard, n_total=m.n_total)
+        solver = self._make_solver(scratch)
+        try:
+            return _loss_of_current_factors(solver, self.lam, scratch)
+        finally:
+            solver.close()
+
+    def _compute_best_iter(self, train_loss) -> int:
+        """Kneedle elbow of log10(reconstruction loss) (main.py:755-770)."""
+        elbow = find_elbow(np.arange(0, len(train_loss)), np.log10(train_loss))
+        if elbow is not None:
+            return int(elbow)
+        warnings.warn("Kneedle elbow not found, using default max_iter=200")
+        return 200
+
+    def _scale_matrices(self, m: AlpineMatrices) -> None:
+        """Column-normalise every W block; H and B absorb the scale (main.py:772-781)."""
+        solver = self._make_solver(m)
+        try:
+            solver.scale()
+            torch.cuda.synchronize(m.W.device)
+        finally:
+            solver.close()
+
+
+def _clone_padded(H: torch.Tensor) -> torch.Tensor:
+    out = _native.padded_rows(H.shape[0], H.shape[1], H.device)
+    out.copy_(H)
+    return out
+
+
+def _loss_of_current_factors(solver, lam, m: AlpineMatrices) -> List[float]:
+    """Loss of (W, H, B) as they are: tr-identity terms from W^T X, W^T W, H H^T and the prediction statistics."""
+    A = solver.wx_product()[:, : m.H.shape[1]].double()                   # W^T X  (K x n_loc)
+    H = m.H.double()
+    W = m.W.double()
+    t1 = float((A * H).sum().item())
+    t2 = float(((W.T @ W) * (H @ H.T)).sum().item())
+    xn = float((m.X_cells_major.double() ** 2).sum().item())
+    vals = torch.tensor([xn, t1, t2], dtype=torch.float64, device=m.W.device)
+    rank, world = dist_info()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(vals)
+    xn, t1, t2 = (float(v) for v in vals.cpu())
+    recon = xn - 2.0 * t1 + t2
+    preds = []
+    row = 0
+    eps = float(solver_eps(solver))
+    for i, B in enumerate(m.Bs):
+        k = B.shape[1]
+        y = m.Ys[i]
+        y_hat = B @ m.H[row:row + k]
+        row += k
+        if solver_loss_type(solver) == "kl-divergence":
+            y_hat = torch.clamp(y_hat, min=eps)
+            p = torch.sum(y * torch.log(torch.clamp(y / y_hat, min=eps)) - y + y_hat).double()
+        else:
+            p = (torch.norm(y - y_hat, p="fro") ** 2).double()
+        if world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(p)
+        preds.append(float(p.item()))
+    total = recon + sum(lam[i] * p for i, p in enumerate(preds))
+    return [total, recon] + preds
+
+
+def solver_eps(solver) -> float:
+    return getattr(solver, "_eps", 1e-6)
+
+
+def solver_loss_type(solver) -> str:
+    return getattr(solver, "_loss_type", "kl-divergence")
