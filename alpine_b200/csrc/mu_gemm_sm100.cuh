@@ -115,7 +115,7 @@ __device__ __forceinline__ bool warp_wait_bar(uint64_t* bar, uint32_t parity, co
 constexpr int kMT = 2;
 constexpr int kRows = kMT * kBM;
 constexpr int kConvWarps = 4 * kMT;
-constexpr int kGemmThreads = (kConvWarps + 3) * 32;
+constexpr int kGemmThreads = (kConvWarps + 3) * 32;  // + X producer, MMA issuer, B producer
 constexpr int kXTileBytes = kRows * kBK * 4;
 constexpr int kAStageCols = kMT * 64;   // per MMA tile: 32 hi + 32 lo columns
 constexpr int kAStages = (kTmemCols - kTmemAOff) / kAStageCols;
@@ -136,7 +136,7 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int Kp, int sx, int s
 // NC = Kp / 16: number of 16-column groups of the accumulator (compile time: the fp32 master sum of a thread's
 // accumulator row lives in 16*NC registers).
 template <int ORIENT, int NC>
-__global__ void __maxnreg__(184)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
   constexpr int Kp = 16 * NC;
@@ -200,7 +200,6 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
   const long long kbT = p.kb_per_tile;
   const long long total = static_cast<long long>(p.num_tiles) * kbT;
   const int cta = blockIdx.x;
@@ -355,26 +354,26 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const uint32_t sX = smem_x_u32 + static_cast<uint32_t>(s) * kXTileBytes;
         const uint32_t a_addr = tmem_base + lane_sel + kTmemAOff + t * kAStageCols + mt * 64;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t hi[16], lo[16];
+        for (int h = 0; h < 4; ++h) {
+          uint32_t hi[8], lo[8];
           if (ORIENT == ORIENT_XH) {
             // tile is [32 cells][256 genes]; this thread owns gene `row`
 #pragma unroll
-            for (int kk = 0; kk < 16; ++kk)
-              ptx::split_tf32_fast(ptx::lds_f32(sX + ((16 * h + kk) * kRows + row) * 4), hi[kk], lo[kk]);
+            for (int kk = 0; kk < 8; ++kk)
+              ptx::split_tf32_fast(ptx::lds_f32(sX + ((8 * h + kk) * kRows + row) * 4), hi[kk], lo[kk]);
           } else {
             // tile is [256 cells][32 genes] with the TMA 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const float4 q = ptx::lds_v4(sX + row * (kBK * 4) + (((4 * h + c) ^ (row & 7)) << 4));
+            for (int c = 0; c < 2; ++c) {
+              const float4 q = ptx::lds_v4(sX + row * (kBK * 4) + (((2 * h + c) ^ (row & 7)) << 4));
               ptx::split_tf32_fast(q.x, hi[4 * c + 0], lo[4 * c + 0]);
               ptx::split_tf32_fast(q.y, hi[4 * c + 1], lo[4 * c + 1]);
               ptx::split_tf32_fast(q.z, hi[4 * c + 2], lo[4 * c + 2]);
               ptx::split_tf32_fast(q.w, hi[4 * c + 3], lo[4 * c + 3]);
             }
           }
-          ptx::tmem_st_x16(a_addr + 16 * h, hi);
-          ptx::tmem_st_x16(a_addr + 32 + 16 * h, lo);
+          ptx::tmem_st_x8(a_addr + 8 * h, hi);
+          ptx::tmem_st_x8(a_addr + 32 + 8 * h, lo);
         }
         ptx::tc_wait_st();
         ptx::tc_fence_before();

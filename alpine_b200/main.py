@@ -361,7 +361,6 @@ class ALPINE:
     # ------------------------------------------------------------------------------------------- hot loop
     def _fit(self, m: AlpineMatrices) -> None:
         """``max_iter`` MU iterations, in place on ``m`` (main.py:486-676); leaves ``self.loss_history``."""
-        n_loc = m.X_cells_major.shape[0]
         full_batch = self.batch_size >= m.n_total
         if self.sampling_method not in ("random", "weighted"):
             raise ValueError(f"Unknown sampling method: {self.sampling_method}. Only 'weighted', and 'random' are supported.")
@@ -384,21 +383,40 @@ class ALPINE:
             solver.close()
         colnames = ["total loss", "reconstruction loss"] + [f"prediction loss({k})" for k in self.covariate_keys]
         self.loss_history = pd.DataFrame(history.tolist(), columns=colnames)
-        del n_loc
 
     def _compute_loss(self, m: AlpineMatrices) -> List[float]:
-        """[total, reconstruction, prediction...] of the current factors (main.py:726-753).
+        """[total, reconstruction, prediction...] of the factors as they are (main.py:726-753).
 
-        Evaluated by the same device kernels the loop uses (trace identity for the reconstruction term); one MU
-        iteration is NOT applied: the statistics pass alone is run on a scratch copy of the factors.
+        Not on the hot path (the loop gets its loss terms from the update kernels): the reconstruction term uses
+        the same trace identity, ||X||^2 - 2 tr(W^T X H^T) + tr(W^T W H H^T), with W^T X from the tcgen05
+        contraction and fp64 traces; the prediction terms are evaluated with torch on the device.
         """
-        scratch = AlpineMatrices(X=m.X, Ys=m.Ys, Ws=[], Hs=[], Bs=[b.clone() for b in m.Bs], W=m.W.clone(),
-                                 H=_clone_padded(m.H), X_cells_major=m.X_cells_major, shard=m.shard, n_total=m.n_total)
-        solver = self._make_solver(scratch)
+        solver = self._make_solver(m)
         try:
-            return _loss_of_current_factors(solver, self.lam, scratch)
+            A = solver.wx_product().double()
         finally:
             solver.close()
+        H, W = m.H.double(), m.W.double()
+        terms = [(m.X_cells_major.double() ** 2).sum(), (A * H).sum(), ((W.T @ W) * (H @ H.T)).sum()]
+        row = 0
+        for i, B in enumerate(m.Bs):
+            k = B.shape[1]
+            y, y_hat = m.Ys[i], B @ m.H[row:row + k]
+            row += k
+            if self.loss_type == "kl-divergence":
+                y_hat = torch.clamp(y_hat, min=self.eps)
+                terms.append(torch.sum(y * torch.log(torch.clamp(y / y_hat, min=self.eps)) - y + y_hat).double())
+            else:
+                terms.append((torch.norm(y - y_hat, p="fro") ** 2).double())
+        vals = torch.stack(terms)
+        if dist_info()[1] > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(vals)
+        vals = vals.cpu().tolist()
+        recon = vals[0] - 2.0 * vals[1] + vals[2]
+        preds = vals[3:]
+        return [recon + sum(self.lam[i] * p for i, p in enumerate(preds)), recon] + preds
 
     def _compute_best_iter(self, train_loss) -> int:
         """Kneedle elbow of log10(reconstruction loss) (main.py:755-770)."""
@@ -416,55 +434,3 @@ class ALPINE:
             torch.cuda.synchronize(m.W.device)
         finally:
             solver.close()
-
-
-def _clone_padded(H: torch.Tensor) -> torch.Tensor:
-    out = _native.padded_rows(H.shape[0], H.shape[1], H.device)
-    out.copy_(H)
-    return out
-
-
-def _loss_of_current_factors(solver, lam, m: AlpineMatrices) -> List[float]:
-    """Loss of (W, H, B) as they are: tr-identity terms from W^T X, W^T W, H H^T and the prediction statistics."""
-    A = solver.wx_product()[:, : m.H.shape[1]].double()                   # W^T X  (K x n_loc)
-    H = m.H.double()
-    W = m.W.double()
-    t1 = float((A * H).sum().item())
-    t2 = float(((W.T @ W) * (H @ H.T)).sum().item())
-    xn = float((m.X_cells_major.double() ** 2).sum().item())
-    vals = torch.tensor([xn, t1, t2], dtype=torch.float64, device=m.W.device)
-    rank, world = dist_info()
-    if world > 1:
-        import torch.distributed as dist
-
-        dist.all_reduce(vals)
-    xn, t1, t2 = (float(v) for v in vals.cpu())
-    recon = xn - 2.0 * t1 + t2
-    preds = []
-    row = 0
-    eps = float(solver_eps(solver))
-    for i, B in enumerate(m.Bs):
-        k = B.shape[1]
-        y = m.Ys[i]
-        y_hat = B @ m.H[row:row + k]
-        row += k
-        if solver_loss_type(solver) == "kl-divergence":
-            y_hat = torch.clamp(y_hat, min=eps)
-            p = torch.sum(y * torch.log(torch.clamp(y / y_hat, min=eps)) - y + y_hat).double()
-        else:
-            p = (torch.norm(y - y_hat, p="fro") ** 2).double()
-        if world > 1:
-            import torch.distributed as dist
-
-            dist.all_reduce(p)
-        preds.append(float(p.item()))
-    total = recon + sum(lam[i] * p for i, p in enumerate(preds))
-    return [total, recon] + preds
-
-
-def solver_eps(solver) -> float:
-    return getattr(solver, "_eps", 1e-6)
-
-
-def solver_loss_type(solver) -> str:
-    return getattr(solver, "_loss_type", "kl-divergence")
