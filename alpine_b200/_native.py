@@ -49,6 +49,8 @@ SIGNATURES = {
     "alpine_transform": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_xh_product": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, ctypes.c_void_p]),
     "alpine_wx_product": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "alpine_profile": (ctypes.c_int, [_c_ctx, ctypes.c_int]),
+    "alpine_profile_read": (ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     "alpine_query": (ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                     ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
 }
@@ -225,6 +227,15 @@ class Solver:
         out = padded_rows(self.K, self.n, self.device)
         _check(self.lib, self.lib.alpine_wx_product(self._ctx, out.data_ptr(), out.stride(0), self._stream()))
         return out
+
+    def profile(self, enable: bool) -> None:
+        _check(self.lib, self.lib.alpine_profile(self._ctx, 1 if enable else 0))
+
+    def profile_read(self):
+        """(total ms, launches) of the contraction kernel since profile(True); CUDA events on the launch stream."""
+        ms, cnt = ctypes.c_double(0.0), ctypes.c_longlong(0)
+        _check(self.lib, self.lib.alpine_profile_read(self._ctx, ctypes.byref(ms), ctypes.byref(cnt)))
+        return float(ms.value), int(cnt.value)
 
     def query(self) -> dict:
         a, b, c, d = ctypes.c_int(), ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

@@ -148,6 +148,9 @@ struct alpine_ctx {
   float* reduce = nullptr;  // [Pt K*ldG | S K*K | hsum K | Q q_total]
 
   GemmPlan plan_xh, plan_wx;
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
+  size_t prof_used = 0;
   bool ws_ready = false;
   bool fit_active = false;
 
@@ -251,6 +254,17 @@ int set_kernel_attrs() {
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<16, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl16));
   CU_TRY(cudaFuncSetAttribute(cov_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU_TRY(cudaFuncSetAttribute(guided_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  return ALPINE_OK;
+}
+
+int prof_mark(alpine_ctx* c, cudaStream_t st) {
+  if (!c->prof) return ALPINE_OK;
+  if (c->prof_used == c->prof_ev.size()) {
+    cudaEvent_t e;
+    CU_TRY(cudaEventCreate(&e));
+    c->prof_ev.push_back(e);
+  }
+  CU_TRY(cudaEventRecord(c->prof_ev[c->prof_used++], st));
   return ALPINE_OK;
 }
 
@@ -368,10 +382,12 @@ int run_gemm(alpine_ctx* c, int orient, const float* Bop, long long ldB, float* 
       other->r.partial = c->partial;
     }
   }
+  AL_TRY(prof_mark(c, st));
   if (orient == ORIENT_XH)
     AL_TRY(launch_gemm_t<ORIENT_XH>(*pl, st));
   else
     AL_TRY(launch_gemm_t<ORIENT_WX>(*pl, st));
+  AL_TRY(prof_mark(c, st));
   ReduceParams r = pl->r;
   r.out = out;
   r.ld = ld_out;
@@ -548,6 +564,7 @@ int alpine_destroy(alpine_ctx* c) {
                   c->own_reduce};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return ALPINE_OK;
 }
@@ -795,6 +812,29 @@ int alpine_wx_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
   AL_TRY(run_gemm(c, ORIENT_WX, c->WT, c->ldG, out, ld_out, st));
   CU_TRY(cudaStreamSynchronize(st));
   return check_kernel_error(c);
+}
+
+int alpine_profile(alpine_ctx* c, int enable) {
+  if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
+  c->prof = enable != 0;
+  if (enable) c->prof_used = 0;
+  return ALPINE_OK;
+}
+
+int alpine_profile_read(alpine_ctx* c, double* gemm_ms_total, long long* gemm_launches) {
+  if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
+  CU_TRY(cudaSetDevice(c->device));
+  double total = 0.0;
+  const size_t pairs = c->prof_used / 2;
+  for (size_t i = 0; i < pairs; ++i) {
+    CU_TRY(cudaEventSynchronize(c->prof_ev[2 * i + 1]));
+    float ms = 0.f;
+    CU_TRY(cudaEventElapsedTime(&ms, c->prof_ev[2 * i], c->prof_ev[2 * i + 1]));
+    total += ms;
+  }
+  if (gemm_ms_total) *gemm_ms_total = total;
+  if (gemm_launches) *gemm_launches = static_cast<long long>(pairs);
+  return ALPINE_OK;
 }
 
 int alpine_query(const alpine_ctx* c, int* num_sms, int* gemm_grid, int* smem_stages, int* k_padded) {

@@ -24,6 +24,8 @@
 //  * Work split: the (super-tile, k-block) space is cut into gridDim.x equal contiguous ranges (stream-K).  Every
 //    contiguous piece of one tile ("segment") is stored to a partial-sum slot; reduce_partials_kernel adds the
 //    slots of a tile in a fixed order, so results are deterministic and no CTA ever waits for another.
+//  * One MMA-issuing warp per 128-row tile: a 128x112x8 tf32 MMA lasts only ~56 cycles, so a single issuing
+//    thread (and any per-instruction register shuffling) would leave the tensor pipe idle.
 //  * Every mbarrier wait is bounded (clock64): a protocol bug reports an error code instead of hanging the GPU.
 #pragma once
 #include "ptx_sm100.cuh"
@@ -115,7 +117,7 @@ __device__ __forceinline__ bool warp_wait_bar(uint64_t* bar, uint32_t parity, co
 constexpr int kMT = 2;
 constexpr int kRows = kMT * kBM;
 constexpr int kConvWarps = 4 * kMT;
-constexpr int kGemmThreads = (kConvWarps + 3) * 32;  // + X producer, MMA issuer, B producer
+constexpr int kGemmThreads = (kConvWarps + 4) * 32;  // + X producer, B producer, one MMA issuer per tile
 constexpr int kXTileBytes = kRows * kBK * 4;
 constexpr int kAStageCols = kMT * 64;   // per MMA tile: 32 hi + 32 lo columns
 constexpr int kAStages = (kTmemCols - kTmemAOff) / kAStageCols;
@@ -140,7 +142,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
   constexpr int Kp = 16 * NC;
-  constexpr int kWarpXProd = kConvWarps, kWarpMma = kConvWarps + 1, kWarpBProd = kConvWarps + 2;
+  constexpr int kWarpXProd = kConvWarps, kWarpBProd = kConvWarps + 1, kWarpMma = kConvWarps + 2;  // + kMT MMA warps
   constexpr int b_tile_bytes = Kp * kBK * 4;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -174,11 +176,11 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     }
     for (int i = 0; i < SB; ++i) {
       ptx::mbar_init(&bfull_bar[i], 1);
-      ptx::mbar_init(&bempty_bar[i], 1);
+      ptx::mbar_init(&bempty_bar[i], kMT);
     }
     for (int i = 0; i < kAStages; ++i) {
       ptx::mbar_init(&cfull_bar[i], kConvWarps);
-      ptx::mbar_init(&aempty_bar[i], 1);
+      ptx::mbar_init(&aempty_bar[i], kMT);
     }
     for (int i = 0; i < kMT; ++i) {
       ptx::mbar_init(&accfull_bar[i], 1);
@@ -192,7 +194,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     ptx::prefetch_tensormap(&tmBhi);
     ptx::prefetch_tensormap(&tmBlo);
   }
-  if (warp == kWarpMma) {
+  if (warp == kWarpMma) {  // the first MMA warp owns the TMEM allocation
     ptx::tmem_alloc(tmem_slot, kTmemCols);
     ptx::tmem_relinquish();
   }
@@ -239,60 +241,60 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == kWarpMma) {
-    // ===================================================== MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_tf32(kBM, Kp);
-      uint32_t it = 0, mc = 0;  // k-block counter, chunk counter
-      bool ok = true;
-      for (long long pos = range_begin; pos < range_end && ok;) {
-        const int kb0 = static_cast<int>(pos % kbT);
-        const long long left = range_end - pos;
-        const int len = static_cast<int>((kbT - kb0) < left ? (kbT - kb0) : left);
-        for (int li = 0; li < len && ok; ++li, ++it) {
-          const int t = it % kAStages;
-          const int sbi = it % SB;
-          const bool c_first = (li % C) == 0;
-          const bool c_last = (li % C) == C - 1 || li == len - 1;
-          if (!wait_bar(&bfull_bar[sbi], (it / SB) & 1, actx, ERR_MMA_BFULL, it, sbi) ||
-              !wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
+  } else if (warp >= kWarpMma) {
+    // ===================================================== MMA issuers: one warp per 128-row tile.
+    // The whole warp runs the loop with warp-uniform values; one elected lane issues (see ptx::mma_tf32_ts_if).
+    const int mt = __shfl_sync(0xffffffffu, warp - kWarpMma, 0);
+    const uint32_t leader = ptx::elect_one();
+    const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
+    const uint32_t smem_b_u32 = __shfl_sync(0xffffffffu, ptx::smem_u32(smem_b), 0);
+    const uint32_t idesc = ptx::make_idesc_tf32(kBM, Kp);
+    const uint32_t d_acc = tb + mt * kAccStride;
+    uint32_t it = 0, mc = 0;  // k-block counter, chunk counter
+    bool ok = true;
+    for (long long pos = range_begin; pos < range_end && ok;) {
+      const int kb0 = static_cast<int>(pos % kbT);
+      const long long left = range_end - pos;
+      const int len = static_cast<int>((kbT - kb0) < left ? (kbT - kb0) : left);
+      for (int li = 0; li < len; ++li, ++it) {
+        const int t = it % kAStages;
+        const int sbi = it % SB;
+        const bool c_first = (li % C) == 0;
+        const bool c_last = (li % C) == C - 1 || li == len - 1;
+        if (!warp_wait_bar(&bfull_bar[sbi], (it / SB) & 1, actx, ERR_MMA_BFULL, it, sbi) ||
+            !warp_wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
+          ok = false;
+          break;
+        }
+        if (c_first && mc > 0) {  // the previous chunk of this accumulator must have been flushed
+          if (!warp_wait_bar(&accempty_bar[mt], (mc - 1) & 1, actx, ERR_MMA_ACCEMPTY, mc, mt)) {
             ok = false;
             break;
           }
-          ptx::tc_fence_after();
-          const uint32_t sb_addr = ptx::smem_u32(smem_b + static_cast<size_t>(sbi) * 2 * b_tile_bytes);
-          const uint64_t dhi = ptx::make_kmajor_sw128_desc(sb_addr);
-          const uint64_t dlo = ptx::make_kmajor_sw128_desc(sb_addr + b_tile_bytes);
-#pragma unroll
-          for (int mt = 0; mt < kMT; ++mt) {
-            if (c_first && mc > 0) {  // the previous chunk of this accumulator must have been flushed
-              if (!wait_bar(&accempty_bar[mt], (mc - 1) & 1, actx, ERR_MMA_ACCEMPTY, mc, mt)) {
-                ok = false;
-                break;
-              }
-              ptx::tc_fence_after();
-            }
-            const uint32_t d_acc = tmem_base + mt * kAccStride;
-            const uint32_t a_hi = tmem_base + kTmemAOff + t * kAStageCols + mt * 64;
-            const uint32_t a_lo = a_hi + 32;
-#pragma unroll
-            for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
-              // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-              const uint64_t bh = dhi + static_cast<uint64_t>(2 * ks);
-              const uint64_t bl = dlo + static_cast<uint64_t>(2 * ks);
-              ptx::mma_tf32_ts(d_acc, a_lo + ks * kUmmaK, bh, idesc, (c_first && ks == 0) ? 0u : 1u);
-              ptx::mma_tf32_ts(d_acc, a_hi + ks * kUmmaK, bl, idesc, 1u);
-              ptx::mma_tf32_ts(d_acc, a_hi + ks * kUmmaK, bh, idesc, 1u);
-            }
-            if (c_last) ptx::tc_commit(&accfull_bar[mt]);
-          }
-          if (!ok) break;
-          ptx::tc_commit(&aempty_bar[t]);
-          ptx::tc_commit(&bempty_bar[sbi]);
-          if (c_last) ++mc;
         }
-        pos += len;
+        ptx::tc_fence_after();
+        const uint32_t sb_addr = smem_b_u32 + static_cast<uint32_t>(sbi) * 2 * b_tile_bytes;
+        const uint64_t dhi = ptx::make_kmajor_sw128_desc(sb_addr);
+        const uint64_t dlo = ptx::make_kmajor_sw128_desc(sb_addr + b_tile_bytes);
+        const uint32_t a_hi = tb + kTmemAOff + t * kAStageCols + mt * 64;
+        const uint32_t a_lo = a_hi + 32;
+#pragma unroll
+        for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
+          // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+          const uint64_t bh = dhi + static_cast<uint64_t>(2 * ks);
+          const uint64_t bl = dlo + static_cast<uint64_t>(2 * ks);
+          ptx::mma_tf32_ts_if(leader, d_acc, a_lo + ks * kUmmaK, bh, idesc, (c_first && ks == 0) ? 0u : 1u);
+          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bl, idesc, 1u);
+          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bh, idesc, 1u);
+        }
+        if (c_last) {
+          ptx::tc_commit_if(leader, &accfull_bar[mt]);
+          ++mc;
+        }
+        ptx::tc_commit_if(leader, &aempty_bar[t]);
+        ptx::tc_commit_if(leader, &bempty_bar[sbi]);
       }
+      pos += len;
     }
     __syncwarp();
   } else {

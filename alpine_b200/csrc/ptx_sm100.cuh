@@ -97,6 +97,46 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                : "memory");
 }
 
+// one lane of a converged warp
+__device__ __forceinline__ uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+// The `_if` variants are executed by a whole converged warp with warp-uniform operands; only lanes with
+// leader != 0 (one elected lane) issue.  Keeping the operands uniform lets ptxas feed the instruction from
+// uniform registers instead of a per-operand R2UR "waterfall" loop.
+__device__ __forceinline__ void mma_tf32_ts_if(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_if(uint32_t leader, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}"
+      ::"r"(smem_u32(bar)),
+      "r"(leader)
+      : "memory");
+}
+
 // D[tmem] (+)= A[tmem] * B[smem desc], kind::tf32, issued by one thread
 __device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
                                             uint32_t accumulate) {

@@ -64,19 +64,27 @@ class MUEngine:
 
     def run(self, max_iter: int, on_iter: Optional[Callable[[int], None]] = None) -> np.ndarray:
         """Returns rows ``[total, reconstruction, prediction_0, ...]`` per iteration (main.py:750-753)."""
-        s = self.solver
-        buf = s.reduce_buffer()
-        s.fit_begin(max_iter)      # leaves this shard's statistics of the initial H / B in the buffer
+        self.begin(max_iter)
         for it in range(max_iter):
-            s.mu_partials()        # X H^T of this shard into the reduce buffer (main.py:596)
-            # The iteration's only data-path collective.  The statistics part [H H^T | rowsum(H) | B statistics]
-            # still holds this shard's values (written by fit_begin / the previous mu_apply), so one message
-            # carries everything the W and B updates need.
-            self._all_reduce(buf)
-            s.mu_apply(it)         # W, B, H updates + loss terms (main.py:597-663, 726-753)
+            self.step(it)
             if on_iter is not None:
                 on_iter(it)
         return self.collect_losses(max_iter)
+
+    def begin(self, max_iter: int) -> None:
+        """||X||^2 and this shard's statistics of the initial H / B (left in the reduce buffer)."""
+        self._buf = self.solver.reduce_buffer()
+        self.solver.fit_begin(max_iter)
+
+    def step(self, it: int) -> None:
+        """One full-batch MU iteration (asynchronous on the current stream)."""
+        s = self.solver
+        s.mu_partials()        # X H^T of this shard into the reduce buffer (main.py:596)
+        # The iteration's only data-path collective.  The statistics part [H H^T | rowsum(H) | B statistics]
+        # still holds this shard's values (written by fit_begin / the previous mu_apply), so one message
+        # carries everything the W and B updates need.
+        self._all_reduce(self._buf)
+        s.mu_apply(it)         # W, B, H updates + loss terms (main.py:597-663, 726-753)
 
     def collect_losses(self, n_iter: int) -> np.ndarray:
         xn, rows = self.solver.losses(n_iter)

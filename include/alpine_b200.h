@@ -91,6 +91,12 @@ int alpine_transform(alpine_ctx* ctx, int n_iter, void* stream);
 int alpine_xh_product(alpine_ctx* ctx, float* out, int64_t ld_out, void* stream);
 int alpine_wx_product(alpine_ctx* ctx, float* out, int64_t ld_out, void* stream);
 
+/* Device-side timing of the contraction kernel (CUDA events on the launch stream around every mu_gemm launch):
+ * alpine_profile(ctx, 1) starts / resets, alpine_profile(ctx, 0) stops; alpine_profile_read synchronises the
+ * recorded events and returns the summed kernel time and the number of launches.  bench.py's roofline figure.   */
+int alpine_profile(alpine_ctx* ctx, int enable);
+int alpine_profile_read(alpine_ctx* ctx, double* gemm_ms_total, long long* gemm_launches);
+
 /* Introspection for bench.py: SM count, grid and pipeline depth used by the contraction kernels. */
 int alpine_query(const alpine_ctx* ctx, int* num_sms, int* gemm_grid, int* smem_stages, int* k_padded);
 
