@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native MU-NMF loop (BASELINE.json metric: MU iterations/sec at 20,000 genes x 100,000
+cells, k = 100, on 1/2/4/8 B200).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework (one process per GPU under torchrun)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+One "step" is one full-batch MU iteration (W update, B updates, H update, loss terms).  Inputs are synthetic
+(seeded, generated on the device), larger than L2 (X is 8 GB), so no L2 flush is needed between steps.
+
+* ``value``    : iterations/s with X, Y, W, H, B resident in HBM; K timed steps between barrier+synchronize,
+                 CUDA events on the launch stream, max over ranks.  At N > 1 the SAME 20k x 100k problem is
+                 sharded by cells over the ranks ("scaling": "strong") with one NCCL all-reduce per iteration.
+* ``e2e``      : the same metric through the public API (``ALPINE.fit`` on host numpy buffers): one fit of K
+                 iterations including validation, host->device upload of X / Y, initialisation, the loop, the loss
+                 read-back and the device->host copy of W / H / B, divided by K.
+* ``roofline`` : the contraction kernel (two launches per step), timed with CUDA events around each launch
+                 inside the timed region; 3xTF32 tensor work against measured bf16 peak / 2.
+* ``cpu_baseline`` : the NumPy oracle port of the reference's step (its 7 GEMMs, gathers and G x n temporaries)
+                 on a bounded column sample of the same workload, on the host cores, extrapolated linearly in cells.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(
+    name="cfg3: 20,000 genes x 100,000 cells dense fp32, k=100 (90 unguided + [5,5] guided, 3 and 4 categories), "
+         "orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, lam=[1e3,1e3], KL loss, full batch",
+    n_genes=20000, n_cells=100000, n_components=90, n_covariate_components=[5, 5], categories=[3, 4],
+    lam=[1e3, 1e3], orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, eps=1e-6,
+)
+METRIC = "MU iterations/sec at 20k genes x 100k cells, k=100"
+UNIT = "iterations/s"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=float(d["hbm_gbs"]), bf16_tflops=float(d["bf16_tflops"]),
+                    bf16_tflops_sustained=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), source="measured")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+                power.append(float(parts[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------------------------- synthetic data
+def synth_device_problem(dev, G, n_loc, col0, wl, seed=0):
+    """Device-resident shard: X (n_loc x G, cells-major), Ys, W, H, Bs.  Low-rank + noise, non-negative."""
+    import torch
+
+    from alpine_b200 import _native
+
+    K = sum(wl["n_covariate_components"]) + wl["n_components"]
+    g = torch.Generator(device=dev)
+    g.manual_seed(1000 + seed)
+    rank = 16
+    Wg = torch.rand((rank, G), device=dev, generator=g).pow_(3.0)         # shared across shards (same seed)
+    X = _native.padded_rows(n_loc, G, dev)
+    gs = torch.Generator(device=dev)
+    gs.manual_seed(2000 + seed + 7919 * (col0 + 1))
+    step = max(1, (1 << 27) // G)
+    for r0 in range(0, n_loc, step):
+        r1 = min(n_loc, r0 + step)
+        Hc = torch.rand((r1 - r0, rank), device=dev, generator=gs).pow_(2.0)
+        blk = Hc @ Wg
+        blk.add_(torch.rand((r1 - r0, G), device=dev, generator=gs).pow_(4.0), alpha=0.5)
+        X[r0:r1] = blk
+    Ys = []
+    for c in wl["categories"]:
+        codes = torch.randint(0, c, (n_loc,), device=dev, generator=gs)
+        Ys.append(torch.nn.functional.one_hot(codes, c).T.contiguous().float())
+    gw = torch.Generator(device=dev)
+    gw.manual_seed(42)
+    W = torch.rand((G, K), device=dev, generator=gw).clamp_(min=wl["eps"])
+    H = _native.padded_rows(K, n_loc, dev)
+    H.copy_(torch.rand((K, n_loc), device=dev, generator=gs).clamp_(min=wl["eps"]))
+    Bs = [torch.rand((c, k), device=dev, generator=gw).clamp_(min=wl["eps"]).contiguous()
+          for c, k in zip(wl["categories"], wl["n_covariate_components"])]
+    return X, Ys, W, H, Bs
+
+
+# ------------------------------------------------------------------------------------------- CPU baseline
+def cpu_baseline(wl, sample_cells=8000, iters=2):
+    """Oracle port of the reference's step (oracle/alpine_oracle.py, literal arithmetic incl. gather and temporaries)
+    on a column sample of the workload; returns (iterations/s extrapolated to the full workload, seconds/iteration
+    on the sample, threads)."""
+    from oracle import alpine_oracle as orc
+
+    G, n = wl["n_genes"], wl["n_cells"]
+    ns = min(sample_cells, n)
+    rng = np.random.default_rng(0)
+    X = rng.random((ns, G), dtype=np.float32).T ** 3   # genes x cells view, as main.py:104
+    Ys = []
+    for c in wl["categories"]:
+        y = np.zeros((c, ns), dtype=np.float32)
+        y[rng.integers(0, c, ns), np.arange(ns)] = 1
+        Ys.append(y)
+    blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
+    K = sum(blocks)
+    st = orc.State(np.maximum(rng.random((G, K), dtype=np.float32), 1e-6),
+                   np.maximum(rng.random((K, ns), dtype=np.float32), 1e-6),
+                   [np.maximum(rng.random((c, k), dtype=np.float32), 1e-6)
+                    for c, k in zip(wl["categories"], wl["n_covariate_components"])], blocks)
+    hp = orc.HyperParams(n_components=wl["n_components"], n_covariate_components=list(wl["n_covariate_components"]),
+                         lam=list(wl["lam"]), orth_W=wl["orth_W"], alpha_W=wl["alpha_W"], l1_ratio_W=wl["l1_ratio_W"],
+                         eps=wl["eps"])
+    orc.mu_step(X, Ys, st, hp, literal_cost=True)  # warm-up (BLAS thread pools, page faults)
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        orc.mu_step(X, Ys, st, hp, literal_cost=True)  # main.py:589-663 incl. the X[:, perm] gather (main.py:520)
+        orc.compute_loss(X, Ys, st, hp)                # main.py:666, 726-753
+    dt = (time.perf_counter() - t0) / iters
+    threads = os.cpu_count() or 1
+    try:
+        from threadpoolctl import threadpool_info
+
+        info = [d.get("num_threads", 0) for d in threadpool_info() if d.get("user_api") == "blas"]
+        if info:
+            threads = max(info)
+    except Exception:
+        pass
+    return 1.0 / (dt * (n / ns)), dt, threads, ns
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's algorithm on the host CPU.  The reference itself is pure Python over
+    torch and needs anndata/scanpy/kneed (absent, no network), and /root/reference does not exist on the GPU box, so
+    the arm times the oracle port; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOAD
+    sample = 8000
+    # each step = one iteration on the sample; K steps + W warm-ups
+    vals = []
+    total_iters = max(1, args.warmup) + max(1, args.steps)
+    v, dt, threads, ns = cpu_baseline(wl, sample_cells=sample, iters=min(total_iters, 4))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "l2": "inputs larger than L2"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                         "sample": f"{ns} of {wl['n_cells']} cells (all {wl['n_genes']} genes), {dt:.3f} s per "
+                                   f"iteration on the sample, extrapolated linearly in cells"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    from alpine_b200 import _native
+    from alpine_b200.engine import MUEngine, shard_bounds
+
+    wl = dict(WORKLOAD)
+    if args.cells:
+        wl["n_cells"] = args.cells
+    if args.genes:
+        wl["n_genes"] = args.genes
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the MU loop has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+    G, n = wl["n_genes"], wl["n_cells"]
+    lo, hi = shard_bounds(n, world, rank)
+    blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
+
+    X, Ys, W, H, Bs = synth_device_problem(dev, G, hi - lo, lo, wl)
+    solver = _native.Solver(dev, G, hi - lo, blocks, wl["categories"])
+    solver.bind_dense(X)
+    solver.bind_labels(Ys)
+    solver.bind_factors(W, H, Bs)
+    solver.set_hparams(wl["lam"], wl["alpha_W"], wl["l1_ratio_W"], wl["orth_W"], wl["eps"])
+    engine = MUEngine(solver, wl["lam"])
+    total = args.warmup + args.steps
+    engine.begin(total)
+    for it in range(args.warmup):
+        engine.step(it)
+
+    def fence():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize(dev)
+
+    fence()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    solver.profile(True)
+    launches0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for it in range(args.warmup, total):
+        engine.step(it)
+    e1.record()
+    fence()
+    ms = e0.elapsed_time(e1)
+    launches = _native.launch_count() - launches0
+    solver.profile(False)
+    gemm_ms, gemm_n = solver.profile_read()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms, gemm_ms / max(gemm_n, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, gemm_ms_avg = float(t[0]), float(t[1])
+    hist = engine.collect_losses(total)  # also checks the kernels' error flag
+    value = args.steps / (ms / 1000.0)
+
+    # ---- roofline of the contraction kernel (per launch, this rank's shard)
+    peaks = load_peaks()
+    K = sum(blocks)
+    n_loc = hi - lo
+    flops = 3.0 * 2.0 * G * n_loc * K          # 3xTF32: three tf32 MMAs per fp32 product
+    tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
+    achieved = flops / (gemm_ms_avg * 1e-3) / 1e12 if gemm_ms_avg > 0 else 0.0
+    hbm_ms = 4.0 * G * n_loc / (peaks["hbm_gbs"] * 1e9) * 1e3
+    roofline = {
+        "kernel": "mu_gemm_kernel (X H^T and W^T X, 3xTF32 tcgen05)", "bound": "tensor",
+        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "traffic": None,
+        "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (no TF32 figure in MEASURED_PEAKS.json; the "
+                       f"kernel is timed inside the step loop)",
+        "avg_launch_ms": gemm_ms_avg, "launches_timed": gemm_n,
+        "hbm_bound_ms_per_launch": hbm_ms, "hbm_frac": hbm_ms / gemm_ms_avg if gemm_ms_avg > 0 else None,
+        "algorithmic": {"tf32_flop_per_launch": flops, "x_bytes_per_launch": 4.0 * G * n_loc},
+    }
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+            "config": {"workload": wl["name"], "parallelism": f"cells sharded over {world} GPU(s)",
+                       "l2": "inputs larger than L2 (X is %.1f GB per GPU)" % (4.0 * G * n_loc / 1e9)},
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
+            "final_loss": {"total": float(hist[-1, 0]), "reconstruction": float(hist[-1, 1])},
+        }
+    solver.close()
+    del X, H, W
+    torch.cuda.empty_cache()
+
+    # ---- e2e through the public API with host buffers (N = 1 process; each rank runs the sharded fit under torchrun)
+    if not args.no_e2e:
+        e2e = run_e2e(args, wl, dev, world, rank)
+        if rank == 0:
+            line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, dt, threads, ns = cpu_baseline(wl, sample_cells=8000, iters=2)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"{ns} of {wl['n_cells']} cells (all {wl['n_genes']} genes), {dt:.3f} s per "
+                                          f"iteration on the sample, extrapolated linearly in cells"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def run_e2e(args, wl, dev, world, rank):
+    """ALPINE.fit on host numpy data: upload, init, K iterations, loss read-back, factors back to the host."""
+    import pandas as pd
+    import torch
+
+    from alpine_b200 import ALPINE
+    from alpine_b200.utils.anndata_compat import AnnData
+
+    G, n = wl["n_genes"], wl["n_cells"]
+    # host data (built on the device for speed, then copied out; not timed)
+    X, Ys, _, _, _ = synth_device_problem(dev, G, n, 0, wl, seed=1)
+    Xh = X.cpu().numpy()
+    obs = {}
+    for i, y in enumerate(Ys):
+        codes = y.argmax(dim=0).cpu().numpy()
+        obs[f"cov{i}"] = pd.Series([f"c{v}" for v in codes], dtype=object)
+    del X, Ys
+    torch.cuda.empty_cache()
+    adata = AnnData(Xh, obs=pd.DataFrame(obs))
+    model = ALPINE(n_components=wl["n_components"], n_covariate_components=list(wl["n_covariate_components"]),
+                   lam=list(wl["lam"]), orth_W=wl["orth_W"], alpha_W=wl["alpha_W"], l1_ratio_W=wl["l1_ratio_W"],
+                   device=str(dev))
+    keys = list(obs.keys())
+    steps = args.steps
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    model.fit(adata, keys, max_iter=steps)
+    torch.cuda.synchronize(dev)
+    dt = time.perf_counter() - t0
+    tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dt = float(tt[0])
+    K = model.total_components
+    n_cat = sum(wl["categories"])
+    h2d = 4.0 * (G * n + n_cat * n) / world
+    d2h = 4.0 * (G * K + K * n + sum(c * k for c, k in zip(wl["categories"], wl["n_covariate_components"]))) + 8.0 * steps * 4
+    return {"value": steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
+            "seconds_per_fit": dt, "iterations_per_fit": steps,
+            "what": "ALPINE(...).fit(adata, keys, max_iter=steps) on host numpy data: validation, encoders, H2D of X/Y, "
+                    "init, the loop, loss read-back, scaling, D2H of W/H/B, store_embeddings"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=0, help="override the workload's cell count (debugging)")
+    ap.add_argument("--genes", type=int, default=0, help="override the workload's gene count (debugging)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()
