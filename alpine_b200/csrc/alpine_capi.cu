@@ -295,12 +295,30 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
   p.R = static_cast<int>(R);
   p.K = c->K;
   p.Kp = c->Kp;
-  p.num_tiles = ceil_div(M, rows);
-  p.kb_per_tile = ceil_div(R, kBK);
-  const long long total = static_cast<long long>(p.num_tiles) * p.kb_per_tile;
+  p.ws.num_tiles = ceil_div(M, rows);
+  p.ws.kb_per_tile = ceil_div(R, kBK);
+  // pieces of the reduction axis: keep the live window of the B operand (two pieces of its hi + lo copies) near
+  // 16 MB so that it is served from L2 while X streams through with evict-first
+  {
+    const double b_bytes = 2.0 * c->K * static_cast<double>(R) * sizeof(float);
+    long long piece_mb = 8;
+    if (const char* e = getenv("ALPINE_B200_PIECE_MB")) piece_mb = atoll(e) > 0 ? atoll(e) : piece_mb;
+    int pieces = static_cast<int>(b_bytes / (piece_mb * 1024.0 * 1024.0) + 0.999);
+    if (pieces < 1) pieces = 1;
+    int plen = ceil_div(p.ws.kb_per_tile, pieces);
+    plen = static_cast<int>(round_up(plen, 8));
+    if (plen > p.ws.kb_per_tile) plen = p.ws.kb_per_tile;
+    p.ws.piece_len = plen;
+    p.ws.pieces = ceil_div(p.ws.kb_per_tile, plen);
+  }
+  const long long total = p.ws.total();
   pl->grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
   const long long per_cta = (total + pl->grid - 1) / pl->grid;
-  p.max_segs = ceil_div(per_cta, p.kb_per_tile) + 1;
+  {
+    const int last_len = p.ws.len_of_piece(p.ws.pieces - 1);
+    const int min_len = last_len < p.ws.piece_len ? last_len : p.ws.piece_len;
+    p.max_segs = ceil_div(per_cta, min_len) + 2;
+  }
   // pipeline depths from the shared-memory budget
   const size_t budget = 227 * 1024 - 1024;
   int sb = 3, sx = 0;
@@ -344,8 +362,7 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
   r.rows = rows;
   r.M = p.M;
   r.K = p.K;
-  r.num_tiles = p.num_tiles;
-  r.kb_per_tile = p.kb_per_tile;
+  r.ws = p.ws;
   r.grid = pl->grid;
   r.max_segs = p.max_segs;
   pl->valid = true;
@@ -391,7 +408,7 @@ int run_gemm(alpine_ctx* c, int orient, const float* Bop, long long ldB, float* 
   ReduceParams r = pl->r;
   r.out = out;
   r.ld = ld_out;
-  dim3 rgrid(r.num_tiles, c->K < 16 ? c->K : 16);
+  dim3 rgrid(r.ws.num_tiles, c->K < 16 ? c->K : 16);
   reduce_partials_kernel<<<rgrid, 256, 0, st>>>(r);
   LAUNCH_CHECK();
   return ALPINE_OK;
@@ -463,7 +480,7 @@ int run_stats(alpine_ctx* c, double* loss_row, cudaStream_t st) {
   f.ldS = c->K;
   f.K = c->K;
   f.loss_row = loss_row;
-  stats_finish_kernel<<<1, 256, 0, st>>>(f);
+  stats_finish_kernel<<<c->q_total + 2 + c->n_cov, 256, 0, st>>>(f);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }

@@ -48,13 +48,45 @@ enum { ORIENT_XH = 0, ORIENT_WX = 1 };
 enum { ERR_NONE = 0, ERR_XPROD_EMPTY = 1, ERR_BPROD_EMPTY = 2, ERR_CONV_XFULL = 3, ERR_CONV_BFULL = 4,
        ERR_CONV_AEMPTY = 5, ERR_MMA_CFULL = 6, ERR_MMA_ACCEMPTY = 7, ERR_EPI_ACCFULL = 8, ERR_MMA_BFULL = 9 };
 
+__host__ __device__ inline long long gemm_range_begin(long long total, int grid, int cta) {
+  return total * cta / grid;
+}
+
+// Work space of one contraction.  The reduction axis (kb_per_tile k-blocks) is cut into `pieces` of piece_len
+// k-blocks (the last may be shorter); a "run" is one (piece, tile) pair and the linear work order is piece-major:
+//   pos -> piece = pos / (num_tiles * piece_len), then tile, then k-block inside the piece.
+// Stream-K hands each CTA a contiguous range of that order, so at any moment all CTAs read the same one or two
+// pieces of the small (B) operand: its live window stays a few MB and is served from L2 instead of HBM.
+struct WorkSpace {
+  int num_tiles, kb_per_tile, piece_len, pieces;
+  __host__ __device__ long long total() const { return static_cast<long long>(num_tiles) * kb_per_tile; }
+  __host__ __device__ int len_of_piece(int pc) const {
+    const int rest = kb_per_tile - pc * piece_len;
+    return rest < piece_len ? rest : piece_len;
+  }
+  // run index (piece * num_tiles + tile), first k-block and k-blocks left in the run at linear position pos
+  __host__ __device__ void decode(long long pos, int& run, int& tile, int& kb, int& left_in_run) const {
+    const long long per_piece = static_cast<long long>(num_tiles) * piece_len;
+    const int pc = static_cast<int>(pos / per_piece);
+    const long long rem = pos - pc * per_piece;
+    const int lp = len_of_piece(pc);
+    tile = static_cast<int>(rem / lp);
+    const int off = static_cast<int>(rem - static_cast<long long>(tile) * lp);
+    kb = pc * piece_len + off;
+    left_in_run = lp - off;
+    run = pc * num_tiles + tile;
+  }
+  __host__ __device__ long long run_begin(int pc, int tile) const {
+    return static_cast<long long>(pc) * num_tiles * piece_len + static_cast<long long>(tile) * len_of_piece(pc);
+  }
+};
+
 struct GemmParams {
   int M;            // rows of D (genes for XH, cells for WX)
   int R;            // reduction length
   int K;            // real component count
   int Kp;           // MMA N: K padded to a multiple of 16 (<= 128)
-  int num_tiles;    // ceil(M / 256)
-  int kb_per_tile;  // ceil(R / 32)
+  WorkSpace ws;     // num_tiles = ceil(M / 256), kb_per_tile = ceil(R / 32), piece decomposition
   int sx;           // X ring depth
   int sb;           // B ring depth
   int chunk;        // k-blocks accumulated in TMEM between two round-to-nearest flushes
@@ -63,9 +95,6 @@ struct GemmParams {
   int* err;         // [8]
 };
 
-__host__ __device__ inline long long gemm_range_begin(long long total, int grid, int cta) {
-  return total * cta / grid;
-}
 
 struct AbortCtx {
   volatile int* flag;  // shared
@@ -202,8 +231,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const long long kbT = p.kb_per_tile;
-  const long long total = static_cast<long long>(p.num_tiles) * kbT;
+  const WorkSpace ws = p.ws;
+  const long long total = ws.total();
   const int cta = blockIdx.x;
   const long long range_begin = gemm_range_begin(total, gridDim.x, cta);
   const long long range_end = gemm_range_begin(total, gridDim.x, cta + 1);
@@ -212,17 +241,25 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // ===================================================== TMA producer of the X ring
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long pos = range_begin; pos < range_end; ++pos, ++it) {
-        const int tile = static_cast<int>(pos / kbT);
-        const int kb = static_cast<int>(pos - tile * kbT);
-        const int s = it % SX;
-        if (!wait_bar(&xempty_bar[s], ((it / SX) & 1) ^ 1, actx, ERR_XPROD_EMPTY, it, s)) break;
-        uint8_t* dst = smem_x + static_cast<size_t>(s) * kXTileBytes;
-        ptx::mbar_arrive_expect_tx(&xfull_bar[s], kXTileBytes);
-        if (ORIENT == ORIENT_XH)  // box {256 genes, 32 cells} at (gene0, cell0): smem [32 cells][256 genes]
-          ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], tile * kRows, kb * kBK, ptx::kEvictFirst);
-        else  // box {32 genes, 256 cells} at (gene0, cell0): smem [256 cells][32 genes], 128B swizzle
-          ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], kb * kBK, tile * kRows, ptx::kEvictFirst);
+      bool ok = true;
+      for (long long pos = range_begin; pos < range_end && ok;) {
+        int run, tile, kb0, len;
+        ws.decode(pos, run, tile, kb0, len);
+        if (len > range_end - pos) len = static_cast<int>(range_end - pos);
+        for (int kb = kb0; kb < kb0 + len; ++kb, ++it) {
+          const int s = it % SX;
+          if (!wait_bar(&xempty_bar[s], ((it / SX) & 1) ^ 1, actx, ERR_XPROD_EMPTY, it, s)) {
+            ok = false;
+            break;
+          }
+          uint8_t* dst = smem_x + static_cast<size_t>(s) * kXTileBytes;
+          ptx::mbar_arrive_expect_tx(&xfull_bar[s], kXTileBytes);
+          if (ORIENT == ORIENT_XH)  // box {256 genes, 32 cells} at (gene0, cell0): smem [32 cells][256 genes]
+            ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], tile * kRows, kb * kBK, ptx::kEvictFirst);
+          else  // box {32 genes, 256 cells} at (gene0, cell0): smem [256 cells][32 genes], 128B swizzle
+            ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], kb * kBK, tile * kRows, ptx::kEvictFirst);
+        }
+        pos += len;
       }
     }
     __syncwarp();
@@ -230,14 +267,23 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     // ===================================================== TMA producer of the B ring
     if (lane == 0) {
       uint32_t it = 0;
-      for (long long pos = range_begin; pos < range_end; ++pos, ++it) {
-        const int kb = static_cast<int>(pos % kbT);
-        const int s = it % SB;
-        if (!wait_bar(&bempty_bar[s], ((it / SB) & 1) ^ 1, actx, ERR_BPROD_EMPTY, it, s)) break;
-        uint8_t* dst = smem_b + static_cast<size_t>(s) * 2 * b_tile_bytes;
-        ptx::mbar_arrive_expect_tx(&bfull_bar[s], 2 * b_tile_bytes);
-        ptx::tma_load_2d(dst, &tmBhi, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
-        ptx::tma_load_2d(dst + b_tile_bytes, &tmBlo, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+      bool ok = true;
+      for (long long pos = range_begin; pos < range_end && ok;) {
+        int run, tile, kb0, len;
+        ws.decode(pos, run, tile, kb0, len);
+        if (len > range_end - pos) len = static_cast<int>(range_end - pos);
+        for (int kb = kb0; kb < kb0 + len; ++kb, ++it) {
+          const int s = it % SB;
+          if (!wait_bar(&bempty_bar[s], ((it / SB) & 1) ^ 1, actx, ERR_BPROD_EMPTY, it, s)) {
+            ok = false;
+            break;
+          }
+          uint8_t* dst = smem_b + static_cast<size_t>(s) * 2 * b_tile_bytes;
+          ptx::mbar_arrive_expect_tx(&bfull_bar[s], 2 * b_tile_bytes);
+          ptx::tma_load_2d(dst, &tmBhi, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+          ptx::tma_load_2d(dst + b_tile_bytes, &tmBlo, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+        }
+        pos += len;
       }
     }
     __syncwarp();
@@ -253,9 +299,9 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     uint32_t it = 0, mc = 0;  // k-block counter, chunk counter
     bool ok = true;
     for (long long pos = range_begin; pos < range_end && ok;) {
-      const int kb0 = static_cast<int>(pos % kbT);
-      const long long left = range_end - pos;
-      const int len = static_cast<int>((kbT - kb0) < left ? (kbT - kb0) : left);
+      int run, tile, kb0, len;
+      ws.decode(pos, run, tile, kb0, len);
+      if (len > range_end - pos) len = static_cast<int>(range_end - pos);
       for (int li = 0; li < len; ++li, ++it) {
         const int t = it % kAStages;
         const int sbi = it % SB;
@@ -332,9 +378,9 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     };
 
     for (long long pos = range_begin; pos < range_end && ok; ++seg) {
-      const int kb0 = static_cast<int>(pos % kbT);
-      const long long left = range_end - pos;
-      const int len = static_cast<int>((kbT - kb0) < left ? (kbT - kb0) : left);
+      int run, tile, kb0, len;
+      ws.decode(pos, run, tile, kb0, len);
+      if (len > range_end - pos) len = static_cast<int>(range_end - pos);
       for (int li = 0; li < len; ++li, ++it) {
         const int s = it % SX;
         const int t = it % kAStages;
@@ -408,34 +454,38 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// out[k][m] = sum over the segments of m's tile, in stream-K order (fixed => deterministic).
-// grid = (num_tiles, ceil(K / rows_per_block)); block = kRows threads is not required: threads stride over rows.
+// out[k][m] = sum over the segments of m's tile, piece by piece in stream-K order (fixed => deterministic).
+// grid = (num_tiles, k-slices); threads stride over the 256 rows of the tile.
 struct ReduceParams {
   const float* partial;
   int rows;  // 256
   int M, K;
-  int num_tiles, kb_per_tile, grid, max_segs;
+  WorkSpace ws;
+  int grid, max_segs;
   float* out;
   long long ld;
 };
 __global__ void reduce_partials_kernel(const ReduceParams p) {
   const int tile = blockIdx.x;
-  const long long kbT = p.kb_per_tile;
-  const long long total = static_cast<long long>(p.num_tiles) * kbT;
-  const long long t_begin = tile * kbT, t_end = t_begin + kbT;
-  // first CTA whose (non-empty) range contains t_begin
-  int c = static_cast<int>(t_begin * p.grid / total);
-  while (c + 1 < p.grid && gemm_range_begin(total, p.grid, c + 1) <= t_begin) ++c;
-  while (c > 0 && gemm_range_begin(total, p.grid, c) > t_begin) --c;
-  __shared__ int s_slots[512];
+  const WorkSpace ws = p.ws;
+  const long long total = ws.total();
+  __shared__ int s_slots[1024];
   __shared__ int s_n;
   if (threadIdx.x == 0) {
     int cnt = 0;
-    for (int q = c; q < p.grid && gemm_range_begin(total, p.grid, q) < t_end; ++q) {
-      const long long b = gemm_range_begin(total, p.grid, q), e = gemm_range_begin(total, p.grid, q + 1);
-      if (e <= b) continue;
-      const int first_tile = static_cast<int>(b / kbT);
-      if (cnt < 512) s_slots[cnt++] = q * p.max_segs + (tile - first_tile);
+    for (int pc = 0; pc < ws.pieces; ++pc) {
+      const long long r_begin = ws.run_begin(pc, tile), r_end = r_begin + ws.len_of_piece(pc);
+      // first CTA whose (non-empty) range contains r_begin
+      int c = static_cast<int>(r_begin * p.grid / total);
+      while (c + 1 < p.grid && gemm_range_begin(total, p.grid, c + 1) <= r_begin) ++c;
+      while (c > 0 && gemm_range_begin(total, p.grid, c) > r_begin) --c;
+      for (int q = c; q < p.grid && gemm_range_begin(total, p.grid, q) < r_end; ++q) {
+        const long long b = gemm_range_begin(total, p.grid, q), e = gemm_range_begin(total, p.grid, q + 1);
+        if (e <= b) continue;
+        int run0, t0, k0, l0;
+        ws.decode(b, run0, t0, k0, l0);  // the CTA's first run; its segments are numbered from there
+        if (cnt < 1024) s_slots[cnt++] = q * p.max_segs + (pc * ws.num_tiles + tile - run0);
+      }
     }
     s_n = cnt;
   }

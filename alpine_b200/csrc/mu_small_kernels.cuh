@@ -529,35 +529,45 @@ struct StatsFinishParams {
   int K;
   double* loss_row;  // [2 + n_cov] or nullptr
 };
-__global__ void stats_finish_kernel(const StatsFinishParams p) {
-  for (int e = threadIdx.x; e < p.q_total; e += blockDim.x) {
-    float acc = 0.f;
-    for (int b = 0; b < p.q_blocks; ++b) acc += p.q_partial[static_cast<size_t>(b) * p.q_total + e];
-    p.stats_q[e] = acc;
+// fixed-order block reduction of a double (256 threads): thread-strided partial sums, then a shared-memory tree
+__device__ __forceinline__ double block_sum_256(double v, double* red) {
+  red[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  const double r = red[0];
+  __syncthreads();
+  return r;
+}
+// grid = q_total + 2 + n_cov blocks of 256 threads: block b < q_total sums one Q entry, then t1, t2, pred_i
+__global__ void __launch_bounds__(256) stats_finish_kernel(const StatsFinishParams p) {
+  __shared__ double red[256];
+  const int b = blockIdx.x;
+  if (b < p.q_total) {
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < p.q_blocks; i += 256) acc += static_cast<double>(p.q_partial[static_cast<size_t>(i) * p.q_total + b]);
+    const double r = block_sum_256(acc, red);
+    if (threadIdx.x == 0) p.stats_q[b] = static_cast<float>(r);
+    return;
   }
   if (p.loss_row == nullptr) return;
-  __shared__ double red[32];
-  double t2 = 0.0;
-  for (int e = threadIdx.x; e < p.K * p.K; e += blockDim.x) {
-    const int a = e / p.K, b = e - a * p.K;
-    t2 += static_cast<double>(p.T[a * p.ldT + b]) * static_cast<double>(p.S[a * p.ldS + b]);
-  }
-  for (int o = 16; o > 0; o >>= 1) t2 += __shfl_down_sync(0xffffffffu, t2, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = t2;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) s += red[w];
-    double t1 = 0.0;
-    for (int i = 0; i < p.t1_n; ++i) t1 += p.t1_partial[i];
-    p.loss_row[0] = t1;
-    p.loss_row[1] = s;
-    for (int i = 0; i < p.n_cov; ++i) {
-      double a = 0.0;
-      for (int b = 0; b < p.q_blocks; ++b) a += p.pred_partial[static_cast<size_t>(b) * p.n_cov + i];
-      p.loss_row[2 + i] = a;
+  const int which = b - p.q_total;  // 0: t1, 1: t2, 2+i: pred_i
+  double acc = 0.0;
+  if (which == 0) {
+    for (int i = threadIdx.x; i < p.t1_n; i += 256) acc += p.t1_partial[i];
+  } else if (which == 1) {
+    for (int e = threadIdx.x; e < p.K * p.K; e += 256) {
+      const int r = e / p.K, c = e - r * p.K;
+      acc += static_cast<double>(p.T[r * p.ldT + c]) * static_cast<double>(p.S[r * p.ldS + c]);
     }
+  } else {
+    const int i = which - 2;
+    for (int q = threadIdx.x; q < p.q_blocks; q += 256) acc += p.pred_partial[static_cast<size_t>(q) * p.n_cov + i];
   }
+  const double r = block_sum_256(acc, red);
+  if (threadIdx.x == 0) p.loss_row[which] = r;
 }
 
 // column sums of W (main.py:776) = row sums of W^T, one block per component, fp64 accumulation, fixed order
