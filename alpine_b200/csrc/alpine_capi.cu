@@ -321,7 +321,8 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
   }
   // pipeline depths from the shared-memory budget
   const size_t budget = 227 * 1024 - 1024;
-  int sb = 3, sx = 0;
+  int sb = 4, sx = 0;
+  if (const char* e = getenv("ALPINE_B200_SB")) sb = atoi(e) >= 2 && atoi(e) <= kMaxBStages ? atoi(e) : sb;
   for (; sb >= 2; --sb) {
     sx = kMaxXStages;
     while (sx >= 2 && gemm_smem_layout(p.Kp, sx, sb).total > budget) --sx;

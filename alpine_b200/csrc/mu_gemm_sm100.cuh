@@ -38,7 +38,7 @@ constexpr int kUmmaK = 8;        // tf32: 32 bytes per MMA k-step
 constexpr int kTmemCols = 512;
 constexpr int kTmemAOff = 256;   // A staging starts here; accumulators occupy [0, 256)
 constexpr int kMaxXStages = 8;
-constexpr int kMaxBStages = 4;
+constexpr int kMaxBStages = 6;
 constexpr int kMaxAStages = 4;
 constexpr long long kTimeoutCycles = 1ll << 30;  // ~0.5 s: a wait that long is a bug, never a hang
 

@@ -1,0 +1,109 @@
+"""NumPy stand-in for ``alpine_b200._native.Solver`` (TEST INFRASTRUCTURE, CPU only).
+
+It implements the ``ShardSolver`` protocol of ``alpine_b200.engine`` with the same per-shard dataflow as the CUDA
+library (X H^T partials -> packed reduce buffer -> W / B / H updates -> statistics of the new H), so that the
+host-side sharding logic (``MUEngine``: one all-reduce per iteration, loss aggregation) can be exercised with
+``torch.distributed``'s gloo backend and world_size 2 on a machine without a GPU.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+
+class NumpyShardSolver:
+    def __init__(self, X_gc, Ys, W, H, Bs, blocks, hp):
+        """X_gc: genes x local cells; Ys: c_i x local cells; W: G x K (replica); H: K x local cells."""
+        self.X, self.Ys, self.W, self.H, self.Bs = X_gc, Ys, W, H, Bs
+        self.blocks, self.hp = blocks, hp
+        self.K = W.shape[1]
+        self.G = W.shape[0]
+        self.n_cov = len(Ys)
+        self.sl, s = [], 0
+        for k in blocks:
+            self.sl.append(slice(s, s + k))
+            s += k
+        self.q_sizes = [Ys[i].shape[0] * blocks[i] for i in range(self.n_cov)]
+        size = self.K * self.G + self.K * self.K + self.K + sum(self.q_sizes)
+        self._buf = torch.zeros(size, dtype=torch.float32)
+        self.rows = []
+
+    # layout [Pt (K x G) | S (K x K) | hsum (K) | Q_i ...]
+    def _views(self):
+        b = self._buf.numpy()
+        o = 0
+        Pt = b[o:o + self.K * self.G].reshape(self.K, self.G); o += self.K * self.G
+        S = b[o:o + self.K * self.K].reshape(self.K, self.K); o += self.K * self.K
+        hs = b[o:o + self.K]; o += self.K
+        Qs = []
+        for i in range(self.n_cov):
+            Qs.append(b[o:o + self.q_sizes[i]].reshape(self.Ys[i].shape[0], self.blocks[i])); o += self.q_sizes[i]
+        return Pt, S, hs, Qs
+
+    def reduce_buffer(self):
+        return self._buf
+
+    def _stats(self):
+        Pt, S, hs, Qs = self._views()
+        H = self.H
+        S[...] = H @ H.T
+        hs[...] = H.sum(axis=1)
+        eps = np.float32(self.hp.eps)
+        pred = []
+        for i in range(self.n_cov):
+            Hi, B, Y = H[self.sl[i]], self.Bs[i], self.Ys[i]
+            yh = B @ Hi
+            if self.hp.loss_type == "kl-divergence":
+                yc = np.maximum(yh, eps)
+                Qs[i][...] = (Y / yc) @ Hi.T
+                pred.append(float(np.sum(Y * np.log(np.maximum(Y / yc, eps)) - Y + yc, dtype=np.float64)))
+            else:
+                Qs[i][...] = Y @ Hi.T
+                pred.append(float(np.sum((Y - yh).astype(np.float64) ** 2)))
+        return pred
+
+    def fit_begin(self, max_iter):
+        self.xn = float(np.sum(self.X.astype(np.float64) ** 2))
+        self.rows = []
+        self._stats()
+
+    def mu_partials(self):
+        Pt, _, _, _ = self._views()
+        Pt[...] = self.H @ self.X.T
+
+    def mu_apply(self, it):
+        hp = self.hp
+        Pt, S, hs, Qs = self._views()
+        eps = np.float32(hp.eps)
+        W = self.W
+        c1, c2 = np.float32((1 - hp.l1_ratio_W) * hp.alpha_W), np.float32(hp.l1_ratio_W * hp.alpha_W)
+        den = 2 * (W @ S) + c1 * W + np.float32(hp.orth_W) * (W.sum(axis=1, keepdims=True) - W) + c2
+        W *= (2 * Pt.T) / np.maximum(den, eps)
+        for i in range(self.n_cov):
+            B, lam = self.Bs[i], np.float32(hp.lam[i])
+            if hp.loss_type == "kl-divergence":
+                B *= (lam * Qs[i]) / np.maximum(lam * hs[self.sl[i]][None, :], eps)
+            else:
+                B *= (2 * Qs[i]) / np.maximum((2 * B) @ S[self.sl[i], self.sl[i]], eps)
+        T = W.T @ W
+        A = W.T @ self.X
+        H = self.H
+        num = 2 * A
+        den = 2 * (T @ H)
+        for i in range(self.n_cov):
+            B, lam, Hi, Y = self.Bs[i], np.float32(hp.lam[i]), H[self.sl[i]], self.Ys[i]
+            if hp.loss_type == "kl-divergence":
+                num[self.sl[i]] += (lam * B.T) @ (Y / np.maximum(B @ Hi, eps))
+                den[self.sl[i]] += ((lam * B.T) @ np.ones_like(Y))
+            else:
+                num[self.sl[i]] += (2 * lam * B.T) @ Y
+                den[self.sl[i]] += (2 * lam * B.T) @ (B @ Hi)
+        H *= num / np.maximum(den, eps)
+        t1 = float(np.sum(A.astype(np.float64) * H.astype(np.float64)))
+        pred = self._stats()
+        _, S2, _, _ = self._views()
+        t2 = float(np.sum(T.astype(np.float64) * S2.astype(np.float64)))
+        self.rows.append([t1, t2] + pred)
+
+    def losses(self, n_iter):
+        return self.xn, np.asarray(self.rows[:n_iter], dtype=np.float64).reshape(n_iter, 2 + self.n_cov)

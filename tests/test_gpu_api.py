@@ -1,0 +1,130 @@
+"""GPU tests of the drop-in Python API (ALPINE.fit / transform / scores) against the oracle."""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from alpine_b200 import ALPINE
+from alpine_b200.utils.anndata_compat import AnnData
+from alpine_b200.utils.synth import make_counts, make_labels
+from oracle import alpine_oracle as orc
+from tests.helpers import rel_fro
+
+pytestmark = pytest.mark.gpu
+
+
+def _adata(n=600, G=400, cats=(3, 4), seed=1, nan_fraction=0.05):
+    X = make_counts(n, G, seed=seed, rank=6)
+    labels = make_labels(n, list(cats), seed=seed, nan_fraction=nan_fraction)
+    obs = pd.DataFrame({f"cov{i}": pd.Series(l, dtype=object) for i, l in enumerate(labels)})
+    obs.index = [f"cell{i}" for i in range(n)]
+    var = pd.DataFrame(index=[f"gene{i}" for i in range(G)])
+    return AnnData(X, obs=obs, var=var)
+
+
+KW = dict(n_components=8, n_covariate_components=[3, 4], lam=[1e3, 5e2], orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5)
+
+
+@pytest.mark.parametrize("loss_type", ["kl-divergence", "frobenius"])
+def test_fit_matches_oracle_from_same_initialisation(loss_type):
+    ad = _adata()
+    keys = ["cov0", "cov1"]
+    n_iter = 10
+    model = ALPINE(device="cuda:0", loss_type=loss_type, **KW)
+    # replicate fit()'s preparation, snapshot the initial factors, then run the hot loop
+    model.covariate_keys, model.sampling_method, model.verbose = keys, "random", False
+    from alpine_b200.utils.encoder import FeatureEncoders
+
+    model.fe = FeatureEncoders(keys)
+    Y = model.fe.fit_transform(ad.obs)
+    X = np.ascontiguousarray(ad.X, dtype=np.float32).T
+    model.batch_size, model.max_iter = X.shape[1], n_iter
+    m = model._initialize_matrices(X, Y)
+    st = orc.State(m.W.cpu().numpy().copy(), m.H.cpu().numpy().copy(), [b.cpu().numpy().copy() for b in m.Bs],
+                   list(model.n_all_components))
+    hp = orc.HyperParams(loss_type=loss_type, **KW)
+    Ys = [np.ascontiguousarray(y.T) for y in Y]
+    model._fit(m)
+    hist_ref, _ = orc.fit_loop(X, Ys, st, hp, n_iter)
+    assert rel_fro(m.W.cpu().numpy(), st.W) < 2e-5
+    assert rel_fro(m.H.cpu().numpy(), st.H) < 2e-5
+    for b, bo in zip(m.Bs, st.Bs):
+        assert rel_fro(b.cpu().numpy(), bo) < 2e-5
+    lh = model.loss_history
+    assert list(lh.columns) == ["total loss", "reconstruction loss", "prediction loss(cov0)", "prediction loss(cov1)"]
+    assert len(lh) == n_iter
+    ref64 = orc.compute_loss(X, Ys, st, hp, dtype=np.float64)
+    assert abs(lh["reconstruction loss"].iloc[-1] - ref64[1]) / ref64[1] < 1e-4
+    np.testing.assert_allclose(lh.iloc[-1, 2:].to_numpy(dtype=float), ref64[2:], rtol=1e-3, atol=1e-6 * X.shape[1])
+    np.testing.assert_allclose(lh["total loss"].iloc[-1], ref64[0], rtol=1e-4)
+    # _compute_loss evaluates the same quantities from the factors as they are
+    now = model._compute_loss(m)
+    np.testing.assert_allclose(now[1], ref64[1], rtol=1e-4)
+    np.testing.assert_allclose(now[2:], ref64[2:], rtol=1e-3, atol=1e-6 * X.shape[1])
+    # scaling (main.py:772-781)
+    model._scale_matrices(m)
+    orc.scale_matrices(st, hp)
+    assert rel_fro(m.W.cpu().numpy(), st.W) < 2e-5
+    assert rel_fro(m.H.cpu().numpy(), st.H) < 2e-5
+
+
+def test_public_fit_transform_scores_roundtrip():
+    ad = _adata()
+    keys = ["cov0", "cov1"]
+    model = ALPINE(device="cuda", **KW)
+    out = model.fit(ad, keys, max_iter=15)
+    assert out is model
+    K = model.total_components
+    mats = model.get_decomposed_matrices()
+    assert set(mats) == {"X", "Ys", "Ws", "Hs", "Bs"}
+    assert [w.shape for w in mats["Ws"]] == [(400, 3), (400, 4), (400, 8)]
+    assert [h.shape for h in mats["Hs"]] == [(3, 600), (4, 600), (8, 600)]
+    assert mats["X"].shape == (400, 600)
+    for w in mats["Ws"]:  # scale_needed: every column sums to one
+        np.testing.assert_allclose(w.sum(axis=0), 1.0, rtol=1e-5)
+    assert ad.obsm["ALPINE_embedding"].shape == (600, 8) and ad.varm["ALPINE_weights"].shape == (400, 8)
+    assert ad.obsm["cov0"].shape == (600, 3) and ad.obsm["cov0_dummy_matrix"].shape[0] == 600
+    # the objective decreased
+    lh = model.loss_history["total loss"].to_numpy()
+    assert lh[-1] < lh[0]
+    # gene scores (main.py:246-273) vs the oracle arithmetic on the same matrices
+    scores = model.get_covariate_gene_scores()
+    ref = orc.covariate_gene_scores(mats["Ws"][:2], mats["Hs"][:2], mats["Ys"])
+    for key, r in zip(keys, ref):
+        assert list(scores[key].index) == model.feature_names
+        np.testing.assert_allclose(scores[key].to_numpy(), r, rtol=1e-5)
+    assert model.get_covariate_gene_scores(ad) is None and "cov0_gene_scores" in ad.varm
+    # transform on held-out cells: same H as the oracle loop from the same H0
+    val = _adata(n=200, seed=9)
+    torch.manual_seed(7)
+    torch.cuda.manual_seed(7)
+    state = torch.cuda.get_rng_state(0)
+    model.transform(val, n_iter=6)
+    torch.cuda.set_rng_state(state, 0)
+    H0 = torch.rand((K, 200), dtype=torch.float32, device="cuda:0").cpu().numpy()
+    W = np.concatenate(mats["Ws"], axis=1)
+    Ht = orc.transform_loop(np.ascontiguousarray(val.X).T, W, H0, 6, model.eps)
+    got = np.concatenate([val.obsm["cov0"].T, val.obsm["cov1"].T, val.obsm["ALPINE_embedding"].T], axis=0)
+    assert rel_fro(got, Ht) < 2e-5
+    assert model.transform(val) is None  # n_iter defaults to max_iter
+    total = model.compute_loss(val)
+    assert np.isfinite(total) and total > 0
+    model.get_normalized_expression(val, library_size=1e4)
+    np.testing.assert_allclose(val.layers["normalized_expression"].sum(axis=1), 1e4, rtol=1e-4)
+
+
+def test_fit_with_automatic_max_iter():
+    ad = _adata(n=300, G=200, cats=(3,), nan_fraction=0.0)
+    model = ALPINE(n_components=6, n_covariate_components=[3], lam=[1e2], device="cuda")
+    with pytest.warns(None) if False else __import__("contextlib").nullcontext():
+        model.fit(ad, ["cov0"])  # warm-up of 200 iterations + Kneedle elbow (main.py:116-131)
+    assert 1 <= model.max_iter <= 200
+    assert len(model.loss_history) == model.max_iter
+
+
+def test_unsupported_modes_raise():
+    ad = _adata(n=200, G=100, cats=(3,), nan_fraction=0.0)
+    with pytest.raises(NotImplementedError):
+        ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0], use_als=True).fit(ad, ["cov0"], max_iter=2)
+    with pytest.raises(NotImplementedError):
+        ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0]).fit(ad, ["cov0"], max_iter=2, batch_size=50)
