@@ -85,8 +85,22 @@ int make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, 
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
+// One contraction out[k][m] = sum_r A(m, r) * B[k][r] over a 2-D fp32 array Xmem[rows][cols] (pitch ldX):
+//   ORIENT_XH: m = column of Xmem, r = row of Xmem;   ORIENT_WX: m = row of Xmem, r = column of Xmem.
+// B is read from a pre-split workspace (hi at Bsplit, lo at Bsplit + K * ldS).
+struct GemmOperands {
+  int orient = ORIENT_XH;
+  const float* Xmem = nullptr;
+  long long ldX = 0, rows = 0, cols = 0;
+  const float* Bsplit = nullptr;
+  long long ldS = 0;
+  bool profiled = false;  // counted by alpine_profile (the two contractions over X)
+};
+enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_COUNT = 4 };
+
 struct GemmPlan {
   bool valid = false;
+  GemmOperands op;
   CUtensorMap tmX, tmBhi, tmBlo;
   GemmParams p{};
   ReduceParams r{};
@@ -129,9 +143,6 @@ struct alpine_ctx {
   float* denG = nullptr;
   float* T = nullptr;      // [K][K]     W^T W
   float* colsum = nullptr; // [K]
-  float* gram_partial = nullptr;
-  float* gram_rs_partial = nullptr;
-  int gram_blocks_max = 0;
   float* q_partial = nullptr;
   double* pred_partial = nullptr;
   int stat_blocks = 0;
@@ -147,7 +158,7 @@ struct alpine_ctx {
   float* own_reduce = nullptr;
   float* reduce = nullptr;  // [Pt K*ldG | S K*K | hsum K | Q q_total]
 
-  GemmPlan plan_xh, plan_wx;
+  GemmPlan plans[PLAN_COUNT];
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
   size_t prof_used = 0;
@@ -188,14 +199,6 @@ int dev_alloc(T** p, size_t count) {
   return ALPINE_OK;
 }
 
-int gram_blocks_for(const alpine_ctx* c, long long L, long long* chunk) {
-  const int want = 2 * c->num_sms;
-  long long ch = round_up((L + want - 1) / want, 32);
-  if (ch < 256) ch = 256;
-  *chunk = ch;
-  return ceil_div(L, ch);
-}
-
 int set_kernel_attrs();
 
 int ensure_workspace(alpine_ctx* c) {
@@ -213,12 +216,6 @@ int ensure_workspace(alpine_ctx* c) {
   AL_TRY(dev_alloc(&c->denG, static_cast<size_t>(c->Kg) * c->ldN));
   AL_TRY(dev_alloc(&c->T, K * K));
   AL_TRY(dev_alloc(&c->colsum, K));
-  long long chunk;
-  int gb = gram_blocks_for(c, c->n, &chunk);
-  int gb2 = gram_blocks_for(c, c->G, &chunk);
-  c->gram_blocks_max = gb > gb2 ? gb : gb2;
-  AL_TRY(dev_alloc(&c->gram_partial, static_cast<size_t>(c->gram_blocks_max) * K * K));
-  AL_TRY(dev_alloc(&c->gram_rs_partial, static_cast<size_t>(c->gram_blocks_max) * K));
   c->stat_blocks = ceil_div(c->n, kStatCells);
   AL_TRY(dev_alloc(&c->q_partial, static_cast<size_t>(c->stat_blocks) * (c->q_total > 0 ? c->q_total : 1)));
   AL_TRY(dev_alloc(&c->pred_partial, static_cast<size_t>(c->stat_blocks) * (c->n_cov > 0 ? c->n_cov : 1)));
@@ -285,11 +282,12 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
   return ALPINE_OK;
 }
 
-// Build the plan of one contraction.  M rows of D, reduction R; the B operand is read from the split workspace.
-int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
+// Build the plan of one contraction (see GemmOperands).
+int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   const int rows = kRows;
-  const long long M = (orient == ORIENT_XH) ? c->G : c->n;
-  const long long R = (orient == ORIENT_XH) ? c->n : c->G;
+  const long long M = (op.orient == ORIENT_XH) ? op.cols : op.rows;
+  const long long R = (op.orient == ORIENT_XH) ? op.rows : op.cols;
+  pl->op = op;
   GemmParams& p = pl->p;
   p.M = static_cast<int>(M);
   p.R = static_cast<int>(R);
@@ -304,7 +302,7 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
     long long piece_mb = 8;
     if (const char* e = getenv("ALPINE_B200_PIECE_MB")) piece_mb = atoll(e) > 0 ? atoll(e) : piece_mb;
     int pieces = static_cast<int>(b_bytes / (piece_mb * 1024.0 * 1024.0) + 0.999);
-    if (pieces < 1) pieces = 1;
+    if (pieces < 1 || p.ws.num_tiles == 1) pieces = 1;
     int plen = ceil_div(p.ws.kb_per_tile, pieces);
     plen = static_cast<int>(round_up(plen, 8));
     if (plen > p.ws.kb_per_tile) plen = p.ws.kb_per_tile;
@@ -335,29 +333,27 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
   p.chunk = 8;
   if (const char* e = getenv("ALPINE_B200_CHUNK")) p.chunk = atoi(e) > 0 ? atoi(e) : p.chunk;
   pl->smem = gemm_smem_layout(p.Kp, sx, sb).total + 1024;
-  // partial-sum slots
+  // partial-sum slots (one buffer shared by all plans: contractions run one after the other on the stream)
   const size_t need = static_cast<size_t>(pl->grid) * p.max_segs * p.K * rows;
   if (need > c->partial_floats) {
     if (c->partial) cudaFree(c->partial);
     c->partial = nullptr;
     CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c->partial), need * sizeof(float)));
     c->partial_floats = need;
-    c->plan_xh.valid = false;
-    c->plan_wx.valid = false;
+    for (auto& other : c->plans) {
+      other.p.partial = c->partial;
+      other.r.partial = c->partial;
+    }
   }
   p.partial = c->partial;
   p.err = c->err;
-  // tensor maps: X is [n cells][G genes] (inner = genes)
-  if (orient == ORIENT_XH)
-    AL_TRY(make_map(&pl->tmX, c->X, c->G, c->n, c->ldX, rows, kBK, false));
+  // tensor maps: Xmem is [rows][cols] (inner = cols)
+  if (op.orient == ORIENT_XH)
+    AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, rows, kBK, false));
   else
-    AL_TRY(make_map(&pl->tmX, c->X, c->G, c->n, c->ldX, kBK, rows, true));
-  {
-    float* sp = (orient == ORIENT_XH) ? c->Hsplit : c->Wsplit;
-    const long long ldS = (orient == ORIENT_XH) ? c->ldN : c->ldG;
-    AL_TRY(make_map(&pl->tmBhi, sp, R, c->K, ldS, kBK, p.Kp, true));
-    AL_TRY(make_map(&pl->tmBlo, sp + static_cast<size_t>(c->K) * ldS, R, c->K, ldS, kBK, p.Kp, true));
-  }
+    AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, kBK, rows, true));
+  AL_TRY(make_map(&pl->tmBhi, op.Bsplit, R, c->K, op.ldS, kBK, p.Kp, true));
+  AL_TRY(make_map(&pl->tmBlo, op.Bsplit + static_cast<size_t>(c->K) * op.ldS, R, c->K, op.ldS, kBK, p.Kp, true));
   ReduceParams& r = pl->r;
   r.partial = c->partial;
   r.rows = rows;
@@ -370,66 +366,66 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, int orient) {
   return ALPINE_OK;
 }
 
-// out[k][m] (ld_out) = contraction of the bound X with B operand [K][ldB]
-int run_gemm(alpine_ctx* c, int orient, const float* Bop, long long ldB, float* out, long long ld_out,
-             cudaStream_t st) {
-  const long long M = (orient == ORIENT_XH) ? c->G : c->n;
-  const long long R = (orient == ORIENT_XH) ? c->n : c->G;
-  if (c->simt) {
-    dim3 grid(ceil_div(M, 128), c->K);
-    if (orient == ORIENT_XH)
-      simt_gemm_kernel<ORIENT_XH><<<grid, 128, 0, st>>>(c->X, c->ldX, Bop, ldB, (int)M, (int)R, c->K, out, ld_out);
-    else
-      simt_gemm_kernel<ORIENT_WX><<<grid, 128, 0, st>>>(c->X, c->ldX, Bop, ldB, (int)M, (int)R, c->K, out, ld_out);
-    LAUNCH_CHECK();
-    return ALPINE_OK;
+GemmOperands plan_operands(const alpine_ctx* c, int which) {
+  GemmOperands op;
+  switch (which) {
+    case PLAN_XH:  // P^T[k][g] = sum_j X[j][g] H[k][j]                                   (main.py:596)
+      op.orient = ORIENT_XH, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
+      op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.profiled = true;
+      break;
+    case PLAN_WX:  // A[k][j] = sum_g X[j][g] W^T[k][g]                                   (main.py:653)
+      op.orient = ORIENT_WX, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
+      op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.profiled = true;
+      break;
+    case PLAN_GRAM_H:  // S[b][a] = sum_j H[a][j] H[b][j]            (H H^T of main.py:599 after the reformulation)
+      op.orient = ORIENT_WX, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
+      op.Bsplit = c->Hsplit, op.ldS = c->ldN;
+      break;
+    default:           // T[b][a] = sum_g W^T[a][g] W^T[b][g]        (W^T W of main.py:654 after the reformulation)
+      op.orient = ORIENT_WX, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
+      op.Bsplit = c->Wsplit, op.ldS = c->ldG;
+      break;
   }
-  GemmPlan* pl = (orient == ORIENT_XH) ? &c->plan_xh : &c->plan_wx;
-  {
-    float* sp = (orient == ORIENT_XH) ? c->Hsplit : c->Wsplit;
-    const long long ldS = (orient == ORIENT_XH) ? c->ldN : c->ldG;
-    split_operand_kernel<<<2 * c->num_sms, 256, 0, st>>>(Bop, ldB, c->K, R, sp, sp + static_cast<size_t>(c->K) * ldS, ldS);
-    LAUNCH_CHECK();
-  }
-  if (!pl->valid) {
-    AL_TRY(build_plan(c, pl, orient));
-    // building one plan may have re-allocated the shared partial buffer
-    GemmPlan* other = (orient == ORIENT_XH) ? &c->plan_wx : &c->plan_xh;
-    if (other->valid) {
-      other->p.partial = c->partial;
-      other->r.partial = c->partial;
-    }
-  }
-  AL_TRY(prof_mark(c, st));
-  if (orient == ORIENT_XH)
-    AL_TRY(launch_gemm_t<ORIENT_XH>(*pl, st));
-  else
-    AL_TRY(launch_gemm_t<ORIENT_WX>(*pl, st));
-  AL_TRY(prof_mark(c, st));
-  ReduceParams r = pl->r;
-  r.out = out;
-  r.ld = ld_out;
-  dim3 rgrid(r.ws.num_tiles, c->K < 16 ? c->K : 16);
-  reduce_partials_kernel<<<rgrid, 256, 0, st>>>(r);
+  return op;
+}
+
+// tf32 hi / lo copies of a small operand [K][R]
+int run_split(alpine_ctx* c, const float* src, long long ld_src, long long R, float* dst, long long ldS,
+              cudaStream_t st) {
+  split_operand_kernel<<<2 * c->num_sms, 256, 0, st>>>(src, ld_src, c->K, R, dst, dst + static_cast<size_t>(c->K) * ldS, ldS);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
 
-int run_gram(alpine_ctx* c, const float* A, long long ld, long long L, float* C, int ldC, float* rowsum,
-             cudaStream_t st) {
-  GramParams g;
-  g.A = A;
-  g.ld = ld;
-  g.K = c->K;
-  g.L = L;
-  const int blocks = gram_blocks_for(c, L, &g.chunk);
-  g.partial = c->gram_partial;
-  g.rs_partial = rowsum ? c->gram_rs_partial : nullptr;
-  const int tiles = ceil_div(c->K, 128);
-  gram_partial_kernel<<<dim3(blocks, tiles * tiles), 256, 0, st>>>(g);
-  LAUNCH_CHECK();
-  gram_finish_kernel<<<ceil_div(static_cast<long long>(c->K) * c->K, 256), 256, 0, st>>>(
-      c->gram_partial, c->gram_rs_partial, blocks, c->K, C, ldC, rowsum);
+// out[k][m] (ld_out) = contraction `which`; its B operand must already be in the split workspace
+int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_t st) {
+  GemmPlan* pl = &c->plans[which];
+  if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which)));
+  const GemmOperands& op = pl->op;
+  if (c->simt) {
+    const float* Bsrc = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->H : c->WT;
+    const long long ldB = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->ldH : c->ldG;
+    dim3 grid(ceil_div(pl->p.M, 128), c->K);
+    if (op.orient == ORIENT_XH)
+      simt_gemm_kernel<ORIENT_XH><<<grid, 128, 0, st>>>(op.Xmem, op.ldX, Bsrc, ldB, pl->p.M, pl->p.R, c->K, out, ld_out);
+    else
+      simt_gemm_kernel<ORIENT_WX><<<grid, 128, 0, st>>>(op.Xmem, op.ldX, Bsrc, ldB, pl->p.M, pl->p.R, c->K, out, ld_out);
+    LAUNCH_CHECK();
+    return ALPINE_OK;
+  }
+  if (op.profiled) AL_TRY(prof_mark(c, st));
+  if (op.orient == ORIENT_XH)
+    AL_TRY(launch_gemm_t<ORIENT_XH>(*pl, st));
+  else
+    AL_TRY(launch_gemm_t<ORIENT_WX>(*pl, st));
+  if (op.profiled) AL_TRY(prof_mark(c, st));
+  ReduceParams r = pl->r;
+  r.out = out;
+  r.ld = ld_out;
+  int ky = ceil_div(4 * c->num_sms, r.ws.num_tiles);  // enough blocks to fill the machine
+  if (ky > c->K) ky = c->K;
+  if (ky < 1) ky = 1;
+  reduce_partials_kernel<<<dim3(r.ws.num_tiles, ky), 256, 0, st>>>(r);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
@@ -465,7 +461,11 @@ int run_stats(alpine_ctx* c, double* loss_row, cudaStream_t st) {
         tab, c->loss_type, c->H, c->ldH, (int)c->n, (float)c->eps, c->q_total, c->q_partial, c->pred_partial);
     LAUNCH_CHECK();
   }
-  AL_TRY(run_gram(c, c->H, c->ldH, c->n, c->red_S(), c->K, c->red_hsum(), st));
+  // S = H H^T as a tcgen05 contraction of H with itself; its split copies also feed the next X H^T
+  AL_TRY(run_split(c, c->H, c->ldH, c->n, c->Hsplit, c->ldN, st));
+  AL_TRY(run_gemm(c, PLAN_GRAM_H, c->red_S(), c->K, st));
+  rowsum_kernel<<<c->K, 256, 0, st>>>(c->H, c->ldH, c->n, c->red_hsum());
+  LAUNCH_CHECK();
   StatsFinishParams f;
   f.q_partial = c->q_partial;
   f.q_blocks = c->stat_blocks;
@@ -577,7 +577,7 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
 int alpine_destroy(alpine_ctx* c) {
   if (c == nullptr) return ALPINE_OK;
   cudaSetDevice(c->device);
-  void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->gram_partial, c->gram_rs_partial, c->q_partial,
+  void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
                   c->pred_partial, c->t1_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
                   c->own_reduce};
   for (void* p : ptrs)
@@ -593,7 +593,7 @@ int alpine_bind_dense(alpine_ctx* c, const float* X, int64_t ldX) {
     return fail(ALPINE_ERR_ARG, "X needs ldX >= n_genes, ldX %% 4 == 0 and a 16-byte aligned base");
   c->X = X;
   c->ldX = ldX;
-  c->plan_xh.valid = c->plan_wx.valid = false;
+  for (auto& pl : c->plans) pl.valid = false;
   return ALPINE_OK;
 }
 
@@ -614,7 +614,7 @@ int alpine_bind_factors(alpine_ctx* c, float* W, int64_t ldW, float* H, int64_t 
   c->H = H;
   c->ldH = ldH;
   for (int i = 0; i < c->n_cov; ++i) c->B[i] = Bs[i];
-  c->plan_xh.valid = c->plan_wx.valid = false;
+  for (auto& pl : c->plans) pl.valid = false;
   return ALPINE_OK;
 }
 
@@ -669,7 +669,7 @@ int alpine_mu_partials(alpine_ctx* c, void* stream) {
   AL_TRY(check_bound(c, true));
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   CU_TRY(cudaSetDevice(c->device));
-  return run_gemm(c, ORIENT_XH, c->H, c->ldH, c->red_Pt(), c->ldG, static_cast<cudaStream_t>(stream));
+  return run_gemm(c, PLAN_XH, c->red_Pt(), c->ldG, static_cast<cudaStream_t>(stream));  // Hsplit is current
 }
 
 int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
@@ -706,9 +706,10 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
     LAUNCH_CHECK();
   }
   // ---- T = W^T W of the new W
-  AL_TRY(run_gram(c, c->WT, c->ldG, c->G, c->T, c->K, nullptr, st));
+  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+  AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));
   // ---- A = W^T X (main.py:653)
-  AL_TRY(run_gemm(c, ORIENT_WX, c->WT, c->ldG, c->A, c->ldN, st));
+  AL_TRY(run_gemm(c, PLAN_WX, c->A, c->ldN, st));
   // ---- guided terms (main.py:637-650) with the old H and the new B
   if (c->n_cov > 0) {
     int kmax = 0, ckmax = 0;
@@ -790,8 +791,9 @@ int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
-  AL_TRY(run_gram(c, c->WT, c->ldG, c->G, c->T, c->K, nullptr, st));       // T = W^T W, loop-invariant
-  AL_TRY(run_gemm(c, ORIENT_WX, c->WT, c->ldG, c->A, c->ldN, st));           // A = W^T X, loop-invariant (main.py:706)
+  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+  AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));  // T = W^T W, loop-invariant
+  AL_TRY(run_gemm(c, PLAN_WX, c->A, c->ldN, st));    // A = W^T X, loop-invariant (main.py:706)
   SymLongParams h{};
   h.Sym = c->T;
   h.ldS = c->K;
@@ -813,7 +815,8 @@ int alpine_xh_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
   CU_TRY(cudaSetDevice(c->device));
   AL_TRY(ensure_workspace(c));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  AL_TRY(run_gemm(c, ORIENT_XH, c->H, c->ldH, out, ld_out, st));
+  AL_TRY(run_split(c, c->H, c->ldH, c->n, c->Hsplit, c->ldN, st));
+  AL_TRY(run_gemm(c, PLAN_XH, out, ld_out, st));
   CU_TRY(cudaStreamSynchronize(st));
   return check_kernel_error(c);
 }
@@ -827,7 +830,8 @@ int alpine_wx_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
-  AL_TRY(run_gemm(c, ORIENT_WX, c->WT, c->ldG, out, ld_out, st));
+  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+  AL_TRY(run_gemm(c, PLAN_WX, out, ld_out, st));
   CU_TRY(cudaStreamSynchronize(st));
   return check_kernel_error(c);
 }
@@ -858,8 +862,8 @@ int alpine_profile_read(alpine_ctx* c, double* gemm_ms_total, long long* gemm_la
 int alpine_query(const alpine_ctx* c, int* num_sms, int* gemm_grid, int* smem_stages, int* k_padded) {
   if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
   if (num_sms) *num_sms = c->num_sms;
-  if (gemm_grid) *gemm_grid = c->plan_xh.valid ? c->plan_xh.grid : 0;
-  if (smem_stages) *smem_stages = c->plan_xh.valid ? c->plan_xh.p.sx : 0;
+  if (gemm_grid) *gemm_grid = c->plans[PLAN_XH].valid ? c->plans[PLAN_XH].grid : 0;
+  if (smem_stages) *smem_stages = c->plans[PLAN_XH].valid ? c->plans[PLAN_XH].p.sx : 0;
   if (k_padded) *k_padded = c->Kp;
   return ALPINE_OK;
 }

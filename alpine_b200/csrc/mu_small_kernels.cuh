@@ -194,14 +194,6 @@ __global__ void __launch_bounds__(kStatCells) cov_stats_kernel(const CovTable ta
 
 // ---------------------------------------------------------------------------------------------------------
 // Post-fit scaling (reference main.py:772-781): column sums of W, then W /= s, H *= s, B /= s.
-__global__ void colsum_finish_kernel(const float* __restrict__ partial, int chunks, int ldP, int K,
-                                     float* __restrict__ s) {
-  for (int k = threadIdx.x + blockIdx.x * blockDim.x; k < K; k += blockDim.x * gridDim.x) {
-    float acc = 0.f;
-    for (int c = 0; c < chunks; ++c) acc += partial[c * ldP + k];
-    s[k] = acc;
-  }
-}
 __global__ void scale_w_kernel(float* __restrict__ W, long long ldW, int G, int K, const float* __restrict__ s) {
   const long long total = static_cast<long long>(G) * K;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -424,89 +416,6 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
       for (int w = 0; w < 8; ++w) s += red[w];
       p.t1_partial[blockIdx.x] = s;
     }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Gram matrix of a K x L matrix with a long L:  C = A A^T  (H H^T, main.py:599 / W^T W, main.py:654 after the
-// reformulation), plus row sums of A.  Block (x = column chunk, y = 128x128 output tile); partials are summed
-// in a fixed order by gram_finish_kernel.
-struct GramParams {
-  const float* A;
-  long long ld;
-  int K;
-  long long L;
-  long long chunk;     // columns per block (multiple of 32)
-  float* partial;      // [gridDim.x][K*K]
-  float* rs_partial;   // [gridDim.x][K] or nullptr
-};
-__global__ void __launch_bounds__(256) gram_partial_kernel(const GramParams p) {
-  constexpr int KW = 128, KI = 8;
-  __shared__ float Aa[32][KW + 1];
-  __shared__ float Ab[32][KW + 1];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int tiles = (p.K + KW - 1) / KW;
-  const int ra = (blockIdx.y / tiles) * KW, cb = (blockIdx.y % tiles) * KW;
-  const long long j_begin = blockIdx.x * p.chunk;
-  const long long j_end = min(p.L, j_begin + p.chunk);
-  float acc[KI][KI];
-  float rs[KI];
-#pragma unroll
-  for (int i = 0; i < KI; ++i) {
-    rs[i] = 0.f;
-#pragma unroll
-    for (int j = 0; j < KI; ++j) acc[i][j] = 0.f;
-  }
-  for (long long j0 = j_begin; j0 < j_end; j0 += 32) {
-    __syncthreads();
-    for (int e = tid; e < KW * 32; e += 256) {
-      const int k = e >> 5, jj = e & 31;
-      const bool jin = j0 + jj < j_end;
-      Aa[jj][k] = (jin && ra + k < p.K) ? p.A[static_cast<long long>(ra + k) * p.ld + j0 + jj] : 0.f;
-      Ab[jj][k] = (jin && cb + k < p.K) ? p.A[static_cast<long long>(cb + k) * p.ld + j0 + jj] : 0.f;
-    }
-    __syncthreads();
-#pragma unroll 4
-    for (int jj = 0; jj < 32; ++jj) {
-      float a[KI], b[KI];
-#pragma unroll
-      for (int i = 0; i < KI; ++i) {
-        a[i] = Aa[jj][ty + 16 * i];
-        b[i] = Ab[jj][tx + 16 * i];
-      }
-#pragma unroll
-      for (int i = 0; i < KI; ++i) {
-        rs[i] += a[i];
-#pragma unroll
-        for (int j = 0; j < KI; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
-    }
-  }
-  float* dst = p.partial + static_cast<size_t>(blockIdx.x) * p.K * p.K;
-#pragma unroll
-  for (int i = 0; i < KI; ++i) {
-    const int r = ra + ty + 16 * i;
-    if (r >= p.K) continue;
-#pragma unroll
-    for (int j = 0; j < KI; ++j) {
-      const int c = cb + tx + 16 * j;
-      if (c < p.K) dst[r * p.K + c] = acc[i][j];
-    }
-    if (p.rs_partial != nullptr && cb == 0 && tx == 0) p.rs_partial[static_cast<size_t>(blockIdx.x) * p.K + r] = rs[i];
-  }
-}
-__global__ void gram_finish_kernel(const float* __restrict__ partial, const float* __restrict__ rs_partial,
-                                   int blocks, int K, float* __restrict__ C, int ldC, float* __restrict__ rowsum) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < K * K) {
-    float acc = 0.f;
-    for (int b = 0; b < blocks; ++b) acc += partial[static_cast<size_t>(b) * K * K + e];
-    C[(e / K) * ldC + (e % K)] = acc;
-  }
-  if (rowsum != nullptr && e < K) {
-    float acc = 0.f;
-    for (int b = 0; b < blocks; ++b) acc += rs_partial[static_cast<size_t>(b) * K + e];
-    rowsum[e] = acc;
   }
 }
 
