@@ -101,6 +101,8 @@ enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_COUNT = 
 struct GemmPlan {
   bool valid = false;
   GemmOperands op;
+  int* d_slot_ofs = nullptr;  // device copies of the reduce kernel's slot lists
+  int* d_slots = nullptr;
   CUtensorMap tmX, tmBhi, tmBlo;
   GemmParams p{};
   ReduceParams r{};
@@ -147,6 +149,7 @@ struct alpine_ctx {
   double* pred_partial = nullptr;
   int stat_blocks = 0;
   double* t1_partial = nullptr;
+  float* hsum_partial = nullptr;  // [sl_blocks_n][K]
   int sl_blocks_n = 0;
   double* sumsq_partial = nullptr;
   double* xnorm2 = nullptr;
@@ -221,6 +224,7 @@ int ensure_workspace(alpine_ctx* c) {
   AL_TRY(dev_alloc(&c->pred_partial, static_cast<size_t>(c->stat_blocks) * (c->n_cov > 0 ? c->n_cov : 1)));
   c->sl_blocks_n = ceil_div(c->n, kSLCols);
   AL_TRY(dev_alloc(&c->t1_partial, static_cast<size_t>(c->sl_blocks_n)));
+  AL_TRY(dev_alloc(&c->hsum_partial, static_cast<size_t>(c->sl_blocks_n) * K));
   AL_TRY(dev_alloc(&c->sumsq_partial, 1024));
   AL_TRY(dev_alloc(&c->xnorm2, 1));
   AL_TRY(dev_alloc(&c->err, 8));
@@ -359,9 +363,22 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   r.rows = rows;
   r.M = p.M;
   r.K = p.K;
-  r.ws = p.ws;
-  r.grid = pl->grid;
-  r.max_segs = p.max_segs;
+  {
+    std::vector<int> ofs(p.ws.num_tiles + 1, 0), slots;
+    for (int t = 0; t < p.ws.num_tiles; ++t) {
+      reduce_slots_of_tile(p.ws, pl->grid, p.max_segs, t, &slots);
+      ofs[t + 1] = static_cast<int>(slots.size());
+    }
+    if (pl->d_slot_ofs) cudaFree(pl->d_slot_ofs);
+    if (pl->d_slots) cudaFree(pl->d_slots);
+    pl->d_slot_ofs = pl->d_slots = nullptr;
+    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&pl->d_slot_ofs), ofs.size() * sizeof(int)));
+    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&pl->d_slots), (slots.size() + 1) * sizeof(int)));
+    CU_TRY(cudaMemcpy(pl->d_slot_ofs, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(pl->d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice));
+    r.slot_ofs = pl->d_slot_ofs;
+    r.slots = pl->d_slots;
+  }
   pl->valid = true;
   return ALPINE_OK;
 }
@@ -422,10 +439,7 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
   ReduceParams r = pl->r;
   r.out = out;
   r.ld = ld_out;
-  int ky = ceil_div(4 * c->num_sms, r.ws.num_tiles);  // enough blocks to fill the machine
-  if (ky > c->K) ky = c->K;
-  if (ky < 1) ky = 1;
-  reduce_partials_kernel<<<dim3(r.ws.num_tiles, ky), 256, 0, st>>>(r);
+  reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, c->K), 256, 0, st>>>(r);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
@@ -447,7 +461,8 @@ int run_sym_long(alpine_ctx* c, const SymLongParams& p, cudaStream_t st) {
 }
 
 // statistics of the current (H, B): S = H H^T, hsum, Q_i (and the prediction-loss partials)
-int run_stats(alpine_ctx* c, double* loss_row, cudaStream_t st) {
+// `fresh_h_update`: the H update kernel just wrote the split copies of H and its per-block row sums
+int run_stats(alpine_ctx* c, double* loss_row, bool fresh_h_update, cudaStream_t st) {
   const CovTable tab = make_cov_table(c);
   if (c->n_cov > 0) {
     int kmax = 0, cmax = 0;
@@ -462,10 +477,12 @@ int run_stats(alpine_ctx* c, double* loss_row, cudaStream_t st) {
     LAUNCH_CHECK();
   }
   // S = H H^T as a tcgen05 contraction of H with itself; its split copies also feed the next X H^T
-  AL_TRY(run_split(c, c->H, c->ldH, c->n, c->Hsplit, c->ldN, st));
+  if (!fresh_h_update) {
+    AL_TRY(run_split(c, c->H, c->ldH, c->n, c->Hsplit, c->ldN, st));
+    rowsum_kernel<<<c->K, 256, 0, st>>>(c->H, c->ldH, c->n, c->red_hsum());
+    LAUNCH_CHECK();
+  }
   AL_TRY(run_gemm(c, PLAN_GRAM_H, c->red_S(), c->K, st));
-  rowsum_kernel<<<c->K, 256, 0, st>>>(c->H, c->ldH, c->n, c->red_hsum());
-  LAUNCH_CHECK();
   StatsFinishParams f;
   f.q_partial = c->q_partial;
   f.q_blocks = c->stat_blocks;
@@ -480,8 +497,11 @@ int run_stats(alpine_ctx* c, double* loss_row, cudaStream_t st) {
   f.S = c->red_S();
   f.ldS = c->K;
   f.K = c->K;
+  f.rowsum_partial = fresh_h_update ? c->hsum_partial : nullptr;
+  f.rs_blocks = c->sl_blocks_n;
+  f.hsum = c->red_hsum();
   f.loss_row = loss_row;
-  stats_finish_kernel<<<c->q_total + 2 + c->n_cov, 256, 0, st>>>(f);
+  stats_finish_kernel<<<c->K + c->q_total + 2 + c->n_cov, 256, 0, st>>>(f);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
@@ -578,10 +598,14 @@ int alpine_destroy(alpine_ctx* c) {
   if (c == nullptr) return ALPINE_OK;
   cudaSetDevice(c->device);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
-                  c->pred_partial, c->t1_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
+                  c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
                   c->own_reduce};
   for (void* p : ptrs)
     if (p) cudaFree(p);
+  for (auto& pl : c->plans) {
+    if (pl.d_slot_ofs) cudaFree(pl.d_slot_ofs);
+    if (pl.d_slots) cudaFree(pl.d_slots);
+  }
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return ALPINE_OK;
@@ -660,7 +684,7 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
-  AL_TRY(run_stats(c, nullptr, st));
+  AL_TRY(run_stats(c, nullptr, false, st));
   c->fit_active = true;
   return ALPINE_OK;
 }
@@ -692,6 +716,9 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   w.c2 = static_cast<float>(c->l1 * c->alpha);
   w.orth = static_cast<float>(c->orth);
   w.eps = static_cast<float>(c->eps);
+  w.split_hi = c->Wsplit;  // B operand of W^T W and W^T X below
+  w.split_lo = c->Wsplit + static_cast<size_t>(c->K) * c->ldG;
+  w.ld_split = c->ldG;
   AL_TRY(run_sym_long<EPI_W>(c, w, st));
   transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
                                                                                        c->W, c->ldW);
@@ -706,7 +733,6 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
     LAUNCH_CHECK();
   }
   // ---- T = W^T W of the new W
-  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));
   // ---- A = W^T X (main.py:653)
   AL_TRY(run_gemm(c, PLAN_WX, c->A, c->ldN, st));
@@ -739,9 +765,13 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   h.Kg = c->Kg;
   h.eps = static_cast<float>(c->eps);
   h.t1_partial = c->t1_partial;
+  h.rowsum_partial = c->hsum_partial;
+  h.split_hi = c->Hsplit;  // B operand of H H^T below and of the next iteration's X H^T
+  h.split_lo = c->Hsplit + static_cast<size_t>(c->K) * c->ldN;
+  h.ld_split = c->ldN;
   AL_TRY(run_sym_long<EPI_H>(c, h, st));
   // ---- statistics of the new H for the next iteration + loss terms of this one (main.py:666, 726-753)
-  AL_TRY(run_stats(c, c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov), st));
+  AL_TRY(run_stats(c, c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov), true, st));
   return ALPINE_OK;
 }
 

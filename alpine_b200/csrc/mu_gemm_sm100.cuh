@@ -28,6 +28,8 @@
 //    thread (and any per-instruction register shuffling) would leave the tensor pipe idle.
 //  * Every mbarrier wait is bounded (clock64): a protocol bug reports an error code instead of hanging the GPU.
 #pragma once
+#include <vector>
+
 #include "ptx_sm100.cuh"
 
 namespace alpine {
@@ -460,46 +462,48 @@ struct ReduceParams {
   const float* partial;
   int rows;  // 256
   int M, K;
-  WorkSpace ws;
-  int grid, max_segs;
+  const int* slot_ofs;  // [num_tiles + 1]  prefix offsets into `slots` (built on the host from the WorkSpace)
+  const int* slots;     // partial-sum slots of every tile, piece by piece in stream-K order
   float* out;
   long long ld;
 };
-__global__ void reduce_partials_kernel(const ReduceParams p) {
-  const int tile = blockIdx.x;
-  const WorkSpace ws = p.ws;
+// Host side: the slots that hold tile `tile` (same enumeration the kernel uses for its segment numbering).
+inline void reduce_slots_of_tile(const WorkSpace& ws, int grid, int max_segs, int tile, std::vector<int>* out) {
   const long long total = ws.total();
-  __shared__ int s_slots[1024];
-  __shared__ int s_n;
-  if (threadIdx.x == 0) {
-    int cnt = 0;
-    for (int pc = 0; pc < ws.pieces; ++pc) {
-      const long long r_begin = ws.run_begin(pc, tile), r_end = r_begin + ws.len_of_piece(pc);
-      // first CTA whose (non-empty) range contains r_begin
-      int c = static_cast<int>(r_begin * p.grid / total);
-      while (c + 1 < p.grid && gemm_range_begin(total, p.grid, c + 1) <= r_begin) ++c;
-      while (c > 0 && gemm_range_begin(total, p.grid, c) > r_begin) --c;
-      for (int q = c; q < p.grid && gemm_range_begin(total, p.grid, q) < r_end; ++q) {
-        const long long b = gemm_range_begin(total, p.grid, q), e = gemm_range_begin(total, p.grid, q + 1);
-        if (e <= b) continue;
-        int run0, t0, k0, l0;
-        ws.decode(b, run0, t0, k0, l0);  // the CTA's first run; its segments are numbered from there
-        if (cnt < 1024) s_slots[cnt++] = q * p.max_segs + (pc * ws.num_tiles + tile - run0);
-      }
+  for (int pc = 0; pc < ws.pieces; ++pc) {
+    const long long r_begin = ws.run_begin(pc, tile), r_end = r_begin + ws.len_of_piece(pc);
+    int c = static_cast<int>(r_begin * grid / total);
+    while (c + 1 < grid && gemm_range_begin(total, grid, c + 1) <= r_begin) ++c;
+    while (c > 0 && gemm_range_begin(total, grid, c) > r_begin) --c;
+    for (int q = c; q < grid && gemm_range_begin(total, grid, q) < r_end; ++q) {
+      const long long b = gemm_range_begin(total, grid, q), e = gemm_range_begin(total, grid, q + 1);
+      if (e <= b) continue;
+      int run0, t0, k0, l0;
+      ws.decode(b, run0, t0, k0, l0);  // the CTA's first run; its segments are numbered from there
+      out->push_back(q * max_segs + (pc * ws.num_tiles + tile - run0));
     }
-    s_n = cnt;
   }
+}
+// grid = (num_tiles * 8, K): one block per (tile, 32-row group, component); lane = row (coalesced 128-byte reads
+// per slot), the 8 warps take the slots round-robin and are combined in a fixed order.
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
+  __shared__ float red[8][32];
+  const int tile = blockIdx.x >> 3, rg = blockIdx.x & 7, k = blockIdx.y;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = rg * 32 + lane;
+  const long long m = static_cast<long long>(tile) * p.rows + r;
+  if (static_cast<long long>(tile) * p.rows + rg * 32 >= p.M) return;  // whole row group out of range
+  const int s0 = p.slot_ofs[tile], s1 = p.slot_ofs[tile + 1];
+  float acc = 0.f;
+  for (int q = s0 + w; q < s1; q += 8)
+    acc += __ldcg(p.partial + (static_cast<size_t>(__ldg(p.slots + q)) * p.K + k) * p.rows + r);
+  red[w][lane] = acc;
   __syncthreads();
-  const int ns = s_n;
-  const int m0 = tile * p.rows;
-  for (int k = blockIdx.y; k < p.K; k += gridDim.y) {
-    for (int r = threadIdx.x; r < p.rows; r += blockDim.x) {
-      if (m0 + r >= p.M) break;
-      float acc = 0.f;
-      for (int q = 0; q < ns; ++q)
-        acc += __ldcg(p.partial + (static_cast<size_t>(s_slots[q]) * p.K + k) * p.rows + r);
-      p.out[static_cast<long long>(k) * p.ld + m0 + r] = acc;
-    }
+  if (w == 0 && m < p.M) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][lane];
+    p.out[static_cast<long long>(k) * p.ld + m] = t;
   }
 }
 

@@ -282,7 +282,11 @@ struct SymLongParams {
   long long ldD;
   int Kg;
   float c1, c2, orth, eps;
-  double* t1_partial;  // EPI_H: [gridDim.x]  sum A .* Hnew
+  double* t1_partial;   // EPI_H: [gridDim.x]  sum A .* Hnew
+  float* rowsum_partial;  // EPI_H: [gridDim.x][K] row sums of the new H over this block's columns, or nullptr
+  float* split_hi;      // EPI_W / EPI_H: tf32 hi / lo copies of the updated matrix (B operand of the next
+  float* split_lo;      //                contraction), pitch ld_split; nullptr to skip
+  long long ld_split;
 };
 template <int KI>
 inline size_t sym_long_smem_bytes(int K) {
@@ -349,6 +353,9 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
     __syncthreads();
   }
   double t1 = 0.0;
+  float rs[KI];
+#pragma unroll
+  for (int i = 0; i < KI; ++i) rs[i] = 0.f;
   const long long col = c0 + 4 * tx;
 #pragma unroll
   for (int i = 0; i < KI; ++i) {
@@ -406,6 +413,37 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
       for (int x = 0; x < 4; ++x)
         if (col + x < p.L) dst[x] = outv[x];
     }
+    if (EPI != EPI_TRANSFORM && p.split_hi != nullptr) {
+      // pitches are multiples of 4 and the pad columns are never read unmasked, so whole float4 groups are written
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) ptx::split_tf32((col + x < p.L) ? outv[x] : 0.f, h[x], l[x]);
+      const long long o = static_cast<long long>(k) * p.ld_split + col;
+      *reinterpret_cast<float4*>(p.split_hi + o) =
+          make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
+      *reinterpret_cast<float4*>(p.split_lo + o) =
+          make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+    }
+    if (EPI == EPI_H && p.rowsum_partial != nullptr) {
+      float v = 0.f;
+#pragma unroll
+      for (int x = 0; x < 4; ++x)
+        if (col + x < p.L) v += outv[x];
+      rs[i] = v;
+    }
+  }
+  if (EPI == EPI_H && p.rowsum_partial != nullptr) {
+    // fixed-order reduction over the 16 threads (tx) that share a row: xor-shuffles inside each half warp
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      float v = rs[i];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      const int k = ty + 16 * i;
+      if (tx == 0 && k < p.K) p.rowsum_partial[static_cast<size_t>(blockIdx.x) * p.K + k] = v;
+    }
   }
   if (EPI == EPI_H) {
     for (int o = 16; o > 0; o >>= 1) t1 += __shfl_down_sync(0xffffffffu, t1, o);
@@ -436,6 +474,9 @@ struct StatsFinishParams {
   const float* S;
   int ldS;
   int K;
+  const float* rowsum_partial;  // [rs_blocks][K] from the H update, or nullptr (row sums computed elsewhere)
+  int rs_blocks;
+  float* hsum;                  // [K]
   double* loss_row;  // [2 + n_cov] or nullptr
 };
 // fixed-order block reduction of a double (256 threads): thread-strided partial sums, then a shared-memory tree
@@ -450,10 +491,19 @@ __device__ __forceinline__ double block_sum_256(double v, double* red) {
   __syncthreads();
   return r;
 }
-// grid = q_total + 2 + n_cov blocks of 256 threads: block b < q_total sums one Q entry, then t1, t2, pred_i
+// grid = K + q_total + 2 + n_cov blocks of 256 threads: K row sums of H, q_total Q entries, then t1, t2, pred_i
 __global__ void __launch_bounds__(256) stats_finish_kernel(const StatsFinishParams p) {
   __shared__ double red[256];
-  const int b = blockIdx.x;
+  int b = blockIdx.x;
+  if (b < p.K) {
+    if (p.rowsum_partial == nullptr) return;
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < p.rs_blocks; i += 256) acc += static_cast<double>(p.rowsum_partial[static_cast<size_t>(i) * p.K + b]);
+    const double r = block_sum_256(acc, red);
+    if (threadIdx.x == 0) p.hsum[b] = static_cast<float>(r);
+    return;
+  }
+  b -= p.K;
   if (b < p.q_total) {
     double acc = 0.0;
     for (int i = threadIdx.x; i < p.q_blocks; i += 256) acc += static_cast<double>(p.q_partial[static_cast<size_t>(i) * p.q_total + b]);
