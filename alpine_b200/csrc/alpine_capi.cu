@@ -246,13 +246,10 @@ int set_kernel_attrs() {
   ALPINE_GEMM_ATTR(1) ALPINE_GEMM_ATTR(2) ALPINE_GEMM_ATTR(3) ALPINE_GEMM_ATTR(4)
   ALPINE_GEMM_ATTR(5) ALPINE_GEMM_ATTR(6) ALPINE_GEMM_ATTR(7) ALPINE_GEMM_ATTR(8)
 #undef ALPINE_GEMM_ATTR
-  const int sl8 = static_cast<int>(sym_long_smem_bytes<8>(128)), sl16 = static_cast<int>(sym_long_smem_bytes<16>(256));
-  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
-  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
-  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<8, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl8));
-  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<16, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl16));
-  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<16, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl16));
-  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<16, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl16));
+  const int sl = static_cast<int>(sym_long_smem_bytes(128));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
+  CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(cov_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU_TRY(cudaFuncSetAttribute(guided_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return ALPINE_OK;
@@ -439,7 +436,14 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
   ReduceParams r = pl->r;
   r.out = out;
   r.ld = ld_out;
-  reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, c->K), 256, 0, st>>>(r);
+  if (pl->p.ws.num_tiles * 8 >= 2 * c->num_sms) {
+    int gy = ceil_div(32 * c->num_sms, pl->p.ws.num_tiles * 8);
+    const int gy_max = ceil_div(c->K, 8);
+    if (gy > gy_max) gy = gy_max;
+    reduce_partials_by_k_kernel<<<dim3(pl->p.ws.num_tiles * 8, gy), 256, 0, st>>>(r);
+  } else {
+    reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, c->K), 256, 0, st>>>(r);
+  }
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
@@ -447,15 +451,7 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
 template <int EPI>
 int run_sym_long(alpine_ctx* c, const SymLongParams& p, cudaStream_t st) {
   const int blocks = ceil_div(p.L, kSLCols);
-  if (c->K <= 128) {
-    auto kern = sym_long_kernel<8, EPI>;
-    const size_t smem = sym_long_smem_bytes<8>(c->K);
-    kern<<<blocks, 256, smem, st>>>(p);
-  } else {
-    auto kern = sym_long_kernel<16, EPI>;
-    const size_t smem = sym_long_smem_bytes<16>(c->K);
-    kern<<<blocks, 256, smem, st>>>(p);
-  }
+  sym_long_kernel<kSLKI, EPI><<<blocks, 256, sym_long_smem_bytes(c->K), st>>>(p);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }

@@ -484,8 +484,24 @@ inline void reduce_slots_of_tile(const WorkSpace& ws, int grid, int max_segs, in
     }
   }
 }
-// grid = (num_tiles * 8, K): one block per (tile, 32-row group, component); lane = row (coalesced 128-byte reads
-// per slot), the 8 warps take the slots round-robin and are combined in a fixed order.
+// Few slots per tile (the X contractions): grid = (num_tiles * 8, gy); block = (tile, 32-row group); lane = row
+// (coalesced 128-byte reads), each warp owns a strided set of components and adds the tile's slots in order.
+__global__ void __launch_bounds__(256) reduce_partials_by_k_kernel(const ReduceParams p) {
+  const int tile = blockIdx.x >> 3, rg = blockIdx.x & 7;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = rg * 32 + lane;
+  const long long m = static_cast<long long>(tile) * p.rows + r;
+  if (m >= p.M) return;
+  const int s0 = p.slot_ofs[tile], s1 = p.slot_ofs[tile + 1];
+  for (int k = blockIdx.y * 8 + w; k < p.K; k += gridDim.y * 8) {
+    float acc = 0.f;
+    for (int q = s0; q < s1; ++q)
+      acc += __ldcg(p.partial + (static_cast<size_t>(__ldg(p.slots + q)) * p.K + k) * p.rows + r);
+    p.out[static_cast<long long>(k) * p.ld + m] = acc;
+  }
+}
+// Many slots per tile (the Gram contractions: one tile, one slot per CTA): grid = (num_tiles * 8, K); one block
+// per (tile, 32-row group, component); the 8 warps take the slots round-robin and are combined in a fixed order.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
   __shared__ float red[8][32];
   const int tile = blockIdx.x >> 3, rg = blockIdx.x & 7, k = blockIdx.y;

@@ -288,22 +288,29 @@ struct SymLongParams {
   float* split_lo;      //                contraction), pitch ld_split; nullptr to skip
   long long ld_split;
 };
-template <int KI>
+constexpr int kSLKI = 8;  // rows per thread: K <= 128 (the contraction kernel's limit as well)
+inline int sym_long_pitch(int K) { return (K + 3) / 4 * 4 + 4; }  // Ss row pitch (floats)
 inline size_t sym_long_smem_bytes(int K) {
-  return (static_cast<size_t>(K) * kSLCols + 32 * KI * 16) * sizeof(float) + kSLCols * sizeof(double);
+  return (static_cast<size_t>(K) * kSLCols + static_cast<size_t>(K) * sym_long_pitch(K)) * sizeof(float) +
+         kSLCols * sizeof(double);
 }
 template <int KI, int EPI>
 __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
-  constexpr int KW = KI * 16;
   extern __shared__ __align__(16) uint8_t sl_smem[];
   double* cs = reinterpret_cast<double*>(sl_smem);                // [64] column sums (EPI_W)
-  float* Ms = reinterpret_cast<float*>(sl_smem + kSLCols * 8);    // [K][64]
-  float* Ss = Ms + static_cast<size_t>(p.K) * kSLCols;            // [32][KW]
+  float* Ms = reinterpret_cast<float*>(sl_smem + kSLCols * 8);    // [K][64]   tile of Mat
+  float* Ss = Ms + static_cast<size_t>(p.K) * kSLCols;            // [K][SP]   Ss[k'][k] = Sym[k'][k] (symmetric)
+  const int SP = (p.K + 3) / 4 * 4 + 4;
   __shared__ double red[8];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const long long c0 = static_cast<long long>(blockIdx.x) * kSLCols;
   const bool full = c0 + kSLCols <= p.L;
 
+  // the whole K x K matrix and the K x 64 tile are staged once: one barrier, no per-chunk global latency
+  for (int e = tid; e < p.K * p.K; e += 256) {
+    const int kk = e / p.K, r = e - kk * p.K;
+    Ss[kk * SP + r] = __ldg(p.Sym + static_cast<long long>(kk) * p.ldS + r);
+  }
   for (int e = tid; e < p.K * 16; e += 256) {
     const int k = e >> 4, c4 = e & 15;
     const long long col = c0 + 4 * c4;
@@ -322,25 +329,22 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
   float4 acc[KI];
 #pragma unroll
   for (int i = 0; i < KI; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-
-  for (int k0 = 0; k0 < p.K; k0 += 32) {
-    __syncthreads();
-    for (int e = tid; e < 32 * KW; e += 256) {
-      const int kk = e / KW, r = e - kk * KW;
-      Ss[e] = (k0 + kk < p.K && r < p.K) ? __ldg(p.Sym + static_cast<long long>(k0 + kk) * p.ldS + r) : 0.f;
-    }
-    __syncthreads();
-    const int kmax = min(32, p.K - k0);
-    for (int kk = 0; kk < kmax; ++kk) {
-      const float4 m = reinterpret_cast<const float4*>(Ms)[(k0 + kk) * 16 + tx];
+  __syncthreads();
+  // rows this thread owns; rows >= K are clamped to a valid address and their results are never used
+  int rsel[KI];
 #pragma unroll
-      for (int i = 0; i < KI; ++i) {
-        const float sv = Ss[kk * KW + ty + 16 * i];
-        acc[i].x = fmaf(sv, m.x, acc[i].x);
-        acc[i].y = fmaf(sv, m.y, acc[i].y);
-        acc[i].z = fmaf(sv, m.z, acc[i].z);
-        acc[i].w = fmaf(sv, m.w, acc[i].w);
-      }
+  for (int i = 0; i < KI; ++i) rsel[i] = min(ty + 16 * i, p.K - 1);
+#pragma unroll 2
+  for (int kk = 0; kk < p.K; ++kk) {
+    const float4 m = reinterpret_cast<const float4*>(Ms)[kk * 16 + tx];
+    const float* srow = Ss + kk * SP;
+#pragma unroll
+    for (int i = 0; i < KI; ++i) {
+      const float sv = srow[rsel[i]];
+      acc[i].x = fmaf(sv, m.x, acc[i].x);
+      acc[i].y = fmaf(sv, m.y, acc[i].y);
+      acc[i].z = fmaf(sv, m.z, acc[i].z);
+      acc[i].w = fmaf(sv, m.w, acc[i].w);
     }
   }
   if (EPI == EPI_W) {

@@ -130,7 +130,21 @@ class ALPINE:
         sampling_method: str = "random",
         verbose: bool = False,
     ) -> "ALPINE":
+        import time
+
+        t0 = time.perf_counter()
+        self.timings: Dict[str, float] = {}
+
+        def lap(name: str) -> None:
+            nonlocal t0
+            if self.device.type == "cuda" and torch.cuda.is_available():
+                torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            self.timings[name] = self.timings.get(name, 0.0) + (t1 - t0)
+            t0 = t1
+
         validation.check_fit_args(self, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose)
+        lap("validate")
         self.feature_names = adata.var_names.tolist()
         self.n_features = adata.shape[1]
         self.covariate_keys = covariate_keys
@@ -144,6 +158,7 @@ class ALPINE:
         self.fe = FeatureEncoders(covariate_keys)
         Y = self.fe.fit_transform(adata.obs)
         self.batch_size = batch_size if batch_size is not None else n_sample
+        lap("encode")
 
         if max_iter is None:
             # warm-up run + Kneedle elbow on log10(reconstruction loss) (main.py:116-131, 755-770)
@@ -154,15 +169,20 @@ class ALPINE:
             del m_warmup
             gc.collect()
             torch.cuda.empty_cache()
+            lap("warmup_fit")
         else:
             self.max_iter = max_iter
 
         m = self._initialize_matrices(X, Y)
+        lap("upload_init")
         self._fit(m)
+        lap("loop")
         if self.scale_needed:
             self._scale_matrices(m)
         self.matrices = m.to_numpy()
+        lap("scale_download")
         self.store_embeddings(adata)
+        lap("store_embeddings")
         return self
 
     def fit_transform(

@@ -27,6 +27,21 @@ def _nonneg_float(value: Any, msg: str) -> None:
     _require(isinstance(value, float) and value >= 0, ValueError, msg)
 
 
+def _all_non_negative(X: np.ndarray) -> bool:
+    """``np.all(X >= 0)`` (main.py:399) without the boolean temporary: a multi-threaded min-reduction; NaN fails
+    both forms."""
+    if X.size == 0:
+        return True
+    try:
+        import torch
+
+        if X.dtype in (np.float32, np.float64) and X.flags.c_contiguous:
+            return bool(torch.from_numpy(X).min().item() >= 0)
+    except Exception:
+        pass
+    return bool(np.all(X >= 0))
+
+
 def check_model_args(m) -> None:
     """main.py:322-381, in the reference's order."""
     _require(m.n_components > 0, ValueError, "n_components must be greater than 0.")
@@ -54,7 +69,7 @@ def check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_meth
     _require(isinstance(adata, AnnData), TypeError, "adata must be an AnnData object.")
     _require(isinstance(adata.X, np.ndarray), TypeError, "adata.X must be a numpy array.")
     _require(adata.X.ndim == 2, ValueError, "adata.X must be a 2D numpy array.")
-    _require(bool(np.all(adata.X >= 0)), ValueError, "All elements in adata.X must be non-negative.")
+    _require(_all_non_negative(adata.X), ValueError, "All elements in adata.X must be non-negative.")
     _require(isinstance(covariate_keys, list), TypeError, "covariate_keys must be a list.")
     _require(len(covariate_keys) == len(m.n_covariate_components), ValueError,
              "Length of covariate_keys must match length of n_covariate_components.")

@@ -379,6 +379,7 @@ def run_e2e(args, wl, dev, world, rank):
     d2h = 4.0 * (G * K + K * n + sum(c * k for c, k in zip(wl["categories"], wl["n_covariate_components"]))) + 8.0 * steps * 4
     return {"value": steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
             "seconds_per_fit": dt, "iterations_per_fit": steps,
+            "phases_s": {k: round(v, 4) for k, v in getattr(model, "timings", {}).items()},
             "what": "ALPINE(...).fit(adata, keys, max_iter=steps) on host numpy data: validation, encoders, H2D of X/Y, "
                     "init, the loop, loss read-back, scaling, D2H of W/H/B, store_embeddings"}
 
