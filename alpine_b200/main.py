@@ -215,7 +215,7 @@ class ALPINE:
         n_sample, G = Xcm.shape
         K = self.total_components
         Xd = _native.padded_rows(n_sample, G, dev)
-        Xd.copy_(torch.from_numpy(Xcm), non_blocking=False)
+        _native.upload_rows(Xd, Xcm)
         # un-reseeded draw from the device generator, as the reference (main.py:687-689)
         H = _native.padded_rows(K, n_sample, dev)
         H.copy_(torch.rand((K, n_sample), dtype=torch.float32, device=dev))
@@ -343,7 +343,7 @@ class ALPINE:
 
         Xcm_host = X_array.T  # cells x genes; C-contiguous when X_array came from fit()
         Xd = _native.padded_rows(n_loc, G, dev)
-        Xd.copy_(torch.from_numpy(np.ascontiguousarray(Xcm_host[lo:hi])))
+        _native.upload_rows(Xd, Xcm_host[lo:hi])
         Ys_host = [np.ascontiguousarray(y.T, dtype=np.float32) for y in Y_list_array]  # c_i x n (main.py:447)
         Ys = [torch.from_numpy(np.ascontiguousarray(y[:, lo:hi])).to(dev) for y in Ys_host]
 
