@@ -319,7 +319,14 @@ def run_gpu_arm(args):
 
     # ---- e2e through the public API with host buffers (N = 1 process; each rank runs the sharded fit under torchrun)
     if not args.no_e2e:
-        e2e = run_e2e(args, wl, dev, world, rank)
+        # every rank holds the full host matrix (the public API takes the same AnnData on every rank)
+        import psutil
+
+        need = 1.6 * world * 4.0 * wl["n_genes"] * wl["n_cells"]
+        if psutil.virtual_memory().available < need:
+            e2e = {"value": None, "unit": UNIT, "skipped": "not enough host memory for %d host copies of X" % world}
+        else:
+            e2e = run_e2e(args, wl, dev, world, rank)
         if rank == 0:
             line["e2e"] = e2e
     if rank == 0 and world == 1 and not args.no_cpu:
