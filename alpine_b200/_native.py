@@ -41,6 +41,7 @@ SIGNATURES = {
     "alpine_reduce_buffer_size": (ctypes.c_int64, [_c_ctx]),
     "alpine_bind_reduce_buffer": (ctypes.c_int, [_c_ctx, _f32p]),
     "alpine_fit_begin": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_batch_begin": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_partials": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_apply": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_fit_losses": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
@@ -234,6 +235,9 @@ class Solver:
     # -- the loop ----------------------------------------------------------------------------------------
     def fit_begin(self, max_iter: int) -> None:
         _check(self.lib, self.lib.alpine_fit_begin(self._ctx, int(max_iter), self._stream()))
+
+    def batch_begin(self) -> None:
+        _check(self.lib, self.lib.alpine_batch_begin(self._ctx, self._stream()))
 
     def mu_partials(self) -> None:
         _check(self.lib, self.lib.alpine_mu_partials(self._ctx, self._stream()))

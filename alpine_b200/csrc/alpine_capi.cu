@@ -685,6 +685,23 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
   return ALPINE_OK;
 }
 
+int alpine_batch_begin(alpine_ctx* c, void* stream) {
+  AL_TRY(check_bound(c, true));
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(ensure_workspace(c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (c->loss_cap < 1) {
+    AL_TRY(dev_alloc(&c->loss_hist, static_cast<size_t>(2 + c->n_cov)));
+    c->loss_cap = 1;
+  }
+  transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
+                                                                                       c->WT, c->ldG);
+  LAUNCH_CHECK();
+  AL_TRY(run_stats(c, nullptr, false, st));
+  c->fit_active = true;
+  return ALPINE_OK;
+}
+
 int alpine_mu_partials(alpine_ctx* c, void* stream) {
   AL_TRY(check_bound(c, true));
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");

@@ -384,11 +384,12 @@ class ALPINE:
         full_batch = self.batch_size >= m.n_total
         if self.sampling_method not in ("random", "weighted"):
             raise ValueError(f"Unknown sampling method: {self.sampling_method}. Only 'weighted', and 'random' are supported.")
-        if self.use_als or not full_batch or self.sampling_method == "weighted":
+        if self.use_als:
             raise NotImplementedError(
-                "alpine_b200 implements the full-batch multiplicative-update path (use_als=False, batch_size=None, "
-                "sampling_method='random'); the ALS and mini-batch variants of the reference (main.py:509-588) are "
-                "listed as next steps in DESIGN.md")
+                "alpine_b200 implements the multiplicative-update path (use_als=False); the block Gauss-Seidel "
+                "variant of the reference (main.py:523-588) is listed as a next step in DESIGN.md")
+        if not full_batch or self.sampling_method == "weighted":
+            return self._fit_minibatch(m)
         solver = self._make_solver(m)
         try:
             engine = MUEngine(solver, self.lam)
@@ -404,20 +405,106 @@ class ALPINE:
         colnames = ["total loss", "reconstruction loss"] + [f"prediction loss({k})" for k in self.covariate_keys]
         self.loss_history = pd.DataFrame(history.tolist(), columns=colnames)
 
-    def _compute_loss(self, m: AlpineMatrices) -> List[float]:
+    def _fit_minibatch(self, m: AlpineMatrices) -> None:
+        """Epochs of mini-batch MU steps (main.py:500-521, 589-663) with the reference's index streams.
+
+        Per batch the cells ``idx`` are gathered into contiguous buffers (rows of the cells-major X, columns of H
+        and Y), one MU step runs on them with the same kernels as the full-batch path, and the H columns are
+        scattered back (``Hs[j][:, idx] = ...``, main.py:662; duplicate indices of the weighted sampler resolve as
+        torch's ``index_put`` does).  The loss of every epoch is evaluated on the full data (main.py:666).
+        """
+        from .utils.sampling import (create_joint_labels_from_dummy_matrices, generate_epoch_indices,
+                                     get_batch_indices, get_num_batches)
+
+        if dist_info()[1] > 1:
+            raise NotImplementedError("mini-batch fitting is single-GPU; cell sharding covers the full-batch path")
+        dev = m.W.device
+        n, G = m.X_cells_major.shape
+        K = self.total_components
+        joint_labels = create_joint_labels_from_dummy_matrices(m.Ys) if m.Ys else [""] * n
+        bs = int(min(self.batch_size, n))
+        solvers: dict = {}
+
+        def batch_solver(size: int):
+            if size not in solvers:
+                Xb = _native.padded_rows(size, G, dev)
+                Hb = _native.padded_rows(K, size, dev)
+                Yb = [torch.empty((y.shape[0], size), dtype=torch.float32, device=dev) for y in m.Ys]
+                s = _native.Solver(dev, G, size, self.n_all_components, [y.shape[0] for y in m.Ys], self.loss_type)
+                s.bind_dense(Xb)
+                s.bind_labels(Yb)
+                s.bind_factors(m.W, Hb, m.Bs)
+                s.set_hparams(self.lam, self.alpha_W, self.l1_ratio_W, self.orth_W, self.eps)
+                solvers[size] = (s, Xb, Hb, Yb)
+            return solvers[size]
+
+        history = []
+        pbar = None
+        if self.verbose:
+            from tqdm import tqdm
+
+            pbar = tqdm(total=self.max_iter, desc="Iteration", ncols=100)
+        # tests replay the reference's recorded sampler output through this hook (one index vector per epoch)
+        stream = getattr(self, "_epoch_index_stream", None)
+        full = self._make_solver(m)  # full-data context for the per-epoch loss (main.py:666)
+        try:
+            full.fit_begin(1)
+            xnorm2 = full.losses(0)[0]
+            for _ in range(self.max_iter):
+                if stream is not None:
+                    epoch_indices = torch.as_tensor(next(stream), dtype=torch.long, device=dev)
+                else:
+                    epoch_indices = generate_epoch_indices(joint_labels=joint_labels,
+                                                           sampling_method=self.sampling_method, device=dev)
+                for b in range(get_num_batches(len(epoch_indices), bs)):
+                    idx = get_batch_indices(epoch_indices, b, bs)
+                    if len(idx) == 0:
+                        break
+                    s, Xb, Hb, Yb = batch_solver(len(idx))
+                    Xb.copy_(m.X_cells_major.index_select(0, idx))
+                    Hb.copy_(m.H.index_select(1, idx))
+                    for yb, y in zip(Yb, m.Ys):
+                        yb.copy_(y.index_select(1, idx))
+                    s.batch_begin()
+                    s.mu_partials()
+                    s.mu_apply(0)
+                    m.H[:, idx] = Hb  # main.py:662; duplicates of the weighted sampler carry identical columns
+                history.append(self._compute_loss(m, solver=full, xnorm2=xnorm2))
+                if pbar is not None:
+                    pbar.set_postfix({"objective loss": history[-1][0]})
+                    pbar.update(1)
+            for s, *_ in solvers.values():
+                s.losses(0)  # synchronise and surface kernel faults
+        finally:
+            if pbar is not None:
+                pbar.close()
+            full.close()
+            for s, *_ in solvers.values():
+                s.close()
+        colnames = ["total loss", "reconstruction loss"] + [f"prediction loss({k})" for k in self.covariate_keys]
+        self.loss_history = pd.DataFrame(history, columns=colnames)
+
+    def _compute_loss(self, m: AlpineMatrices, solver=None, xnorm2: Optional[float] = None) -> List[float]:
         """[total, reconstruction, prediction...] of the factors as they are (main.py:726-753).
 
         Not on the hot path (the loop gets its loss terms from the update kernels): the reconstruction term uses
         the same trace identity, ||X||^2 - 2 tr(W^T X H^T) + tr(W^T W H H^T), with W^T X from the tcgen05
         contraction and fp64 traces; the prediction terms are evaluated with torch on the device.
         """
-        solver = self._make_solver(m)
+        own = solver is None
+        if own:
+            solver = self._make_solver(m)
         try:
+            if xnorm2 is None:
+                solver.fit_begin(1)  # ||X||^2 by the library's fp64 reduction (no fp64 copy of X)
+                xnorm2 = solver.losses(0)[0]
             A = solver.wx_product().double()
         finally:
-            solver.close()
+            if own:
+                solver.close()
         H, W = m.H.double(), m.W.double()
-        terms = [(m.X_cells_major.double() ** 2).sum(), (A * H).sum(), ((W.T @ W) * (H @ H.T)).sum()]
+        terms = [torch.tensor(float(xnorm2), dtype=torch.float64, device=H.device), (A * H).sum(),
+                 ((W.T @ W) * (H @ H.T)).sum()]
         row = 0
         for i, B in enumerate(m.Bs):
             k = B.shape[1]

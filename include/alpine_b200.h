@@ -65,6 +65,10 @@ int alpine_bind_reduce_buffer(alpine_ctx* ctx, float* buf);
 /* Start a fit: ||X||_F^2, tf32 split of the initial H, initial statistics (H H^T, B statistics).
  * max_iter sizes the device-side loss history.  Replaces the head of _fit (main.py:486-498).              */
 int alpine_fit_begin(alpine_ctx* ctx, int max_iter, void* stream);
+/* Start a mini-batch step on freshly gathered batch data (main.py:509-521): refreshes the W^T copy from the bound W
+ * (another context may have updated it) and the statistics of the bound H / B, without the ||X||^2 pass.  Follow
+ * with alpine_mu_partials + alpine_mu_apply(ctx, 0, ...); the loss terms of a batch step are not meaningful.     */
+int alpine_batch_begin(alpine_ctx* ctx, void* stream);
 /* First half of one full-batch iteration: numerator X H^T of the W update (main.py:596) into the reduce
  * buffer, next to the statistics written by the previous iteration.  No data-path collective inside.      */
 int alpine_mu_partials(alpine_ctx* ctx, void* stream);

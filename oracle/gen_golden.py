@@ -57,6 +57,17 @@ CASES = {
         kw=dict(n_components=6, n_covariate_components=[3, 2], lam=[1e2, 1e3],
                 orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, use_als=True),
     ),
+    # mini-batch epochs (main.py:509-521): ragged last batch; index streams recorded from the reference's sampler
+    "mb_random": dict(
+        n_cells=203, n_genes=130, cats=[3, 4], rank=6, n_iter=6, nan_fraction=0.05, batch_size=64,
+        kw=dict(n_components=9, n_covariate_components=[4, 3], lam=[1e3, 5e2],
+                orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
+    ),
+    # class-balanced sampling with replacement (sampling.py:18-33): duplicate cells inside a batch
+    "mb_weighted": dict(
+        n_cells=160, n_genes=96, cats=[3], rank=5, n_iter=6, batch_size=50, sampling_method="weighted",
+        kw=dict(n_components=6, n_covariate_components=[3], lam=[1e3], alpha_W=0.3),
+    ),
     "kl_long200": dict(
         n_cells=500, n_genes=300, cats=[3], rank=8, n_iter=200, keep_every=200,
         kw=dict(n_components=9, n_covariate_components=[3], lam=[1e3],
@@ -80,6 +91,19 @@ def run_case(ref_main, name: str, spec: dict) -> dict:
     Y = fe.fit_transform(obs) if keys else []
 
     model = ref_shim.make_reference_model(ref_main, n, keys, max_iter=1, **spec["kw"])
+    epoch_streams = []
+    if "batch_size" in spec:
+        model.batch_size = spec["batch_size"]
+        model.sampling_method = spec.get("sampling_method", "random")
+        sampler = ref_main.generate_epoch_indices  # the reference's own sampler; only its output is recorded
+
+        def recording_sampler(*a, **k):
+            idx = sampler(*a, **k)
+            epoch_streams.append(idx.cpu().numpy().astype(np.int64))
+            return idx
+
+        ref_main.generate_epoch_indices = recording_sampler
+        torch.manual_seed(spec.get("sampler_seed", 7))
     mats = model._initialize_matrices(X, Y)
     out = {
         "X_cells_by_genes": Xcg,
@@ -107,6 +131,11 @@ def run_case(ref_main, name: str, spec: dict) -> dict:
             for i in range(len(keys)):
                 out[f"B{i}_it{it + 1}"] = mats.Bs[i].numpy().copy()
     out["kept_iters"] = np.asarray(kept, dtype=np.int64)
+    if "batch_size" in spec:
+        ref_main.generate_epoch_indices = sampler
+        out["batch_size"] = np.int64(spec["batch_size"])
+        for it, idx in enumerate(epoch_streams):
+            out[f"epoch_idx_it{it + 1}"] = idx
     out["loss_history_ref_fp32"] = np.asarray(losses)
 
     # fp64 re-evaluation of the reference's loss formula from its final factors
@@ -146,7 +175,10 @@ def main() -> None:
     ref_main = ref_shim.import_reference()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)  # deterministic summation order in the fixtures
+    only = set(sys.argv[1:])
     for name, spec in CASES.items():
+        if only and name not in only:
+            continue
         data = run_case(ref_main, name, spec)
         path = os.path.join(OUT, f"{name}.npz")
         np.savez_compressed(path, **data)

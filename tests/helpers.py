@@ -20,9 +20,20 @@ CASE_KW = {
     "kl_lam0": dict(n_components=5, n_covariate_components=[2], lam=[0.0], alpha_W=1.5, l1_ratio_W=1.0),
     "als_reg": dict(n_components=6, n_covariate_components=[3, 2], lam=[1e2, 1e3],
                     orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, use_als=True),
+    "mb_random": dict(n_components=9, n_covariate_components=[4, 3], lam=[1e3, 5e2],
+                      orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
+    "mb_weighted": dict(n_components=6, n_covariate_components=[3], lam=[1e3], alpha_W=0.3),
     "kl_long200": dict(n_components=9, n_covariate_components=[3], lam=[1e3],
                        orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
 }
+
+
+MINIBATCH_CASES = ("mb_random", "mb_weighted")
+
+
+def full_batch_mu_names():
+    """Fixtures of the full-batch, non-ALS loop (what alpine_mu_partials / alpine_mu_apply iterate)."""
+    return [n for n in golden_names() if not CASE_KW[n].get("use_als", False) and n not in MINIBATCH_CASES]
 
 
 def golden_names():
@@ -47,6 +58,15 @@ def inputs_of(g):
     st = orc.State(g["W0"].copy(), g["H0"].copy(), [g[f"B0_{i}"].copy() for i in range(n_cov)],
                    [int(b) for b in g["blocks"]])
     return X, Ys, st
+
+
+def epoch_batches(g, it):
+    """Batch index vectors of epoch ``it`` (1-based): the recorded sampler stream cut as sampling.py:58-71 does;
+    one ``None`` (= full batch in natural order) for the full-batch fixtures."""
+    if "batch_size" not in g:
+        return [None]
+    idx, bs = g[f"epoch_idx_it{it}"], int(g["batch_size"])
+    return [idx[b0:b0 + bs] for b0 in range(0, len(idx), bs)]
 
 
 def rel_fro(a, b):

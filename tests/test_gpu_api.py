@@ -126,5 +126,68 @@ def test_unsupported_modes_raise():
     ad = _adata(n=200, G=100, cats=(3,), nan_fraction=0.0)
     with pytest.raises(NotImplementedError):
         ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0], use_als=True).fit(ad, ["cov0"], max_iter=2)
-    with pytest.raises(NotImplementedError):
-        ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0]).fit(ad, ["cov0"], max_iter=2, batch_size=50)
+
+
+def _model_on_golden(name, g, **extra):
+    """ALPINE + AlpineMatrices holding a golden fixture's inputs and initial factors on cuda:0."""
+    from alpine_b200 import _native
+    from alpine_b200.main import AlpineMatrices
+    from tests.gpu_utils import to_dev_padded
+    from tests.helpers import CASE_KW
+
+    kw = dict(CASE_KW[name])
+    kw.update(extra)
+    dev = torch.device("cuda:0")
+    n_cov = int(g["n_cov"])
+    model = ALPINE(device="cuda:0", **kw)
+    model.covariate_keys = [f"cov{i}" for i in range(n_cov)]
+    model.verbose = False
+    Xd = to_dev_padded(g["X_cells_by_genes"], dev)
+    n = Xd.shape[0]
+    W = torch.from_numpy(g["W0"].copy()).to(dev)
+    H = to_dev_padded(g["H0"], dev)
+    Ys = [torch.from_numpy(np.ascontiguousarray(g[f"Y{i}_cells_by_cat"].T)).to(dev) for i in range(n_cov)]
+    Bs = [torch.from_numpy(g[f"B0_{i}"].copy()).to(dev) for i in range(n_cov)]
+    Ws, Hs, col = [], [], 0
+    for k in model.n_all_components:
+        Ws.append(W[:, col:col + k])
+        Hs.append(H[col:col + k, :])
+        col += k
+    m = AlpineMatrices(X=Xd.T, Ys=Ys, Ws=Ws, Hs=Hs, Bs=Bs, W=W, H=H, X_cells_major=Xd, shard=(0, n), n_total=n)
+    return model, m
+
+
+@pytest.mark.parametrize("name", ["mb_random", "mb_weighted"])
+def test_minibatch_epochs_match_reference_golden(name):
+    """Mini-batch epochs (main.py:509-521, 589-663) replaying the index streams the reference's sampler produced
+    (oracle/gen_golden.py): ragged last batch, and duplicate cells inside a batch for the weighted sampler."""
+    from tests.helpers import load_golden
+
+    g = load_golden(name)
+    model, m = _model_on_golden(name, g)
+    n_iter = int(g["kept_iters"][-1])
+    model.batch_size = int(g["batch_size"])
+    model.sampling_method = "weighted" if name == "mb_weighted" else "random"
+    model.max_iter = 1
+    ref_hist = g["loss_history_ref_fp32"]
+    for it in range(1, n_iter + 1):
+        model._epoch_index_stream = iter([g[f"epoch_idx_it{it}"]])
+        model._fit(m)  # one epoch, as the fixture generator drives the reference
+        assert rel_fro(m.W.cpu().numpy(), g[f"W_it{it}"]) < 1e-4, (name, it, "W")
+        assert rel_fro(m.H.cpu().numpy(), g[f"H_it{it}"]) < 1e-4, (name, it, "H")
+        for i, b in enumerate(m.Bs):
+            assert rel_fro(b.cpu().numpy(), g[f"B{i}_it{it}"]) < 1e-4, (name, it, f"B{i}")
+        row = model.loss_history.iloc[-1].to_numpy(dtype=float)
+        np.testing.assert_allclose(row[1], ref_hist[it - 1][1], rtol=2e-3)
+        np.testing.assert_allclose(row[2:], ref_hist[it - 1][2:], rtol=1e-3, atol=1e-6 * m.n_total)
+    recon = model.loss_history["reconstruction loss"].iloc[-1]
+    assert abs(recon - float(g["final_recon_fp64"])) / float(g["final_recon_fp64"]) < 1e-4
+
+
+def test_minibatch_public_fit_runs_with_own_sampler():
+    ad = _adata(n=500, G=300, cats=(3,), nan_fraction=0.0)
+    for method in ("random", "weighted"):
+        model = ALPINE(n_components=5, n_covariate_components=[3], lam=[1e2], device="cuda")
+        model.fit(ad, ["cov0"], max_iter=4, batch_size=128, sampling_method=method)
+        lh = model.loss_history["total loss"].to_numpy()
+        assert len(lh) == 4 and np.all(np.isfinite(lh)) and lh[-1] < lh[0]

@@ -11,7 +11,7 @@ import pytest
 import torch
 
 from oracle import alpine_oracle as orc
-from tests.helpers import CASE_KW, golden_names, hp_of, inputs_of, load_golden, rel_fro
+from tests.helpers import CASE_KW, full_batch_mu_names, golden_names, hp_of, inputs_of, load_golden, rel_fro
 
 pytestmark = pytest.mark.gpu
 
@@ -75,7 +75,7 @@ def test_contraction_is_deterministic():
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if not CASE_KW[n].get("use_als", False)])
+@pytest.mark.parametrize("name", full_batch_mu_names())
 def test_trajectory_matches_reference_golden(name):
     """Per-iteration W/H/B against the unmodified reference's trajectory (tests/golden, oracle/gen_golden.py)."""
     gu = _gpu_utils()
@@ -166,7 +166,7 @@ def test_long_run_top100_rankings_match_reference():
                                       np.argsort(-Wref[:, k], kind="stable")[:100])
 
 
-@pytest.mark.parametrize("name", [n for n in golden_names() if not CASE_KW[n].get("use_als", False)])
+@pytest.mark.parametrize("name", full_batch_mu_names())
 def test_scale_and_transform_match_reference_golden(name):
     gu = _gpu_utils()
     g = load_golden(name)

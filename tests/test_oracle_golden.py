@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import alpine_oracle as orc
-from tests.helpers import CASE_KW, golden_names, hp_of, inputs_of, load_golden, rel_fro
+from tests.helpers import CASE_KW, epoch_batches, golden_names, hp_of, inputs_of, load_golden, rel_fro
 
 TRAJ_TOL = 2e-6  # Frobenius-relative, per kept iteration (<= 10 iterations)
 LONG_TOL = 5e-5  # 200 iterations of drift
@@ -24,7 +24,8 @@ def test_step_trajectory_matches_reference(name):
     n_iter = int(max(kept))
     tol = LONG_TOL if n_iter > 20 else TRAJ_TOL
     for it in range(1, n_iter + 1):
-        (orc.als_step if use_als else orc.mu_step)(X, Ys, st, hp)
+        for idx in epoch_batches(g, it):
+            (orc.als_step if use_als else orc.mu_step)(X, Ys, st, hp, idx=idx)
         if it in kept:
             assert rel_fro(st.W, g[f"W_it{it}"]) < tol, (name, it, "W")
             assert rel_fro(st.H, g[f"H_it{it}"]) < tol, (name, it, "H")
