@@ -40,6 +40,8 @@ SIGNATURES = {
                                           ctypes.c_double, ctypes.c_double]),
     "alpine_reduce_buffer_size": (ctypes.c_int64, [_c_ctx]),
     "alpine_bind_reduce_buffer": (ctypes.c_int, [_c_ctx, _f32p]),
+    "alpine_bind_csr": (ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                       ctypes.c_void_p]),
     "alpine_fit_begin": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_batch_begin": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_partials": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
@@ -197,6 +199,17 @@ class Solver:
         assert X.is_cuda and X.dtype == torch.float32 and X.shape == (self.n, self.G) and X.stride(1) == 1
         self._keep["X"] = X
         _check(self.lib, self.lib.alpine_bind_dense(self._ctx, X.data_ptr(), X.stride(0) if self.n > 1 else max(X.stride(0), self.G)))
+
+    def bind_csr(self, indptr: torch.Tensor, indices: torch.Tensor, values: torch.Tensor) -> None:
+        """Sparse X as device CSR over cells: indptr (n_cells + 1, int64), indices (nnz, int32 gene ids), values
+        (nnz, fp32).  The library converts it into its own tile lists; the tensors are not kept."""
+        assert indptr.is_cuda and indptr.dtype == torch.int64 and indptr.shape == (self.n + 1,) and indptr.is_contiguous()
+        assert indices.is_cuda and indices.dtype == torch.int32 and indices.is_contiguous()
+        assert values.is_cuda and values.dtype == torch.float32 and values.is_contiguous()
+        assert indices.shape == values.shape and indices.dim() == 1
+        self._keep.pop("X", None)
+        _check(self.lib, self.lib.alpine_bind_csr(self._ctx, indptr.data_ptr(), indices.data_ptr(), values.data_ptr(),
+                                                  int(values.shape[0]), self._stream()))
 
     def bind_labels(self, Ys: List[torch.Tensor]) -> None:
         assert len(Ys) == self.n_cov

@@ -12,6 +12,7 @@
 
 #include "mu_gemm_sm100.cuh"
 #include "mu_small_kernels.cuh"
+#include "csr_tiles.cuh"
 
 using namespace alpine;
 
@@ -95,6 +96,10 @@ struct GemmOperands {
   const float* Bsplit = nullptr;
   long long ldS = 0;
   bool profiled = false;  // counted by alpine_profile (the two contractions over X)
+  // sparse X: tile lists instead of Xmem (csr_tiles.cuh)
+  const long long* sp_ofs = nullptr;
+  const uint2* sp_ent = nullptr;
+  const int* a_inexact = nullptr;
 };
 enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_COUNT = 4 };
 
@@ -124,6 +129,13 @@ struct alpine_ctx {
 
   const float* X = nullptr;
   long long ldX = 0;
+  // sparse X (alpine_bind_csr): library-owned tile lists, one copy per contraction orientation
+  bool sparse = false;
+  long long nnz = 0;
+  long long* sp_ofs[2] = {nullptr, nullptr};
+  uint2* sp_ent[2] = {nullptr, nullptr};
+  double* sp_xnorm2 = nullptr;
+  int* flags = nullptr;  // [0] X has values that are not tf32-exact, [1] constant 1 (operands that are never exact)
   const float* Y[kMaxCov] = {nullptr};
   float* W = nullptr;
   long long ldW = 0;
@@ -204,6 +216,14 @@ int dev_alloc(T** p, size_t count) {
 
 int set_kernel_attrs();
 
+int ensure_flags(alpine_ctx* c) {
+  if (c->flags != nullptr) return ALPINE_OK;
+  AL_TRY(dev_alloc(&c->flags, 2));
+  const int init[2] = {1, 1};  // conservative until a pass over X has looked at the values
+  CU_TRY(cudaMemcpy(c->flags, init, sizeof(init), cudaMemcpyHostToDevice));
+  return ALPINE_OK;
+}
+
 int ensure_workspace(alpine_ctx* c) {
   if (c->ws_ready) return ALPINE_OK;
   CU_TRY(cudaSetDevice(c->device));
@@ -229,6 +249,7 @@ int ensure_workspace(alpine_ctx* c) {
   AL_TRY(dev_alloc(&c->xnorm2, 1));
   AL_TRY(dev_alloc(&c->err, 8));
   CU_TRY(cudaMemset(c->err, 0, 8 * sizeof(int)));
+  AL_TRY(ensure_flags(c));
   CU_TRY(cudaMemset(c->t1_partial, 0, sizeof(double) * c->sl_blocks_n));
   if (c->reduce == nullptr) {
     AL_TRY(dev_alloc(&c->own_reduce, static_cast<size_t>(c->reduce_floats())));
@@ -240,12 +261,15 @@ int ensure_workspace(alpine_ctx* c) {
 
 int set_kernel_attrs() {
   const int big = 227 * 1024;
-#define ALPINE_GEMM_ATTR(NC)                                                                                   \
-  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_XH, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)); \
-  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<ORIENT_WX, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define ALPINE_GEMM_ATTR1(O, NC, SRC) \
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<O, NC, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define ALPINE_GEMM_ATTR(NC)                                                             \
+  ALPINE_GEMM_ATTR1(ORIENT_XH, NC, SRC_DENSE) ALPINE_GEMM_ATTR1(ORIENT_WX, NC, SRC_DENSE) \
+  ALPINE_GEMM_ATTR1(ORIENT_XH, NC, SRC_TILES) ALPINE_GEMM_ATTR1(ORIENT_WX, NC, SRC_TILES)
   ALPINE_GEMM_ATTR(1) ALPINE_GEMM_ATTR(2) ALPINE_GEMM_ATTR(3) ALPINE_GEMM_ATTR(4)
   ALPINE_GEMM_ATTR(5) ALPINE_GEMM_ATTR(6) ALPINE_GEMM_ATTR(7) ALPINE_GEMM_ATTR(8)
 #undef ALPINE_GEMM_ATTR
+#undef ALPINE_GEMM_ATTR1
   const int sl = static_cast<int>(sym_long_smem_bytes(128));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
@@ -266,12 +290,12 @@ int prof_mark(alpine_ctx* c, cudaStream_t st) {
   return ALPINE_OK;
 }
 
-template <int ORIENT>
+template <int ORIENT, int SRC>
 int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
   switch (pl.p.Kp / 16) {
 #define ALPINE_GEMM_CASE(NC)                                                                     \
   case NC:                                                                                       \
-    mu_gemm_kernel<ORIENT, NC><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmBhi, pl.tmBlo, pl.p); \
+    mu_gemm_kernel<ORIENT, NC, SRC><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmBhi, pl.tmBlo, pl.p); \
     break;
     ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
     ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
@@ -348,8 +372,13 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   }
   p.partial = c->partial;
   p.err = c->err;
+  p.sp_ofs = op.sp_ofs;
+  p.sp_ent = op.sp_ent;
+  p.a_inexact = op.a_inexact;
   // tensor maps: Xmem is [rows][cols] (inner = cols)
-  if (op.orient == ORIENT_XH)
+  if (op.sp_ofs != nullptr)
+    memset(&pl->tmX, 0, sizeof(pl->tmX));  // the tile-list producer does not use TMA for X
+  else if (op.orient == ORIENT_XH)
     AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, rows, kBK, false));
   else
     AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, kBK, rows, true));
@@ -386,18 +415,22 @@ GemmOperands plan_operands(const alpine_ctx* c, int which) {
     case PLAN_XH:  // P^T[k][g] = sum_j X[j][g] H[k][j]                                   (main.py:596)
       op.orient = ORIENT_XH, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
       op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.profiled = true;
+      op.a_inexact = c->flags;
+      if (c->sparse) op.Xmem = nullptr, op.sp_ofs = c->sp_ofs[ORIENT_XH], op.sp_ent = c->sp_ent[ORIENT_XH];
       break;
     case PLAN_WX:  // A[k][j] = sum_g X[j][g] W^T[k][g]                                   (main.py:653)
       op.orient = ORIENT_WX, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
       op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.profiled = true;
+      op.a_inexact = c->flags;
+      if (c->sparse) op.Xmem = nullptr, op.sp_ofs = c->sp_ofs[ORIENT_WX], op.sp_ent = c->sp_ent[ORIENT_WX];
       break;
     case PLAN_GRAM_H:  // S[b][a] = sum_j H[a][j] H[b][j]            (H H^T of main.py:599 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
-      op.Bsplit = c->Hsplit, op.ldS = c->ldN;
+      op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.a_inexact = c->flags + 1;
       break;
     default:           // T[b][a] = sum_g W^T[a][g] W^T[b][g]        (W^T W of main.py:654 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
-      op.Bsplit = c->Wsplit, op.ldS = c->ldG;
+      op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.a_inexact = c->flags + 1;
       break;
   }
   return op;
@@ -416,7 +449,7 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
   GemmPlan* pl = &c->plans[which];
   if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which)));
   const GemmOperands& op = pl->op;
-  if (c->simt) {
+  if (c->simt && op.sp_ofs == nullptr) {
     const float* Bsrc = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->H : c->WT;
     const long long ldB = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->ldH : c->ldG;
     dim3 grid(ceil_div(pl->p.M, 128), c->K);
@@ -428,10 +461,16 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
     return ALPINE_OK;
   }
   if (op.profiled) AL_TRY(prof_mark(c, st));
-  if (op.orient == ORIENT_XH)
-    AL_TRY(launch_gemm_t<ORIENT_XH>(*pl, st));
-  else
-    AL_TRY(launch_gemm_t<ORIENT_WX>(*pl, st));
+  if (op.sp_ofs != nullptr) {
+    if (op.orient == ORIENT_XH)
+      AL_TRY((launch_gemm_t<ORIENT_XH, SRC_TILES>(*pl, st)));
+    else
+      AL_TRY((launch_gemm_t<ORIENT_WX, SRC_TILES>(*pl, st)));
+  } else if (op.orient == ORIENT_XH) {
+    AL_TRY((launch_gemm_t<ORIENT_XH, SRC_DENSE>(*pl, st)));
+  } else {
+    AL_TRY((launch_gemm_t<ORIENT_WX, SRC_DENSE>(*pl, st)));
+  }
   if (op.profiled) AL_TRY(prof_mark(c, st));
   ReduceParams r = pl->r;
   r.out = out;
@@ -504,7 +543,7 @@ int run_stats(alpine_ctx* c, double* loss_row, bool fresh_h_update, cudaStream_t
 
 int check_bound(const alpine_ctx* c, bool need_labels) {
   if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
-  if (c->X == nullptr) return fail(ALPINE_ERR_STATE, "alpine_bind_dense has not been called");
+  if (c->X == nullptr && !c->sparse) return fail(ALPINE_ERR_STATE, "alpine_bind_dense / alpine_bind_csr has not been called");
   if (c->W == nullptr || c->H == nullptr) return fail(ALPINE_ERR_STATE, "alpine_bind_factors has not been called");
   if (need_labels) {
     for (int i = 0; i < c->n_cov; ++i)
@@ -530,7 +569,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 2; }
+int alpine_abi_version(void) { return 3; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -595,7 +634,7 @@ int alpine_destroy(alpine_ctx* c) {
   cudaSetDevice(c->device);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
                   c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
-                  c->own_reduce};
+                  c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   for (auto& pl : c->plans) {
@@ -613,6 +652,84 @@ int alpine_bind_dense(alpine_ctx* c, const float* X, int64_t ldX) {
     return fail(ALPINE_ERR_ARG, "X needs ldX >= n_genes, ldX %% 4 == 0 and a 16-byte aligned base");
   c->X = X;
   c->ldX = ldX;
+  c->sparse = false;
+  if (c->flags) {
+    const int one = 1;
+    CU_TRY(cudaMemcpy(c->flags, &one, sizeof(int), cudaMemcpyHostToDevice));
+  }
+  for (auto& pl : c->plans) pl.valid = false;
+  return ALPINE_OK;
+}
+
+int alpine_bind_csr(alpine_ctx* c, const int64_t* indptr, const int32_t* indices, const float* values, int64_t nnz,
+                    void* stream) {
+  if (c == nullptr || indptr == nullptr || (nnz > 0 && (indices == nullptr || values == nullptr)))
+    return fail(ALPINE_ERR_ARG, "null argument");
+  if (nnz < 0) return fail(ALPINE_ERR_ARG, "negative nnz");
+  CU_TRY(cudaSetDevice(c->device));
+  AL_TRY(ensure_flags(c));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  for (int o = 0; o < 2; ++o) {
+    if (c->sp_ofs[o]) cudaFree(c->sp_ofs[o]);
+    if (c->sp_ent[o]) cudaFree(c->sp_ent[o]);
+    c->sp_ofs[o] = nullptr;
+    c->sp_ent[o] = nullptr;
+  }
+  const int kb_xh = ceil_div(c->n, kBK), kb_wx = ceil_div(c->G, kBK);
+  const long long nb_xh = static_cast<long long>(ceil_div(c->G, kRows)) * kb_xh;
+  const long long nb_wx = static_cast<long long>(ceil_div(c->n, kRows)) * kb_wx;
+  unsigned int *cnt_xh = nullptr, *cnt_wx = nullptr;
+  int* err = nullptr;
+  double* partial = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(cnt_xh), cudaFree(cnt_wx), cudaFree(err), cudaFree(partial);
+  };
+#define CSR_TRY(expr)                                                                                        \
+  do {                                                                                                       \
+    cudaError_t e__ = (expr);                                                                                \
+    if (e__ != cudaSuccess) {                                                                                \
+      cleanup();                                                                                             \
+      return fail(ALPINE_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    }                                                                                                        \
+  } while (0)
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&cnt_xh), nb_xh * sizeof(unsigned int)));
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&cnt_wx), nb_wx * sizeof(unsigned int)));
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&err), 2 * sizeof(int)));
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&partial), 1024 * sizeof(double)));
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&c->sp_ofs[ORIENT_XH]), (nb_xh + 1) * sizeof(long long)));
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&c->sp_ofs[ORIENT_WX]), (nb_wx + 1) * sizeof(long long)));
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&c->sp_ent[ORIENT_XH]), (nnz > 0 ? nnz : 1) * sizeof(uint2)));
+  CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&c->sp_ent[ORIENT_WX]), (nnz > 0 ? nnz : 1) * sizeof(uint2)));
+  if (c->sp_xnorm2 == nullptr) CSR_TRY(cudaMalloc(reinterpret_cast<void**>(&c->sp_xnorm2), sizeof(double)));
+  CSR_TRY(cudaMemsetAsync(cnt_xh, 0, nb_xh * sizeof(unsigned int), st));
+  CSR_TRY(cudaMemsetAsync(cnt_wx, 0, nb_wx * sizeof(unsigned int), st));
+  CSR_TRY(cudaMemsetAsync(err, 0, 2 * sizeof(int), st));
+  CSR_TRY(cudaMemsetAsync(c->flags, 0, sizeof(int), st));
+  CsrView m{reinterpret_cast<const long long*>(indptr), indices, values, c->n, static_cast<int>(c->G)};
+  const int grid = 8 * c->num_sms;
+  csr_tile_count_kernel<<<grid, 256, 0, st>>>(m, kb_xh, kb_wx, cnt_xh, cnt_wx, err);
+  csr_tile_scan_kernel<<<1, 1024, 0, st>>>(cnt_xh, nb_xh, c->sp_ofs[ORIENT_XH]);
+  csr_tile_scan_kernel<<<1, 1024, 0, st>>>(cnt_wx, nb_wx, c->sp_ofs[ORIENT_WX]);
+  csr_tile_fill_kernel<<<grid, 256, 0, st>>>(m, kb_xh, kb_wx, c->sp_ofs[ORIENT_XH], c->sp_ofs[ORIENT_WX], cnt_xh, cnt_wx,
+                                            c->sp_ent[ORIENT_XH], c->sp_ent[ORIENT_WX]);
+  // ||X||_F^2 (first term of the trace identity that replaces main.py:736) and the tf32-exactness flag
+  sumsq_flat_kernel<<<1024, 256, 0, st>>>(values, nnz, partial, c->flags);
+  sum_double_kernel<<<1, 32, 0, st>>>(partial, 1024, c->sp_xnorm2);
+  g_launches.fetch_add(6, std::memory_order_relaxed);
+  CSR_TRY(cudaGetLastError());
+  int h_err[2] = {0, 0};
+  long long total = 0;
+  CSR_TRY(cudaMemcpyAsync(h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, st));
+  CSR_TRY(cudaMemcpyAsync(&total, c->sp_ofs[ORIENT_WX] + nb_wx, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  CSR_TRY(cudaStreamSynchronize(st));
+#undef CSR_TRY
+  cleanup();
+  if (h_err[0]) return fail(ALPINE_ERR_ARG, "CSR column index outside [0, n_genes)");
+  if (h_err[1]) return fail(ALPINE_ERR_ARG, "CSR values must be finite and non-negative");
+  if (total != nnz) return fail(ALPINE_ERR_ARG, "indptr covers %lld nonzeros but nnz = %lld", total, (long long)nnz);
+  c->X = nullptr;
+  c->sparse = true;
+  c->nnz = nnz;
   for (auto& pl : c->plans) pl.valid = false;
   return ALPINE_OK;
 }
@@ -671,11 +788,16 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
     c->loss_cap = max_iter;
   }
   // ||X||_F^2 (first term of the trace identity that replaces main.py:736)
-  const int sb = 1024;
-  sumsq_partial_kernel<<<sb, 256, 0, st>>>(c->X, c->ldX, c->n, (int)c->G, c->sumsq_partial);
-  LAUNCH_CHECK();
-  sum_double_kernel<<<1, 32, 0, st>>>(c->sumsq_partial, sb, c->xnorm2);
-  LAUNCH_CHECK();
+  if (c->sparse) {
+    CU_TRY(cudaMemcpyAsync(c->xnorm2, c->sp_xnorm2, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  } else {
+    const int sb = 1024;
+    CU_TRY(cudaMemsetAsync(c->flags, 0, sizeof(int), st));
+    sumsq_partial_kernel<<<sb, 256, 0, st>>>(c->X, c->ldX, c->n, (int)c->G, c->sumsq_partial, c->flags);
+    LAUNCH_CHECK();
+    sum_double_kernel<<<1, 32, 0, st>>>(c->sumsq_partial, sb, c->xnorm2);
+    LAUNCH_CHECK();
+  }
   // W^T master copy for the gene-side kernels
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);

@@ -27,6 +27,11 @@
 //  * One MMA-issuing warp per 128-row tile: a 128x112x8 tf32 MMA lasts only ~56 cycles, so a single issuing
 //    thread (and any per-instruction register shuffling) would leave the tensor pipe idle.
 //  * Every mbarrier wait is bounded (clock64): a protocol bug reports an error code instead of hanging the GPU.
+//  * SRC_TILES (sparse X): instead of TMA, the X-producer warp expands per-(super-tile, k-block) nonzero lists
+//    (csr_tiles.cuh, built once from the CSR matrix) into the same dense shared-memory tile, so HBM only sees
+//    8 bytes per nonzero while everything downstream (split, TMEM staging, MMAs, drains) is unchanged.
+//  * Count matrices: when every X value is exactly representable in tf32 (integers < 2048, detected on the
+//    device), the lo half of A is zero and the Alo*Bhi products are skipped (2 instead of 3 MMAs per k-step).
 #pragma once
 #include <vector>
 
@@ -45,6 +50,15 @@ constexpr int kMaxAStages = 4;
 constexpr long long kTimeoutCycles = 1ll << 30;  // ~0.5 s: a wait that long is a bug, never a hang
 
 enum { ORIENT_XH = 0, ORIENT_WX = 1 };
+enum { SRC_DENSE = 0, SRC_TILES = 1 };
+
+// Byte offset of element (row of the 256-row super-tile, reduction column of the 32-deep k-block) inside the
+// shared-memory X tile, i.e. where the TMA box of the dense path puts it (and where the converters read it).
+__host__ __device__ inline uint32_t x_tile_offset(int orient, int row, int col) {
+  if (orient == ORIENT_XH) return static_cast<uint32_t>(col * 256 + row) * 4u;  // [32][256], no swizzle
+  return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>((col >> 2) ^ (row & 7)) << 4) +
+         (static_cast<uint32_t>(col & 3) << 2);                                   // [256][32], 128B swizzle
+}
 
 // error codes written to GemmParams::err[0]; err[1..4] = blockIdx, threadIdx, k-block counter, aux
 enum { ERR_NONE = 0, ERR_XPROD_EMPTY = 1, ERR_BPROD_EMPTY = 2, ERR_CONV_XFULL = 3, ERR_CONV_BFULL = 4,
@@ -95,6 +109,29 @@ struct GemmParams {
   int max_segs;     // partial slots per CTA
   float* partial;   // [gridDim.x * max_segs][K][256]
   int* err;         // [8]
+  // SRC_TILES: nonzeros of X grouped by (super-tile, k-block); entry = {x_tile_offset, fp32 bits}
+  const long long* sp_ofs;  // [num_tiles * kb_per_tile + 1]
+  const uint2* sp_ent;
+  const int* a_inexact;     // device flag: 0 => every A value is tf32-exact (lo == 0), skip the Alo*Bhi MMAs
+};
+
+// Walks the k-blocks of a CTA's stream-K range in execution order.
+struct KbIter {
+  WorkSpace ws;
+  long long pos, end;
+  int tile, kb, left;
+  __device__ KbIter(const WorkSpace& w, long long b, long long e) : ws(w), pos(b), end(e), tile(0), kb(0), left(0) {}
+  __device__ bool next(long long& blk) {
+    if (left == 0) {
+      if (pos >= end) return false;
+      int run;
+      ws.decode(pos, run, tile, kb, left);
+      if (left > end - pos) left = static_cast<int>(end - pos);
+    }
+    blk = static_cast<long long>(tile) * ws.kb_per_tile + kb;
+    ++kb, --left, ++pos;
+    return true;
+  }
 };
 
 
@@ -168,7 +205,7 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int Kp, int sx, int s
 
 // NC = Kp / 16: number of 16-column groups of the accumulator (compile time: the fp32 master sum of a thread's
 // accumulator row lives in 16*NC registers).
-template <int ORIENT, int NC>
+template <int ORIENT, int NC, int SRC>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
@@ -220,7 +257,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     *abort_flag = 0;
     ptx::fence_barrier_init();
   }
-  if (warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
+  if (SRC == SRC_DENSE && warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
   if (warp == kWarpBProd && lane == 0) {
     ptx::prefetch_tensormap(&tmBhi);
     ptx::prefetch_tensormap(&tmBlo);
@@ -238,8 +275,75 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int cta = blockIdx.x;
   const long long range_begin = gemm_range_begin(total, gridDim.x, cta);
   const long long range_end = gemm_range_begin(total, gridDim.x, cta + 1);
+  const bool a_exact = (*p.a_inexact == 0);
 
-  if (warp == kWarpXProd) {
+  if (warp == kWarpXProd && SRC == SRC_TILES) {
+    // ===================================================== sparse producer of the X ring (whole warp)
+    // Per k-block: zero the 32 KB stage, then scatter the block's nonzeros.  Entry loads run one k-block ahead
+    // (registers), their offsets two k-blocks ahead, so no global-memory latency sits on the ring's critical path.
+    constexpr int NE = 16;  // entries per lane kept in registers: 512 per k-block (mean at 5 % density: 410)
+    const uint32_t smem_x_u32 = ptx::smem_u32(smem_x);
+    KbIter ahead(ws, range_begin, range_end);
+    long long blk = 0, o_beg = 0, o_end = 0, cur_beg = 0;
+    int cur_cnt = 0;
+    uint2 cur[NE], nxt[NE];
+    auto load_entries = [&](long long beg, int cnt, uint2(&e)[NE]) {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) {
+        const int idx = i * 32 + lane;
+        e[i] = (idx < cnt) ? __ldcs(p.sp_ent + beg + idx) : make_uint2(0u, 0u);
+      }
+    };
+    bool have_next = ahead.next(blk);
+    if (have_next) {
+      cur_beg = __ldg(p.sp_ofs + blk);
+      cur_cnt = static_cast<int>(__ldg(p.sp_ofs + blk + 1) - cur_beg);
+      load_entries(cur_beg, cur_cnt, cur);
+      have_next = ahead.next(blk);
+      if (have_next) {
+        o_beg = __ldg(p.sp_ofs + blk);
+        o_end = __ldg(p.sp_ofs + blk + 1);
+      }
+    }
+    bool ok = true;
+    for (uint32_t it = 0; it < static_cast<uint32_t>(range_end - range_begin) && ok; ++it) {
+      const int s = it % SX;
+      // entries of the next k-block, offsets of the one after
+      const long long nxt_beg = o_beg;
+      const int nxt_cnt = have_next ? static_cast<int>(o_end - o_beg) : 0;
+      load_entries(nxt_beg, nxt_cnt, nxt);
+      if (have_next) {
+        have_next = ahead.next(blk);
+        if (have_next) {
+          o_beg = __ldg(p.sp_ofs + blk);
+          o_end = __ldg(p.sp_ofs + blk + 1);
+        }
+      }
+      if (!warp_wait_bar(&xempty_bar[s], ((it / SX) & 1) ^ 1, actx, ERR_XPROD_EMPTY, it, s)) {
+        ok = false;
+        break;
+      }
+      const uint32_t sX = smem_x_u32 + static_cast<uint32_t>(s) * kXTileBytes;
+#pragma unroll 8
+      for (int i = 0; i < kXTileBytes / (32 * 16); ++i) ptx::sts_zero_v4(sX + (i * 32 + lane) * 16);
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NE; ++i)
+        if (i * 32 + lane < cur_cnt) ptx::sts_f32(sX + cur[i].x, cur[i].y);
+      for (int idx = NE * 32 + lane; idx < cur_cnt; idx += 32) {  // rare: a k-block denser than 512 nonzeros
+        const uint2 e = __ldcs(p.sp_ent + cur_beg + idx);
+        ptx::sts_f32(sX + e.x, e.y);
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&xfull_bar[s]);
+#pragma unroll
+      for (int i = 0; i < NE; ++i) cur[i] = nxt[i];
+      cur_beg = nxt_beg;
+      cur_cnt = nxt_cnt;
+    }
+    __syncwarp();
+  } else if (warp == kWarpXProd) {
     // ===================================================== TMA producer of the X ring
     if (lane == 0) {
       uint32_t it = 0;
@@ -298,6 +402,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t smem_b_u32 = __shfl_sync(0xffffffffu, ptx::smem_u32(smem_b), 0);
     const uint32_t idesc = ptx::make_idesc_tf32(kBM, Kp);
     const uint32_t d_acc = tb + mt * kAccStride;
+    const bool ex = __shfl_sync(0xffffffffu, a_exact ? 1 : 0, 0) != 0;  // warp-uniform by construction
     uint32_t it = 0, mc = 0;  // k-block counter, chunk counter
     bool ok = true;
     for (long long pos = range_begin; pos < range_end && ok;) {
@@ -331,8 +436,9 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
           const uint64_t bh = dhi + static_cast<uint64_t>(2 * ks);
           const uint64_t bl = dlo + static_cast<uint64_t>(2 * ks);
-          ptx::mma_tf32_ts_if(leader, d_acc, a_lo + ks * kUmmaK, bh, idesc, (c_first && ks == 0) ? 0u : 1u);
-          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bl, idesc, 1u);
+          const uint32_t fresh = (c_first && ks == 0) ? 0u : 1u;
+          if (!ex) ptx::mma_tf32_ts_if(leader, d_acc, a_lo + ks * kUmmaK, bh, idesc, fresh);
+          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bl, idesc, ex ? fresh : 1u);
           ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bh, idesc, 1u);
         }
         if (c_last) {
@@ -423,7 +529,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
           ptx::tmem_st_x8(a_addr + 8 * h, hi);
-          ptx::tmem_st_x8(a_addr + 32 + 8 * h, lo);
+          if (!a_exact) ptx::tmem_st_x8(a_addr + 32 + 8 * h, lo);
         }
         ptx::tc_wait_st();
         ptx::tc_fence_before();

@@ -26,9 +26,12 @@ struct CovTable {
 
 // ---------------------------------------------------------------------------------------------------------
 // sum of squares of a pitched matrix in fp64 (||X||_F^2), two-stage deterministic reduction
+// also raises *inexact when some value is not exactly representable in tf32 (low 13 mantissa bits set): only
+// then does the contraction kernel need the lo half of the 3xTF32 split of X
 __global__ void sumsq_partial_kernel(const float* __restrict__ X, long long ld, long long rows, int cols,
-                                     double* __restrict__ partial) {
+                                     double* __restrict__ partial, int* __restrict__ inexact) {
   double acc = 0.0;
+  unsigned int low = 0u;
   const int cols4 = cols >> 2;  // ld % 4 == 0 and base 16B aligned => float4 loads are aligned per row
   for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
     const float4* p4 = reinterpret_cast<const float4*>(X + r * ld);
@@ -36,13 +39,16 @@ __global__ void sumsq_partial_kernel(const float* __restrict__ X, long long ld, 
     for (int c = threadIdx.x; c < cols4; c += blockDim.x) {
       const float4 v = __ldg(p4 + c);
       s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+      low |= (__float_as_uint(v.x) | __float_as_uint(v.y) | __float_as_uint(v.z) | __float_as_uint(v.w)) & 0x1FFFu;
     }
     for (int c = (cols4 << 2) + threadIdx.x; c < cols; c += blockDim.x) {
       const float v = X[r * ld + c];
       s += v * v;
+      low |= __float_as_uint(v) & 0x1FFFu;
     }
     acc += static_cast<double>(s);
   }
+  if (__any_sync(0xffffffffu, low != 0u) && (threadIdx.x & 31) == 0) *inexact = 1;
   __shared__ double red[32];
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;

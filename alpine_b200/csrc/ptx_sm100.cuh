@@ -55,6 +55,13 @@ __device__ __forceinline__ float4 lds_v4(uint32_t addr) {
   return v;
 }
 
+__device__ __forceinline__ void sts_f32(uint32_t addr, uint32_t bits) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(bits) : "memory");
+}
+__device__ __forceinline__ void sts_zero_v4(uint32_t addr) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 // L2 cache-policy descriptors (the encodings createpolicy.fractional produces).
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;

@@ -25,7 +25,7 @@ import torch
 
 from . import _native, validation
 from .engine import MUEngine, dist_info, shard_bounds
-from .utils.anndata_compat import AnnData
+from .utils.anndata_compat import AnnData, is_sparse
 from .utils.encoder import FeatureEncoders
 from .utils.kneedle import find_elbow
 
@@ -50,6 +50,7 @@ class AlpineMatrices:
     W: Optional[torch.Tensor] = field(default=None, repr=False)
     H: Optional[torch.Tensor] = field(default=None, repr=False)
     X_cells_major: Optional[torch.Tensor] = field(default=None, repr=False)
+    X_csr: Optional[tuple] = field(default=None, repr=False)  # sparse input: device (indptr, indices, values) over cells
     X_host: Optional[np.ndarray] = field(default=None, repr=False)
     Ys_host: Optional[List[np.ndarray]] = field(default=None, repr=False)
     shard: tuple = (0, 0)
@@ -57,7 +58,12 @@ class AlpineMatrices:
 
     def to_numpy(self) -> Dict[str, Union[Float32Array, List[Float32Array]]]:
         # the reference copies X back from the device (main.py:38); the host copy it came from is identical
-        X = self.X_host if self.X_host is not None else self.X.cpu().numpy().astype(np.float32)
+        if self.X_host is not None:
+            X = self.X_host
+        elif self.X is not None:
+            X = self.X.cpu().numpy().astype(np.float32)
+        else:
+            raise RuntimeError("sparse AlpineMatrices without a host copy of X")
         Ys = self.Ys_host if self.Ys_host is not None else [y.cpu().numpy().astype(np.float32) for y in self.Ys]
         return {
             "X": X,
@@ -66,6 +72,24 @@ class AlpineMatrices:
             "Hs": [h.cpu().numpy().astype(np.float32) for h in _gather_cells(self.Hs, self.shard, self.n_total)],
             "Bs": [b.cpu().numpy().astype(np.float32) for b in self.Bs],
         }
+
+
+def _as_csr_f32(X):
+    """Canonical fp32 CSR over cells of a scipy.sparse matrix (duplicates summed, indices sorted)."""
+    import scipy.sparse as sp
+
+    X = sp.csr_matrix(X, dtype=np.float32)
+    X.sum_duplicates()
+    return X
+
+
+def _upload_csr(Xcsr, lo: int, hi: int, dev):
+    """Rows [lo, hi) of a host CSR matrix as device (indptr int64 rebased to 0, indices int32, values fp32)."""
+    p0, p1 = int(Xcsr.indptr[lo]), int(Xcsr.indptr[hi])
+    indptr = torch.from_numpy(np.asarray(Xcsr.indptr[lo:hi + 1], dtype=np.int64) - p0).to(dev)
+    indices = torch.from_numpy(np.ascontiguousarray(Xcsr.indices[p0:p1], dtype=np.int32)).to(dev)
+    values = torch.from_numpy(np.ascontiguousarray(Xcsr.data[p0:p1], dtype=np.float32)).to(dev)
+    return indptr, indices, values
 
 
 def _gather_cells(Hs: List[torch.Tensor], shard, n_total: int) -> List[torch.Tensor]:
@@ -153,7 +177,11 @@ class ALPINE:
 
         # The reference transposes to genes x cells (main.py:104); that view shares the cells-major buffer, which
         # is the layout the kernels stream, so the "transpose" stays a view here as well.
-        X = np.ascontiguousarray(adata.X, dtype=np.float32).T
+        if is_sparse(adata.X):
+            # CSR over cells (AnnData's layout for count matrices); .T is the genes x cells view of the same data
+            X = _as_csr_f32(adata.X).T
+        else:
+            X = np.ascontiguousarray(adata.X, dtype=np.float32).T
         n_sample = X.shape[1]
         self.fe = FeatureEncoders(covariate_keys)
         Y = self.fe.fit_transform(adata.obs)
@@ -208,21 +236,26 @@ class ALPINE:
         The reference recomputes the loop-invariant ``2 W^T X`` every iteration; here ``A = W^T X`` (one sweep of X)
         and ``T = W^T W`` are formed once and each iteration is ``H *= 2A / max(2 T H, eps)`` on K x n only.
         """
-        Xcm = np.ascontiguousarray(adata.X, dtype=np.float32)
-        if not np.all(Xcm >= 0):
+        sparse = is_sparse(adata.X)
+        Xcm = _as_csr_f32(adata.X) if sparse else np.ascontiguousarray(adata.X, dtype=np.float32)
+        if not np.all((Xcm.data if sparse else Xcm) >= 0):
             raise ValueError("All elements in adata.X must be non-negative.")
         dev = self._cuda_device()
         n_sample, G = Xcm.shape
         K = self.total_components
-        Xd = _native.padded_rows(n_sample, G, dev)
-        _native.upload_rows(Xd, Xcm)
+        if not sparse:
+            Xd = _native.padded_rows(n_sample, G, dev)
+            _native.upload_rows(Xd, Xcm)
         # un-reseeded draw from the device generator, as the reference (main.py:687-689)
         H = _native.padded_rows(K, n_sample, dev)
         H.copy_(torch.rand((K, n_sample), dtype=torch.float32, device=dev))
         W = torch.cat([torch.tensor(w, dtype=torch.float32, device=dev) for w in self.matrices["Ws"]], dim=1).contiguous()
         solver = _native.Solver(dev, G, n_sample, [K], [])
         try:
-            solver.bind_dense(Xd)
+            if sparse:
+                solver.bind_csr(*_upload_csr(Xcm, 0, n_sample, dev))
+            else:
+                solver.bind_dense(Xd)
             solver.bind_factors(W, H, [])
             solver.set_hparams([], 0.0, 0.0, 0.0, self.eps)
             solver.transform(n_iter)
@@ -247,7 +280,7 @@ class ALPINE:
         validation.check_adata(adata)
         if "ALPINE_embedding" not in adata.obsm:
             raise ValueError("ALPINE_embedding not found in adata.obsm. Please transform the data first.")
-        X = np.asarray(adata.X).astype(np.float32).T
+        X = (adata.X.toarray() if is_sparse(adata.X) else np.asarray(adata.X)).astype(np.float32).T
         Hs = [np.asarray(adata.obsm[c]).T for c in self.covariate_keys] + [np.asarray(adata.obsm["ALPINE_embedding"]).T]
         Ws = [np.asarray(adata.varm[c]) for c in self.covariate_keys] + [np.asarray(adata.varm["ALPINE_weights"])]
         W, H = np.concatenate(Ws, axis=1), np.concatenate(Hs, axis=0)
@@ -342,8 +375,13 @@ class ALPINE:
         K = self.total_components
 
         Xcm_host = X_array.T  # cells x genes; C-contiguous when X_array came from fit()
-        Xd = _native.padded_rows(n_loc, G, dev)
-        _native.upload_rows(Xd, Xcm_host[lo:hi])
+        X_csr = None
+        if is_sparse(X_array):
+            X_csr = _upload_csr(_as_csr_f32(Xcm_host), lo, hi, dev)
+            Xd = None
+        else:
+            Xd = _native.padded_rows(n_loc, G, dev)
+            _native.upload_rows(Xd, Xcm_host[lo:hi])
         Ys_host = [np.ascontiguousarray(y.T, dtype=np.float32) for y in Y_list_array]  # c_i x n (main.py:447)
         Ys = [torch.from_numpy(np.ascontiguousarray(y[:, lo:hi])).to(dev) for y in Ys_host]
 
@@ -366,13 +404,16 @@ class ALPINE:
             del full
         Bs = [torch.rand((y.shape[0], k), dtype=torch.float32, device=dev).clamp(min=eps).contiguous()
               for (y, k) in zip(Ys_host, self.n_covariate_components)]  # main.py:466-470
-        return AlpineMatrices(X=Xd.T, Ys=Ys, Ws=Ws, Hs=Hs, Bs=Bs, W=W, H=H, X_cells_major=Xd, X_host=X_array,
-                              Ys_host=Ys_host, shard=(lo, hi), n_total=n)
+        return AlpineMatrices(X=Xd.T if Xd is not None else None, Ys=Ys, Ws=Ws, Hs=Hs, Bs=Bs, W=W, H=H,
+                              X_cells_major=Xd, X_csr=X_csr, X_host=X_array, Ys_host=Ys_host, shard=(lo, hi), n_total=n)
 
     def _make_solver(self, m: AlpineMatrices) -> "_native.Solver":
-        n_loc, G = m.X_cells_major.shape
+        n_loc, G = m.H.shape[1], m.W.shape[0]
         solver = _native.Solver(m.W.device, G, n_loc, self.n_all_components, [y.shape[0] for y in m.Ys], self.loss_type)
-        solver.bind_dense(m.X_cells_major)
+        if m.X_csr is not None:
+            solver.bind_csr(*m.X_csr)
+        else:
+            solver.bind_dense(m.X_cells_major)
         solver.bind_labels(m.Ys)
         solver.bind_factors(m.W, m.H, m.Bs)
         solver.set_hparams(self.lam, self.alpha_W, self.l1_ratio_W, self.orth_W, self.eps)
@@ -418,6 +459,8 @@ class ALPINE:
 
         if dist_info()[1] > 1:
             raise NotImplementedError("mini-batch fitting is single-GPU; cell sharding covers the full-batch path")
+        if m.X_csr is not None:
+            raise NotImplementedError("mini-batch fitting needs a dense adata.X; the CSR path is full-batch")
         dev = m.W.device
         n, G = m.X_cells_major.shape
         K = self.total_components

@@ -57,7 +57,8 @@ except Exception:  # ImportError or a broken install
             return self.var.index
 
         def copy(self) -> "AnnData":
-            out = AnnData(np.array(self.X, copy=True), self.obs.copy(), self.var.copy())
+            X = self.X.copy() if is_sparse(self.X) else np.array(self.X, copy=True)
+            out = AnnData(X, self.obs.copy(), self.var.copy())
             out.obsm = {k: np.array(v, copy=True) for k, v in self.obsm.items()}
             out.varm = {k: (v.copy() if hasattr(v, "copy") else v) for k, v in self.varm.items()}
             out.layers = {k: np.array(v, copy=True) for k, v in self.layers.items()}

@@ -3,7 +3,8 @@
 Reference: ``ALPINE._validate_init_args`` (main.py:322-381), ``_validate_fit_args`` (main.py:383-434), the checks
 at the head of ``transform`` (main.py:155-164) and the ComponentOptimizer validators (optimization.py:512-604).
 Quirks that are kept on purpose: ``lam`` entries and ``alpha_W`` / ``orth_W`` / ``l1_ratio_W`` /
-``eps`` must be ``float`` instances (an ``int`` is rejected); ``adata.X`` must be a dense ``np.ndarray``;
+``eps`` must be ``float`` instances (an ``int`` is rejected); ``adata.X`` must be a dense ``np.ndarray`` (or, as an
+extension, a ``scipy.sparse`` matrix, which selects the CSR path);
 covariate columns must have dtype kind ``'O'``; the ``batch_size`` / ``max_iter`` checks can never fire because of
 how the reference chains ``and`` (main.py:420-428) and are therefore omitted.
 """
@@ -13,7 +14,7 @@ from typing import Any, Callable, Sequence, Tuple
 
 import numpy as np
 
-from .utils.anndata_compat import AnnData
+from .utils.anndata_compat import AnnData, is_sparse
 
 LOSS_TYPES = ["kl-divergence", "frobenius"]
 
@@ -67,9 +68,15 @@ def check_model_args(m) -> None:
 def check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose) -> None:
     """main.py:383-434."""
     _require(isinstance(adata, AnnData), TypeError, "adata must be an AnnData object.")
-    _require(isinstance(adata.X, np.ndarray), TypeError, "adata.X must be a numpy array.")
-    _require(adata.X.ndim == 2, ValueError, "adata.X must be a 2D numpy array.")
-    _require(_all_non_negative(adata.X), ValueError, "All elements in adata.X must be non-negative.")
+    if is_sparse(adata.X):
+        # extension over the reference (which raises the TypeError below for sparse input, main.py:395-396): a
+        # scipy.sparse matrix takes the CSR tile-list path of the kernels (BASELINE north_star, config 4)
+        _require(adata.X.ndim == 2, ValueError, "adata.X must be a 2D numpy array.")
+        _require(_all_non_negative(np.asarray(adata.X.data)), ValueError, "All elements in adata.X must be non-negative.")
+    else:
+        _require(isinstance(adata.X, np.ndarray), TypeError, "adata.X must be a numpy array.")
+        _require(adata.X.ndim == 2, ValueError, "adata.X must be a 2D numpy array.")
+        _require(_all_non_negative(adata.X), ValueError, "All elements in adata.X must be non-negative.")
     _require(isinstance(covariate_keys, list), TypeError, "covariate_keys must be a list.")
     _require(len(covariate_keys) == len(m.n_covariate_components), ValueError,
              "Length of covariate_keys must match length of n_covariate_components.")

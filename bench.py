@@ -41,6 +41,13 @@ WORKLOAD = dict(
     n_genes=20000, n_cells=100000, n_components=90, n_covariate_components=[5, 5], categories=[3, 4],
     lam=[1e3, 1e3], orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, eps=1e-6,
 )
+# BASELINE.json configs[3]: the sparse scaling workload (not the default bench line; `--workload cfg4`)
+WORKLOAD_CFG4 = dict(
+    name="cfg4: 30,000 genes x 1,000,000 cells CSR (5% density, 1 + Poisson(1) counts), k=100 (90 unguided + [5,5] "
+         "guided, 3 and 4 categories), orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, lam=[1e3,1e3], KL loss, full batch",
+    n_genes=30000, n_cells=1000000, n_components=90, n_covariate_components=[5, 5], categories=[3, 4],
+    lam=[1e3, 1e3], orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, eps=1e-6, density=0.05,
+)
 METRIC = "MU iterations/sec at 20k genes x 100k cells, k=100"
 UNIT = "iterations/s"
 
@@ -144,6 +151,27 @@ def synth_device_problem(dev, G, n_loc, col0, wl, seed=0):
     return X, Ys, W, H, Bs
 
 
+def synth_device_csr(dev, G, n_loc, col0, wl, seed=0):
+    """Device-resident CSR shard over cells: Bernoulli(density) mask x (1 + Poisson(1)) counts, built chunk-wise."""
+    import torch
+
+    gs = torch.Generator(device=dev)
+    gs.manual_seed(3000 + seed + 7919 * (col0 + 1))
+    step = max(1, (1 << 26) // G)
+    counts, cols, vals = [], [], []
+    for r0 in range(0, n_loc, step):
+        r1 = min(n_loc, r0 + step)
+        mask = torch.rand((r1 - r0, G), device=dev, generator=gs) < wl["density"]
+        counts.append(mask.sum(dim=1))
+        c = mask.nonzero()[:, 1].to(torch.int32)
+        cols.append(c)
+        vals.append(1.0 + torch.poisson(torch.ones(c.shape[0], device=dev), generator=gs))
+        del mask
+    indptr = torch.zeros(n_loc + 1, dtype=torch.int64, device=dev)
+    indptr[1:] = torch.cumsum(torch.cat(counts), 0)
+    return indptr, torch.cat(cols), torch.cat(vals).float()
+
+
 # ------------------------------------------------------------------------------------------- CPU baseline
 def cpu_baseline(wl, sample_cells=8000, iters=2):
     """Oracle port of the reference's step (oracle/alpine_oracle.py, literal arithmetic incl. gather and temporaries)
@@ -221,7 +249,8 @@ def run_gpu_arm(args):
     from alpine_b200 import _native
     from alpine_b200.engine import MUEngine, shard_bounds
 
-    wl = dict(WORKLOAD)
+    sparse = args.workload == "cfg4"
+    wl = dict(WORKLOAD_CFG4 if sparse else WORKLOAD)
     if args.cells:
         wl["n_cells"] = args.cells
     if args.genes:
@@ -241,9 +270,23 @@ def run_gpu_arm(args):
     lo, hi = shard_bounds(n, world, rank)
     blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
 
-    X, Ys, W, H, Bs = synth_device_problem(dev, G, hi - lo, lo, wl)
     solver = _native.Solver(dev, G, hi - lo, blocks, wl["categories"])
-    solver.bind_dense(X)
+    nnz = 0
+    if sparse:
+        wl_small = dict(wl, n_genes=4)  # labels and factors from the dense generator, X from the CSR generator
+        _, Ys, _, H, Bs = synth_device_problem(dev, 4, hi - lo, lo, wl_small)
+        gw = torch.Generator(device=dev)
+        gw.manual_seed(42)
+        W = torch.rand((G, sum(blocks)), device=dev, generator=gw).clamp_(min=wl["eps"])
+        X = None
+        csr = synth_device_csr(dev, G, hi - lo, lo, wl)
+        nnz = int(csr[2].shape[0])
+        solver.bind_csr(*csr)
+        del csr
+        torch.cuda.empty_cache()
+    else:
+        X, Ys, W, H, Bs = synth_device_problem(dev, G, hi - lo, lo, wl)
+        solver.bind_dense(X)
     solver.bind_labels(Ys)
     solver.bind_factors(W, H, Bs)
     solver.set_hparams(wl["lam"], wl["alpha_W"], wl["l1_ratio_W"], wl["orth_W"], wl["eps"])
@@ -290,32 +333,38 @@ def run_gpu_arm(args):
     flops = 3.0 * 2.0 * G * n_loc * K          # 3xTF32: three tf32 MMAs per fp32 product
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     achieved = flops / (gemm_ms_avg * 1e-3) / 1e12 if gemm_ms_avg > 0 else 0.0
-    hbm_ms = 4.0 * G * n_loc / (peaks["hbm_gbs"] * 1e9) * 1e3
+    x_bytes = 8.0 * nnz if sparse else 4.0 * G * n_loc
+    if sparse:
+        flops = 2.0 * 2.0 * G * n_loc * K      # integer counts are tf32-exact: two tf32 MMAs per fp32 product
+    hbm_ms = x_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
     roofline = {
-        "kernel": "mu_gemm_kernel (X H^T and W^T X, 3xTF32 tcgen05)", "bound": "tensor",
+        "kernel": "mu_gemm_kernel (X H^T and W^T X, %s tcgen05)" % ("2xTF32 on tf32-exact counts, CSR tile lists" if sparse else "3xTF32"),
+        "bound": "tensor",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
         "traffic": None,
         "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (no TF32 figure in MEASURED_PEAKS.json; the "
                        f"kernel is timed inside the step loop)",
         "avg_launch_ms": gemm_ms_avg, "launches_timed": gemm_n,
         "hbm_bound_ms_per_launch": hbm_ms, "hbm_frac": hbm_ms / gemm_ms_avg if gemm_ms_avg > 0 else None,
-        "algorithmic": {"tf32_flop_per_launch": flops, "x_bytes_per_launch": 4.0 * G * n_loc},
+        "algorithmic": {"tf32_flop_per_launch": flops, "x_bytes_per_launch": x_bytes},
     }
 
     line = None
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "metric": METRIC if not sparse else "MU iterations/sec at 30k genes x 1M cells CSR, k=100", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
             "config": {"workload": wl["name"], "parallelism": f"cells sharded over {world} GPU(s)",
-                       "l2": "inputs larger than L2 (X is %.1f GB per GPU)" % (4.0 * G * n_loc / 1e9)},
+                       "l2": "inputs larger than L2 (X is %.1f GB per GPU)" % (x_bytes / 1e9)},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "final_loss": {"total": float(hist[-1, 0]), "reconstruction": float(hist[-1, 1])},
         }
     solver.close()
     del X, H, W
     torch.cuda.empty_cache()
+    if sparse:  # the sparse scaling workload has no host-API / CPU legs (the reference rejects sparse input)
+        args.no_e2e = args.no_cpu = True
 
     # ---- e2e through the public API with host buffers (N = 1 process; each rank runs the sharded fit under torchrun)
     if not args.no_e2e:
@@ -399,6 +448,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=0, help="override the workload's cell count (debugging)")
     ap.add_argument("--genes", type=int, default=0, help="override the workload's gene count (debugging)")
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg3 = the headline dense workload; cfg4 = BASELINE configs[3], 30k x 1M CSR (scaling study)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

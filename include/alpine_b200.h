@@ -49,6 +49,14 @@ int alpine_destroy(alpine_ctx* ctx);
 
 /* Bind the expression matrix (AlpineMatrices.X, main.py:445). */
 int alpine_bind_dense(alpine_ctx* ctx, const float* X_cells_major, int64_t ldX);
+/* Bind a SPARSE expression matrix instead (north_star's optional CSR variant; the reference itself rejects sparse
+ * input, main.py:395-396): device-resident CSR over cells, the layout AnnData keeps for count matrices --
+ * indptr[n_cells + 1] (int64), indices[nnz] (int32 gene ids, unique within a row), values[nnz] (fp32, finite, >= 0).
+ * The call converts the matrix once into the two tile-list copies the contraction kernel streams (8 bytes per
+ * nonzero each, csrc/csr_tiles.cuh), computes ||X||_F^2 and synchronises `stream`; the CSR arrays are not
+ * referenced afterwards.  Mathematically identical to alpine_bind_dense on the densified matrix.                */
+int alpine_bind_csr(alpine_ctx* ctx, const int64_t* indptr, const int32_t* indices, const float* values, int64_t nnz,
+                    void* stream);
 /* Bind the one-hot label matrix of covariate i (AlpineMatrices.Ys[i], main.py:446-449). */
 int alpine_bind_labels(alpine_ctx* ctx, int i, const float* Y);
 /* Bind the factor matrices that the updates mutate in place (AlpineMatrices.Ws/Hs/Bs, main.py:454-470). */

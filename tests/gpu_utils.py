@@ -14,20 +14,34 @@ def to_dev_padded(a: np.ndarray, device) -> torch.Tensor:
     return t
 
 
+def csr_to_dev(X_cells_by_genes, device):
+    """(indptr int64, indices int32, values fp32) device tensors of the CSR form (over cells) of a dense or scipy
+    matrix."""
+    import scipy.sparse as sp
+
+    m = sp.csr_matrix(X_cells_by_genes, dtype=np.float32)
+    m.sum_duplicates()
+    return (torch.from_numpy(m.indptr.astype(np.int64)).to(device), torch.from_numpy(m.indices.astype(np.int32)).to(device),
+            torch.from_numpy(m.data.astype(np.float32)).to(device))
+
+
 class DeviceProblem:
     """X (cells x genes), Ys (c_i x n), W0 (G x K), H0 (K x n), Bs0 on the GPU, bound to a native Solver."""
 
-    def __init__(self, X_cells_by_genes, Ys, W0, H0, Bs0, blocks, kw, device="cuda:0"):
+    def __init__(self, X_cells_by_genes, Ys, W0, H0, Bs0, blocks, kw, device="cuda:0", sparse=False):
         self.device = torch.device(device)
         n, G = X_cells_by_genes.shape
-        self.X = to_dev_padded(X_cells_by_genes, self.device)
+        self.X = None if sparse else to_dev_padded(X_cells_by_genes, self.device)
         self.Ys = [torch.from_numpy(np.ascontiguousarray(y, dtype=np.float32)).to(self.device) for y in Ys]
         self.W = torch.from_numpy(np.ascontiguousarray(W0, dtype=np.float32)).to(self.device)
         self.H = to_dev_padded(H0, self.device)
         self.Bs = [torch.from_numpy(np.ascontiguousarray(b, dtype=np.float32)).to(self.device) for b in Bs0]
         self.solver = _native.Solver(self.device, G, n, blocks, [y.shape[0] for y in Ys],
                                      kw.get("loss_type", "kl-divergence"))
-        self.solver.bind_dense(self.X)
+        if sparse:
+            self.solver.bind_csr(*csr_to_dev(X_cells_by_genes, self.device))
+        else:
+            self.solver.bind_dense(self.X)
         self.solver.bind_labels(self.Ys)
         self.solver.bind_factors(self.W, self.H, self.Bs)
         self.solver.set_hparams(kw.get("lam", []), kw.get("alpha_W", 0.0), kw.get("l1_ratio_W", 0.0),
@@ -48,10 +62,10 @@ class DeviceProblem:
         return self.W.cpu().numpy(), self.H.cpu().numpy(), [b.cpu().numpy() for b in self.Bs]
 
 
-def problem_from_golden(name, g, device="cuda:0") -> DeviceProblem:
+def problem_from_golden(name, g, device="cuda:0", sparse=False) -> DeviceProblem:
     n_cov = int(g["n_cov"])
     Ys = [np.ascontiguousarray(g[f"Y{i}_cells_by_cat"].T) for i in range(n_cov)]
     kw = dict(CASE_KW[name])
     kw.pop("use_als", None)
     return DeviceProblem(g["X_cells_by_genes"], Ys, g["W0"], g["H0"], [g[f"B0_{i}"] for i in range(n_cov)],
-                         [int(b) for b in g["blocks"]], kw, device)
+                         [int(b) for b in g["blocks"]], kw, device, sparse=sparse)
