@@ -46,6 +46,9 @@ SIGNATURES = {
     "alpine_batch_begin": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_partials": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_apply": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_reduce_stats_offset": (ctypes.c_int64, [_c_ctx]),
+    "alpine_als_block": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_als_finish": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_fit_losses": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]),
     "alpine_scale": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
@@ -257,6 +260,23 @@ class Solver:
 
     def mu_apply(self, it: int) -> None:
         _check(self.lib, self.lib.alpine_mu_apply(self._ctx, int(it), self._stream()))
+
+    # -- block Gauss-Seidel sweep (use_als=True, main.py:523-588) ------------------------------------------
+    @property
+    def n_blocks(self) -> int:
+        return len(self.k_blocks)
+
+    def gram_view(self) -> torch.Tensor:
+        """The H H^T part (K*K floats) of the reduce buffer: the per-block exchange of the ALS sweep."""
+        buf = self.reduce_buffer()
+        o = int(self.lib.alpine_reduce_stats_offset(self._ctx))
+        return buf[o:o + self.K * self.K]
+
+    def als_block(self, b: int) -> None:
+        _check(self.lib, self.lib.alpine_als_block(self._ctx, int(b), self._stream()))
+
+    def als_finish(self, it: int) -> None:
+        _check(self.lib, self.lib.alpine_als_finish(self._ctx, int(it), self._stream()))
 
     def losses(self, n_iter: int):
         """(||X||_F^2, rows[n_iter][2 + n_cov]) of this shard; synchronises the stream."""

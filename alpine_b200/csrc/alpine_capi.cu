@@ -93,15 +93,17 @@ struct GemmOperands {
   int orient = ORIENT_XH;
   const float* Xmem = nullptr;
   long long ldX = 0, rows = 0, cols = 0;
-  const float* Bsplit = nullptr;
+  const float* Bsplit = nullptr;  // hi copy of the whole K-row operand; the lo copy follows K * ldS floats later
   long long ldS = 0;
+  int k0 = 0, Kop = 0;            // component rows [k0, k0 + Kop) of the B operand take part (Kop = 0: all K)
   bool profiled = false;  // counted by alpine_profile (the two contractions over X)
   // sparse X: tile lists instead of Xmem (csr_tiles.cuh)
   const long long* sp_ofs = nullptr;
   const uint2* sp_ent = nullptr;
   const int* a_inexact = nullptr;
 };
-enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_COUNT = 4 };
+// PLAN_WX_BLOCK + b: W_b^T X of component block b alone (block Gauss-Seidel sweep, main.py:567)
+enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_WX_BLOCK = 4, PLAN_COUNT = 4 + kMaxCov + 1 };
 
 struct GemmPlan {
   bool valid = false;
@@ -316,14 +318,15 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   GemmParams& p = pl->p;
   p.M = static_cast<int>(M);
   p.R = static_cast<int>(R);
-  p.K = c->K;
-  p.Kp = c->Kp;
+  const int Kop = op.Kop > 0 ? op.Kop : c->K;
+  p.K = Kop;
+  p.Kp = static_cast<int>(round_up(Kop, 16));
   p.ws.num_tiles = ceil_div(M, rows);
   p.ws.kb_per_tile = ceil_div(R, kBK);
   // pieces of the reduction axis: keep the live window of the B operand (two pieces of its hi + lo copies) near
   // 16 MB so that it is served from L2 while X streams through with evict-first
   {
-    const double b_bytes = 2.0 * c->K * static_cast<double>(R) * sizeof(float);
+    const double b_bytes = 2.0 * Kop * static_cast<double>(R) * sizeof(float);
     long long piece_mb = 8;
     if (const char* e = getenv("ALPINE_B200_PIECE_MB")) piece_mb = atoll(e) > 0 ? atoll(e) : piece_mb;
     int pieces = static_cast<int>(b_bytes / (piece_mb * 1024.0 * 1024.0) + 0.999);
@@ -382,8 +385,9 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
     AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, rows, kBK, false));
   else
     AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, kBK, rows, true));
-  AL_TRY(make_map(&pl->tmBhi, op.Bsplit, R, c->K, op.ldS, kBK, p.Kp, true));
-  AL_TRY(make_map(&pl->tmBlo, op.Bsplit + static_cast<size_t>(c->K) * op.ldS, R, c->K, op.ldS, kBK, p.Kp, true));
+  const float* b_hi = op.Bsplit + static_cast<size_t>(op.k0) * op.ldS;
+  AL_TRY(make_map(&pl->tmBhi, b_hi, R, Kop, op.ldS, kBK, p.Kp, true));
+  AL_TRY(make_map(&pl->tmBlo, b_hi + static_cast<size_t>(c->K) * op.ldS, R, Kop, op.ldS, kBK, p.Kp, true));
   ReduceParams& r = pl->r;
   r.partial = c->partial;
   r.rows = rows;
@@ -428,10 +432,17 @@ GemmOperands plan_operands(const alpine_ctx* c, int which) {
       op.orient = ORIENT_WX, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
       op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.a_inexact = c->flags + 1;
       break;
-    default:           // T[b][a] = sum_g W^T[a][g] W^T[b][g]        (W^T W of main.py:654 after the reformulation)
+    case PLAN_GRAM_W:  // T[b][a] = sum_g W^T[a][g] W^T[b][g]        (W^T W of main.py:654 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
       op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.a_inexact = c->flags + 1;
       break;
+    default: {         // A[k][j] = sum_g X[j][g] W^T[k][g] for the rows k of one component block     (main.py:567)
+      op = plan_operands(c, PLAN_WX);
+      const int b = which - PLAN_WX_BLOCK;
+      for (int i = 0; i < b; ++i) op.k0 += c->kblk[i];
+      op.Kop = c->kblk[b];
+      break;
+    }
   }
   return op;
 }
@@ -449,7 +460,7 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
   GemmPlan* pl = &c->plans[which];
   if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which)));
   const GemmOperands& op = pl->op;
-  if (c->simt && op.sp_ofs == nullptr) {
+  if (c->simt && op.sp_ofs == nullptr && which < PLAN_WX_BLOCK) {
     const float* Bsrc = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->H : c->WT;
     const long long ldB = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->ldH : c->ldG;
     dim3 grid(ceil_div(pl->p.M, 128), c->K);
@@ -477,11 +488,11 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
   r.ld = ld_out;
   if (pl->p.ws.num_tiles * 8 >= 2 * c->num_sms) {
     int gy = ceil_div(32 * c->num_sms, pl->p.ws.num_tiles * 8);
-    const int gy_max = ceil_div(c->K, 8);
+    const int gy_max = ceil_div(pl->p.K, 8);
     if (gy > gy_max) gy = gy_max;
     reduce_partials_by_k_kernel<<<dim3(pl->p.ws.num_tiles * 8, gy), 256, 0, st>>>(r);
   } else {
-    reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, c->K), 256, 0, st>>>(r);
+    reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, pl->p.K), 256, 0, st>>>(r);
   }
   LAUNCH_CHECK();
   return ALPINE_OK;
@@ -569,7 +580,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 3; }
+int alpine_abi_version(void) { return 4; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -802,6 +813,9 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
+  // split copies of the whole W^T: the simultaneous update rewrites all of them before their first use, the
+  // block-wise sweep (alpine_als_block) only the rows of the block it has just updated
+  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_stats(c, nullptr, false, st));
   c->fit_active = true;
   return ALPINE_OK;
@@ -819,6 +833,9 @@ int alpine_batch_begin(alpine_ctx* c, void* stream) {
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
+  // split copies of the whole W^T: the simultaneous update rewrites all of them before their first use, the
+  // block-wise sweep (alpine_als_block) only the rows of the block it has just updated
+  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_stats(c, nullptr, false, st));
   c->fit_active = true;
   return ALPINE_OK;
@@ -844,6 +861,7 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   w.Mat = c->WT;
   w.ldM = c->ldG;
   w.K = c->K;
+  w.r0 = 0, w.r1 = c->K;
   w.L = c->G;
   w.Num = c->red_Pt();
   w.ldNum = c->ldG;
@@ -891,6 +909,7 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   h.Mat = c->H;
   h.ldM = c->ldH;
   h.K = c->K;
+  h.r0 = 0, h.r1 = c->K;
   h.L = c->n;
   h.Num = c->A;
   h.ldNum = c->ldN;
@@ -908,6 +927,100 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   // ---- statistics of the new H for the next iteration + loss terms of this one (main.py:666, 726-753)
   AL_TRY(run_stats(c, c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov), true, st));
   return ALPINE_OK;
+}
+
+int64_t alpine_reduce_stats_offset(const alpine_ctx* c) { return c ? static_cast<int64_t>(c->K) * c->ldG : 0; }
+
+int alpine_als_block(alpine_ctx* c, int b, void* stream) {
+  AL_TRY(check_bound(c, true));
+  if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
+  if (b < 0 || b >= c->n_blocks) return fail(ALPINE_ERR_ARG, "block %d outside [0, %d)", b, c->n_blocks);
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int r0 = 0;
+  for (int i = 0; i < b; ++i) r0 += c->kblk[i];
+  const int r1 = r0 + c->kblk[b];
+  // ---- W_b update (main.py:527-545): den = 2 W_cat (H_cat H_b^T) + (1-l1) alpha W_b + W_b orth(k_b) + l1 alpha
+  SymLongParams w{};
+  w.Sym = c->red_S();
+  w.ldS = c->K;
+  w.Mat = c->WT;
+  w.ldM = c->ldG;
+  w.K = c->K;
+  w.r0 = r0, w.r1 = r1;
+  w.L = c->G;
+  w.Num = c->red_Pt();  // X H^T of the iteration's first sweep: H_b is still the H it was computed from
+  w.ldNum = c->ldG;
+  w.c1 = static_cast<float>((1.0 - c->l1) * c->alpha);
+  w.c2 = static_cast<float>(c->l1 * c->alpha);
+  w.orth = static_cast<float>(c->orth);
+  w.eps = static_cast<float>(c->eps);
+  w.split_hi = c->Wsplit;
+  w.split_lo = c->Wsplit + static_cast<size_t>(c->K) * c->ldG;
+  w.ld_split = c->ldG;
+  AL_TRY(run_sym_long<EPI_W>(c, w, st));
+  // ---- B_b update (main.py:548-562) from the statistics of (H_b, B_b), both unchanged since they were taken
+  CovTable one;
+  one.n_cov = 0;
+  if (b < c->n_cov) {
+    const CovTable tab = make_cov_table(c);
+    one.n_cov = 1;
+    one.d[0] = tab.d[b];
+    b_update_kernel<<<1, 128, c->ccov[b] * c->kblk[b] * sizeof(float), st>>>(one, c->loss_type, c->red_Q(), c->red_hsum(),
+                                                                             c->red_S(), c->K, (float)c->eps);
+    LAUNCH_CHECK();
+  }
+  // ---- T = W^T W with the new W_b, A_b = W_b^T X (main.py:565-568): one sweep of X with a k_b-wide B operand
+  AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));
+  AL_TRY(run_gemm(c, PLAN_WX_BLOCK + b, c->A + static_cast<size_t>(r0) * c->ldN, c->ldN, st));
+  if (b < c->n_cov) {
+    const size_t smem = (static_cast<size_t>(c->ccov[b]) * c->kblk[b] + 3ull * c->kblk[b] * 128) * sizeof(float);
+    if (smem > 200 * 1024) return fail(ALPINE_ERR_ARG, "covariate block too large for the guided-terms kernel");
+    guided_terms_kernel<<<dim3(ceil_div(c->n, 128), 1), 128, smem, st>>>(one, c->loss_type, c->H, c->ldH, (int)c->n,
+                                                                        (float)c->eps, c->numG, c->denG, c->ldN);
+    LAUNCH_CHECK();
+  }
+  // ---- H_b update (main.py:570-588): den = 2 (W_b^T W_cat) H_cat + guided terms
+  SymLongParams h{};
+  h.Sym = c->T;
+  h.ldS = c->K;
+  h.Mat = c->H;
+  h.ldM = c->ldH;
+  h.K = c->K;
+  h.r0 = r0, h.r1 = r1;
+  h.L = c->n;
+  h.Num = c->A;
+  h.ldNum = c->ldN;
+  h.numG = c->numG;
+  h.denG = c->denG;
+  h.ldD = c->ldN;
+  h.Kg = c->Kg;
+  h.eps = static_cast<float>(c->eps);
+  h.t1_partial = nullptr;  // the loss terms are taken once all blocks are done (alpine_als_finish)
+  h.rowsum_partial = c->hsum_partial;
+  h.split_hi = c->Hsplit;
+  h.split_lo = c->Hsplit + static_cast<size_t>(c->K) * c->ldN;
+  h.ld_split = c->ldN;
+  AL_TRY(run_sym_long<EPI_H>(c, h, st));
+  // ---- the next block's W update needs H_cat H^T with this block's new rows (this shard's part; all-reduced by
+  //      the caller under cell sharding).  The last block's is taken by alpine_als_finish.
+  if (b + 1 < c->n_blocks) AL_TRY(run_gemm(c, PLAN_GRAM_H, c->red_S(), c->K, st));
+  return ALPINE_OK;
+}
+
+int alpine_als_finish(alpine_ctx* c, int iter, void* stream) {
+  AL_TRY(check_bound(c, true));
+  if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
+  if (iter < 0 || iter >= c->loss_cap) return fail(ALPINE_ERR_ARG, "iteration %d outside [0, %d)", iter, c->loss_cap);
+  CU_TRY(cudaSetDevice(c->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
+                                                                                       c->W, c->ldW);
+  LAUNCH_CHECK();
+  // every A_b was formed with its final W_b, every H_b is final: t1 = sum A .* H (main.py:666 via the trace identity)
+  dot_partial_kernel<<<c->sl_blocks_n, 256, 0, st>>>(c->A, c->ldN, c->H, c->ldH, c->K, c->n, c->t1_partial);
+  LAUNCH_CHECK();
+  return run_stats(c, c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov), true, st);
 }
 
 int alpine_fit_losses(alpine_ctx* c, int n_iter, double* xnorm2, double* rows, void* stream) {
@@ -965,6 +1078,7 @@ int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
   h.Mat = c->H;
   h.ldM = c->ldH;
   h.K = c->K;
+  h.r0 = 0, h.r1 = c->K;
   h.L = c->n;
   h.Num = c->A;
   h.ldNum = c->ldN;

@@ -293,6 +293,10 @@ struct SymLongParams {
   float* split_hi;      // EPI_W / EPI_H: tf32 hi / lo copies of the updated matrix (B operand of the next
   float* split_lo;      //                contraction), pitch ld_split; nullptr to skip
   long long ld_split;
+  // rows [r0, r1) of Mat are updated (all K rows take part in Z).  The whole matrix for the simultaneous update
+  // (main.py:589-663); one component block for the block Gauss-Seidel ("ALS") sweep (main.py:523-588), where the
+  // orthogonality term also only couples the columns of that block (main.py:541).
+  int r0, r1;
 };
 constexpr int kSLKI = 8;  // rows per thread: K <= 128 (the contraction kernel's limit as well)
 inline int sym_long_pitch(int K) { return (K + 3) / 4 * 4 + 4; }  // Ss row pitch (floats)
@@ -357,7 +361,7 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
     // rowsum_k W[g][:] in fp64 so that (rowsum - w) does not cancel (the reference sums the other K-1 entries)
     if (tid < kSLCols) {
       double sacc = 0.0;
-      for (int k = 0; k < p.K; ++k) sacc += static_cast<double>(Ms[k * kSLCols + tid]);
+      for (int k = p.r0; k < p.r1; ++k) sacc += static_cast<double>(Ms[k * kSLCols + tid]);
       cs[tid] = sacc;
     }
     __syncthreads();
@@ -370,7 +374,7 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
 #pragma unroll
   for (int i = 0; i < KI; ++i) {
     const int k = ty + 16 * i;
-    if (k >= p.K || col >= p.L) continue;
+    if (k < p.r0 || k >= p.r1 || col >= p.L) continue;
     const float4 old4 = reinterpret_cast<const float4*>(Ms)[k * 16 + tx];
     const float oldv[4] = {old4.x, old4.y, old4.z, old4.w};
     const float zv[4] = {acc[i].x, acc[i].y, acc[i].z, acc[i].w};
@@ -452,10 +456,10 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
       v += __shfl_xor_sync(0xffffffffu, v, 2);
       v += __shfl_xor_sync(0xffffffffu, v, 1);
       const int k = ty + 16 * i;
-      if (tx == 0 && k < p.K) p.rowsum_partial[static_cast<size_t>(blockIdx.x) * p.K + k] = v;
+      if (tx == 0 && k >= p.r0 && k < p.r1) p.rowsum_partial[static_cast<size_t>(blockIdx.x) * p.K + k] = v;
     }
   }
-  if (EPI == EPI_H) {
+  if (EPI == EPI_H && p.t1_partial != nullptr) {
     for (int o = 16; o > 0; o >>= 1) t1 += __shfl_down_sync(0xffffffffu, t1, o);
     if ((tid & 31) == 0) red[tid >> 5] = t1;
     __syncthreads();
@@ -537,6 +541,28 @@ __global__ void __launch_bounds__(256) stats_finish_kernel(const StatsFinishPara
   }
   const double r = block_sum_256(acc, red);
   if (threadIdx.x == 0) p.loss_row[which] = r;
+}
+
+// t1 partials  sum A .* H  over 64-column blocks (same layout as the EPI_H partials), for the block-wise sweep where
+// no single H-update launch sees all rows
+__global__ void __launch_bounds__(256) dot_partial_kernel(const float* __restrict__ A, long long ldA,
+                                                          const float* __restrict__ H, long long ldH, int K, long long L,
+                                                          double* __restrict__ partial) {
+  __shared__ double red[256];
+  const long long c0 = static_cast<long long>(blockIdx.x) * kSLCols;
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < K * kSLCols; e += 256) {
+    const int k = e / kSLCols;
+    const long long col = c0 + (e - k * kSLCols);
+    if (col < L) acc += static_cast<double>(A[k * ldA + col]) * static_cast<double>(H[k * ldH + col]);
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
 // column sums of W (main.py:776) = row sums of W^T, one block per component, fp64 accumulation, fixed order

@@ -35,6 +35,7 @@ class ShardSolver(Protocol):
     def fit_begin(self, max_iter: int) -> None: ...
     def mu_partials(self) -> None: ...
     def mu_apply(self, it: int) -> None: ...
+    # block Gauss-Seidel sweep only: n_blocks, als_block(b), gram_view(), als_finish(it)
     def losses(self, n_iter: int) -> Tuple[float, np.ndarray]: ...
 
 
@@ -50,10 +51,11 @@ def dist_info(group=None) -> Tuple[int, int]:
 class MUEngine:
     """Runs ``max_iter`` full-batch MU iterations on this rank's shard and returns the global loss history."""
 
-    def __init__(self, solver: ShardSolver, lam: Sequence[float], group=None):
+    def __init__(self, solver: ShardSolver, lam: Sequence[float], group=None, use_als: bool = False):
         self.solver = solver
         self.lam = [float(v) for v in lam]
         self.group = group
+        self.use_als = bool(use_als)
         self.rank, self.world = dist_info(group)
 
     def _all_reduce(self, t: torch.Tensor) -> None:
@@ -79,12 +81,30 @@ class MUEngine:
     def step(self, it: int) -> None:
         """One full-batch MU iteration (asynchronous on the current stream)."""
         s = self.solver
+        if self.use_als:
+            return self._als_step(it)
         s.mu_partials()        # X H^T of this shard into the reduce buffer (main.py:596)
         # The iteration's only data-path collective.  The statistics part [H H^T | rowsum(H) | B statistics]
         # still holds this shard's values (written by fit_begin / the previous mu_apply), so one message
         # carries everything the W and B updates need.
         self._all_reduce(self._buf)
         s.mu_apply(it)         # W, B, H updates + loss terms (main.py:597-663, 726-753)
+
+    def _als_step(self, it: int) -> None:
+        """One block Gauss-Seidel sweep (use_als=True, main.py:523-588): blocks in order, each W_b, B_b, H_b.
+
+        X H_b^T is needed with the H_b the block starts from, which is the H of the iteration start for every b, so
+        one sweep of X (and one all-reduce of the packed buffer) serves all blocks; after a block's H update only
+        H H^T changes for the blocks that follow: K*K floats are exchanged per block."""
+        s = self.solver
+        s.mu_partials()
+        self._all_reduce(self._buf)
+        n_blocks = s.n_blocks
+        for b in range(n_blocks):
+            s.als_block(b)
+            if b + 1 < n_blocks:
+                self._all_reduce(s.gram_view())
+        s.als_finish(it)
 
     def collect_losses(self, n_iter: int) -> np.ndarray:
         xn, rows = self.solver.losses(n_iter)

@@ -425,15 +425,11 @@ class ALPINE:
         full_batch = self.batch_size >= m.n_total
         if self.sampling_method not in ("random", "weighted"):
             raise ValueError(f"Unknown sampling method: {self.sampling_method}. Only 'weighted', and 'random' are supported.")
-        if self.use_als:
-            raise NotImplementedError(
-                "alpine_b200 implements the multiplicative-update path (use_als=False); the block Gauss-Seidel "
-                "variant of the reference (main.py:523-588) is listed as a next step in DESIGN.md")
         if not full_batch or self.sampling_method == "weighted":
             return self._fit_minibatch(m)
         solver = self._make_solver(m)
         try:
-            engine = MUEngine(solver, self.lam)
+            engine = MUEngine(solver, self.lam, use_als=self.use_als)
             pbar = None
             if self.verbose:
                 from tqdm import tqdm
@@ -510,7 +506,12 @@ class ALPINE:
                         yb.copy_(y.index_select(1, idx))
                     s.batch_begin()
                     s.mu_partials()
-                    s.mu_apply(0)
+                    if self.use_als:  # main.py:523-588 on the batch
+                        for blk in range(s.n_blocks):
+                            s.als_block(blk)
+                        s.als_finish(0)
+                    else:
+                        s.mu_apply(0)
                     m.H[:, idx] = Hb  # main.py:662; duplicates of the weighted sampler carry identical columns
                 history.append(self._compute_loss(m, solver=full, xnorm2=xnorm2))
                 if pbar is not None:

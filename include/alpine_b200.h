@@ -84,6 +84,16 @@ int alpine_mu_partials(alpine_ctx* ctx, void* stream);
  * (main.py:615-628), H update (main.py:631-663), loss terms of iteration `iter` (main.py:666, 726-753) and
  * the statistics for the next iteration.                                                                  */
 int alpine_mu_apply(alpine_ctx* ctx, int iter, void* stream);
+/* Block Gauss-Seidel ("ALS") sweep, use_als=True (main.py:523-588).  One iteration is
+ *   alpine_mu_partials            X H^T for all blocks in one sweep of X (every H_b is still unchanged when its W_b
+ *                                 update consumes its columns)           [+ all-reduce of the whole reduce buffer]
+ *   for b in 0 .. n_blocks-1:     alpine_als_block(ctx, b): W_b, B_b, H_b updates (main.py:527-588), one k_b-wide
+ *                                 sweep of X for W_b^T X, then this shard's new H H^T into the reduce buffer
+ *                                 [+ all-reduce of its K*K floats at alpine_reduce_stats_offset, except after the last]
+ *   alpine_als_finish(ctx, iter)  row-major W, loss terms of the iteration, statistics for the next one.          */
+int64_t alpine_reduce_stats_offset(const alpine_ctx* ctx);
+int alpine_als_block(alpine_ctx* ctx, int block, void* stream);
+int alpine_als_finish(alpine_ctx* ctx, int iter, void* stream);
 /* Synchronise and read back the loss terms: xnorm2 = ||X||_F^2 and, per iteration, 2 + n_cov doubles
  * [ tr(W^T X H^T), tr(W^T W H H^T), pred_0, ... ] of THIS shard; all are additive across shards and
  * recon = xnorm2 - 2*t1 + t2 (the trace identity that replaces main.py:736).  Also reports kernel faults. */

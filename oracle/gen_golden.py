@@ -68,6 +68,11 @@ CASES = {
         n_cells=160, n_genes=96, cats=[3], rank=5, n_iter=6, batch_size=50, sampling_method="weighted",
         kw=dict(n_components=6, n_covariate_components=[3], lam=[1e3], alpha_W=0.3),
     ),
+    "mb_als": dict(
+        n_cells=150, n_genes=90, cats=[3, 2], rank=5, n_iter=5, batch_size=64,
+        kw=dict(n_components=6, n_covariate_components=[3, 2], lam=[1e2, 1e3],
+                orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, use_als=True),
+    ),
     "kl_long200": dict(
         n_cells=500, n_genes=300, cats=[3], rank=8, n_iter=200, keep_every=200,
         kw=dict(n_components=9, n_covariate_components=[3], lam=[1e3],

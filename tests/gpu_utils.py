@@ -48,12 +48,17 @@ class DeviceProblem:
                                 kw.get("orth_W", 0.0), kw.get("eps", 1e-6))
         self.solver.reduce_buffer()
 
-    def run(self, n_iter, on_iter=None):
+    def run(self, n_iter, on_iter=None, use_als=False):
         s = self.solver
         s.fit_begin(n_iter)
         for it in range(n_iter):
             s.mu_partials()
-            s.mu_apply(it)
+            if use_als:  # block Gauss-Seidel sweep (main.py:523-588)
+                for b in range(s.n_blocks):
+                    s.als_block(b)
+                s.als_finish(it)
+            else:
+                s.mu_apply(it)
             if on_iter is not None:
                 on_iter(it + 1)
         return s.losses(n_iter)

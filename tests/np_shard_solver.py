@@ -105,5 +105,56 @@ class NumpyShardSolver:
         t2 = float(np.sum(T.astype(np.float64) * S2.astype(np.float64)))
         self.rows.append([t1, t2] + pred)
 
+    # ---- block Gauss-Seidel sweep (same split as alpine_als_block / alpine_als_finish)
+    @property
+    def n_blocks(self):
+        return len(self.blocks)
+
+    def gram_view(self):
+        o = self.K * self.G
+        return self._buf[o:o + self.K * self.K]
+
+    def als_block(self, b):
+        hp = self.hp
+        Pt, S, hs, Qs = self._views()
+        eps = np.float32(hp.eps)
+        sl = self.sl[b]
+        W, H = self.W, self.H
+        c1, c2 = np.float32((1 - hp.l1_ratio_W) * hp.alpha_W), np.float32(hp.l1_ratio_W * hp.alpha_W)
+        Wb = W[:, sl]
+        den = 2 * (W @ S[:, sl]) + c1 * Wb + np.float32(hp.orth_W) * (Wb.sum(axis=1, keepdims=True) - Wb) + c2
+        W[:, sl] = Wb * ((2 * Pt[sl].T) / np.maximum(den, eps))
+        if b < self.n_cov:
+            B, lam = self.Bs[b], np.float32(hp.lam[b])
+            if hp.loss_type == "kl-divergence":
+                B *= (lam * Qs[b]) / np.maximum(lam * hs[sl][None, :], eps)
+            else:
+                B *= (2 * Qs[b]) / np.maximum((2 * B) @ S[sl, sl], eps)
+        T = W.T @ W
+        if not hasattr(self, "A"):
+            self.A = np.zeros_like(H)
+        self.A[sl] = W[:, sl].T @ self.X
+        num = 2 * self.A[sl]
+        den = 2 * (T[sl] @ H)
+        if b < self.n_cov:
+            B, lam, Hi, Y = self.Bs[b], np.float32(hp.lam[b]), H[sl], self.Ys[b]
+            if hp.loss_type == "kl-divergence":
+                num = num + (lam * B.T) @ (Y / np.maximum(B @ Hi, eps))
+                den = den + (lam * B.T) @ np.ones_like(Y)
+            else:
+                num = num + (2 * lam * B.T) @ Y
+                den = den + (2 * lam * B.T) @ (B @ Hi)
+        H[sl] = H[sl] * (num / np.maximum(den, eps))
+        if b + 1 < len(self.blocks):
+            S[...] = H @ H.T
+
+    def als_finish(self, it):
+        t1 = float(np.sum(self.A.astype(np.float64) * self.H.astype(np.float64)))
+        pred = self._stats()
+        _, S2, _, _ = self._views()
+        T = self.W.T @ self.W
+        t2 = float(np.sum(T.astype(np.float64) * S2.astype(np.float64)))
+        self.rows.append([t1, t2] + pred)
+
     def losses(self, n_iter):
         return self.xn, np.asarray(self.rows[:n_iter], dtype=np.float64).reshape(n_iter, 2 + self.n_cov)

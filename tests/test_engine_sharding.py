@@ -52,7 +52,7 @@ def _run_rank(rank, world, port, name, n_iter, out_dir):
         solver = NumpyShardSolver(np.ascontiguousarray(X[:, lo:hi]), [np.ascontiguousarray(y[:, lo:hi]) for y in Ys],
                                   st.W.copy(), np.ascontiguousarray(st.H[:, lo:hi]), [b.copy() for b in st.Bs],
                                   st.blocks, hp)
-        engine = MUEngine(solver, hp.lam)
+        engine = MUEngine(solver, hp.lam, use_als=CASE_KW[name].get("use_als", False))
         assert (engine.rank, engine.world) == (rank, world)
         hist = engine.run(n_iter)
         np.savez(os.path.join(out_dir, f"rank{rank}.npz"), W=solver.W, H=solver.H, hist=hist, lo=lo, hi=hi,
@@ -61,14 +61,14 @@ def _run_rank(rank, world, port, name, n_iter, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["kl_reg_nan", "frob_reg"])
+@pytest.mark.parametrize("name", ["kl_reg_nan", "frob_reg", "als_reg"])
 def test_two_rank_run_matches_oracle(name, tmp_path):
     world, n_iter = 2, 5
     mp.spawn(_run_rank, args=(world, _free_port(), name, n_iter, str(tmp_path)), nprocs=world, join=True)
     g = load_golden(name)
     hp = hp_of(name)
     X, Ys, st = inputs_of(g)
-    hist_ref, _ = orc.fit_loop(X, Ys, st, hp, n_iter)
+    hist_ref, _ = orc.fit_loop(X, Ys, st, hp, n_iter, use_als=CASE_KW[name].get("use_als", False))
     ref64 = orc.compute_loss(X, Ys, st, hp, dtype=np.float64)
     parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     H = np.concatenate([p["H"] for p in parts], axis=1)

@@ -122,10 +122,38 @@ def test_fit_with_automatic_max_iter():
     assert len(model.loss_history) == model.max_iter
 
 
+def test_als_public_fit_matches_oracle():
+    ad = _adata(n=400, G=250, cats=(3, 4), nan_fraction=0.03)
+    keys = ["cov0", "cov1"]
+    model = ALPINE(device="cuda:0", use_als=True, **KW)
+    model.covariate_keys, model.sampling_method, model.verbose = keys, "random", False
+    from alpine_b200.utils.encoder import FeatureEncoders
+
+    model.fe = FeatureEncoders(keys)
+    Y = model.fe.fit_transform(ad.obs)
+    X = np.ascontiguousarray(ad.X, dtype=np.float32).T
+    model.batch_size, model.max_iter = X.shape[1], 6
+    m = model._initialize_matrices(X, Y)
+    st = orc.State(m.W.cpu().numpy().copy(), m.H.cpu().numpy().copy(), [b.cpu().numpy().copy() for b in m.Bs],
+                   list(model.n_all_components))
+    hp = orc.HyperParams(**KW)
+    Ys = [np.ascontiguousarray(y.T) for y in Y]
+    model._fit(m)
+    orc.fit_loop(X, Ys, st, hp, 6, use_als=True)
+    assert rel_fro(m.W.cpu().numpy(), st.W) < 2e-5 and rel_fro(m.H.cpu().numpy(), st.H) < 2e-5
+    ref64 = orc.compute_loss(X, Ys, st, hp, dtype=np.float64)
+    assert abs(model.loss_history["reconstruction loss"].iloc[-1] - ref64[1]) / ref64[1] < 1e-4
+    out = ALPINE(device="cuda", use_als=True, **KW).fit(ad, keys, max_iter=5)
+    assert len(out.loss_history) == 5 and np.isfinite(out.loss_history.to_numpy()).all()
+
+
 def test_unsupported_modes_raise():
+    import scipy.sparse as sp
+
     ad = _adata(n=200, G=100, cats=(3,), nan_fraction=0.0)
-    with pytest.raises(NotImplementedError):
-        ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0], use_als=True).fit(ad, ["cov0"], max_iter=2)
+    ad.X = sp.csr_matrix(ad.X)
+    with pytest.raises(NotImplementedError):  # the CSR path is full-batch
+        ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0]).fit(ad, ["cov0"], max_iter=2, batch_size=50)
 
 
 def _model_on_golden(name, g, **extra):
@@ -157,7 +185,7 @@ def _model_on_golden(name, g, **extra):
     return model, m
 
 
-@pytest.mark.parametrize("name", ["mb_random", "mb_weighted"])
+@pytest.mark.parametrize("name", ["mb_random", "mb_weighted", "mb_als"])
 def test_minibatch_epochs_match_reference_golden(name):
     """Mini-batch epochs (main.py:509-521, 589-663) replaying the index streams the reference's sampler produced
     (oracle/gen_golden.py): ragged last batch, and duplicate cells inside a batch for the weighted sampler."""

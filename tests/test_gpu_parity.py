@@ -115,6 +115,64 @@ def test_trajectory_matches_reference_golden(name):
     np.testing.assert_allclose(recon_hist, ref_hist[:, 1], rtol=2e-3)
 
 
+@pytest.mark.parametrize("sparse", [False, True])
+def test_als_trajectory_matches_reference_golden(sparse):
+    """use_als=True (block Gauss-Seidel sweep, main.py:523-588) against the unmodified reference's trajectory."""
+    gu = _gpu_utils()
+    name = "als_reg"
+    g = load_golden(name)
+    kept = [int(i) for i in g["kept_iters"]]
+    n_cov = int(g["n_cov"])
+    prob = gu.problem_from_golden(name, g, sparse=sparse)
+
+    def check(it):
+        if it in kept:
+            W, H, Bs = prob.host()
+            assert rel_fro(W, g[f"W_it{it}"]) < EXPECTED_TOL, (it, "W")
+            assert rel_fro(H, g[f"H_it{it}"]) < EXPECTED_TOL, (it, "H")
+            for i in range(n_cov):
+                assert rel_fro(Bs[i], g[f"B{i}_it{it}"]) < PARITY_TOL, (it, f"B{i}")
+
+    n_iter = max(kept)
+    xn, rows = prob.run(n_iter, on_iter=check, use_als=True)
+    recon = xn - 2.0 * rows[-1, 0] + rows[-1, 1]
+    assert abs(recon - float(g["final_recon_fp64"])) / float(g["final_recon_fp64"]) < PARITY_TOL
+    ref_hist = g["loss_history_ref_fp32"]
+    np.testing.assert_allclose(xn - 2.0 * rows[:, 0] + rows[:, 1], ref_hist[:, 1], rtol=2e-3)
+    for i in range(n_cov):
+        np.testing.assert_allclose(rows[:, 2 + i], ref_hist[:, 2 + i], rtol=1e-3, atol=1e-6 * prob.solver.n)
+
+
+def test_als_matches_oracle_at_wider_blocks():
+    """ALS with component blocks wider than one MMA N-group (k_b = 40, 24, 36) and a ragged cell count."""
+    gu = _gpu_utils()
+    from alpine_b200.utils.synth import labels_to_dummies, make_counts, make_labels
+
+    n, G, blocks = 1531, 900, [40, 24, 36]
+    kw = dict(n_components=36, n_covariate_components=[40, 24], lam=[1e2, 3e2], orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5)
+    X = make_counts(n, G, seed=4, rank=10)
+    Ycg, _ = labels_to_dummies(make_labels(n, [5, 3], seed=4, nan_fraction=0.02))
+    Ys = [np.ascontiguousarray(y.T) for y in Ycg]
+    rng = np.random.default_rng(1)
+    K = sum(blocks)
+    W0 = np.maximum(rng.random((G, K), dtype=np.float32), 1e-6)
+    H0 = np.maximum(rng.random((K, n), dtype=np.float32), 1e-6)
+    B0 = [np.maximum(rng.random((c, k), dtype=np.float32), 1e-6) for c, k in zip([5, 3], blocks)]
+    hp = orc.HyperParams(**kw)
+    st = orc.State(W0.copy(), H0.copy(), [b.copy() for b in B0], blocks)
+    prob = gu.DeviceProblem(X, Ys, W0, H0, B0, blocks, kw)
+
+    def check(it):
+        orc.als_step(X.T, Ys, st, hp)
+        W, H, Bs = prob.host()
+        assert max(rel_fro(W, st.W), rel_fro(H, st.H)) < EXPECTED_TOL, it
+        assert max(rel_fro(a, b) for a, b in zip(Bs, st.Bs)) < PARITY_TOL, it
+
+    xn, rows = prob.run(6, on_iter=check, use_als=True)
+    ref = orc.compute_loss(X.T, Ys, st, hp, dtype=np.float64)
+    assert abs((xn - 2.0 * rows[-1, 0] + rows[-1, 1]) - ref[1]) / ref[1] < PARITY_TOL
+
+
 def test_trajectory_matches_oracle_cfg1_shapes():
     """BASELINE config[0] shapes (2,000 genes x 5,000 cells, 20+[5] components) for 10 iterations vs the oracle."""
     gu = _gpu_utils()
