@@ -100,7 +100,6 @@ struct GemmOperands {
   // sparse X: tile lists instead of Xmem (csr_tiles.cuh)
   const long long* sp_ofs = nullptr;
   const uint2* sp_ent = nullptr;
-  const int* a_inexact = nullptr;
 };
 // PLAN_WX_BLOCK + b: W_b^T X of component block b alone (block Gauss-Seidel sweep, main.py:567)
 enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_WX_BLOCK = 4, PLAN_COUNT = 4 + kMaxCov + 1 };
@@ -137,7 +136,8 @@ struct alpine_ctx {
   long long* sp_ofs[2] = {nullptr, nullptr};
   uint2* sp_ent[2] = {nullptr, nullptr};
   double* sp_xnorm2 = nullptr;
-  int* flags = nullptr;  // [0] X has values that are not tf32-exact, [1] constant 1 (operands that are never exact)
+  int* flags = nullptr;  // device: [0] raised by the ||X||^2 pass when some X value is not tf32-exact
+  bool x_exact = false;  // host copy of !flags[0] once that pass has run: X needs no lo half (count matrices)
   const float* Y[kMaxCov] = {nullptr};
   float* W = nullptr;
   long long ldW = 0;
@@ -221,7 +221,7 @@ int set_kernel_attrs();
 int ensure_flags(alpine_ctx* c) {
   if (c->flags != nullptr) return ALPINE_OK;
   AL_TRY(dev_alloc(&c->flags, 2));
-  const int init[2] = {1, 1};  // conservative until a pass over X has looked at the values
+  const int init[2] = {1, 1};
   CU_TRY(cudaMemcpy(c->flags, init, sizeof(init), cudaMemcpyHostToDevice));
   return ALPINE_OK;
 }
@@ -263,11 +263,11 @@ int ensure_workspace(alpine_ctx* c) {
 
 int set_kernel_attrs() {
   const int big = 227 * 1024;
-#define ALPINE_GEMM_ATTR1(O, NC, SRC) \
-  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<O, NC, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-#define ALPINE_GEMM_ATTR(NC)                                                             \
-  ALPINE_GEMM_ATTR1(ORIENT_XH, NC, SRC_DENSE) ALPINE_GEMM_ATTR1(ORIENT_WX, NC, SRC_DENSE) \
-  ALPINE_GEMM_ATTR1(ORIENT_XH, NC, SRC_TILES) ALPINE_GEMM_ATTR1(ORIENT_WX, NC, SRC_TILES)
+#define ALPINE_GEMM_ATTR1(O, NC, EX) \
+  CU_TRY(cudaFuncSetAttribute(mu_gemm_kernel<O, NC, EX>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+#define ALPINE_GEMM_ATTR(NC)                                                     \
+  ALPINE_GEMM_ATTR1(ORIENT_XH, NC, false) ALPINE_GEMM_ATTR1(ORIENT_WX, NC, false) \
+  ALPINE_GEMM_ATTR1(ORIENT_XH, NC, true) ALPINE_GEMM_ATTR1(ORIENT_WX, NC, true)
   ALPINE_GEMM_ATTR(1) ALPINE_GEMM_ATTR(2) ALPINE_GEMM_ATTR(3) ALPINE_GEMM_ATTR(4)
   ALPINE_GEMM_ATTR(5) ALPINE_GEMM_ATTR(6) ALPINE_GEMM_ATTR(7) ALPINE_GEMM_ATTR(8)
 #undef ALPINE_GEMM_ATTR
@@ -292,12 +292,12 @@ int prof_mark(alpine_ctx* c, cudaStream_t st) {
   return ALPINE_OK;
 }
 
-template <int ORIENT, int SRC>
+template <int ORIENT, bool EXACT>
 int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
   switch (pl.p.Kp / 16) {
 #define ALPINE_GEMM_CASE(NC)                                                                     \
   case NC:                                                                                       \
-    mu_gemm_kernel<ORIENT, NC, SRC><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmBhi, pl.tmBlo, pl.p); \
+    mu_gemm_kernel<ORIENT, NC, EXACT><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmBhi, pl.tmBlo, pl.p); \
     break;
     ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
     ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
@@ -323,11 +323,11 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   p.Kp = static_cast<int>(round_up(Kop, 16));
   p.ws.num_tiles = ceil_div(M, rows);
   p.ws.kb_per_tile = ceil_div(R, kBK);
-  // pieces of the reduction axis: keep the live window of the B operand (two pieces of its hi + lo copies) near
-  // 16 MB so that it is served from L2 while X streams through with evict-first
+  // pieces of the reduction axis: the live window of the B operand (one piece of its hi + lo copies, two around
+  // a piece boundary) stays in L2 (evict-last) while X streams through with evict-first
   {
     const double b_bytes = 2.0 * Kop * static_cast<double>(R) * sizeof(float);
-    long long piece_mb = 8;
+    long long piece_mb = 24;
     if (const char* e = getenv("ALPINE_B200_PIECE_MB")) piece_mb = atoll(e) > 0 ? atoll(e) : piece_mb;
     int pieces = static_cast<int>(b_bytes / (piece_mb * 1024.0 * 1024.0) + 0.999);
     if (pieces < 1 || p.ws.num_tiles == 1) pieces = 1;
@@ -339,12 +339,7 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   }
   const long long total = p.ws.total();
   pl->grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
-  const long long per_cta = (total + pl->grid - 1) / pl->grid;
-  {
-    const int last_len = p.ws.len_of_piece(p.ws.pieces - 1);
-    const int min_len = last_len < p.ws.piece_len ? last_len : p.ws.piece_len;
-    p.max_segs = ceil_div(per_cta, min_len) + 2;
-  }
+  p.max_segs = max_segments_per_cta(p.ws, pl->grid);
   // pipeline depths from the shared-memory budget
   const size_t budget = 227 * 1024 - 1024;
   int sb = 4, sx = 0;
@@ -358,8 +353,6 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   if (const char* e = getenv("ALPINE_B200_SX")) sx = atoi(e) < sx ? (atoi(e) < 1 ? 1 : atoi(e)) : sx;
   p.sx = sx;
   p.sb = sb;
-  p.chunk = 8;
-  if (const char* e = getenv("ALPINE_B200_CHUNK")) p.chunk = atoi(e) > 0 ? atoi(e) : p.chunk;
   pl->smem = gemm_smem_layout(p.Kp, sx, sb).total + 1024;
   // partial-sum slots (one buffer shared by all plans: contractions run one after the other on the stream)
   const size_t need = static_cast<size_t>(pl->grid) * p.max_segs * p.K * rows;
@@ -377,7 +370,6 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   p.err = c->err;
   p.sp_ofs = op.sp_ofs;
   p.sp_ent = op.sp_ent;
-  p.a_inexact = op.a_inexact;
   // tensor maps: Xmem is [rows][cols] (inner = cols)
   if (op.sp_ofs != nullptr)
     memset(&pl->tmX, 0, sizeof(pl->tmX));  // the tile-list producer does not use TMA for X
@@ -419,22 +411,20 @@ GemmOperands plan_operands(const alpine_ctx* c, int which) {
     case PLAN_XH:  // P^T[k][g] = sum_j X[j][g] H[k][j]                                   (main.py:596)
       op.orient = ORIENT_XH, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
       op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.profiled = true;
-      op.a_inexact = c->flags;
       if (c->sparse) op.Xmem = nullptr, op.sp_ofs = c->sp_ofs[ORIENT_XH], op.sp_ent = c->sp_ent[ORIENT_XH];
       break;
     case PLAN_WX:  // A[k][j] = sum_g X[j][g] W^T[k][g]                                   (main.py:653)
       op.orient = ORIENT_WX, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
       op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.profiled = true;
-      op.a_inexact = c->flags;
       if (c->sparse) op.Xmem = nullptr, op.sp_ofs = c->sp_ofs[ORIENT_WX], op.sp_ent = c->sp_ent[ORIENT_WX];
       break;
     case PLAN_GRAM_H:  // S[b][a] = sum_j H[a][j] H[b][j]            (H H^T of main.py:599 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
-      op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.a_inexact = c->flags + 1;
+      op.Bsplit = c->Hsplit, op.ldS = c->ldN;
       break;
     case PLAN_GRAM_W:  // T[b][a] = sum_g W^T[a][g] W^T[b][g]        (W^T W of main.py:654 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
-      op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.a_inexact = c->flags + 1;
+      op.Bsplit = c->Wsplit, op.ldS = c->ldG;
       break;
     default: {         // A[k][j] = sum_g X[j][g] W^T[k][g] for the rows k of one component block     (main.py:567)
       op = plan_operands(c, PLAN_WX);
@@ -472,15 +462,16 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
     return ALPINE_OK;
   }
   if (op.profiled) AL_TRY(prof_mark(c, st));
-  if (op.sp_ofs != nullptr) {
+  // op.profiled marks the contractions whose A operand is X; only those can use the count-matrix variant
+  if (op.profiled && c->x_exact) {
     if (op.orient == ORIENT_XH)
-      AL_TRY((launch_gemm_t<ORIENT_XH, SRC_TILES>(*pl, st)));
+      AL_TRY((launch_gemm_t<ORIENT_XH, true>(*pl, st)));
     else
-      AL_TRY((launch_gemm_t<ORIENT_WX, SRC_TILES>(*pl, st)));
+      AL_TRY((launch_gemm_t<ORIENT_WX, true>(*pl, st)));
   } else if (op.orient == ORIENT_XH) {
-    AL_TRY((launch_gemm_t<ORIENT_XH, SRC_DENSE>(*pl, st)));
+    AL_TRY((launch_gemm_t<ORIENT_XH, false>(*pl, st)));
   } else {
-    AL_TRY((launch_gemm_t<ORIENT_WX, SRC_DENSE>(*pl, st)));
+    AL_TRY((launch_gemm_t<ORIENT_WX, false>(*pl, st)));
   }
   if (op.profiled) AL_TRY(prof_mark(c, st));
   ReduceParams r = pl->r;
@@ -664,10 +655,7 @@ int alpine_bind_dense(alpine_ctx* c, const float* X, int64_t ldX) {
   c->X = X;
   c->ldX = ldX;
   c->sparse = false;
-  if (c->flags) {
-    const int one = 1;
-    CU_TRY(cudaMemcpy(c->flags, &one, sizeof(int), cudaMemcpyHostToDevice));
-  }
+  c->x_exact = false;  // until alpine_fit_begin has looked at the values
   for (auto& pl : c->plans) pl.valid = false;
   return ALPINE_OK;
 }
@@ -728,9 +716,10 @@ int alpine_bind_csr(alpine_ctx* c, const int64_t* indptr, const int32_t* indices
   sum_double_kernel<<<1, 32, 0, st>>>(partial, 1024, c->sp_xnorm2);
   g_launches.fetch_add(6, std::memory_order_relaxed);
   CSR_TRY(cudaGetLastError());
-  int h_err[2] = {0, 0};
+  int h_err[2] = {0, 0}, h_inexact = 1;
   long long total = 0;
   CSR_TRY(cudaMemcpyAsync(h_err, err, sizeof(h_err), cudaMemcpyDeviceToHost, st));
+  CSR_TRY(cudaMemcpyAsync(&h_inexact, c->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
   CSR_TRY(cudaMemcpyAsync(&total, c->sp_ofs[ORIENT_WX] + nb_wx, sizeof(long long), cudaMemcpyDeviceToHost, st));
   CSR_TRY(cudaStreamSynchronize(st));
 #undef CSR_TRY
@@ -740,6 +729,7 @@ int alpine_bind_csr(alpine_ctx* c, const int64_t* indptr, const int32_t* indices
   if (total != nnz) return fail(ALPINE_ERR_ARG, "indptr covers %lld nonzeros but nnz = %lld", total, (long long)nnz);
   c->X = nullptr;
   c->sparse = true;
+  c->x_exact = (h_inexact == 0);
   c->nnz = nnz;
   for (auto& pl : c->plans) pl.valid = false;
   return ALPINE_OK;
@@ -808,6 +798,10 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
     LAUNCH_CHECK();
     sum_double_kernel<<<1, 32, 0, st>>>(c->sumsq_partial, sb, c->xnorm2);
     LAUNCH_CHECK();
+    int h_inexact = 1;  // one 4-byte read-back per fit selects the 2-MMA kernel variant for count matrices
+    CU_TRY(cudaMemcpyAsync(&h_inexact, c->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    c->x_exact = (h_inexact == 0);
   }
   // W^T master copy for the gene-side kernels
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,

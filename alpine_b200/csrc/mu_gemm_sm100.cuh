@@ -21,17 +21,20 @@
 //    Alo*Bhi + Ahi*Blo + Ahi*Bhi (small terms first).  The tensor core accumulates with round-toward-zero, so
 //    after every `chunk` k-blocks the accumulator is drained into an fp32 master sum held in the registers of
 //    the epilogue threads (round-to-nearest adds); the drain of one tile overlaps the MMAs of the other.
-//  * Work split: the (super-tile, k-block) space is cut into gridDim.x equal contiguous ranges (stream-K).  Every
-//    contiguous piece of one tile ("segment") is stored to a partial-sum slot; reduce_partials_kernel adds the
-//    slots of a tile in a fixed order, so results are deterministic and no CTA ever waits for another.
+//  * Work split (stream-K inside pieces): the reduction axis is cut into pieces whose B-operand window fits L2;
+//    the (super-tile, k-block) units of every piece are cut into gridDim.x equal contiguous ranges, so all CTAs
+//    move through the pieces together and the small operand is read from HBM about once.  Every contiguous
+//    run inside one tile ("segment") is stored to a partial-sum slot; the reduce kernels add the slots of a
+//    tile in a fixed order, so results are deterministic and no CTA ever waits for another.
 //  * One MMA-issuing warp per 128-row tile: a 128x112x8 tf32 MMA lasts only ~56 cycles, so a single issuing
 //    thread (and any per-instruction register shuffling) would leave the tensor pipe idle.
 //  * Every mbarrier wait is bounded (clock64): a protocol bug reports an error code instead of hanging the GPU.
 //  * SRC_TILES (sparse X): instead of TMA, the X-producer warp expands per-(super-tile, k-block) nonzero lists
 //    (csr_tiles.cuh, built once from the CSR matrix) into the same dense shared-memory tile, so HBM only sees
 //    8 bytes per nonzero while everything downstream (split, TMEM staging, MMAs, drains) is unchanged.
-//  * Count matrices: when every X value is exactly representable in tf32 (integers < 2048, detected on the
-//    device), the lo half of A is zero and the Alo*Bhi products are skipped (2 instead of 3 MMAs per k-step).
+//  * Count matrices (EXACT): when every X value is exactly representable in tf32 (integers < 2048, detected by
+//    the pass that computes ||X||^2), the lo half of A is zero and the Alo*Bhi products are skipped (2 instead
+//    of 3 MMAs per k-step).
 #pragma once
 #include <vector>
 
@@ -95,6 +98,30 @@ struct WorkSpace {
   __host__ __device__ long long run_begin(int pc, int tile) const {
     return static_cast<long long>(pc) * num_tiles * piece_len + static_cast<long long>(tile) * len_of_piece(pc);
   }
+  // Share of CTA `cta` in piece pc: the piece's (tile, k-block) units are cut into `grid` equal contiguous ranges,
+  // so all CTAs walk through the pieces together and only one piece of the B operand is live at a time.
+  __host__ __device__ void cta_range(int pc, int grid, int cta, long long& b, long long& e) const {
+    const long long units = static_cast<long long>(num_tiles) * len_of_piece(pc);
+    const long long base = static_cast<long long>(pc) * num_tiles * piece_len;
+#ifdef ALPINE_B200_GLOBAL_SPLIT  // A/B build only: one contiguous range per CTA over the whole piece-major order
+    const long long gb = total() * cta / grid, ge = total() * (cta + 1) / grid;
+    b = gb > base ? gb : base;
+    e = ge < base + units ? ge : base + units;
+    if (e < b) e = b;
+#else
+    b = base + units * cta / grid;
+    e = base + units * (cta + 1) / grid;
+#endif
+  }
+  // number of segments (contiguous runs inside one tile) CTA `cta` executes in piece pc
+  __host__ __device__ int cta_segments(int pc, int grid, int cta) const {
+    long long b, e;
+    cta_range(pc, grid, cta, b, e);
+    if (e <= b) return 0;
+    const long long base = static_cast<long long>(pc) * num_tiles * piece_len;
+    const int lp = len_of_piece(pc);
+    return static_cast<int>((e - 1 - base) / lp - (b - base) / lp) + 1;
+  }
 };
 
 struct GemmParams {
@@ -105,25 +132,26 @@ struct GemmParams {
   WorkSpace ws;     // num_tiles = ceil(M / 256), kb_per_tile = ceil(R / 32), piece decomposition
   int sx;           // X ring depth
   int sb;           // B ring depth
-  int chunk;        // k-blocks accumulated in TMEM between two round-to-nearest flushes
   int max_segs;     // partial slots per CTA
   float* partial;   // [gridDim.x * max_segs][K][256]
   int* err;         // [8]
   // SRC_TILES: nonzeros of X grouped by (super-tile, k-block); entry = {x_tile_offset, fp32 bits}
-  const long long* sp_ofs;  // [num_tiles * kb_per_tile + 1]
+  const long long* sp_ofs;  // [num_tiles * kb_per_tile + 1]; nullptr => dense X through TMA
   const uint2* sp_ent;
-  const int* a_inexact;     // device flag: 0 => every A value is tf32-exact (lo == 0), skip the Alo*Bhi MMAs
 };
 
 // Walks the k-blocks of a CTA's stream-K range in execution order.
 struct KbIter {
   WorkSpace ws;
   long long pos, end;
-  int tile, kb, left;
-  __device__ KbIter(const WorkSpace& w, long long b, long long e) : ws(w), pos(b), end(e), tile(0), kb(0), left(0) {}
+  int tile, kb, left, pc, grid, cta;
+  __device__ KbIter(const WorkSpace& w, int g, int c) : ws(w), pos(0), end(0), tile(0), kb(0), left(0), pc(-1), grid(g), cta(c) {}
   __device__ bool next(long long& blk) {
     if (left == 0) {
-      if (pos >= end) return false;
+      while (pos >= end) {
+        if (++pc >= ws.pieces) return false;
+        ws.cta_range(pc, grid, cta, pos, end);
+      }
       int run;
       ws.decode(pos, run, tile, kb, left);
       if (left > end - pos) left = static_cast<int>(end - pos);
@@ -181,6 +209,19 @@ __device__ __forceinline__ bool warp_wait_bar(uint64_t* bar, uint32_t parity, co
   return __all_sync(0xffffffffu, ok);
 }
 
+// Position in a ring of n slots without integer division: slot index and parity of the completed wraps.
+struct RingPos {
+  int s = 0;
+  uint32_t ph = 0;
+  __device__ __forceinline__ void advance(int n) {
+    if (++s == n) {
+      s = 0;
+      ph ^= 1u;
+    }
+  }
+};
+constexpr int kChunk = 8;  // k-blocks accumulated in TMEM between two round-to-nearest flushes (power of two)
+
 // Fixed geometry: a super-tile is 2 MMA tiles (256 rows of X); 8 converter/epilogue warps, one thread per row.
 constexpr int kMT = 2;
 constexpr int kRows = kMT * kBM;
@@ -205,7 +246,7 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int Kp, int sx, int s
 
 // NC = Kp / 16: number of 16-column groups of the accumulator (compile time: the fp32 master sum of a thread's
 // accumulator row lives in 16*NC registers).
-template <int ORIENT, int NC, int SRC>
+template <int ORIENT, int NC, bool EXACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
@@ -218,7 +259,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int SX = p.sx, SB = p.sb, C = p.chunk;
+  const int SX = p.sx, SB = p.sb;
+  constexpr int C = kChunk;
   const GemmSmemLayout lay = gemm_smem_layout(Kp, SX, SB);
   uint8_t* smem_x = smem + lay.x_off;
   uint8_t* smem_b = smem + lay.b_off;
@@ -257,7 +299,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     *abort_flag = 0;
     ptx::fence_barrier_init();
   }
-  if (SRC == SRC_DENSE && warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
+  const bool tiles = p.sp_ofs != nullptr;  // SRC_TILES
+  if (!tiles && warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
   if (warp == kWarpBProd && lane == 0) {
     ptx::prefetch_tensormap(&tmBhi);
     ptx::prefetch_tensormap(&tmBlo);
@@ -271,19 +314,21 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const WorkSpace ws = p.ws;
-  const long long total = ws.total();
   const int cta = blockIdx.x;
-  const long long range_begin = gemm_range_begin(total, gridDim.x, cta);
-  const long long range_end = gemm_range_begin(total, gridDim.x, cta + 1);
-  const bool a_exact = (*p.a_inexact == 0);
 
-  if (warp == kWarpXProd && SRC == SRC_TILES) {
+  if (warp == kWarpXProd && tiles) {
     // ===================================================== sparse producer of the X ring (whole warp)
     // Per k-block: zero the 32 KB stage, then scatter the block's nonzeros.  Entry loads run one k-block ahead
     // (registers), their offsets two k-blocks ahead, so no global-memory latency sits on the ring's critical path.
     constexpr int NE = 16;  // entries per lane kept in registers: 512 per k-block (mean at 5 % density: 410)
     const uint32_t smem_x_u32 = ptx::smem_u32(smem_x);
-    KbIter ahead(ws, range_begin, range_end);
+    KbIter ahead(ws, gridDim.x, cta);
+    long long my_units = 0;
+    for (int pc = 0; pc < ws.pieces; ++pc) {
+      long long b, e;
+      ws.cta_range(pc, gridDim.x, cta, b, e);
+      my_units += e - b;
+    }
     long long blk = 0, o_beg = 0, o_end = 0, cur_beg = 0;
     int cur_cnt = 0;
     uint2 cur[NE], nxt[NE];
@@ -306,8 +351,9 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
     }
     bool ok = true;
-    for (uint32_t it = 0; it < static_cast<uint32_t>(range_end - range_begin) && ok; ++it) {
-      const int s = it % SX;
+    RingPos rx;
+    for (uint32_t it = 0; it < static_cast<uint32_t>(my_units) && ok; ++it, rx.advance(SX)) {
+      const int s = rx.s;
       // entries of the next k-block, offsets of the one after
       const long long nxt_beg = o_beg;
       const int nxt_cnt = have_next ? static_cast<int>(o_end - o_beg) : 0;
@@ -319,7 +365,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           o_end = __ldg(p.sp_ofs + blk + 1);
         }
       }
-      if (!warp_wait_bar(&xempty_bar[s], ((it / SX) & 1) ^ 1, actx, ERR_XPROD_EMPTY, it, s)) {
+      if (!warp_wait_bar(&xempty_bar[s], rx.ph ^ 1u, actx, ERR_XPROD_EMPTY, it, s)) {
         ok = false;
         break;
       }
@@ -348,13 +394,17 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;
       bool ok = true;
+      RingPos rx;
+      for (int pc = 0; pc < ws.pieces && ok; ++pc) {
+      long long range_begin, range_end;
+      ws.cta_range(pc, gridDim.x, cta, range_begin, range_end);
       for (long long pos = range_begin; pos < range_end && ok;) {
         int run, tile, kb0, len;
         ws.decode(pos, run, tile, kb0, len);
         if (len > range_end - pos) len = static_cast<int>(range_end - pos);
-        for (int kb = kb0; kb < kb0 + len; ++kb, ++it) {
-          const int s = it % SX;
-          if (!wait_bar(&xempty_bar[s], ((it / SX) & 1) ^ 1, actx, ERR_XPROD_EMPTY, it, s)) {
+        for (int kb = kb0; kb < kb0 + len; ++kb, ++it, rx.advance(SX)) {
+          const int s = rx.s;
+          if (!wait_bar(&xempty_bar[s], rx.ph ^ 1u, actx, ERR_XPROD_EMPTY, it, s)) {
             ok = false;
             break;
           }
@@ -367,6 +417,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
         pos += len;
       }
+      }
     }
     __syncwarp();
   } else if (warp == kWarpBProd) {
@@ -374,13 +425,17 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     if (lane == 0) {
       uint32_t it = 0;
       bool ok = true;
+      RingPos rb;
+      for (int pc = 0; pc < ws.pieces && ok; ++pc) {
+      long long range_begin, range_end;
+      ws.cta_range(pc, gridDim.x, cta, range_begin, range_end);
       for (long long pos = range_begin; pos < range_end && ok;) {
         int run, tile, kb0, len;
         ws.decode(pos, run, tile, kb0, len);
         if (len > range_end - pos) len = static_cast<int>(range_end - pos);
-        for (int kb = kb0; kb < kb0 + len; ++kb, ++it) {
-          const int s = it % SB;
-          if (!wait_bar(&bempty_bar[s], ((it / SB) & 1) ^ 1, actx, ERR_BPROD_EMPTY, it, s)) {
+        for (int kb = kb0; kb < kb0 + len; ++kb, ++it, rb.advance(SB)) {
+          const int s = rb.s;
+          if (!wait_bar(&bempty_bar[s], rb.ph ^ 1u, actx, ERR_BPROD_EMPTY, it, s)) {
             ok = false;
             break;
           }
@@ -390,6 +445,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           ptx::tma_load_2d(dst + b_tile_bytes, &tmBlo, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
         }
         pos += len;
+      }
       }
     }
     __syncwarp();
@@ -402,19 +458,22 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t smem_b_u32 = __shfl_sync(0xffffffffu, ptx::smem_u32(smem_b), 0);
     const uint32_t idesc = ptx::make_idesc_tf32(kBM, Kp);
     const uint32_t d_acc = tb + mt * kAccStride;
-    const bool ex = __shfl_sync(0xffffffffu, a_exact ? 1 : 0, 0) != 0;  // warp-uniform by construction
     uint32_t it = 0, mc = 0;  // k-block counter, chunk counter
     bool ok = true;
+    RingPos rb;
+    for (int pc = 0; pc < ws.pieces && ok; ++pc) {
+    long long range_begin, range_end;
+    ws.cta_range(pc, gridDim.x, cta, range_begin, range_end);
     for (long long pos = range_begin; pos < range_end && ok;) {
       int run, tile, kb0, len;
       ws.decode(pos, run, tile, kb0, len);
       if (len > range_end - pos) len = static_cast<int>(range_end - pos);
-      for (int li = 0; li < len; ++li, ++it) {
+      for (int li = 0; li < len; ++li, ++it, rb.advance(SB)) {
         const int t = it % kAStages;
-        const int sbi = it % SB;
+        const int sbi = rb.s;
         const bool c_first = (li % C) == 0;
         const bool c_last = (li % C) == C - 1 || li == len - 1;
-        if (!warp_wait_bar(&bfull_bar[sbi], (it / SB) & 1, actx, ERR_MMA_BFULL, it, sbi) ||
+        if (!warp_wait_bar(&bfull_bar[sbi], rb.ph, actx, ERR_MMA_BFULL, it, sbi) ||
             !warp_wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
           ok = false;
           break;
@@ -437,8 +496,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           const uint64_t bh = dhi + static_cast<uint64_t>(2 * ks);
           const uint64_t bl = dlo + static_cast<uint64_t>(2 * ks);
           const uint32_t fresh = (c_first && ks == 0) ? 0u : 1u;
-          if (!ex) ptx::mma_tf32_ts_if(leader, d_acc, a_lo + ks * kUmmaK, bh, idesc, fresh);
-          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bl, idesc, ex ? fresh : 1u);
+          if (!EXACT) ptx::mma_tf32_ts_if(leader, d_acc, a_lo + ks * kUmmaK, bh, idesc, fresh);
+          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bl, idesc, EXACT ? fresh : 1u);
           ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bh, idesc, 1u);
         }
         if (c_last) {
@@ -450,6 +509,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       pos += len;
     }
+    }
     __syncwarp();
   } else {
     // ===================================================== converter + flush/epilogue warps (one thread per X row)
@@ -460,6 +520,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t smem_x_u32 = ptx::smem_u32(smem_x);
     uint32_t it = 0, fc = 0, seg = 0;  // k-block counter, flushed-chunk counter, segment counter
     bool ok = true;
+    RingPos rx;
     // fp32 master sum of this thread's accumulator row.  The tensor core adds into its accumulator with
     // round-toward-zero, which biases long sums of positive terms low (~2.5e-8 per MMA); chunks of C k-blocks
     // are therefore summed here with round-to-nearest.
@@ -485,12 +546,15 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       return true;
     };
 
+    for (int pc = 0; pc < ws.pieces && ok; ++pc) {
+    long long range_begin, range_end;
+    ws.cta_range(pc, gridDim.x, cta, range_begin, range_end);
     for (long long pos = range_begin; pos < range_end && ok; ++seg) {
       int run, tile, kb0, len;
       ws.decode(pos, run, tile, kb0, len);
       if (len > range_end - pos) len = static_cast<int>(range_end - pos);
-      for (int li = 0; li < len; ++li, ++it) {
-        const int s = it % SX;
+      for (int li = 0; li < len; ++li, ++it, rx.advance(SX)) {
+        const int s = rx.s;
         const int t = it % kAStages;
         // ---- lagged flush: the chunk that ended kAStages k-blocks ago (its MMAs are the ones the aempty wait
         //      below waits for anyway), overlapped with the other tile's MMAs
@@ -501,7 +565,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         }
         // ---- X tile: shared memory fp32 -> (hi, lo) -> tensor memory stage t
-        if (!warp_wait_bar(&xfull_bar[s], (it / SX) & 1, actx, ERR_CONV_XFULL, it, s) ||
+        if (!warp_wait_bar(&xfull_bar[s], rx.ph, actx, ERR_CONV_XFULL, it, s) ||
             !warp_wait_bar(&aempty_bar[t], ((it / kAStages) & 1) ^ 1, actx, ERR_CONV_AEMPTY, it, t)) {
           ok = false;
           break;
@@ -529,7 +593,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
           ptx::tmem_st_x8(a_addr + 8 * h, hi);
-          if (!a_exact) ptx::tmem_st_x8(a_addr + 32 + 8 * h, lo);
+          if (!EXACT) ptx::tmem_st_x8(a_addr + 32 + 8 * h, lo);
         }
         ptx::tc_wait_st();
         ptx::tc_fence_before();
@@ -553,6 +617,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       pos += len;
     }
+    }
   }
 
   ptx::tc_fence_before();
@@ -575,20 +640,30 @@ struct ReduceParams {
 };
 // Host side: the slots that hold tile `tile` (same enumeration the kernel uses for its segment numbering).
 inline void reduce_slots_of_tile(const WorkSpace& ws, int grid, int max_segs, int tile, std::vector<int>* out) {
-  const long long total = ws.total();
   for (int pc = 0; pc < ws.pieces; ++pc) {
     const long long r_begin = ws.run_begin(pc, tile), r_end = r_begin + ws.len_of_piece(pc);
-    int c = static_cast<int>(r_begin * grid / total);
-    while (c + 1 < grid && gemm_range_begin(total, grid, c + 1) <= r_begin) ++c;
-    while (c > 0 && gemm_range_begin(total, grid, c) > r_begin) --c;
-    for (int q = c; q < grid && gemm_range_begin(total, grid, q) < r_end; ++q) {
-      const long long b = gemm_range_begin(total, grid, q), e = gemm_range_begin(total, grid, q + 1);
-      if (e <= b) continue;
-      int run0, t0, k0, l0;
-      ws.decode(b, run0, t0, k0, l0);  // the CTA's first run; its segments are numbered from there
-      out->push_back(q * max_segs + (pc * ws.num_tiles + tile - run0));
+    const long long base = static_cast<long long>(pc) * ws.num_tiles * ws.piece_len;
+    const int lp = ws.len_of_piece(pc);
+    for (int q = 0; q < grid; ++q) {
+      long long b, e;
+      ws.cta_range(pc, grid, q, b, e);
+      if (e <= b || e <= r_begin || b >= r_end) continue;
+      int before = 0;  // segments CTA q has stored in earlier pieces, then earlier tiles of this piece
+      for (int p2 = 0; p2 < pc; ++p2) before += ws.cta_segments(p2, grid, q);
+      const int first_tile = static_cast<int>((b - base) / lp);
+      out->push_back(q * max_segs + before + (tile - first_tile));
     }
   }
+}
+// Largest number of segments any CTA stores (slots per CTA).
+inline int max_segments_per_cta(const WorkSpace& ws, int grid) {
+  int best = 1;
+  for (int q = 0; q < grid; ++q) {
+    int n = 0;
+    for (int pc = 0; pc < ws.pieces; ++pc) n += ws.cta_segments(pc, grid, q);
+    best = n > best ? n : best;
+  }
+  return best;
 }
 // Few slots per tile (the X contractions): grid = (num_tiles * 8, gy); block = (tile, 32-row group); lane = row
 // (coalesced 128-byte reads), each warp owns a strided set of components and adds the tile's slots in order.
