@@ -370,6 +370,7 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
   p.err = c->err;
   p.sp_ofs = op.sp_ofs;
   p.sp_ent = op.sp_ent;
+  p.sp_total = c->nnz;
   // tensor maps: Xmem is [rows][cols] (inner = cols)
   if (op.sp_ofs != nullptr)
     memset(&pl->tmX, 0, sizeof(pl->tmX));  // the tile-list producer does not use TMA for X

@@ -5,8 +5,8 @@
 //   ORIENT_XH  (X H^T,  main.py:596):  rows = genes, reduction = cells   -> block (g / 256, j / 32)
 //   ORIENT_WX  (W^T X,  main.py:653):  rows = cells, reduction = genes   -> block (j / 256, g / 32)
 //
-// and every entry carries the byte offset of its element inside the dense shared-memory tile plus the fp32 value,
-// so the producer warp of the kernel only zero-fills a stage and scatters.  8 bytes per nonzero and orientation,
+// and every entry carries the byte offset of its element inside the shared-memory tile (row-major, 128-byte rows,
+// TMA-style swizzle; the same form for both orientations) plus the fp32 value, so the producer warp only scatters.  8 bytes per nonzero and orientation,
 // read front to back with coalesced 256-byte warp loads; the order of the entries inside a block is irrelevant
 // (distinct positions), so the atomically assigned slots do not make results non-deterministic.  Column ids must
 // be unique within a row (canonical CSR: scipy's sum_duplicates()).
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(256) csr_tile_fill_kernel(const CsrView m, int
       {
         const long long blk = static_cast<long long>(g >> 8) * kb_xh + (j >> 5);
         const unsigned int slot = atomicAdd(cur_xh + blk, 1u);
-        ent_xh[ofs_xh[blk] + slot] = make_uint2(x_tile_offset(ORIENT_XH, g & 255, static_cast<int>(j & 31)), bits);
+        ent_xh[ofs_xh[blk] + slot] = make_uint2(x_tile_offset(ORIENT_WX, g & 255, static_cast<int>(j & 31)), bits);
       }
       {
         const long long blk = (j >> 8) * kb_wx + (g >> 5);

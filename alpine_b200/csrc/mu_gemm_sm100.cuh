@@ -29,9 +29,13 @@
 //  * One MMA-issuing warp per 128-row tile: a 128x112x8 tf32 MMA lasts only ~56 cycles, so a single issuing
 //    thread (and any per-instruction register shuffling) would leave the tensor pipe idle.
 //  * Every mbarrier wait is bounded (clock64): a protocol bug reports an error code instead of hanging the GPU.
-//  * SRC_TILES (sparse X): instead of TMA, the X-producer warp expands per-(super-tile, k-block) nonzero lists
-//    (csr_tiles.cuh, built once from the CSR matrix) into the same dense shared-memory tile, so HBM only sees
-//    8 bytes per nonzero while everything downstream (split, TMEM staging, MMAs, drains) is unchanged.
+//  * SRC_TILES (sparse X): instead of TMA, the X-producer warp scatters per-(super-tile, k-block) nonzero lists
+//    (csr_tiles.cuh, built once from the CSR matrix) into a zeroed shared-memory tile, so HBM only sees 8 bytes
+//    per nonzero while everything downstream (split, TMEM staging, MMAs, drains) is unchanged.  The tile is
+//    row-major + swizzled for both orientations (the lists carry ready-made offsets), and every converter
+//    thread clears the 128 bytes it has just read, so a stage returns to the producer already zeroed: no
+//    zero-fill traffic through L2 (the L2->SM path, ~43 B/cycle/SM, is what bounds this kernel) and no
+//    single-warp memset.
 //  * Count matrices (EXACT): when every X value is exactly representable in tf32 (integers < 2048, detected by
 //    the pass that computes ||X||^2), the lo half of A is zero and the Alo*Bhi products are skipped (2 instead
 //    of 3 MMAs per k-step).
@@ -57,6 +61,7 @@ enum { SRC_DENSE = 0, SRC_TILES = 1 };
 
 // Byte offset of element (row of the 256-row super-tile, reduction column of the 32-deep k-block) inside the
 // shared-memory X tile, i.e. where the TMA box of the dense path puts it (and where the converters read it).
+// The tile lists of the sparse path use the ORIENT_WX form for both contractions.
 __host__ __device__ inline uint32_t x_tile_offset(int orient, int row, int col) {
   if (orient == ORIENT_XH) return static_cast<uint32_t>(col * 256 + row) * 4u;  // [32][256], no swizzle
   return static_cast<uint32_t>(row) * 128u + (static_cast<uint32_t>((col >> 2) ^ (row & 7)) << 4) +
@@ -138,6 +143,7 @@ struct GemmParams {
   // SRC_TILES: nonzeros of X grouped by (super-tile, k-block); entry = {x_tile_offset, fp32 bits}
   const long long* sp_ofs;  // [num_tiles * kb_per_tile + 1]; nullptr => dense X through TMA
   const uint2* sp_ent;
+  long long sp_total;       // entries in sp_ent
 };
 
 // Walks the k-blocks of a CTA's stream-K range in execution order.
@@ -301,6 +307,10 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
   const bool tiles = p.sp_ofs != nullptr;  // SRC_TILES
   if (!tiles && warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
+  if (tiles) {  // the sparse producer only scatters nonzeros: stages start zeroed and are re-zeroed by their readers
+    const uint32_t base = ptx::smem_u32(smem_x);
+    for (int i = threadIdx.x; i < SX * (kXTileBytes / 16); i += kGemmThreads) ptx::sts_zero_v4(base + i * 16);
+  }
   if (warp == kWarpBProd && lane == 0) {
     ptx::prefetch_tensormap(&tmBhi);
     ptx::prefetch_tensormap(&tmBlo);
@@ -318,8 +328,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   if (warp == kWarpXProd && tiles) {
     // ===================================================== sparse producer of the X ring (whole warp)
-    // Per k-block: zero the 32 KB stage, then scatter the block's nonzeros.  Entry loads run one k-block ahead
-    // (registers), their offsets two k-blocks ahead, so no global-memory latency sits on the ring's critical path.
+    // Per k-block: scatter the block's nonzeros into a stage its readers left zeroed.  Entry loads run one k-block
+    // ahead (registers), their offsets two k-blocks ahead, so no global-memory latency sits on the critical path.
     constexpr int NE = 16;  // entries per lane kept in registers: 512 per k-block (mean at 5 % density: 410)
     const uint32_t smem_x_u32 = ptx::smem_u32(smem_x);
     KbIter ahead(ws, gridDim.x, cta);
@@ -358,6 +368,12 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       const long long nxt_beg = o_beg;
       const int nxt_cnt = have_next ? static_cast<int>(o_end - o_beg) : 0;
       load_entries(nxt_beg, nxt_cnt, nxt);
+      {
+        // The lists of consecutive k-blocks of a tile are adjacent in memory: pull the lines about four k-blocks
+        // ahead into L2, so that the register prefetch above sees L2 latency instead of HBM latency.
+        const long long pf = nxt_beg + 4ll * nxt_cnt + static_cast<long long>(lane) * ((nxt_cnt >> 5) + 1);
+        if (nxt_cnt > 0 && pf < p.sp_total) ptx::prefetch_l2(p.sp_ent + pf);
+      }
       if (have_next) {
         have_next = ahead.next(blk);
         if (have_next) {
@@ -370,9 +386,6 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         break;
       }
       const uint32_t sX = smem_x_u32 + static_cast<uint32_t>(s) * kXTileBytes;
-#pragma unroll 8
-      for (int i = 0; i < kXTileBytes / (32 * 16); ++i) ptx::sts_zero_v4(sX + (i * 32 + lane) * 16);
-      __syncwarp();
 #pragma unroll
       for (int i = 0; i < NE; ++i)
         if (i * 32 + lane < cur_cnt) ptx::sts_f32(sX + cur[i].x, cur[i].y);
@@ -576,16 +589,19 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           uint32_t hi[8], lo[8];
-          if (ORIENT == ORIENT_XH) {
+          if (ORIENT == ORIENT_XH && !tiles) {
             // tile is [32 cells][256 genes]; this thread owns gene `row`
 #pragma unroll
             for (int kk = 0; kk < 8; ++kk)
               ptx::split_tf32_fast(ptx::lds_f32(sX + ((8 * h + kk) * kRows + row) * 4), hi[kk], lo[kk]);
           } else {
-            // tile is [256 cells][32 genes] with the TMA 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+            // tile is [256 rows][32] with the TMA 128B swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+            // (W^T X, and both contractions of the sparse path)
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
-              const float4 q = ptx::lds_v4(sX + row * (kBK * 4) + (((2 * h + c) ^ (row & 7)) << 4));
+              const uint32_t qa = sX + row * (kBK * 4) + (((2 * h + c) ^ (row & 7)) << 4);
+              const float4 q = ptx::lds_v4(qa);
+              if (tiles) ptx::sts_zero_v4(qa);  // hand the stage back zeroed
               ptx::split_tf32_fast(q.x, hi[4 * c + 0], lo[4 * c + 0]);
               ptx::split_tf32_fast(q.y, hi[4 * c + 1], lo[4 * c + 1]);
               ptx::split_tf32_fast(q.z, hi[4 * c + 2], lo[4 * c + 2]);

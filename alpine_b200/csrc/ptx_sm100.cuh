@@ -62,6 +62,10 @@ __device__ __forceinline__ void sts_zero_v4(uint32_t addr) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %1, %1, %1};" ::"r"(addr), "r"(0u) : "memory");
 }
 
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(p)) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 // L2 cache-policy descriptors (the encodings createpolicy.fractional produces).
 constexpr uint64_t kEvictNormal = 0x1000000000000000ull;
