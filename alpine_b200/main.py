@@ -55,6 +55,7 @@ class AlpineMatrices:
     Ys_host: Optional[List[np.ndarray]] = field(default=None, repr=False)
     shard: tuple = (0, 0)
     n_total: int = 0
+    solver: Optional[object] = field(default=None, repr=False)  # native context kept between _fit and _scale_matrices
 
     def to_numpy(self) -> Dict[str, Union[Float32Array, List[Float32Array]]]:
         # the reference copies X back from the device (main.py:38); the host copy it came from is identical
@@ -203,10 +204,15 @@ class ALPINE:
 
         m = self._initialize_matrices(X, Y)
         lap("upload_init")
-        self._fit(m)
-        lap("loop")
-        if self.scale_needed:
-            self._scale_matrices(m)
+        try:
+            self._fit(m, keep_solver=True)
+            lap("loop")
+            if self.scale_needed:
+                self._scale_matrices(m)
+        finally:
+            if m.solver is not None:
+                m.solver.close()
+                m.solver = None
         self.matrices = m.to_numpy()
         lap("scale_download")
         self.store_embeddings(adata)
@@ -420,8 +426,10 @@ class ALPINE:
         return solver
 
     # ------------------------------------------------------------------------------------------- hot loop
-    def _fit(self, m: AlpineMatrices) -> None:
-        """``max_iter`` MU iterations, in place on ``m`` (main.py:486-676); leaves ``self.loss_history``."""
+    def _fit(self, m: AlpineMatrices, keep_solver: bool = False) -> None:
+        """``max_iter`` MU iterations, in place on ``m`` (main.py:486-676); leaves ``self.loss_history``.
+
+        ``keep_solver`` leaves the native context (workspaces, plans) on ``m.solver`` for ``_scale_matrices``."""
         full_batch = self.batch_size >= m.n_total
         if self.sampling_method not in ("random", "weighted"):
             raise ValueError(f"Unknown sampling method: {self.sampling_method}. Only 'weighted', and 'random' are supported.")
@@ -438,7 +446,10 @@ class ALPINE:
             with (pbar if pbar is not None else nullcontext()):
                 history = engine.run(self.max_iter, on_iter=(lambda it: pbar.update(1)) if pbar is not None else None)
         finally:
-            solver.close()
+            if keep_solver:
+                m.solver = solver
+            else:
+                solver.close()
         colnames = ["total loss", "reconstruction loss"] + [f"prediction loss({k})" for k in self.covariate_keys]
         self.loss_history = pd.DataFrame(history.tolist(), columns=colnames)
 
@@ -579,9 +590,11 @@ class ALPINE:
 
     def _scale_matrices(self, m: AlpineMatrices) -> None:
         """Column-normalise every W block; H and B absorb the scale (main.py:772-781)."""
-        solver = self._make_solver(m)
+        own = m.solver is None
+        solver = self._make_solver(m) if own else m.solver
         try:
             solver.scale()
             torch.cuda.synchronize(m.W.device)
         finally:
-            solver.close()
+            if own:
+                solver.close()

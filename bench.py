@@ -62,6 +62,56 @@ def load_peaks():
     return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback")
 
 
+def load_traffic(key):
+    """Measured DRAM bytes per launch of the contraction kernel (ncu --set full), profiles/r1_traffic.json."""
+    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    try:
+        with open(path) as f:
+            d = json.load(f).get(key)
+        vals = [v for v in (d.get("xh_bytes"), d.get("wx_bytes")) if v]
+        return (sum(vals) / len(vals), d.get("source")) if vals else (None, None)
+    except Exception:
+        return None, None
+
+
+def cublas_tf32_peak(dev, seconds=1.5):
+    """cuBLAS TF32 GEMM throughput on this GPU (8192^3, fp32 in/out with allow_tf32): best of 10 launches (burst)
+    and back to back for `seconds` (sustained, i.e. at the clocks the power cap allows).  MEASURED_PEAKS.json has no
+    TF32 figure; SURVEY.md 8 d3 asks for one measured on the box."""
+    import torch
+
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        n = 8192
+        a = torch.randn((n, n), device=dev)
+        b = torch.randn((n, n), device=dev)
+        c = torch.empty((n, n), device=dev)
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        torch.cuda.synchronize(dev)
+        best = float("inf")
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, e0.elapsed_time(e1))
+        reps = max(10, int(seconds * 1000.0 / best))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            torch.matmul(a, b, out=c)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        sustained = e0.elapsed_time(e1) / reps
+        fl = 2.0 * n ** 3
+        return {"burst": fl / best / 1e9, "sustained": fl / sustained / 1e9}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ------------------------------------------------------------------------------------------------ clocks
 class ClockSampler:
     FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -337,11 +387,19 @@ def run_gpu_arm(args):
     if sparse:
         flops = 2.0 * 2.0 * G * n_loc * K      # integer counts are tf32-exact: two tf32 MMAs per fp32 product
     hbm_ms = x_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+    traffic, traffic_src = (None, None)
+    if world == 1 and not args.cells and not args.genes:
+        traffic, traffic_src = load_traffic("cfg3_n1" if not sparse else "none")
+    step_bound_ms = 2.0 * max(flops / (tf32_peak * 1e12), x_bytes / (peaks["hbm_gbs"] * 1e9)) * 1e3
     roofline = {
         "kernel": "mu_gemm_kernel (X H^T and W^T X, %s tcgen05)" % ("2xTF32 on tf32-exact counts, CSR tile lists" if sparse else "3xTF32"),
         "bound": "tensor",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
-        "traffic": None,
+        "traffic": traffic, "traffic_source": traffic_src,
+        "iteration": {"what": "whole MU iteration against the slower of (two contractions at the tensor peak, two "
+                              "sweeps of X at HBM bandwidth) -- BASELINE north_star's roofline",
+                      "bound_ms": step_bound_ms, "measured_ms": ms / args.steps,
+                      "frac": step_bound_ms / (ms / args.steps)},
         "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (no TF32 figure in MEASURED_PEAKS.json; the "
                        f"kernel is timed inside the step loop)",
         "avg_launch_ms": gemm_ms_avg, "launches_timed": gemm_n,
@@ -378,6 +436,11 @@ def run_gpu_arm(args):
             e2e = run_e2e(args, wl, dev, world, rank)
         if rank == 0:
             line["e2e"] = e2e
+    if rank == 0 and world == 1 and not args.no_tf32_peak:
+        # after every timed region, so that its heat does not touch them
+        tf = cublas_tf32_peak(dev)
+        line["roofline"]["cublas_tf32_tflops"] = tf
+        line["roofline"]["frac_of_cublas_tf32_sustained"] = line["roofline"]["achieved"] / tf["sustained"]
     if rank == 0 and world == 1 and not args.no_cpu:
         v, dt, threads, ns = cpu_baseline(wl, sample_cells=8000, iters=2)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
@@ -452,6 +515,7 @@ def main():
                     help="cfg3 = the headline dense workload; cfg4 = BASELINE configs[3], 30k x 1M CSR (scaling study)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-tf32-peak", action="store_true", help="skip the cuBLAS TF32 reference measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
