@@ -168,7 +168,9 @@ class ALPINE:
             self.timings[name] = self.timings.get(name, 0.0) + (t1 - t0)
             t0 = t1
 
-        validation.check_fit_args(self, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose)
+        # the non-negativity scan of a large dense X is done on the device after the upload (same ValueError)
+        self._nonneg_pending = validation.check_fit_args(self, adata, covariate_keys, batch_size, max_iter,
+                                                         sampling_method, verbose, defer_nonneg=True)
         lap("validate")
         self.feature_names = adata.var_names.tolist()
         self.n_features = adata.shape[1]
@@ -374,6 +376,12 @@ class ALPINE:
         dev = self._cuda_device()
         torch.manual_seed(self.random_state)
         torch.cuda.manual_seed(self.random_state)
+        # The draws below take an explicit generator of THIS device with the same seed: the same Philox stream as
+        # the freshly seeded default generator (so the factors equal the reference's on the same device type), but
+        # not shared with other threads -- ComponentOptimizer runs one fit per GPU from worker threads, and the
+        # global seeding calls above race between them.
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(self.random_state)
         G, n = X_array.shape
         rank, world = dist_info()
         lo, hi = shard_bounds(n, world, rank)
@@ -388,6 +396,15 @@ class ALPINE:
         else:
             Xd = _native.padded_rows(n_loc, G, dev)
             _native.upload_rows(Xd, Xcm_host[lo:hi])
+            if getattr(self, "_nonneg_pending", False):
+                self._nonneg_pending = False
+                ok = torch.tensor([1.0 if (n_loc == 0 or bool(Xd.min() >= 0)) else 0.0], device=dev)  # NaN fails
+                if world > 1:
+                    import torch.distributed as dist
+
+                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank raises, or none
+                if float(ok.item()) != 1.0:
+                    raise ValueError(validation.NONNEG_MSG)
         Ys_host = [np.ascontiguousarray(y.T, dtype=np.float32) for y in Y_list_array]  # c_i x n (main.py:447)
         Ys = [torch.from_numpy(np.ascontiguousarray(y[:, lo:hi])).to(dev) for y in Ys_host]
 
@@ -397,18 +414,18 @@ class ALPINE:
         col = 0
         Ws = []
         for k in self.n_all_components:  # main.py:454-458
-            W[:, col:col + k] = torch.rand((G, k), dtype=torch.float32, device=dev).clamp(min=eps)
+            W[:, col:col + k] = torch.rand((G, k), dtype=torch.float32, device=dev, generator=gen).clamp(min=eps)
             Ws.append(W[:, col:col + k])
             col += k
         row = 0
         Hs = []
         for k in self.n_all_components:  # main.py:460-464
-            full = torch.rand((k, n), dtype=torch.float32, device=dev).clamp(min=eps)
+            full = torch.rand((k, n), dtype=torch.float32, device=dev, generator=gen).clamp(min=eps)
             H[row:row + k, :] = full[:, lo:hi]
             Hs.append(H[row:row + k, :])
             row += k
             del full
-        Bs = [torch.rand((y.shape[0], k), dtype=torch.float32, device=dev).clamp(min=eps).contiguous()
+        Bs = [torch.rand((y.shape[0], k), dtype=torch.float32, device=dev, generator=gen).clamp(min=eps).contiguous()
               for (y, k) in zip(Ys_host, self.n_covariate_components)]  # main.py:466-470
         return AlpineMatrices(X=Xd.T if Xd is not None else None, Ys=Ys, Ws=Ws, Hs=Hs, Bs=Bs, W=W, H=H,
                               X_cells_major=Xd, X_csr=X_csr, X_host=X_array, Ys_host=Ys_host, shard=(lo, hi), n_total=n)

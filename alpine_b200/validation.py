@@ -65,18 +65,41 @@ def check_model_args(m) -> None:
              "random_state must be a non-negative integer.")
 
 
-def check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose) -> None:
-    """main.py:383-434."""
+NONNEG_MSG = "All elements in adata.X must be non-negative."
+
+
+def check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose,
+                   defer_nonneg: bool = False) -> bool:
+    """main.py:383-434.  Returns True when the (expensive) non-negativity scan of a dense ``adata.X`` was deferred:
+    the caller then checks the minimum on the device after the upload it has to do anyway and raises the same
+    ``ValueError``.  The order of errors stays the reference's: if a later check fails, the scan is run on the host
+    first, because the reference would have reported a negative X before that later error."""
+    deferred = False
+    try:
+        deferred = _check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose, defer_nonneg)
+    except (TypeError, ValueError):
+        if _check_fit_args.last_deferred:
+            _require(_all_non_negative(adata.X), ValueError, NONNEG_MSG)
+        raise
+    return deferred
+
+
+def _check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_method, verbose, defer_nonneg) -> bool:
+    _check_fit_args.last_deferred = False
+    deferred = False
     _require(isinstance(adata, AnnData), TypeError, "adata must be an AnnData object.")
     if is_sparse(adata.X):
         # extension over the reference (which raises the TypeError below for sparse input, main.py:395-396): a
         # scipy.sparse matrix takes the CSR tile-list path of the kernels (BASELINE north_star, config 4)
         _require(adata.X.ndim == 2, ValueError, "adata.X must be a 2D numpy array.")
-        _require(_all_non_negative(np.asarray(adata.X.data)), ValueError, "All elements in adata.X must be non-negative.")
+        _require(_all_non_negative(np.asarray(adata.X.data)), ValueError, NONNEG_MSG)
     else:
         _require(isinstance(adata.X, np.ndarray), TypeError, "adata.X must be a numpy array.")
         _require(adata.X.ndim == 2, ValueError, "adata.X must be a 2D numpy array.")
-        _require(_all_non_negative(adata.X), ValueError, "All elements in adata.X must be non-negative.")
+        if defer_nonneg and adata.X.size > (1 << 24):
+            deferred = _check_fit_args.last_deferred = True
+        else:
+            _require(_all_non_negative(adata.X), ValueError, NONNEG_MSG)
     _require(isinstance(covariate_keys, list), TypeError, "covariate_keys must be a list.")
     _require(len(covariate_keys) == len(m.n_covariate_components), ValueError,
              "Length of covariate_keys must match length of n_covariate_components.")
@@ -87,6 +110,10 @@ def check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_meth
                  f"Covariate '{key}' in adata.obs must be a categorical or object type variable.")
     _require(isinstance(sampling_method, str), TypeError, "sampling_method must be a string.")
     _require(isinstance(verbose, bool), TypeError, "verbose must be a boolean.")
+    return deferred
+
+
+_check_fit_args.last_deferred = False
 
 
 def check_trained(m) -> None:

@@ -219,3 +219,21 @@ def test_minibatch_public_fit_runs_with_own_sampler():
         model.fit(ad, ["cov0"], max_iter=4, batch_size=128, sampling_method=method)
         lh = model.loss_history["total loss"].to_numpy()
         assert len(lh) == 4 and np.all(np.isfinite(lh)) and lh[-1] < lh[0]
+
+
+def test_large_negative_matrix_is_rejected_after_the_deferred_device_check():
+    """The non-negativity scan of a large dense X runs on the device after the upload; the error is the reference's
+    (main.py:399-400)."""
+    n, G = 5000, 4000  # > 2**24 elements: the host scan is deferred
+    X = np.ones((n, G), dtype=np.float32)
+    X[4321, 1234] = -0.5
+    obs = pd.DataFrame({"cov0": pd.Series(["a", "b"] * (n // 2), dtype=object)})
+    ad = AnnData(X, obs=obs)
+    model = ALPINE(n_components=4, n_covariate_components=[2], lam=[1.0], device="cuda")
+    with pytest.raises(ValueError, match="non-negative"):
+        model.fit(ad, ["cov0"], max_iter=2)
+    X[4321, 1234] = np.nan
+    with pytest.raises(ValueError, match="non-negative"):
+        model.fit(ad, ["cov0"], max_iter=2)
+    X[4321, 1234] = 0.5
+    assert model.fit(ad, ["cov0"], max_iter=2) is model
