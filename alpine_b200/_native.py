@@ -46,6 +46,9 @@ SIGNATURES = {
     "alpine_batch_begin": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_partials": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_apply": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_peer_export": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+    "alpine_peer_import": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_mu_apply_peer": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_reduce_stats_offset": (ctypes.c_int64, [_c_ctx]),
     "alpine_als_block": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_als_finish": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
@@ -181,6 +184,13 @@ class Solver:
 
     # -- lifetime ----------------------------------------------------------------------------------------
     def close(self) -> None:
+        if getattr(self, "_ctx", None) and getattr(self, "peer", False):
+            import torch.distributed as dist
+
+            torch.cuda.synchronize(self.device)
+            if dist.is_initialized():
+                dist.barrier(group=self._peer_group)  # no peer may still be reading this rank's exchange block
+            self.peer = False
         if getattr(self, "_ctx", None):
             self.lib.alpine_destroy(self._ctx)
             self._ctx = None
@@ -239,8 +249,40 @@ class Solver:
         _check(self.lib, self.lib.alpine_set_hparams(self._ctx, arr, float(alpha_W), float(l1_ratio_W), float(orth_W),
                                                      float(eps)))
 
+    # -- peer exchange over NVLink (one process per GPU) ----------------------------------------------------
+    def enable_peer_exchange(self, group=None) -> bool:
+        """Collective over the ranks of ``group``: share every rank's exchange block through CUDA IPC so that the W
+        update exchanges over peer memory (``mu_apply_peer``) instead of an all-reduce.  Must be called before
+        ``reduce_buffer`` / ``fit_begin``.  Returns False (on every rank) when some rank could not set it up; the
+        caller then stays on the all-reduce path."""
+        import torch.distributed as dist
+
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        handle = (ctypes.c_ubyte * 64)()
+        ok = self.lib.alpine_peer_export(self._ctx, ctypes.cast(handle, ctypes.c_void_p)) == 0
+        mine = torch.tensor(list(bytes(handle)), dtype=torch.uint8, device=self.device)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=group)
+        flag = torch.tensor([1 if ok else 0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        if int(flag.item()) == 1:
+            blob = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
+            buf = ctypes.create_string_buffer(blob, len(blob))
+            ok = self.lib.alpine_peer_import(self._ctx, rank, world, ctypes.cast(buf, ctypes.c_void_p)) == 0
+            flag = torch.tensor([1 if ok else 0], device=self.device)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        self.peer = int(flag.item()) == 1
+        self._peer_group = group
+        dist.barrier(group=group)
+        return self.peer
+
+    def mu_apply_peer(self, it: int) -> None:
+        _check(self.lib, self.lib.alpine_mu_apply_peer(self._ctx, int(it), self._stream()))
+
     def reduce_buffer(self) -> torch.Tensor:
         """Allocate and bind the per-iteration all-reduce payload [X H^T | H H^T | rowsum(H) | B statistics]."""
+        if getattr(self, "peer", False):
+            raise AlpineNativeError("this solver exchanges over peer memory; there is no caller-owned reduce buffer")
         if "reduce" not in self._keep:
             size = int(self.lib.alpine_reduce_buffer_size(self._ctx))
             buf = torch.zeros(size, dtype=torch.float32, device=self.device)

@@ -13,6 +13,7 @@
 #include "mu_gemm_sm100.cuh"
 #include "mu_small_kernels.cuh"
 #include "csr_tiles.cuh"
+#include "peer_exchange.cuh"
 
 using namespace alpine;
 
@@ -175,6 +176,22 @@ struct alpine_ctx {
   float* own_reduce = nullptr;
   float* reduce = nullptr;  // [Pt K*ldG | S K*K | hsum K | Q q_total]
 
+  // peer exchange over NVLink (alpine_peer_export / _import): this rank's block and the peers' mapped blocks
+  float* xchg = nullptr;            // [ reduce buffer | W^T | flags ]
+  float* peer_base[kMaxPeers] = {nullptr};
+  bool peer_opened[kMaxPeers] = {false};
+  int peer_rank = -1, peer_world = 0, peer_epoch = 0;
+  float* sum_small = nullptr;       // [S | hsum | Q] summed over the ranks (peer mode)
+  bool peer_on() const { return peer_world > 1; }
+  long long xchg_wt_off() const { return round_up_ll(reduce_floats(), 64); }
+  long long xchg_flag_off() const { return xchg_wt_off() + round_up_ll(static_cast<long long>(K) * ldG, 64); }
+  long long xchg_floats() const { return xchg_flag_off() + kPeerFlagInts; }
+  static long long round_up_ll(long long v, long long m) { return (v + m - 1) / m * m; }
+  // the statistics the W / B updates consume: all-reduced in place by the caller, or summed over peers
+  const float* use_S() const { return peer_on() ? sum_small : red_S(); }
+  const float* use_hsum() const { return use_S() + static_cast<size_t>(K) * K; }
+  const float* use_Q() const { return use_hsum() + K; }
+
   GemmPlan plans[PLAN_COUNT];
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
@@ -187,6 +204,7 @@ struct alpine_ctx {
   float* red_hsum() const { return red_S() + static_cast<size_t>(K) * K; }
   float* red_Q() const { return red_hsum() + K; }
   long long reduce_floats() const { return static_cast<long long>(K) * ldG + static_cast<long long>(K) * K + K + q_total; }
+  long long small_floats() const { return static_cast<long long>(K) * K + K + q_total; }
 };
 
 namespace {
@@ -492,7 +510,8 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
 
 template <int EPI>
 int run_sym_long(alpine_ctx* c, const SymLongParams& p, cudaStream_t st) {
-  const int blocks = ceil_div(p.L, kSLCols);
+  const int blocks = ceil_div(p.L - p.col0, kSLCols);
+  if (blocks <= 0) return ALPINE_OK;
   sym_long_kernel<kSLKI, EPI><<<blocks, 256, sym_long_smem_bytes(c->K), st>>>(p);
   LAUNCH_CHECK();
   return ALPINE_OK;
@@ -572,7 +591,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 4; }
+int alpine_abi_version(void) { return 5; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -635,6 +654,13 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
 int alpine_destroy(alpine_ctx* c) {
   if (c == nullptr) return ALPINE_OK;
   cudaSetDevice(c->device);
+  for (int q = 0; q < kMaxPeers; ++q)
+    if (c->peer_opened[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
+  if (c->xchg != nullptr) {
+    c->WT = nullptr;  // lives inside the exchange block
+    cudaFree(c->xchg);
+  }
+  cudaFree(c->sum_small);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
                   c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
                   c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags};
@@ -843,15 +869,35 @@ int alpine_mu_partials(alpine_ctx* c, void* stream) {
   return run_gemm(c, PLAN_XH, c->red_Pt(), c->ldG, static_cast<cudaStream_t>(stream));  // Hsplit is current
 }
 
-int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
+}  // extern "C"
+
+namespace {
+
+PeerTable make_peer_table(const alpine_ctx* c) {
+  PeerTable t{};
+  t.world = c->peer_world;
+  t.rank = c->peer_rank;
+  for (int q = 0; q < c->peer_world; ++q) {
+    t.flags[q] = reinterpret_cast<int*>(c->peer_base[q] + c->xchg_flag_off());
+    t.small[q] = c->peer_base[q] + static_cast<size_t>(c->K) * c->ldG;
+  }
+  return t;
+}
+
+// One simultaneous-update iteration after alpine_mu_partials.  peer = false: the reduce buffer holds the complete
+// numerator and statistics (single GPU, or all-reduced by the caller).  peer = true: csrc/peer_exchange.cuh.
+int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   AL_TRY(check_bound(c, true));
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   if (iter < 0 || iter >= c->loss_cap) return fail(ALPINE_ERR_ARG, "iteration %d outside [0, %d)", iter, c->loss_cap);
+  if (peer != c->peer_on())
+    return fail(ALPINE_ERR_STATE, peer ? "alpine_peer_import has not been called"
+                                       : "this context exchanges over peer memory: call alpine_mu_apply_peer");
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // ---- W update (main.py:592-612) on W^T, then refresh the caller's row-major W
   SymLongParams w{};
-  w.Sym = c->red_S();
+  w.Sym = c->use_S();
   w.ldS = c->K;
   w.Mat = c->WT;
   w.ldM = c->ldG;
@@ -867,7 +913,37 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   w.split_hi = c->Wsplit;  // B operand of W^T W and W^T X below
   w.split_lo = c->Wsplit + static_cast<size_t>(c->K) * c->ldG;
   w.ld_split = c->ldG;
-  AL_TRY(run_sym_long<EPI_W>(c, w, st));
+  if (!peer) {
+    AL_TRY(run_sym_long<EPI_W>(c, w, st));
+  } else {
+    const int epoch = ++c->peer_epoch;
+    const PeerTable pt = make_peer_table(c);
+    peer_signal_kernel<<<1, 32, 0, st>>>(pt, 0, epoch);  // this rank's partials are in its exchange block
+    LAUNCH_CHECK();
+    const int n_small = static_cast<int>(c->small_floats());
+    const int sb = ceil_div(n_small, 256) < 64 ? ceil_div(n_small, 256) : 64;
+    peer_wait_small_kernel<<<sb, 256, 0, st>>>(pt, epoch, n_small, c->sum_small, c->err);
+    LAUNCH_CHECK();
+    // this rank's gene slice, in whole 64-column tiles
+    const long long tiles = ceil_div(c->G, kSLCols);
+    const long long g0 = tiles * c->peer_rank / c->peer_world * kSLCols;
+    long long g1 = tiles * (c->peer_rank + 1) / c->peer_world * kSLCols;
+    if (g1 > c->G) g1 = c->G;
+    w.col0 = g0;
+    w.L = g1;
+    w.n_peers = c->peer_world;
+    for (int q = 0; q < c->peer_world; ++q) {
+      w.num_peer[q] = c->peer_base[q];  // the partial numerator leads every exchange block
+      w.mat_peer[q] = (q == c->peer_rank) ? nullptr : c->peer_base[q] + c->xchg_wt_off();
+    }
+    w.split_hi = w.split_lo = nullptr;  // taken from the gathered W^T below
+    AL_TRY(run_sym_long<EPI_W>(c, w, st));
+    peer_signal_kernel<<<1, 32, 0, st>>>(pt, 1, epoch);  // this rank's slice of the new W^T is in every block
+    LAUNCH_CHECK();
+    peer_wait_kernel<<<1, 32, 0, st>>>(pt, 1, epoch, c->err);
+    LAUNCH_CHECK();
+    AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+  }
   transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
                                                                                        c->W, c->ldW);
   LAUNCH_CHECK();
@@ -876,8 +952,8 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   if (c->n_cov > 0) {
     int ckmax = 0;
     for (int i = 0; i < c->n_cov; ++i) ckmax = c->ccov[i] * c->kblk[i] > ckmax ? c->ccov[i] * c->kblk[i] : ckmax;
-    b_update_kernel<<<c->n_cov, 128, ckmax * sizeof(float), st>>>(tab, c->loss_type, c->red_Q(), c->red_hsum(),
-                                                                  c->red_S(), c->K, (float)c->eps);
+    b_update_kernel<<<c->n_cov, 128, ckmax * sizeof(float), st>>>(tab, c->loss_type, c->use_Q(), c->use_hsum(),
+                                                                  c->use_S(), c->K, (float)c->eps);
     LAUNCH_CHECK();
   }
   // ---- T = W^T W of the new W
@@ -924,12 +1000,60 @@ int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) {
   return ALPINE_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int alpine_mu_apply(alpine_ctx* c, int iter, void* stream) { return mu_apply_impl(c, iter, stream, false); }
+int alpine_mu_apply_peer(alpine_ctx* c, int iter, void* stream) { return mu_apply_impl(c, iter, stream, true); }
+
+int alpine_peer_export(alpine_ctx* c, void* handle_out) {
+  if (c == nullptr || handle_out == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
+  if (c->ws_ready || c->reduce != nullptr)
+    return fail(ALPINE_ERR_STATE, "alpine_peer_export must come before alpine_bind_reduce_buffer / alpine_fit_begin");
+  CU_TRY(cudaSetDevice(c->device));
+  CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c->xchg), c->xchg_floats() * sizeof(float)));
+  CU_TRY(cudaMemset(c->xchg, 0, c->xchg_floats() * sizeof(float)));
+  AL_TRY(dev_alloc(&c->sum_small, static_cast<size_t>(c->small_floats())));
+  c->reduce = c->xchg;                          // [X H^T | H H^T | rowsum H | B statistics] partials of this rank
+  c->WT = c->xchg + c->xchg_wt_off();           // peers store their gene slices of the new W^T here
+  cudaIpcMemHandle_t h;
+  CU_TRY(cudaIpcGetMemHandle(&h, c->xchg));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, sizeof(h));
+  return ALPINE_OK;
+}
+
+int alpine_peer_import(alpine_ctx* c, int rank, int world, const void* handles) {
+  if (c == nullptr || handles == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
+  if (c->xchg == nullptr) return fail(ALPINE_ERR_STATE, "alpine_peer_export has not been called");
+  if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
+    return fail(ALPINE_ERR_ARG, "peer exchange needs 2..%d ranks (rank %d of %d)", kMaxPeers, rank, world);
+  CU_TRY(cudaSetDevice(c->device));
+  for (int q = 0; q < world; ++q) {
+    if (q == rank) {
+      c->peer_base[q] = c->xchg;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, static_cast<const char*>(handles) + 64 * q, sizeof(h));
+    void* p = nullptr;
+    CU_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[q] = static_cast<float*>(p);
+    c->peer_opened[q] = true;
+  }
+  c->peer_rank = rank;
+  c->peer_world = world;
+  return ALPINE_OK;
+}
+
 int64_t alpine_reduce_stats_offset(const alpine_ctx* c) { return c ? static_cast<int64_t>(c->K) * c->ldG : 0; }
 
 int alpine_als_block(alpine_ctx* c, int b, void* stream) {
   AL_TRY(check_bound(c, true));
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   if (b < 0 || b >= c->n_blocks) return fail(ALPINE_ERR_ARG, "block %d outside [0, %d)", b, c->n_blocks);
+  if (c->peer_on()) return fail(ALPINE_ERR_STATE, "the block-wise sweep exchanges through the caller's all-reduce, not peer memory");
   CU_TRY(cudaSetDevice(c->device));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int r0 = 0;

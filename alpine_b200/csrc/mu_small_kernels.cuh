@@ -9,6 +9,19 @@ namespace alpine {
 
 enum { LOSS_KL = 0, LOSS_FROB = 1 };
 constexpr int kMaxCov = 8;
+constexpr int kMaxPeers = 8;
+
+// loads / stores of memory that another GPU writes / reads inside the same fit: never served from a stale L1 line
+__device__ __forceinline__ float4 ld_sys_v4(const float* p) {
+  float4 v;
+  asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ float ld_sys_f32(const float* p) {
+  float v;
+  asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
 
 struct CovDesc {
   int row0;         // first row of the block in H / first column in W
@@ -293,6 +306,13 @@ struct SymLongParams {
   float* split_hi;      // EPI_W / EPI_H: tf32 hi / lo copies of the updated matrix (B operand of the next
   float* split_lo;      //                contraction), pitch ld_split; nullptr to skip
   long long ld_split;
+  // Peer mode (EPI_W under cell sharding, csrc/peer_exchange.cuh): the block handles columns col0 + 64 * blockIdx.x
+  // (this rank's gene slice), the numerator is the sum over the ranks' partial X H^T read from their memory over
+  // NVLink in rank order (identical on every rank), and the updated columns are also stored into every peer's W^T.
+  long long col0;
+  int n_peers;                    // 0: single-GPU / NCCL path (Num is already the complete numerator)
+  const float* num_peer[kMaxPeers];
+  float* mat_peer[kMaxPeers];     // peers' W^T (nullptr for this rank itself)
   // rows [r0, r1) of Mat are updated (all K rows take part in Z).  The whole matrix for the simultaneous update
   // (main.py:589-663); one component block for the block Gauss-Seidel ("ALS") sweep (main.py:523-588), where the
   // orthogonality term also only couples the columns of that block (main.py:541).
@@ -313,7 +333,7 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
   const int SP = (p.K + 3) / 4 * 4 + 4;
   __shared__ double red[8];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const long long c0 = static_cast<long long>(blockIdx.x) * kSLCols;
+  const long long c0 = p.col0 + static_cast<long long>(blockIdx.x) * kSLCols;
   const bool full = c0 + kSLCols <= p.L;
 
   // the whole K x K matrix and the K x 64 tile are staged once: one barrier, no per-chunk global latency
@@ -381,7 +401,18 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
     float nv[4] = {0.f, 0.f, 0.f, 0.f}, gn[4] = {0.f, 0.f, 0.f, 0.f}, gd[4] = {0.f, 0.f, 0.f, 0.f};
     const float* nsrc = p.Num + static_cast<long long>(k) * p.ldNum + col;
     const bool g_on = (EPI == EPI_H) && (k < p.Kg);
-    if (full) {
+    if (EPI == EPI_W && p.n_peers > 0) {
+      const long long o = static_cast<long long>(k) * p.ldNum + col;
+      for (int q = 0; q < p.n_peers; ++q) {  // fixed rank order: bit-identical sums on every rank
+        if (full) {
+          const float4 t = ld_sys_v4(p.num_peer[q] + o);
+          nv[0] += t.x, nv[1] += t.y, nv[2] += t.z, nv[3] += t.w;
+        } else {
+          for (int x = 0; x < 4; ++x)
+            if (col + x < p.L) nv[x] += ld_sys_f32(p.num_peer[q] + o + x);
+        }
+      }
+    } else if (full) {
       const float4 t = *reinterpret_cast<const float4*>(nsrc);
       nv[0] = t.x, nv[1] = t.y, nv[2] = t.z, nv[3] = t.w;
       if (g_on) {
@@ -426,6 +457,18 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
     } else {
       for (int x = 0; x < 4; ++x)
         if (col + x < p.L) dst[x] = outv[x];
+    }
+    if (EPI == EPI_W && p.n_peers > 0) {
+      for (int q = 0; q < p.n_peers; ++q) {
+        if (p.mat_peer[q] == nullptr) continue;
+        float* pd = p.mat_peer[q] + static_cast<long long>(k) * p.ldM + col;
+        if (full) {
+          *reinterpret_cast<float4*>(pd) = make_float4(outv[0], outv[1], outv[2], outv[3]);
+        } else {
+          for (int x = 0; x < 4; ++x)
+            if (col + x < p.L) pd[x] = outv[x];
+        }
+      }
     }
     if (EPI != EPI_TRANSFORM && p.split_hi != nullptr) {
       // pitches are multiples of 4 and the pad columns are never read unmasked, so whole float4 groups are written

@@ -75,7 +75,8 @@ class MUEngine:
 
     def begin(self, max_iter: int) -> None:
         """||X||^2 and this shard's statistics of the initial H / B (left in the reduce buffer)."""
-        self._buf = self.solver.reduce_buffer()
+        self.peer = bool(getattr(self.solver, "peer", False)) and self.world > 1 and not self.use_als
+        self._buf = None if self.peer else self.solver.reduce_buffer()
         self.solver.fit_begin(max_iter)
 
     def step(self, it: int) -> None:
@@ -83,6 +84,11 @@ class MUEngine:
         s = self.solver
         if self.use_als:
             return self._als_step(it)
+        if self.peer:
+            # exchange over NVLink peer memory inside the W-update kernels (csrc/peer_exchange.cuh): no collective
+            s.mu_partials()
+            s.mu_apply_peer(it)
+            return
         s.mu_partials()        # X H^T of this shard into the reduce buffer (main.py:596)
         # The iteration's only data-path collective.  The statistics part [H H^T | rowsum(H) | B statistics]
         # still holds this shard's values (written by fit_begin / the previous mu_apply), so one message
@@ -111,7 +117,7 @@ class MUEngine:
         n_cov = rows.shape[1] - 2
         packed = np.concatenate([[xn], rows.reshape(-1)]).astype(np.float64)
         if self.world > 1:
-            dev = self.solver.reduce_buffer().device
+            dev = getattr(self.solver, "device", None) or self.solver.reduce_buffer().device
             t = torch.from_numpy(packed).to(dev)
             self._all_reduce(t)
             packed = t.cpu().numpy()

@@ -12,6 +12,7 @@ There is no CPU path: ``device`` must be a CUDA device with an sm_100 GPU behind
 from __future__ import annotations
 
 import gc
+import os
 import warnings
 from contextlib import nullcontext
 from copy import copy, deepcopy
@@ -454,6 +455,10 @@ class ALPINE:
             return self._fit_minibatch(m)
         solver = self._make_solver(m)
         try:
+            if dist_info()[1] > 1 and not self.use_als and os.environ.get("ALPINE_B200_PEER", "1") != "0":
+                # exchange over NVLink peer memory inside the W-update kernels; falls back to the NCCL all-reduce
+                # (on every rank) when CUDA IPC is not available between the processes
+                solver.enable_peer_exchange()
             engine = MUEngine(solver, self.lam, use_als=self.use_als)
             pbar = None
             if self.verbose:

@@ -340,6 +340,11 @@ def run_gpu_arm(args):
     solver.bind_labels(Ys)
     solver.bind_factors(W, H, Bs)
     solver.set_hparams(wl["lam"], wl["alpha_W"], wl["l1_ratio_W"], wl["orth_W"], wl["eps"])
+    exchange = "none (single GPU)"
+    if world > 1:
+        peer = os.environ.get("ALPINE_B200_PEER", "1") != "0" and solver.enable_peer_exchange()
+        exchange = ("NVLink peer memory inside the W-update kernels (reduce-scatter + update + all-gather)" if peer
+                    else "NCCL all-reduce of the packed buffer")
     engine = MUEngine(solver, wl["lam"])
     total = args.warmup + args.steps
     engine.begin(total)
@@ -413,7 +418,7 @@ def run_gpu_arm(args):
             "metric": METRIC if not sparse else "MU iterations/sec at 30k genes x 1M cells CSR, k=100", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": wl["name"], "parallelism": f"cells sharded over {world} GPU(s)",
+            "config": {"workload": wl["name"], "parallelism": f"cells sharded over {world} GPU(s)", "exchange": exchange,
                        "l2": "inputs larger than L2 (X is %.1f GB per GPU)" % (x_bytes / 1e9)},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "final_loss": {"total": float(hist[-1, 0]), "reconstruction": float(hist[-1, 1])},

@@ -84,6 +84,16 @@ int alpine_mu_partials(alpine_ctx* ctx, void* stream);
  * (main.py:615-628), H update (main.py:631-663), loss terms of iteration `iter` (main.py:666, 726-753) and
  * the statistics for the next iteration.                                                                  */
 int alpine_mu_apply(alpine_ctx* ctx, int iter, void* stream);
+/* Cell sharding over NVLink peer memory instead of a library collective (csrc/peer_exchange.cuh).  One process per
+ * GPU: every rank calls alpine_peer_export right after alpine_create (it allocates the rank's exchange block --
+ * reduce buffer + W^T + flags -- and returns its 64-byte CUDA IPC handle), the handles are exchanged by the host
+ * (any transport), every rank calls alpine_peer_import with all `world` handles (world <= 8), and a host barrier
+ * follows.  Then one iteration is  alpine_mu_partials + alpine_mu_apply_peer : the W update runs on this rank's
+ * gene slice with the numerator summed straight from the peers' memory and the new slice stored into every peer's
+ * W^T; W and B stay bit-identical across ranks.  Destroy the contexts only after a host barrier.               */
+int alpine_peer_export(alpine_ctx* ctx, void* ipc_handle_64_bytes);
+int alpine_peer_import(alpine_ctx* ctx, int rank, int world, const void* ipc_handles);
+int alpine_mu_apply_peer(alpine_ctx* ctx, int iter, void* stream);
 /* Block Gauss-Seidel ("ALS") sweep, use_als=True (main.py:523-588).  One iteration is
  *   alpine_mu_partials            X H^T for all blocks in one sweep of X (every H_b is still unchanged when its W_b
  *                                 update consumes its columns)           [+ all-reduce of the whole reduce buffer]

@@ -39,7 +39,7 @@ def main():
     Yh = [torch.nn.functional.one_hot(torch.randint(0, c, (n,), generator=g), c).T.float().contiguous() for c in cats]
     n_iter = 8
 
-    def run(lo, hi, use_dist):
+    def run(lo, hi, use_dist, peer=False):
         X = _native.padded_rows(hi - lo, G, dev)
         X.copy_(Xh[lo:hi])
         H = _native.padded_rows(K, hi - lo, dev)
@@ -48,6 +48,8 @@ def main():
         Bs = [b.clone().to(dev) for b in Bh]
         Ys = [y[:, lo:hi].contiguous().to(dev) for y in Yh]
         s = build(dev, X, Ys, W, H, Bs, blocks, cats, kw)
+        if peer:
+            assert s.enable_peer_exchange(), "CUDA IPC peer exchange could not be set up"
         eng = MUEngine(s, kw["lam"])
         if not use_dist:
             eng.world = 1
@@ -58,6 +60,11 @@ def main():
 
     lo, hi = shard_bounds(n, world, rank)
     Wd, Hd, Bd, hist_d = run(lo, hi, True)
+    # the same sharded fit exchanging over NVLink peer memory instead of the NCCL all-reduce
+    Wp, Hp, Bp, hist_p = run(lo, hi, True, peer=True)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, Wp.tobytes())
+    same_w = all(g == gathered[0] for g in gathered)  # W must be bit-identical on every rank
     ok = True
     if rank == 0:
         W1, H1, B1, hist_1 = run(0, n, False)
@@ -74,6 +81,12 @@ def main():
               f"{np.array2string(col_err, precision=2)}  pred abs err / n {pred_abs:.2e}")
         print("  last rows:", hist_d[-1], hist_1[-1])
         ok = eW < 1e-5 and eH < 1e-5 and eB < 1e-5 and col_err[1] < 1e-5 and pred_abs < 1e-6
+        ePW, ePH = rel(Wp, W1), rel(Hp, H1[:, lo:hi])
+        ePB = max(rel(a, b) for a, b in zip(Bp, B1))
+        p_err = np.max(np.abs(hist_p[:, :2] - hist_1[:, :2]) / np.abs(hist_1[:, :2]))
+        print(f"  peer exchange: W {ePW:.2e}  H(block0) {ePH:.2e}  B {ePB:.2e}  loss rel err {p_err:.2e}  "
+              f"W bit-identical across ranks: {same_w}")
+        ok = ok and ePW < 1e-5 and ePH < 1e-5 and ePB < 1e-5 and p_err < 1e-5 and same_w
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     dist.barrier()
