@@ -182,6 +182,7 @@ struct alpine_ctx {
   bool peer_opened[kMaxPeers] = {false};
   int peer_rank = -1, peer_world = 0, peer_epoch = 0;
   float* sum_small = nullptr;       // [S | hsum | Q] summed over the ranks (peer mode)
+  float* sum_P = nullptr;           // [K][ldG]: this rank's gene slice of the summed numerator (peer mode)
   bool peer_on() const { return peer_world > 1; }
   long long xchg_wt_off() const { return round_up_ll(reduce_floats(), 64); }
   long long xchg_flag_off() const { return xchg_wt_off() + round_up_ll(static_cast<long long>(K) * ldG, 64); }
@@ -661,6 +662,7 @@ int alpine_destroy(alpine_ctx* c) {
     cudaFree(c->xchg);
   }
   cudaFree(c->sum_small);
+  cudaFree(c->sum_P);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
                   c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
                   c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags};
@@ -918,29 +920,24 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   } else {
     const int epoch = ++c->peer_epoch;
     const PeerTable pt = make_peer_table(c);
-    peer_signal_kernel<<<1, 32, 0, st>>>(pt, 0, epoch);  // this rank's partials are in its exchange block
-    LAUNCH_CHECK();
-    const int n_small = static_cast<int>(c->small_floats());
-    const int sb = ceil_div(n_small, 256) < 64 ? ceil_div(n_small, 256) : 64;
-    peer_wait_small_kernel<<<sb, 256, 0, st>>>(pt, epoch, n_small, c->sum_small, c->err);
-    LAUNCH_CHECK();
     // this rank's gene slice, in whole 64-column tiles
     const long long tiles = ceil_div(c->G, kSLCols);
     const long long g0 = tiles * c->peer_rank / c->peer_world * kSLCols;
     long long g1 = tiles * (c->peer_rank + 1) / c->peer_world * kSLCols;
     if (g1 > c->G) g1 = c->G;
+    const int n_small = static_cast<int>(c->small_floats());
+    peer_gather_reduce_kernel<<<2 * c->num_sms, 256, 0, st>>>(pt, epoch, n_small, c->sum_small, c->K, c->ldG, g0, g1,
+                                                              c->sum_P, c->err);
+    LAUNCH_CHECK();
     w.col0 = g0;
     w.L = g1;
+    w.Num = c->sum_P;
     w.n_peers = c->peer_world;
-    for (int q = 0; q < c->peer_world; ++q) {
-      w.num_peer[q] = c->peer_base[q];  // the partial numerator leads every exchange block
+    for (int q = 0; q < c->peer_world; ++q)
       w.mat_peer[q] = (q == c->peer_rank) ? nullptr : c->peer_base[q] + c->xchg_wt_off();
-    }
     w.split_hi = w.split_lo = nullptr;  // taken from the gathered W^T below
     AL_TRY(run_sym_long<EPI_W>(c, w, st));
-    peer_signal_kernel<<<1, 32, 0, st>>>(pt, 1, epoch);  // this rank's slice of the new W^T is in every block
-    LAUNCH_CHECK();
-    peer_wait_kernel<<<1, 32, 0, st>>>(pt, 1, epoch, c->err);
+    peer_signal_wait_kernel<<<1, 32, 0, st>>>(pt, 1, epoch, c->err);  // every slice of the new W^T is in every block
     LAUNCH_CHECK();
     AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   }
@@ -1015,6 +1012,7 @@ int alpine_peer_export(alpine_ctx* c, void* handle_out) {
   CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c->xchg), c->xchg_floats() * sizeof(float)));
   CU_TRY(cudaMemset(c->xchg, 0, c->xchg_floats() * sizeof(float)));
   AL_TRY(dev_alloc(&c->sum_small, static_cast<size_t>(c->small_floats())));
+  AL_TRY(dev_alloc(&c->sum_P, static_cast<size_t>(c->K) * c->ldG));
   c->reduce = c->xchg;                          // [X H^T | H H^T | rowsum H | B statistics] partials of this rank
   c->WT = c->xchg + c->xchg_wt_off();           // peers store their gene slices of the new W^T here
   cudaIpcMemHandle_t h;

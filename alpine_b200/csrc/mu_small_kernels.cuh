@@ -307,11 +307,9 @@ struct SymLongParams {
   float* split_lo;      //                contraction), pitch ld_split; nullptr to skip
   long long ld_split;
   // Peer mode (EPI_W under cell sharding, csrc/peer_exchange.cuh): the block handles columns col0 + 64 * blockIdx.x
-  // (this rank's gene slice), the numerator is the sum over the ranks' partial X H^T read from their memory over
-  // NVLink in rank order (identical on every rank), and the updated columns are also stored into every peer's W^T.
+  // (this rank's gene slice) and the updated columns are also stored into every peer's W^T over NVLink.
   long long col0;
-  int n_peers;                    // 0: single-GPU / NCCL path (Num is already the complete numerator)
-  const float* num_peer[kMaxPeers];
+  int n_peers;                    // 0: single-GPU / NCCL path
   float* mat_peer[kMaxPeers];     // peers' W^T (nullptr for this rank itself)
   // rows [r0, r1) of Mat are updated (all K rows take part in Z).  The whole matrix for the simultaneous update
   // (main.py:589-663); one component block for the block Gauss-Seidel ("ALS") sweep (main.py:523-588), where the
@@ -401,18 +399,7 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
     float nv[4] = {0.f, 0.f, 0.f, 0.f}, gn[4] = {0.f, 0.f, 0.f, 0.f}, gd[4] = {0.f, 0.f, 0.f, 0.f};
     const float* nsrc = p.Num + static_cast<long long>(k) * p.ldNum + col;
     const bool g_on = (EPI == EPI_H) && (k < p.Kg);
-    if (EPI == EPI_W && p.n_peers > 0) {
-      const long long o = static_cast<long long>(k) * p.ldNum + col;
-      for (int q = 0; q < p.n_peers; ++q) {  // fixed rank order: bit-identical sums on every rank
-        if (full) {
-          const float4 t = ld_sys_v4(p.num_peer[q] + o);
-          nv[0] += t.x, nv[1] += t.y, nv[2] += t.z, nv[3] += t.w;
-        } else {
-          for (int x = 0; x < 4; ++x)
-            if (col + x < p.L) nv[x] += ld_sys_f32(p.num_peer[q] + o + x);
-        }
-      }
-    } else if (full) {
+    if (full) {
       const float4 t = *reinterpret_cast<const float4*>(nsrc);
       nv[0] = t.x, nv[1] = t.y, nv[2] = t.z, nv[3] = t.w;
       if (g_on) {

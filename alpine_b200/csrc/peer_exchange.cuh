@@ -4,15 +4,14 @@
 // Every rank owns an "exchange block" [ reduce buffer (its partial X H^T, H H^T, rowsum H, B statistics) | W^T |
 // flags ].  One iteration on rank r, all in stream order:
 //   1. the contraction + reduce kernels leave the partial X_r H_r^T in the block              (alpine_mu_partials)
-//   2. peer_signal_kernel: system-scope fence, then ready[r] = epoch in every peer's block
-//   3. peer_wait_small_kernel: wait until ready[q] == epoch for all q, then sum the small statistics of all ranks
-//      (rank order) into a local buffer
-//   4. sym_long_kernel<EPI_W> on THIS RANK'S GENE SLICE only: numerator = sum over ranks of their partials, read
-//      straight from peer memory; the updated columns of W^T are stored locally and into every peer's W^T
-//      ("two-shot" all-reduce with the update between reduce-scatter and all-gather: 2 x 7/8 x 8 MB per GPU)
-//   5. peer_signal_kernel: done[r] = epoch;  6. peer_wait_kernel: wait for done[q] == epoch for all q
+//   2. peer_gather_reduce_kernel: system-scope fence, ready[r] = epoch in every peer's block; wait until
+//      ready[q] == epoch for all q; then sum over the ranks (rank order), with loads straight from peer memory,
+//      the small statistics and THIS RANK'S GENE SLICE of the numerator ("reduce-scatter")
+//   3. sym_long_kernel<EPI_W> on the gene slice: the updated columns of W^T are stored locally and into every
+//      peer's W^T ("all-gather" by peer stores; with step 2: 2 x 7/8 x 8 MB per GPU over NVLink, the update between)
+//   4. peer_signal_wait_kernel: done[r] = epoch everywhere, wait for done[q] == epoch for all q
 // after which W^T is complete on every rank, bit-identical (same summation order everywhere).  A rank overwrites its
-// partials only after step 6 of the same iteration, i.e. after every peer has finished reading them.
+// partials only after step 4 of the same iteration, i.e. after every peer has finished reading them.
 // All waits are bounded and report through the context's error flag instead of hanging the GPU.
 #pragma once
 #include "mu_small_kernels.cuh"
@@ -59,22 +58,59 @@ __device__ __forceinline__ bool peer_wait_all(const PeerTable& t, int which, int
   return bad == 0;
 }
 
-__global__ void __launch_bounds__(256) peer_wait_kernel(const PeerTable t, int which, int epoch, int* err) {
+// done[r] = epoch on every rank, then wait until every rank has said so: one launch between the W-update kernel
+// (whose stores into the peers' W^T precede the fence in stream order) and the first consumer of the gathered W^T
+__global__ void __launch_bounds__(32) peer_signal_wait_kernel(const PeerTable t, int which, int epoch, int* err) {
+  __threadfence_system();
+  if (threadIdx.x < t.world) {
+    volatile int* f = t.flags[threadIdx.x] + which * kMaxPeers + t.rank;
+    *f = epoch;
+  }
+  __threadfence_system();
   peer_wait_all(t, which, epoch, err);
 }
 
-// wait for every rank's partials, then out[e] = sum over ranks (in rank order) of their small statistics
-__global__ void __launch_bounds__(256) peer_wait_small_kernel(const PeerTable t, int epoch, int n_small,
-                                                              float* __restrict__ out, int* err) {
+// "Reduce-scatter" by peer loads: block 0 first publishes ready[r] = epoch (this rank's partials are complete: the
+// kernels that wrote them precede this one in the stream); every block then waits for all ranks and sums, in rank
+// order,  (a) the small statistics [S | hsum | Q] of all ranks -> small_out  and  (b) the columns [g0, g1) of the
+// partial numerators (K x ldG at the head of every exchange block) -> p_out (same pitch).  One thread per float4,
+// all peers' loads in flight together, so the NVLink latency is paid once, not per peer.
+__global__ void __launch_bounds__(256) peer_gather_reduce_kernel(const PeerTable t, int epoch, int n_small,
+                                                                 float* __restrict__ small_out, int K, long long ldG,
+                                                                 long long g0, long long g1,
+                                                                 float* __restrict__ p_out, int* err) {
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    if (threadIdx.x < t.world) {
+      volatile int* f = t.flags[threadIdx.x] + 0 * kMaxPeers + t.rank;
+      *f = epoch;
+    }
+    __threadfence_system();
+  }
   peer_wait_all(t, 0, epoch, err);  // every block polls this rank's own flag array (local memory)
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_small; e += gridDim.x * blockDim.x) {
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nth = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long e = tid; e < n_small; e += nth) {
     float v[kMaxPeers];
 #pragma unroll
-    for (int q = 0; q < kMaxPeers; ++q) v[q] = (q < t.world) ? ld_sys_f32(t.small[q] + e) : 0.f;  // loads in flight together
+    for (int q = 0; q < kMaxPeers; ++q) v[q] = (q < t.world) ? ld_sys_f32(t.small[q] + e) : 0.f;
     float acc = 0.f;
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q) acc += v[q];
-    out[e] = acc;
+    small_out[e] = acc;
+  }
+  const long long w4 = (g1 - g0 + 3) >> 2;  // g0 is a multiple of 64 and ldG of 4: whole float4 groups stay in the pitch
+  for (long long e = tid; e < static_cast<long long>(K) * w4; e += nth) {
+    const long long k = e / w4, c = g0 + ((e - k * w4) << 2);
+    const long long o = k * ldG + c;
+    float4 v[kMaxPeers];
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q)
+      v[q] = (q < t.world) ? ld_sys_v4(t.small[q] - static_cast<long long>(K) * ldG + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < kMaxPeers; ++q) acc.x += v[q].x, acc.y += v[q].y, acc.z += v[q].z, acc.w += v[q].w;
+    *reinterpret_cast<float4*>(p_out + o) = acc;
   }
 }
 
