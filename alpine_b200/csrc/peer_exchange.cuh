@@ -44,7 +44,7 @@ __device__ __forceinline__ bool peer_wait_all(const PeerTable& t, int which, int
     volatile int* f = t.flags[t.rank] + which * kMaxPeers + threadIdx.x;
     const long long t0 = clock64();
     while (*f < epoch) {
-      if (clock64() - t0 > (4ll << 30)) {  // ~2 s
+      if (clock64() - t0 > (20ll << 30)) {  // ~10 s: a peer that late is lost, not slow
         if (atomicCAS(err, 0, ERR_PEER_TIMEOUT) == 0) {
           err[1] = t.rank, err[2] = threadIdx.x, err[3] = which, err[4] = epoch;
         }

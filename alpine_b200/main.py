@@ -455,9 +455,11 @@ class ALPINE:
             return self._fit_minibatch(m)
         solver = self._make_solver(m)
         try:
-            if dist_info()[1] > 1 and not self.use_als and os.environ.get("ALPINE_B200_PEER", "1") != "0":
-                # exchange over NVLink peer memory inside the W-update kernels; falls back to the NCCL all-reduce
-                # (on every rank) when CUDA IPC is not available between the processes
+            if dist_info()[1] > 1 and not self.use_als and os.environ.get("ALPINE_B200_PEER", "0") == "1":
+                # Opt-in: exchange over NVLink peer memory inside the W-update kernels instead of the NCCL
+                # all-reduce (falls back to it, on every rank, when CUDA IPC is not available).  Mapping the peers'
+                # exchange blocks costs ~0.2 s per fit and saves ~35 us per iteration at 8 GPUs, so it only pays
+                # for very long fits; bench.py's device-resident arm uses it.
                 solver.enable_peer_exchange()
             engine = MUEngine(solver, self.lam, use_als=self.use_als)
             pbar = None

@@ -501,7 +501,11 @@ def run_e2e(args, wl, dev, world, rank):
     n_cat = sum(wl["categories"])
     h2d = 4.0 * (G * n + n_cat * n) / world
     d2h = 4.0 * (G * K + K * n + sum(c * k for c, k in zip(wl["categories"], wl["n_covariate_components"]))) + 8.0 * steps * 4
+    peer_fit = os.environ.get("ALPINE_B200_PEER", "0") == "1"
     return {"value": steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
+            "exchange": ("none (single GPU)" if world == 1 else
+                         "NVLink peer memory (ALPINE_B200_PEER=1)" if peer_fit else
+                         "NCCL all-reduce (ALPINE.fit's default: mapping peer memory costs ~0.2 s per fit)"),
             "seconds_per_fit": dt, "iterations_per_fit": steps,
             "phases_s": {k: round(v, 4) for k, v in getattr(model, "timings", {}).items()},
             "what": "ALPINE(...).fit(adata, keys, max_iter=steps) on host numpy data: validation, encoders, H2D of X/Y, "
