@@ -70,9 +70,10 @@ class AlpineMatrices:
         return {
             "X": X,
             "Ys": Ys,
-            "Ws": [w.cpu().numpy().astype(np.float32) for w in self.Ws],
-            "Hs": [h.cpu().numpy().astype(np.float32) for h in _gather_cells(self.Hs, self.shard, self.n_total)],
-            "Bs": [b.cpu().numpy().astype(np.float32) for b in self.Bs],
+            "Ws": [w.cpu().numpy().astype(np.float32, copy=False) for w in self.Ws],
+            "Hs": [h.cpu().numpy().astype(np.float32, copy=False)
+                   for h in _gather_cells(self.Hs, self.shard, self.n_total)],
+            "Bs": [b.cpu().numpy().astype(np.float32, copy=False) for b in self.Bs],
         }
 
 
@@ -218,7 +219,7 @@ class ALPINE:
                 m.solver = None
         self.matrices = m.to_numpy()
         lap("scale_download")
-        self.store_embeddings(adata)
+        self.store_embeddings(adata, _dummy_matrices=Y)  # the encoders were fitted on this adata a moment ago
         lap("store_embeddings")
         return self
 
@@ -345,13 +346,13 @@ class ALPINE:
         scale = np.where(totals > 0, totals / target, 1.0).astype(np.float32)
         adata.layers["normalized_expression"] = Xn / scale[:, None]
 
-    def store_embeddings(self, adata: AnnData) -> None:
+    def store_embeddings(self, adata: AnnData, _dummy_matrices=None) -> None:
         """Write embeddings / weights into the AnnData slots of main.py:303-320."""
         validation.check_trained(self)
         validation.check_adata(adata)
         adata.obsm["ALPINE_embedding"] = copy(self.matrices["Hs"][-1].T)
         adata.varm["ALPINE_weights"] = copy(self.matrices["Ws"][-1])
-        dummy_matrices = self.fe.transform(adata.obs)
+        dummy_matrices = _dummy_matrices if _dummy_matrices is not None else self.fe.transform(adata.obs)
         for i, covariate in enumerate(self.covariate_keys):
             adata.obsm[covariate] = copy(self.matrices["Hs"][i].T)
             adata.obsm[f"{covariate}_dummy_matrix"] = dummy_matrices[i]
