@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 from typing import List, Optional, Sequence
 
 import torch
@@ -112,7 +113,14 @@ def padded_rows(rows: int, cols: int, device, dtype=torch.float32, fill: Optiona
     return buf[:, :cols]
 
 
-_RING: dict = {}
+class _RingStore(threading.local):
+    """Per-thread pinned staging ring (ComponentOptimizer uploads from one worker thread per GPU)."""
+
+    def __init__(self):
+        self.rings: dict = {}
+
+
+_RING = _RingStore()
 
 
 def _host_copy_threads() -> int:
@@ -142,10 +150,11 @@ def upload_rows(dst: torch.Tensor, src, chunk_bytes: int = 16 << 20, n_buffers: 
         return
     chunk_rows = max(1, chunk_bytes // (cols * 4))
     key = (chunk_rows * cols, n_buffers)
-    if key not in _RING:
-        _RING.clear()  # keep at most one ring alive
-        _RING[key] = [torch.empty(chunk_rows * cols, dtype=torch.float32, pin_memory=True) for _ in range(n_buffers)]
-    bufs = _RING[key]
+    rings = _RING.rings
+    if key not in rings:
+        rings.clear()  # keep at most one ring alive per thread
+        rings[key] = [torch.empty(chunk_rows * cols, dtype=torch.float32, pin_memory=True) for _ in range(n_buffers)]
+    bufs = rings[key]
     events = [None] * n_buffers
     stream = torch.cuda.current_stream(dst.device)
     old_threads = torch.get_num_threads()

@@ -165,7 +165,7 @@ class ALPINE:
         def lap(name: str) -> None:
             nonlocal t0
             if self.device.type == "cuda" and torch.cuda.is_available():
-                torch.cuda.synchronize()
+                torch.cuda.synchronize(self._cuda_device())
             t1 = time.perf_counter()
             self.timings[name] = self.timings.get(name, 0.0) + (t1 - t0)
             t0 = t1

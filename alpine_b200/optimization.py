@@ -194,10 +194,18 @@ class ComponentOptimizer:
                                   max_evals=n_new + len(self.trials.trials), trials=self.trials,
                                   rstate=np.random.default_rng(self.random_state))
         else:
+            # Random search: the suggestions do not depend on earlier results, so floor(n_gpus / n_splits) trials
+            # are evaluated at a time and all their fold fits go through ONE device queue (8 GPUs: 2 trials x 3
+            # folds in flight, the queue keeps every GPU busy).  Same suggestions, same scores and the same trial
+            # order as evaluating them one by one.
             rng = np.random.default_rng(self.random_state + len(self.trials.trials))
-            for _ in range(n_new):
-                vals = _sample_space(rng, self._ranges, n_cov)
-                self.trials.add(vals, self.objective(_vals_to_space(vals, n_cov)))
+            batch = max(1, len(self.devices) // max(1, self.n_splits))
+            todo = n_new
+            while todo > 0:
+                vals = [_sample_space(rng, self._ranges, n_cov) for _ in range(min(batch, todo))]
+                for v, result in zip(vals, self._evaluate([_vals_to_space(v, n_cov) for v in vals])):
+                    self.trials.add(v, result)
+                todo -= len(vals)
             best = self.trials.best_vals()
         if best is None:
             raise RuntimeError("Hyperparameter optimization did not return any result.")
@@ -228,19 +236,43 @@ class ComponentOptimizer:
         return total - sum(guided), guided
 
     def objective(self, space):
+        return self._evaluate([space])[0]
+
+    def _trial_args(self, space) -> Optional[dict]:
+        """Model arguments of one suggestion, or None when the component split is infeasible (optimization.py:185-188)."""
         n_cov = len(self.covariate_keys)
         lam = [space[f"lam_{i}"] for i in range(n_cov)]
         n_components, n_covariate_components = self._distribute_components(space)
         if not (sum(n_covariate_components) <= n_components and all(n >= 2 for n in n_covariate_components)):
-            return {"loss": np.inf, "status": STATUS_FAIL}  # optimization.py:185-188, 217-218
-        args = {"n_components": n_components, "n_covariate_components": n_covariate_components, "lam": lam,
+            return None
+        return {"n_components": n_components, "n_covariate_components": n_covariate_components, "lam": lam,
                 "orth_W": space["orth_W"], "alpha_W": space["alpha_W"], "l1_ratio_W": space["l1_ratio_W"]}
-        score = self.calc_score(args)
-        params = dict(args, lam=list(lam),
-                      max_iter=self.iter_records[-1] if self.max_iter_detect else self.max_iter, score=score)
+
+    def _evaluate(self, spaces: List[dict]) -> List[dict]:
+        """Objective of one or several suggestions (optimization.py:178-218); all their fold fits share one device
+        queue.  With ``max_iter=None`` every trial of a batch detects its own iteration count; the running mean is
+        taken over after the batch instead of after the first trial."""
+        all_args = [self._trial_args(sp) for sp in spaces]
+        folds = self._folds()
+        jobs = [(a, tr, va) for a in all_args if a is not None for tr, va in folds]
+        self.last_scheduler = DeviceScheduler(self.devices)
+        out = self.last_scheduler.map(self._fit_fold, jobs) if jobs else []
+        results, pos = [], 0
+        for a in all_args:
+            if a is None:
+                results.append({"loss": np.inf, "status": STATUS_FAIL})  # optimization.py:217-218
+                continue
+            mine = out[pos:pos + len(folds)]
+            pos += len(folds)
+            if self.max_iter_detect:
+                self.iter_records.extend(m for _, m in mine)
+            score = float(np.mean([s for s, _ in mine]))
+            params = dict(a, lam=list(a["lam"]),
+                          max_iter=self.iter_records[-1] if self.max_iter_detect else self.max_iter, score=score)
+            results.append({"loss": score, "status": STATUS_OK, "params": params})
         if self.max_iter_detect and len(self.iter_records) >= self.n_splits:
             self.max_iter = int(sum(self.iter_records) / len(self.iter_records))
-        return {"loss": score, "status": STATUS_OK, "params": params}
+        return results
 
     # ------------------------------------------------------------------------------------------------ scoring
     def _folds(self):
@@ -272,7 +304,8 @@ class ComponentOptimizer:
         return self.scorer(val_adata, self.covariate_keys, self.random_state), model.max_iter
 
     def calc_score(self, args):
-        """Mean CV score of one hyper-parameter setting; the folds run concurrently, one per GPU."""
+        """Mean CV score of one hyper-parameter setting (optimization.py:220-287); the folds run concurrently, one
+        per GPU."""
         jobs = [(args, tr, va) for tr, va in self._folds()]
         self.last_scheduler = DeviceScheduler(self.devices)
         out = self.last_scheduler.map(self._fit_fold, jobs)

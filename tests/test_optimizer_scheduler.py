@@ -106,6 +106,25 @@ def test_search_dispatches_folds_over_devices_and_builds_history(tmp_path):
     assert isinstance(opt.fit_the_best_param(), _FakeModel)
 
 
+def test_batched_trials_fill_all_devices_and_match_sequential_search():
+    """8 GPUs, 3 folds: two trials (6 fold fits) are in flight at a time; suggestions, scores and trial order are
+    those of the one-device search."""
+    runs = []
+    for devices in (["cuda:0"], [f"cuda:{i}" for i in range(8)]):
+        _FakeModel.seen = []
+        opt = ComponentOptimizer(_adata(), ["batch", "cond"], max_iter=5, device="cpu", random_state=5)
+        opt.model_factory = _FakeModel
+        opt.devices = devices
+        opt.search_hyperparams(n_total_components_range=(10, 30), n_splits=3, max_evals=7)
+        runs.append((opt, list(_FakeModel.seen)))
+    (one, seen1), (eight, seen8) = runs
+    assert [t["misc"]["vals"] for t in one.trials.trials] == [t["misc"]["vals"] for t in eight.trials.trials]
+    assert [t["result"]["loss"] for t in one.trials.trials] == [t["result"]["loss"] for t in eight.trials.trials]
+    assert one.best_param == eight.best_param
+    assert len(seen1) == len(seen8) and len(set(seen8)) > 3     # more GPUs busy than one trial's three folds
+    assert set(seen1) == {"cuda:0"}
+
+
 def test_optimizer_validation():
     ad = _adata()
     with pytest.raises(TypeError):
