@@ -12,6 +12,7 @@ Like the reference, the mean CV score is handed to the optimiser as its "loss" (
 from __future__ import annotations
 
 import pickle
+import threading
 from copy import copy
 from typing import Callable, List, Optional, Tuple
 
@@ -20,7 +21,7 @@ import pandas as pd
 
 from .main import ALPINE
 from .scheduler import DeviceScheduler, visible_devices
-from .utils.anndata_compat import AnnData
+from .utils.anndata_compat import HAVE_ANNDATA, AnnData
 
 STATUS_OK, STATUS_FAIL = "ok", "fail"
 
@@ -133,6 +134,8 @@ class ComponentOptimizer:
             print("Owing to max_iter being None, it will be determine by the average of the first n_splits iterations.")
         # scheduling: one fit per GPU (the reference runs the folds one after the other on one device)
         self.devices: List[str] = visible_devices(device)
+        self._fold_cache: dict = {}
+        self._fold_lock = threading.Lock()
         self.scorer: Callable = default_scorer
         self.model_factory: Callable[..., ALPINE] = ALPINE
 
@@ -287,11 +290,27 @@ class ComponentOptimizer:
         skf = StratifiedKFold(n_splits=self.n_splits, shuffle=True, random_state=self.random_state)
         return list(skf.split(np.zeros(len(joint)), joint))
 
+    def _fold_adata(self, idx) -> AnnData:
+        """``self.adata[idx].copy()`` (optimization.py:242-243).  The folds are the same for every trial, so the
+        row subsets of X and obs are materialised once per fold and every job gets its own AnnData around them
+        (fresh obsm / varm / layers, its own obs frame): fits never write to X, and concurrent trials must not share
+        the slots they do write."""
+        key = (len(idx), int(idx[0]) if len(idx) else -1, int(np.sum(idx)))
+        with self._fold_lock:
+            hit = self._fold_cache.get(key)
+            if hit is None:
+                sub = self.adata[idx]
+                sub = sub.copy() if HAVE_ANNDATA else sub  # the stand-in's subsetting already copies
+                hit = self._fold_cache[key] = sub
+        if HAVE_ANNDATA:  # pragma: no cover - real anndata: keep the reference's semantics literally
+            return hit.copy()
+        return AnnData(hit.X, obs=hit.obs.copy(), var=hit.var)
+
     def _fit_fold(self, job, device: str):
         """One fold: fit on the training cells, transform the validation cells, score the embedding."""
         args, train_idx, val_idx = job
-        train_adata = self.adata[train_idx].copy()
-        val_adata = self.adata[val_idx].copy()
+        train_adata = self._fold_adata(train_idx)
+        val_adata = self._fold_adata(val_idx)
         model = self.model_factory(
             n_covariate_components=args["n_covariate_components"], n_components=args["n_components"],
             lam=[float(v) for v in args["lam"]], orth_W=float(args["orth_W"]), alpha_W=float(args["alpha_W"]),
@@ -299,7 +318,8 @@ class ComponentOptimizer:
             loss_type=self.loss_type, device=device)
         model.fit(adata=train_adata, covariate_keys=self.covariate_keys, max_iter=self.max_iter,
                   batch_size=self.batch_size, sampling_method=self.sampling_method, verbose=False)
-        model.store_embeddings(train_adata)
+        # (the reference stores the embeddings into train_adata again here, optimization.py:267; fit has just done
+        # that and train_adata is dropped, so the call is skipped)
         model.transform(val_adata)
         return self.scorer(val_adata, self.covariate_keys, self.random_state), model.max_iter
 
