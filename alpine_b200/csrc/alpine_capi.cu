@@ -607,9 +607,12 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
   int dev_count = 0;
   CU_TRY(cudaGetDeviceCount(&dev_count));
   if (device < 0 || device >= dev_count) return fail(ALPINE_ERR_ARG, "device %d not present (%d devices)", device, dev_count);
-  cudaDeviceProp prop;
-  CU_TRY(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) return fail(ALPINE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+  // (attributes, not cudaGetDeviceProperties: that call takes ~0.1 s and a context is created per fit)
+  int cc_major = 0, cc_minor = 0, sm_count = 0;
+  CU_TRY(cudaDeviceGetAttribute(&cc_major, cudaDevAttrComputeCapabilityMajor, device));
+  CU_TRY(cudaDeviceGetAttribute(&cc_minor, cudaDevAttrComputeCapabilityMinor, device));
+  CU_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+  if (cc_major != 10) return fail(ALPINE_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, cc_major, cc_minor);
   alpine_ctx* c = new alpine_ctx();
   c->device = device;
   c->G = n_genes;
@@ -617,7 +620,7 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
   c->n_blocks = n_blocks;
   c->n_cov = n_cov;
   c->loss_type = loss_type;
-  c->num_sms = prop.multiProcessorCount;
+  c->num_sms = sm_count;
   int K = 0, Kg = 0, q = 0;
   for (int i = 0; i < n_blocks; ++i) {
     if (k_blocks[i] <= 0) {

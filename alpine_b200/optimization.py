@@ -92,8 +92,8 @@ def default_scorer(val_adata, covariate_keys: List[str], random_state: int) -> f
     except ImportError:
         from sklearn.cluster import KMeans
 
-        joint = val_adata.obs[covariate_keys].astype(str).agg("_".join, axis=1)
-        k = int(max(2, min(joint.nunique(), len(emb) - 1)))
+        n_joint = len(val_adata.obs[covariate_keys].astype(str).drop_duplicates())  # distinct joint labels
+        k = int(max(2, min(n_joint, len(emb) - 1)))
         clusters = KMeans(n_clusters=k, n_init=4, random_state=random_state).fit_predict(emb)
     score = 0.0
     for key in covariate_keys:
