@@ -50,6 +50,7 @@ SIGNATURES = {
     "alpine_peer_export": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_peer_import": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "alpine_mu_apply_peer": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_peer_disable": (ctypes.c_int, [_c_ctx]),
     "alpine_reduce_stats_offset": (ctypes.c_int64, [_c_ctx]),
     "alpine_als_block": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_als_finish": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
@@ -304,6 +305,8 @@ class Solver:
             flag = torch.tensor([1 if ok else 0], device=self.device)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         self.peer = int(flag.item()) == 1
+        if not self.peer:
+            self.lib.alpine_peer_disable(self._ctx)  # every rank falls back to the all-reduce path together
         self._peer_group = group
         dist.barrier(group=group)
         return self.peer

@@ -592,7 +592,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 5; }
+int alpine_abi_version(void) { return 6; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -1045,6 +1045,15 @@ int alpine_peer_import(alpine_ctx* c, int rank, int world, const void* handles) 
   }
   c->peer_rank = rank;
   c->peer_world = world;
+  return ALPINE_OK;
+}
+
+int alpine_peer_disable(alpine_ctx* c) {
+  if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
+  // back to the caller-side all-reduce (another rank could not map the peers): the exchange block, if any, keeps
+  // serving as this rank's private reduce buffer / W^T storage
+  c->peer_world = 0;
+  c->peer_rank = -1;
   return ALPINE_OK;
 }
 

@@ -94,6 +94,8 @@ int alpine_mu_apply(alpine_ctx* ctx, int iter, void* stream);
 int alpine_peer_export(alpine_ctx* ctx, void* ipc_handle_64_bytes);
 int alpine_peer_import(alpine_ctx* ctx, int rank, int world, const void* ipc_handles);
 int alpine_mu_apply_peer(alpine_ctx* ctx, int iter, void* stream);
+/* Return to the caller-side all-reduce (alpine_mu_apply), e.g. when some other rank failed to map the peers. */
+int alpine_peer_disable(alpine_ctx* ctx);
 /* Block Gauss-Seidel ("ALS") sweep, use_als=True (main.py:523-588).  One iteration is
  *   alpine_mu_partials            X H^T for all blocks in one sweep of X (every H_b is still unchanged when its W_b
  *                                 update consumes its columns)           [+ all-reduce of the whole reduce buffer]

@@ -299,3 +299,45 @@ def test_degenerate_and_maximal_shapes_match_oracle(shape, mode):
     # the trace identity subtracts quantities of size ||X||^2 held in fp32 factors: its absolute error is ~1e-7 ||X||^2,
     # which only shows when the fit is near-exact (a single cell is a rank-1 problem: recon / ||X||^2 = 7e-5)
     assert abs(recon - ref[1]) <= 1e-4 * ref[1] + 1e-6 * xn
+
+
+def test_peer_exchange_fallback_keeps_the_all_reduce_path_working():
+    """A rank that exported its exchange block but then falls back (another rank could not map the peers) must run
+    the ordinary path on the block's storage (W^T lives inside it) with unchanged results."""
+    import ctypes
+
+    gu = _gpu_utils()
+    from alpine_b200 import _native
+
+    name = "kl_reg_nan"
+    g = load_golden(name)
+    n_cov = int(g["n_cov"])
+    Ys = [np.ascontiguousarray(g[f"Y{i}_cells_by_cat"].T) for i in range(n_cov)]
+    kw = dict(CASE_KW[name])
+    dev = torch.device("cuda:0")
+    n, G = g["X_cells_by_genes"].shape
+    X = gu.to_dev_padded(g["X_cells_by_genes"], dev)
+    W = torch.from_numpy(g["W0"].copy()).to(dev)
+    H = gu.to_dev_padded(g["H0"], dev)
+    Yd = [torch.from_numpy(y).to(dev) for y in Ys]
+    Bd = [torch.from_numpy(g[f"B0_{i}"].copy()).to(dev) for i in range(n_cov)]
+    s = _native.Solver(dev, G, n, [int(b) for b in g["blocks"]], [y.shape[0] for y in Ys])
+    handle = (ctypes.c_ubyte * 64)()
+    assert s.lib.alpine_peer_export(s._ctx, ctypes.cast(handle, ctypes.c_void_p)) == 0
+    assert s.lib.alpine_peer_disable(s._ctx) == 0
+    s.bind_dense(X)
+    s.bind_labels(Yd)
+    s.bind_factors(W, H, Bd)
+    s.set_hparams(kw["lam"], kw["alpha_W"], kw["l1_ratio_W"], kw["orth_W"], 1e-6)
+    with pytest.raises(_native.AlpineNativeError):
+        s.fit_begin(3)
+        s.mu_partials()
+        s.mu_apply_peer(0)  # no peers were imported
+    s.fit_begin(5)
+    for it in range(5):
+        s.mu_partials()
+        s.mu_apply(it)
+    s.losses(5)
+    assert rel_fro(W.cpu().numpy(), g["W_it5"]) < EXPECTED_TOL
+    assert rel_fro(H.cpu().numpy(), g["H_it5"]) < EXPECTED_TOL
+    s.close()
