@@ -95,6 +95,20 @@ def _upload_csr(Xcsr, lo: int, hi: int, dev):
     return indptr, indices, values
 
 
+def _csr_take_rows(csr, idx: torch.Tensor):
+    """Rows ``idx`` (with repetition, in order) of a device CSR triple -> a new device CSR triple."""
+    indptr, indices, values = csr
+    starts = indptr[idx]
+    counts = indptr[idx + 1] - starts
+    new_indptr = torch.zeros(idx.numel() + 1, dtype=torch.int64, device=indptr.device)
+    torch.cumsum(counts, 0, out=new_indptr[1:])
+    total = int(new_indptr[-1].item())
+    # position p of the output belongs to row r(p) = searchsorted(new_indptr, p) and is element p - new_indptr[r] of it
+    row_of = torch.repeat_interleave(torch.arange(idx.numel(), device=indptr.device), counts, output_size=total)
+    src = starts[row_of] + (torch.arange(total, device=indptr.device) - new_indptr[row_of])
+    return new_indptr, indices[src].contiguous(), values[src].contiguous()
+
+
 def _gather_cells(Hs: List[torch.Tensor], shard, n_total: int) -> List[torch.Tensor]:
     """All ranks' column blocks of every H block, concatenated along cells (identity without sharding)."""
     rank, world = dist_info()
@@ -481,8 +495,8 @@ class ALPINE:
     def _fit_minibatch(self, m: AlpineMatrices) -> None:
         """Epochs of mini-batch MU steps (main.py:500-521, 589-663) with the reference's index streams.
 
-        Per batch the cells ``idx`` are gathered into contiguous buffers (rows of the cells-major X, columns of H
-        and Y), one MU step runs on them with the same kernels as the full-batch path, and the H columns are
+        Per batch the cells ``idx`` are gathered into contiguous buffers (rows of the cells-major X -- or of the CSR
+        matrix --, columns of H and Y), one MU step runs on them with the same kernels as the full-batch path, and the H columns are
         scattered back (``Hs[j][:, idx] = ...``, main.py:662; duplicate indices of the weighted sampler resolve as
         torch's ``index_put`` does).  The loss of every epoch is evaluated on the full data (main.py:666).
         """
@@ -491,10 +505,9 @@ class ALPINE:
 
         if dist_info()[1] > 1:
             raise NotImplementedError("mini-batch fitting is single-GPU; cell sharding covers the full-batch path")
-        if m.X_csr is not None:
-            raise NotImplementedError("mini-batch fitting needs a dense adata.X; the CSR path is full-batch")
         dev = m.W.device
-        n, G = m.X_cells_major.shape
+        n, G = m.H.shape[1], m.W.shape[0]
+        sparse = m.X_csr is not None
         K = self.total_components
         joint_labels = create_joint_labels_from_dummy_matrices(m.Ys) if m.Ys else [""] * n
         bs = int(min(self.batch_size, n))
@@ -502,11 +515,12 @@ class ALPINE:
 
         def batch_solver(size: int):
             if size not in solvers:
-                Xb = _native.padded_rows(size, G, dev)
+                Xb = None if sparse else _native.padded_rows(size, G, dev)
                 Hb = _native.padded_rows(K, size, dev)
                 Yb = [torch.empty((y.shape[0], size), dtype=torch.float32, device=dev) for y in m.Ys]
                 s = _native.Solver(dev, G, size, self.n_all_components, [y.shape[0] for y in m.Ys], self.loss_type)
-                s.bind_dense(Xb)
+                if not sparse:
+                    s.bind_dense(Xb)
                 s.bind_labels(Yb)
                 s.bind_factors(m.W, Hb, m.Bs)
                 s.set_hparams(self.lam, self.alpha_W, self.l1_ratio_W, self.orth_W, self.eps)
@@ -536,7 +550,10 @@ class ALPINE:
                     if len(idx) == 0:
                         break
                     s, Xb, Hb, Yb = batch_solver(len(idx))
-                    Xb.copy_(m.X_cells_major.index_select(0, idx))
+                    if sparse:  # the batch's cells as their own CSR matrix -> tile lists (once per batch)
+                        s.bind_csr(*_csr_take_rows(m.X_csr, idx))
+                    else:
+                        Xb.copy_(m.X_cells_major.index_select(0, idx))
                     Hb.copy_(m.H.index_select(1, idx))
                     for yb, y in zip(Yb, m.Ys):
                         yb.copy_(y.index_select(1, idx))

@@ -147,13 +147,32 @@ def test_als_public_fit_matches_oracle():
     assert len(out.loss_history) == 5 and np.isfinite(out.loss_history.to_numpy()).all()
 
 
-def test_unsupported_modes_raise():
+@pytest.mark.parametrize("method", ["random", "weighted"])
+def test_sparse_minibatch_equals_dense_minibatch(method):
+    """Mini-batch epochs on CSR input: the batch's rows are re-tiled on the device; same index stream => same fit."""
     import scipy.sparse as sp
 
+    ad = _adata(n=500, G=300, cats=(3,), nan_fraction=0.02)
+    ad.X[np.random.default_rng(3).random(ad.X.shape) < 0.6] = 0.0
+    ad_sp = AnnData(sp.csr_matrix(ad.X), obs=ad.obs.copy(), var=ad.var.copy())
+    rng = np.random.default_rng(9)
+    streams = [rng.permutation(500) if method == "random" else rng.integers(0, 500, 500) for _ in range(3)]
+    fits = []
+    for data in (ad, ad_sp):
+        model = ALPINE(n_components=5, n_covariate_components=[3], lam=[1e2], alpha_W=0.1, device="cuda")
+        model._epoch_index_stream = iter([s.copy() for s in streams])
+        model.fit(data, ["cov0"], max_iter=3, batch_size=128, sampling_method=method)
+        fits.append((data.obsm["ALPINE_embedding"].copy(), data.varm["ALPINE_weights"].copy(),
+                     model.loss_history.to_numpy()))
+    np.testing.assert_allclose(fits[1][0], fits[0][0], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(fits[1][1], fits[0][1], rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(fits[1][2], fits[0][2], rtol=1e-5)
+
+
+def test_unsupported_modes_raise():
     ad = _adata(n=200, G=100, cats=(3,), nan_fraction=0.0)
-    ad.X = sp.csr_matrix(ad.X)
-    with pytest.raises(NotImplementedError):  # the CSR path is full-batch
-        ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0]).fit(ad, ["cov0"], max_iter=2, batch_size=50)
+    with pytest.raises(ValueError):
+        ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0]).fit(ad, ["cov0"], max_iter=2, sampling_method="nope")
 
 
 def _model_on_golden(name, g, **extra):
