@@ -1,0 +1,88 @@
+"""Run the UNMODIFIED reference next to the oracle on fresh random cases (build container only).
+
+The committed fixtures (tests/golden) pin the oracle on nine fixed cases; this test draws new shapes and
+hyper-parameters every time the suite runs here and steps the reference's own ``_fit`` (through oracle/ref_shim.py)
+and the oracle side by side.  /root/reference does not exist on the GPU box: the test skips there.
+"""
+import numpy as np
+import pandas as pd
+import pytest
+import torch
+
+from oracle import alpine_oracle as orc
+from oracle import ref_shim
+from tests.helpers import rel_fro
+
+pytestmark = pytest.mark.skipif(not ref_shim.reference_available(), reason="reference tree not present")
+
+
+def _case(seed, loss_type, use_als, batch_size=None):
+    rng = np.random.default_rng(seed)
+    n, G = int(rng.integers(40, 120)), int(rng.integers(30, 90))
+    cats = [int(rng.integers(2, 5)) for _ in range(int(rng.integers(1, 3)))]
+    kcov = [int(rng.integers(2, 5)) for _ in cats]
+    kw = dict(n_components=int(rng.integers(3, 8)), n_covariate_components=kcov,
+              lam=[float(10 ** rng.uniform(0, 3)) for _ in cats], orth_W=float(rng.uniform(0, 0.5)),
+              alpha_W=float(rng.uniform(0, 1)), l1_ratio_W=float(rng.uniform(0, 1)), loss_type=loss_type, use_als=use_als)
+    Xcg = rng.gamma(0.5, 2.0, size=(n, G)).astype(np.float32)
+    labels = []
+    for c in cats:
+        lab = np.array([f"c{v}" for v in rng.integers(0, c, n)], dtype=object)
+        lab[rng.random(n) < 0.05] = np.nan
+        labels.append(lab)
+    return n, G, kw, Xcg, labels, batch_size
+
+
+@pytest.mark.parametrize("loss_type,use_als,batch", [("kl-divergence", False, None), ("frobenius", False, None),
+                                                     ("kl-divergence", True, None), ("frobenius", True, None),
+                                                     ("kl-divergence", False, 17), ("kl-divergence", True, 23)])
+def test_oracle_steps_with_the_reference(loss_type, use_als, batch):
+    ref_main = ref_shim.import_reference()
+    from alpine.utils.encoder import FeatureEncoders  # the reference's own encoder
+
+    torch.set_num_threads(1)
+    seed = int(np.random.SeedSequence().entropy % (2 ** 31))
+    n, G, kw, Xcg, labels, bs = _case(seed, loss_type, use_als, batch)
+    keys = [f"cov{i}" for i in range(len(labels))]
+    obs = pd.DataFrame({k: pd.Series(l, dtype=object) for k, l in zip(keys, labels)})
+    X = Xcg.T
+    Y = FeatureEncoders(keys).fit_transform(obs)
+    model = ref_shim.make_reference_model(ref_main, n, keys, max_iter=1, **kw)
+    streams = []
+    sampler = ref_main.generate_epoch_indices
+    if bs is not None:
+        model.batch_size = bs
+
+        def recording(*a, **k):
+            idx = sampler(*a, **k)
+            streams.append(idx.cpu().numpy().astype(np.int64))
+            return idx
+
+        ref_main.generate_epoch_indices = recording
+    try:
+        mats = model._initialize_matrices(X, Y)
+        blocks = list(model.n_all_components)
+        st = orc.State(torch.cat(mats.Ws, 1).numpy().copy(), torch.cat(mats.Hs, 0).numpy().copy(),
+                       [b.numpy().copy() for b in mats.Bs], blocks)
+        okw = dict(kw)
+        okw.pop("use_als")
+        hp = orc.HyperParams(**okw)
+        Ys = [np.ascontiguousarray(y.T) for y in Y]
+        step = orc.als_step if use_als else orc.mu_step
+        for it in range(4):
+            model._fit(mats)
+            if bs is None:
+                step(X, Ys, st, hp)
+            else:
+                idx = streams[-1]
+                for b0 in range(0, len(idx), bs):
+                    step(X, Ys, st, hp, idx=idx[b0:b0 + bs])
+            msg = f"seed {seed} iteration {it + 1}"
+            assert rel_fro(st.W, torch.cat(mats.Ws, 1).numpy()) < 5e-6, msg
+            assert rel_fro(st.H, torch.cat(mats.Hs, 0).numpy()) < 5e-6, msg
+            for i in range(len(keys)):
+                assert rel_fro(st.Bs[i], mats.Bs[i].numpy()) < 5e-6, msg
+            ref_loss = model.loss_history.iloc[-1].to_numpy(dtype=np.float64)
+            np.testing.assert_allclose(orc.compute_loss(X, Ys, st, hp)[:2], ref_loss[:2], rtol=5e-5, err_msg=msg)
+    finally:
+        ref_main.generate_epoch_indices = sampler
