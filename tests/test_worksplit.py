@@ -39,3 +39,17 @@ CASES = [
 def test_segments_match_reduce_slot_lists(exe, case):
     r = subprocess.run([exe] + [str(v) for v in case], capture_output=True, text=True)
     assert r.returncode == 0 and r.stdout.startswith("OK"), r.stdout + r.stderr
+
+
+def test_random_work_spaces(exe):
+    """Seeded random (tiles, k-blocks, piece length, grid) combinations, including grids larger than the work."""
+    import random
+
+    rng = random.Random(1234)
+    for _ in range(60):
+        tiles = rng.choice([1, 2, 3, 7, 40, 118, 391, 1000])
+        kb = rng.choice([1, 2, 5, 33, 157, 625, 3125, 9000])
+        piece = max(1, min(kb, rng.choice([1, 4, 8, 64, 312, 1048, 100000])))
+        grid = rng.choice([1, 2, 5, 64, 132, 148])
+        r = subprocess.run([exe, str(tiles), str(kb), str(piece), str(grid)], capture_output=True, text=True)
+        assert r.returncode == 0 and r.stdout.startswith("OK"), (tiles, kb, piece, grid, r.stdout + r.stderr)
