@@ -342,10 +342,10 @@ def run_gpu_arm(args):
     solver.set_hparams(wl["lam"], wl["alpha_W"], wl["l1_ratio_W"], wl["orth_W"], wl["eps"])
     exchange = "none (single GPU)"
     if world > 1:
-        peer = os.environ.get("ALPINE_B200_PEER", "1") != "0" and solver.enable_peer_exchange()
+        peer = (os.environ.get("ALPINE_B200_PEER", "1") != "0" and not args.use_als) and solver.enable_peer_exchange()
         exchange = ("NVLink peer memory inside the W-update kernels (reduce-scatter + update + all-gather)" if peer
                     else "NCCL all-reduce of the packed buffer")
-    engine = MUEngine(solver, wl["lam"])
+    engine = MUEngine(solver, wl["lam"], use_als=args.use_als)
     total = args.warmup + args.steps
     engine.begin(total)
     for it in range(args.warmup):
@@ -418,7 +418,7 @@ def run_gpu_arm(args):
             "metric": METRIC if not sparse else "MU iterations/sec at 30k genes x 1M cells CSR, k=100", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": wl["name"], "parallelism": f"cells sharded over {world} GPU(s)", "exchange": exchange,
+            "config": {"workload": wl["name"] + (", use_als=True" if args.use_als else ""), "parallelism": f"cells sharded over {world} GPU(s)", "exchange": exchange,
                        "l2": "inputs larger than L2 (X is %.1f GB per GPU)" % (x_bytes / 1e9)},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "final_loss": {"total": float(hist[-1, 0]), "reconstruction": float(hist[-1, 1])},
@@ -529,6 +529,8 @@ def main():
     ap.add_argument("--genes", type=int, default=0, help="override the workload's gene count (debugging)")
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
                     help="cfg3 = the headline dense workload; cfg4 = BASELINE configs[3], 30k x 1M CSR (scaling study)")
+    ap.add_argument("--use-als", action="store_true",
+                    help="time the block Gauss-Seidel sweep (use_als=True, main.py:523-588) instead of the default update")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tf32-peak", action="store_true", help="skip the cuBLAS TF32 reference measurement")
