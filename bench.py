@@ -16,8 +16,9 @@ One "step" is one full-batch MU iteration (W update, B updates, H update, loss t
                  read-back and the device->host copy of W / H / B, divided by K.
 * ``roofline`` : the contraction kernel (two launches per step), timed with CUDA events around each launch
                  inside the timed region; 3xTF32 tensor work against measured bf16 peak / 2.
-* ``cpu_baseline`` : the NumPy oracle port of the reference's step (its 7 GEMMs, gathers and G x n temporaries)
-                 on a bounded column sample of the same workload, on the host cores, extrapolated linearly in cells.
+* ``cpu_baseline`` : the reference's step restated with its own torch-CPU operators (oracle/torch_port.py: its 7
+                 GEMMs, randperm gather and G x n temporaries) on a bounded column sample of the same workload, all
+                 host cores, extrapolated linearly in cells.
 """
 from __future__ import annotations
 
@@ -224,51 +225,51 @@ def synth_device_csr(dev, G, n_loc, col0, wl, seed=0):
 
 # ------------------------------------------------------------------------------------------- CPU baseline
 def cpu_baseline(wl, sample_cells=8000, iters=2):
-    """Oracle port of the reference's step (oracle/alpine_oracle.py, literal arithmetic incl. gather and temporaries)
-    on a column sample of the workload; returns (iterations/s extrapolated to the full workload, seconds/iteration
-    on the sample, threads)."""
+    """The reference's step on the host CPU: oracle/torch_port.py restates main.py:589-663 and 726-753 with the same
+    torch operators the reference runs on device="cpu" (MKL GEMMs, torch threading, its per-iteration randperm and
+    X[:, perm] gather, its G x n temporaries), pinned on the reference-generated fixtures.  Timed on a column sample
+    of the workload with every host core; returns (iterations/s extrapolated linearly in cells to the full
+    workload, seconds/iteration on the sample, threads, sample cells)."""
+    import torch
+
     from oracle import alpine_oracle as orc
+    from oracle import torch_port as tp
 
-    G, n = wl["n_genes"], wl["n_cells"]
-    ns = min(sample_cells, n)
-    rng = np.random.default_rng(0)
-    X = rng.random((ns, G), dtype=np.float32).T ** 3   # genes x cells view, as main.py:104
-    Ys = []
-    for c in wl["categories"]:
-        y = np.zeros((c, ns), dtype=np.float32)
-        y[rng.integers(0, c, ns), np.arange(ns)] = 1
-        Ys.append(y)
-    blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
-    K = sum(blocks)
-    st = orc.State(np.maximum(rng.random((G, K), dtype=np.float32), 1e-6),
-                   np.maximum(rng.random((K, ns), dtype=np.float32), 1e-6),
-                   [np.maximum(rng.random((c, k), dtype=np.float32), 1e-6)
-                    for c, k in zip(wl["categories"], wl["n_covariate_components"])], blocks)
-    hp = orc.HyperParams(n_components=wl["n_components"], n_covariate_components=list(wl["n_covariate_components"]),
-                         lam=list(wl["lam"]), orth_W=wl["orth_W"], alpha_W=wl["alpha_W"], l1_ratio_W=wl["l1_ratio_W"],
-                         eps=wl["eps"])
-    orc.mu_step(X, Ys, st, hp, literal_cost=True)  # warm-up (BLAS thread pools, page faults)
-    t0 = time.perf_counter()
-    for _ in range(iters):
-        orc.mu_step(X, Ys, st, hp, literal_cost=True)  # main.py:589-663 incl. the X[:, perm] gather (main.py:520)
-        orc.compute_loss(X, Ys, st, hp)                # main.py:666, 726-753
-    dt = (time.perf_counter() - t0) / iters
     threads = os.cpu_count() or 1
+    old_threads = torch.get_num_threads()
+    torch.set_num_threads(threads)  # torchrun exports OMP_NUM_THREADS=1
     try:
-        from threadpoolctl import threadpool_info
-
-        info = [d.get("num_threads", 0) for d in threadpool_info() if d.get("user_api") == "blas"]
-        if info:
-            threads = max(info)
-    except Exception:
-        pass
+        G, n = wl["n_genes"], wl["n_cells"]
+        ns = min(sample_cells, n)
+        g = torch.Generator().manual_seed(0)
+        X = torch.rand((ns, G), generator=g).pow_(3).T   # genes x cells view of a cells-major buffer, as main.py:104
+        Ys = []
+        for c in wl["categories"]:
+            codes = torch.randint(0, c, (ns,), generator=g)
+            Ys.append(torch.nn.functional.one_hot(codes, c).T.contiguous().float())
+        blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
+        K = sum(blocks)
+        W = torch.rand((G, K), generator=g).clamp_(min=1e-6)
+        H = torch.rand((K, ns), generator=g).clamp_(min=1e-6)
+        Bs = [torch.rand((c, k), generator=g).clamp_(min=1e-6) for c, k in zip(wl["categories"], wl["n_covariate_components"])]
+        hp = orc.HyperParams(n_components=wl["n_components"], n_covariate_components=list(wl["n_covariate_components"]),
+                             lam=list(wl["lam"]), orth_W=wl["orth_W"], alpha_W=wl["alpha_W"],
+                             l1_ratio_W=wl["l1_ratio_W"], eps=wl["eps"])
+        tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(ns))  # warm-up (thread pools, page faults)
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(ns))  # main.py:502-663
+            tp.compute_loss(X, Ys, W, H, Bs, blocks, hp)                      # main.py:666, 726-753
+        dt = (time.perf_counter() - t0) / iters
+    finally:
+        torch.set_num_threads(old_threads)
     return 1.0 / (dt * (n / ns)), dt, threads, ns
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's algorithm on the host CPU.  The reference itself is pure Python over
     torch and needs anndata/scanpy/kneed (absent, no network), and /root/reference does not exist on the GPU box, so
-    the arm times the oracle port; rank 0 only."""
+    the arm times the torch-CPU port of its step (oracle/torch_port.py, same operators and BLAS); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return

@@ -10,6 +10,12 @@ import pytest
 from oracle import alpine_oracle as orc
 from tests.helpers import CASE_KW, epoch_batches, golden_names, hp_of, inputs_of, load_golden, rel_fro
 
+def full_batch_mu_names_for_torch():
+    from tests.helpers import full_batch_mu_names
+
+    return [n for n in full_batch_mu_names() if n != "kl_long200"]
+
+
 TRAJ_TOL = 2e-6  # Frobenius-relative, per kept iteration (<= 10 iterations)
 LONG_TOL = 5e-5  # 200 iterations of drift
 
@@ -94,3 +100,30 @@ def test_long_run_top100_rankings_match_reference():
         top_ref = np.argsort(-Wref[:, k], kind="stable")[:100]
         top_got = np.argsort(-st.W[:, k], kind="stable")[:100]
         np.testing.assert_array_equal(top_got, top_ref)
+
+
+@pytest.mark.parametrize("name", full_batch_mu_names_for_torch())
+def test_torch_port_matches_reference(name):
+    """The torch-CPU restatement that bench.py times as the CPU baseline, on the reference's own trajectories."""
+    import torch
+
+    from oracle import torch_port as tp
+
+    torch.set_num_threads(1)
+    g = load_golden(name)
+    hp = hp_of(name)
+    X, Ys, st = inputs_of(g)
+    Xt = torch.from_numpy(np.ascontiguousarray(X))
+    Yt = [torch.from_numpy(y.copy()) for y in Ys]
+    W, H = torch.from_numpy(st.W.copy()), torch.from_numpy(st.H.copy())
+    Bs = [torch.from_numpy(b.copy()) for b in st.Bs]
+    kept = [int(i) for i in g["kept_iters"] if int(i) <= 10]
+    for it in range(1, max(kept) + 1):
+        tp.mu_step(Xt, Yt, W, H, Bs, st.blocks, hp, perm=torch.randperm(X.shape[1]))
+        if it in kept:
+            assert rel_fro(W.numpy(), g[f"W_it{it}"]) < TRAJ_TOL and rel_fro(H.numpy(), g[f"H_it{it}"]) < TRAJ_TOL
+            for i in range(len(Ys)):
+                assert rel_fro(Bs[i].numpy(), g[f"B{i}_it{it}"]) < TRAJ_TOL
+    if max(kept) == int(g["kept_iters"][-1]):
+        loss = tp.compute_loss(Xt, Yt, W, H, Bs, st.blocks, hp)
+        np.testing.assert_allclose(loss[:2], g["loss_history_ref_fp32"][max(kept) - 1][:2], rtol=5e-5)
