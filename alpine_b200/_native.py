@@ -33,6 +33,8 @@ SIGNATURES = {
                                      ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.POINTER(ctypes.c_int),
                                      ctypes.c_int]),
     "alpine_destroy": (ctypes.c_int, [_c_ctx]),
+    "alpine_workspace_bytes": (ctypes.c_int64, [_c_ctx]),
+    "alpine_bind_workspace": (ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_int64]),
     "alpine_bind_dense": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64]),
     "alpine_bind_labels": (ctypes.c_int, [_c_ctx, ctypes.c_int, _f32p]),
     "alpine_bind_factors": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, _f32p, ctypes.c_int64,
@@ -212,6 +214,11 @@ class Solver:
         _check(self.lib, self.lib.alpine_create(ctypes.byref(self._ctx), self.dev_index, self.G, self.n,
                                                 len(self.k_blocks), kb, self.n_cov, cc, LOSS_TYPES[loss_type]))
         self._keep: dict = {}
+        # per-fit workspaces come out of torch's caching allocator: no cudaMalloc / cudaFree per context
+        nbytes = int(self.lib.alpine_workspace_bytes(self._ctx))
+        arena = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        _check(self.lib, self.lib.alpine_bind_workspace(self._ctx, arena.data_ptr(), nbytes))
+        self._keep["arena"] = arena
 
     # -- lifetime ----------------------------------------------------------------------------------------
     def close(self, collective: bool = True) -> None:

@@ -172,7 +172,7 @@ struct alpine_ctx {
   int loss_cap = 0;
   int* err = nullptr;
   float* partial = nullptr;
-  size_t partial_floats = 0;
+  size_t partial_floats = 0, partial_hint = 0;
   float* own_reduce = nullptr;
   float* reduce = nullptr;  // [Pt K*ldG | S K*K | hsum K | Q q_total]
 
@@ -192,6 +192,16 @@ struct alpine_ctx {
   const float* use_S() const { return peer_on() ? sum_small : red_S(); }
   const float* use_hsum() const { return use_S() + static_cast<size_t>(K) * K; }
   const float* use_Q() const { return use_hsum() + K; }
+
+  // Workspace arena lent by the caller (alpine_bind_workspace): a bump allocator over it replaces cudaMalloc /
+  // cudaFree for the per-fit buffers, so that creating and destroying a context costs no driver allocation calls
+  // (torch's caching allocator owns the memory).  Anything that does not fit falls back to cudaMalloc.
+  char* arena = nullptr;
+  size_t arena_size = 0, arena_used = 0;
+  bool in_arena(const void* q) const {
+    const char* b = static_cast<const char*>(q);
+    return arena != nullptr && b >= arena && b < arena + arena_size;
+  }
 
   GemmPlan plans[PLAN_COUNT];
   bool prof = false;
@@ -235,11 +245,30 @@ int dev_alloc(T** p, size_t count) {
   return ALPINE_OK;
 }
 
+constexpr size_t kWsAlign = 256;
+inline size_t ws_bytes(size_t count, size_t elem) { return ((count > 0 ? count : 1) * elem + kWsAlign - 1) / kWsAlign * kWsAlign; }
+
+// workspace buffer of `count` elements: from the caller's arena when it fits, else cudaMalloc
+template <typename T>
+int ws_alloc(alpine_ctx* c, T** p, size_t count) {
+  if (*p != nullptr) return ALPINE_OK;
+  const size_t bytes = ws_bytes(count, sizeof(T));
+  if (c->arena != nullptr && c->arena_used + bytes <= c->arena_size) {
+    *p = reinterpret_cast<T*>(c->arena + c->arena_used);
+    c->arena_used += bytes;
+    return ALPINE_OK;
+  }
+  return dev_alloc(p, count);
+}
+inline void ws_free(const alpine_ctx* c, void* q) {
+  if (q != nullptr && !c->in_arena(q)) cudaFree(q);
+}
+
 int set_kernel_attrs();
 
 int ensure_flags(alpine_ctx* c) {
   if (c->flags != nullptr) return ALPINE_OK;
-  AL_TRY(dev_alloc(&c->flags, 2));
+  AL_TRY(ws_alloc(c, &c->flags, 2));
   const int init[2] = {1, 1};
   CU_TRY(cudaMemcpy(c->flags, init, sizeof(init), cudaMemcpyHostToDevice));
   return ALPINE_OK;
@@ -250,30 +279,30 @@ int ensure_workspace(alpine_ctx* c) {
   CU_TRY(cudaSetDevice(c->device));
   AL_TRY(set_kernel_attrs());
   const size_t K = c->K;
-  AL_TRY(dev_alloc(&c->WT, K * c->ldG));
-  AL_TRY(dev_alloc(&c->A, K * c->ldN));
-  AL_TRY(dev_alloc(&c->Hsplit, 2 * K * c->ldN));
-  AL_TRY(dev_alloc(&c->Wsplit, 2 * K * c->ldG));
+  AL_TRY(ws_alloc(c, &c->WT, K * c->ldG));
+  AL_TRY(ws_alloc(c, &c->A, K * c->ldN));
+  AL_TRY(ws_alloc(c, &c->Hsplit, 2 * K * c->ldN));
+  AL_TRY(ws_alloc(c, &c->Wsplit, 2 * K * c->ldG));
   CU_TRY(cudaMemset(c->Hsplit, 0, 2 * K * c->ldN * sizeof(float)));
   CU_TRY(cudaMemset(c->Wsplit, 0, 2 * K * c->ldG * sizeof(float)));
-  AL_TRY(dev_alloc(&c->numG, static_cast<size_t>(c->Kg) * c->ldN));
-  AL_TRY(dev_alloc(&c->denG, static_cast<size_t>(c->Kg) * c->ldN));
-  AL_TRY(dev_alloc(&c->T, K * K));
-  AL_TRY(dev_alloc(&c->colsum, K));
+  AL_TRY(ws_alloc(c, &c->numG, static_cast<size_t>(c->Kg) * c->ldN));
+  AL_TRY(ws_alloc(c, &c->denG, static_cast<size_t>(c->Kg) * c->ldN));
+  AL_TRY(ws_alloc(c, &c->T, K * K));
+  AL_TRY(ws_alloc(c, &c->colsum, K));
   c->stat_blocks = ceil_div(c->n, kStatCells);
-  AL_TRY(dev_alloc(&c->q_partial, static_cast<size_t>(c->stat_blocks) * (c->q_total > 0 ? c->q_total : 1)));
-  AL_TRY(dev_alloc(&c->pred_partial, static_cast<size_t>(c->stat_blocks) * (c->n_cov > 0 ? c->n_cov : 1)));
+  AL_TRY(ws_alloc(c, &c->q_partial, static_cast<size_t>(c->stat_blocks) * (c->q_total > 0 ? c->q_total : 1)));
+  AL_TRY(ws_alloc(c, &c->pred_partial, static_cast<size_t>(c->stat_blocks) * (c->n_cov > 0 ? c->n_cov : 1)));
   c->sl_blocks_n = ceil_div(c->n, kSLCols);
-  AL_TRY(dev_alloc(&c->t1_partial, static_cast<size_t>(c->sl_blocks_n)));
-  AL_TRY(dev_alloc(&c->hsum_partial, static_cast<size_t>(c->sl_blocks_n) * K));
-  AL_TRY(dev_alloc(&c->sumsq_partial, 1024));
-  AL_TRY(dev_alloc(&c->xnorm2, 1));
-  AL_TRY(dev_alloc(&c->err, 8));
+  AL_TRY(ws_alloc(c, &c->t1_partial, static_cast<size_t>(c->sl_blocks_n)));
+  AL_TRY(ws_alloc(c, &c->hsum_partial, static_cast<size_t>(c->sl_blocks_n) * K));
+  AL_TRY(ws_alloc(c, &c->sumsq_partial, 1024));
+  AL_TRY(ws_alloc(c, &c->xnorm2, 1));
+  AL_TRY(ws_alloc(c, &c->err, 8));
   CU_TRY(cudaMemset(c->err, 0, 8 * sizeof(int)));
   AL_TRY(ensure_flags(c));
   CU_TRY(cudaMemset(c->t1_partial, 0, sizeof(double) * c->sl_blocks_n));
   if (c->reduce == nullptr) {
-    AL_TRY(dev_alloc(&c->own_reduce, static_cast<size_t>(c->reduce_floats())));
+    AL_TRY(ws_alloc(c, &c->own_reduce, static_cast<size_t>(c->reduce_floats())));
     c->reduce = c->own_reduce;
   }
   c->ws_ready = true;
@@ -328,13 +357,52 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
   return ALPINE_OK;
 }
 
+// Work space, grid and slot count of one contraction; returns the floats its partial-sum slots need.
+size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p, int* grid_out);
+int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop);
+
 // Build the plan of one contraction (see GemmOperands).
 int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
-  const int rows = kRows;
-  const long long M = (op.orient == ORIENT_XH) ? op.cols : op.rows;
   const long long R = (op.orient == ORIENT_XH) ? op.rows : op.cols;
   pl->op = op;
   GemmParams& p = pl->p;
+  const size_t need = plan_geometry(c, op, p, &pl->grid);
+  const int Kop = p.K;
+  // pipeline depths from the shared-memory budget
+  const size_t budget = 227 * 1024 - 1024;
+  int sb = 4, sx = 0;
+  if (const char* e = getenv("ALPINE_B200_SB")) sb = atoi(e) >= 2 && atoi(e) <= kMaxBStages ? atoi(e) : sb;
+  for (; sb >= 2; --sb) {
+    sx = kMaxXStages;
+    while (sx >= 2 && gemm_smem_layout(p.Kp, sx, sb).total > budget) --sx;
+    if (sx >= 3 || sb == 2) break;
+  }
+  if (sx < 2) return fail(ALPINE_ERR_ARG, "K=%d does not fit the shared-memory pipeline", c->K);
+  if (const char* e = getenv("ALPINE_B200_SX")) sx = atoi(e) < sx ? (atoi(e) < 1 ? 1 : atoi(e)) : sx;
+  p.sx = sx;
+  p.sb = sb;
+  pl->smem = gemm_smem_layout(p.Kp, sx, sb).total + 1024;
+  // partial-sum slots (one buffer shared by all plans: contractions run one after the other on the stream)
+  if (need > c->partial_floats) {
+    ws_free(c, c->partial);
+    c->partial = nullptr;
+    // with an arena, size the buffer for the largest of this context's standard plans at once (a bump allocator
+    // cannot give memory back)
+    const size_t want = (c->arena != nullptr && c->partial_hint > need) ? c->partial_hint : need;
+    AL_TRY(ws_alloc(c, &c->partial, want));
+    c->partial_floats = want;
+    for (auto& other : c->plans) {
+      other.p.partial = c->partial;
+      other.r.partial = c->partial;
+    }
+  }
+  return build_plan_tail(c, pl, op, R, Kop);
+}
+
+size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p, int* grid_out) {
+  const int rows = kRows;
+  const long long M = (op.orient == ORIENT_XH) ? op.cols : op.rows;
+  const long long R = (op.orient == ORIENT_XH) ? op.rows : op.cols;
   p.M = static_cast<int>(M);
   p.R = static_cast<int>(R);
   const int Kop = op.Kop > 0 ? op.Kop : c->K;
@@ -357,34 +425,15 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
     p.ws.pieces = ceil_div(p.ws.kb_per_tile, plen);
   }
   const long long total = p.ws.total();
-  pl->grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
-  p.max_segs = max_segments_per_cta(p.ws, pl->grid);
-  // pipeline depths from the shared-memory budget
-  const size_t budget = 227 * 1024 - 1024;
-  int sb = 4, sx = 0;
-  if (const char* e = getenv("ALPINE_B200_SB")) sb = atoi(e) >= 2 && atoi(e) <= kMaxBStages ? atoi(e) : sb;
-  for (; sb >= 2; --sb) {
-    sx = kMaxXStages;
-    while (sx >= 2 && gemm_smem_layout(p.Kp, sx, sb).total > budget) --sx;
-    if (sx >= 3 || sb == 2) break;
-  }
-  if (sx < 2) return fail(ALPINE_ERR_ARG, "K=%d does not fit the shared-memory pipeline", c->K);
-  if (const char* e = getenv("ALPINE_B200_SX")) sx = atoi(e) < sx ? (atoi(e) < 1 ? 1 : atoi(e)) : sx;
-  p.sx = sx;
-  p.sb = sb;
-  pl->smem = gemm_smem_layout(p.Kp, sx, sb).total + 1024;
-  // partial-sum slots (one buffer shared by all plans: contractions run one after the other on the stream)
-  const size_t need = static_cast<size_t>(pl->grid) * p.max_segs * p.K * rows;
-  if (need > c->partial_floats) {
-    if (c->partial) cudaFree(c->partial);
-    c->partial = nullptr;
-    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c->partial), need * sizeof(float)));
-    c->partial_floats = need;
-    for (auto& other : c->plans) {
-      other.p.partial = c->partial;
-      other.r.partial = c->partial;
-    }
-  }
+  const int grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
+  p.max_segs = max_segments_per_cta(p.ws, grid);
+  if (grid_out) *grid_out = grid;
+  return static_cast<size_t>(grid) * p.max_segs * p.K * rows;
+}
+
+int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop) {
+  const int rows = kRows;
+  GemmParams& p = pl->p;
   p.partial = c->partial;
   p.err = c->err;
   p.sp_ofs = op.sp_ofs;
@@ -411,11 +460,11 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
       reduce_slots_of_tile(p.ws, pl->grid, p.max_segs, t, &slots);
       ofs[t + 1] = static_cast<int>(slots.size());
     }
-    if (pl->d_slot_ofs) cudaFree(pl->d_slot_ofs);
-    if (pl->d_slots) cudaFree(pl->d_slots);
+    ws_free(c, pl->d_slot_ofs);
+    ws_free(c, pl->d_slots);
     pl->d_slot_ofs = pl->d_slots = nullptr;
-    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&pl->d_slot_ofs), ofs.size() * sizeof(int)));
-    CU_TRY(cudaMalloc(reinterpret_cast<void**>(&pl->d_slots), (slots.size() + 1) * sizeof(int)));
+    AL_TRY(ws_alloc(c, &pl->d_slot_ofs, ofs.size()));
+    AL_TRY(ws_alloc(c, &pl->d_slots, slots.size() + 1));
     CU_TRY(cudaMemcpy(pl->d_slot_ofs, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(pl->d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice));
     r.slot_ofs = pl->d_slot_ofs;
@@ -592,7 +641,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 6; }
+int alpine_abi_version(void) { return 7; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -664,19 +713,60 @@ int alpine_destroy(alpine_ctx* c) {
     c->WT = nullptr;  // lives inside the exchange block
     cudaFree(c->xchg);
   }
-  cudaFree(c->sum_small);
-  cudaFree(c->sum_P);
+  ws_free(c, c->sum_small);
+  ws_free(c, c->sum_P);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
                   c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
                   c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  for (void* p : ptrs) ws_free(c, p);
   for (auto& pl : c->plans) {
-    if (pl.d_slot_ofs) cudaFree(pl.d_slot_ofs);
-    if (pl.d_slots) cudaFree(pl.d_slots);
+    ws_free(c, pl.d_slot_ofs);
+    ws_free(c, pl.d_slots);
   }
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
+  return ALPINE_OK;
+}
+
+int64_t alpine_workspace_bytes(const alpine_ctx* c) {
+  if (c == nullptr) return 0;
+  const size_t K = c->K, f = sizeof(float);
+  size_t b = 0;
+  b += ws_bytes(K * c->ldG, f) + ws_bytes(K * c->ldN, f);                  // W^T, A
+  b += ws_bytes(2 * K * c->ldN, f) + ws_bytes(2 * K * c->ldG, f);          // split copies
+  b += 2 * ws_bytes(static_cast<size_t>(c->Kg) * c->ldN, f);              // guided terms
+  b += ws_bytes(K * K, f) + ws_bytes(K, f);
+  const size_t stat_blocks = ceil_div(c->n, kStatCells), sl_blocks = ceil_div(c->n, kSLCols);
+  b += ws_bytes(stat_blocks * (c->q_total > 0 ? c->q_total : 1), f) + ws_bytes(stat_blocks * (c->n_cov > 0 ? c->n_cov : 1), 8);
+  b += ws_bytes(sl_blocks, 8) + ws_bytes(sl_blocks * K, f) + ws_bytes(1024, 8) + 4 * kWsAlign;
+  b += ws_bytes(static_cast<size_t>(c->reduce_floats()), f);
+  // partial-sum slots of the largest standard plan, and the slot lists of all of them
+  size_t hint = 0;
+  for (int which = 0; which < PLAN_WX_BLOCK; ++which) {
+    GemmParams p{};
+    int grid = 0;
+    const size_t need = plan_geometry(c, plan_operands(c, which), p, &grid);
+    hint = need > hint ? need : hint;
+    b += ws_bytes(p.ws.num_tiles + 1, 4) + ws_bytes(static_cast<size_t>(p.ws.num_tiles) * p.ws.pieces * 3 + grid + 1, 4);
+  }
+  b += ws_bytes(hint, f);
+  return static_cast<int64_t>(b + (2u << 20));  // + loss history, flags, alignment slack
+}
+
+int alpine_bind_workspace(alpine_ctx* c, void* base, int64_t bytes) {
+  if (c == nullptr || base == nullptr || bytes <= 0) return fail(ALPINE_ERR_ARG, "null / empty workspace");
+  if (c->ws_ready || c->arena != nullptr) return fail(ALPINE_ERR_STATE, "the workspace must be bound once, right after alpine_create");
+  if ((reinterpret_cast<uintptr_t>(base) & (kWsAlign - 1)) != 0) return fail(ALPINE_ERR_ARG, "workspace must be 256-byte aligned");
+  c->arena = static_cast<char*>(base);
+  c->arena_size = static_cast<size_t>(bytes);
+  c->arena_used = 0;
+  size_t hint = 0;
+  for (int which = 0; which < PLAN_WX_BLOCK; ++which) {
+    GemmParams p{};
+    const size_t need = plan_geometry(c, plan_operands(c, which), p, nullptr);
+    hint = need > hint ? need : hint;
+  }
+  c->partial_hint = hint;
   return ALPINE_OK;
 }
 
@@ -815,9 +905,9 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
   AL_TRY(ensure_workspace(c));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (max_iter > c->loss_cap) {
-    if (c->loss_hist) cudaFree(c->loss_hist);
+    ws_free(c, c->loss_hist);
     c->loss_hist = nullptr;
-    AL_TRY(dev_alloc(&c->loss_hist, static_cast<size_t>(max_iter) * (2 + c->n_cov)));
+    AL_TRY(ws_alloc(c, &c->loss_hist, static_cast<size_t>(max_iter) * (2 + c->n_cov)));
     c->loss_cap = max_iter;
   }
   // ||X||_F^2 (first term of the trace identity that replaces main.py:736)
@@ -853,7 +943,7 @@ int alpine_batch_begin(alpine_ctx* c, void* stream) {
   AL_TRY(ensure_workspace(c));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c->loss_cap < 1) {
-    AL_TRY(dev_alloc(&c->loss_hist, static_cast<size_t>(2 + c->n_cov)));
+    AL_TRY(ws_alloc(c, &c->loss_hist, static_cast<size_t>(2 + c->n_cov)));
     c->loss_cap = 1;
   }
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
@@ -1014,8 +1104,8 @@ int alpine_peer_export(alpine_ctx* c, void* handle_out) {
   CU_TRY(cudaSetDevice(c->device));
   CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c->xchg), c->xchg_floats() * sizeof(float)));
   CU_TRY(cudaMemset(c->xchg, 0, c->xchg_floats() * sizeof(float)));
-  AL_TRY(dev_alloc(&c->sum_small, static_cast<size_t>(c->small_floats())));
-  AL_TRY(dev_alloc(&c->sum_P, static_cast<size_t>(c->K) * c->ldG));
+  AL_TRY(ws_alloc(c, &c->sum_small, static_cast<size_t>(c->small_floats())));
+  AL_TRY(ws_alloc(c, &c->sum_P, static_cast<size_t>(c->K) * c->ldG));
   c->reduce = c->xchg;                          // [X H^T | H H^T | rowsum H | B statistics] partials of this rank
   c->WT = c->xchg + c->xchg_wt_off();           // peers store their gene slices of the new W^T here
   cudaIpcMemHandle_t h;

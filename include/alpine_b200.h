@@ -47,6 +47,12 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
                   const int* k_blocks, int n_cov, const int* c_cov, int loss_type);
 int alpine_destroy(alpine_ctx* ctx);
 
+/* Optional: lend the context one device buffer for all of its per-fit workspaces (W^T copy, split operands, W^T X,
+ * partial sums ...).  With it, creating and destroying a context performs no cudaMalloc / cudaFree (the host
+ * binding takes the buffer from torch's caching allocator); without it, or for what does not fit, the library
+ * allocates by itself.  Call right after alpine_create; `base` 256-byte aligned, alive until alpine_destroy.   */
+int64_t alpine_workspace_bytes(const alpine_ctx* ctx);
+int alpine_bind_workspace(alpine_ctx* ctx, void* base, int64_t bytes);
 /* Bind the expression matrix (AlpineMatrices.X, main.py:445). */
 int alpine_bind_dense(alpine_ctx* ctx, const float* X_cells_major, int64_t ldX);
 /* Bind a SPARSE expression matrix instead (north_star's optional CSR variant; the reference itself rejects sparse
