@@ -79,6 +79,14 @@ class NumpyShardSolver:
         c1, c2 = np.float32((1 - hp.l1_ratio_W) * hp.alpha_W), np.float32(hp.l1_ratio_W * hp.alpha_W)
         den = 2 * (W @ S) + c1 * W + np.float32(hp.orth_W) * (W.sum(axis=1, keepdims=True) - W) + c2
         W *= (2 * Pt.T) / np.maximum(den, eps)
+        self._apply_after_w(it)
+
+    def _apply_after_w(self, it):
+        """B updates, H update, loss terms and statistics, given the new W (shared by both exchange modes)."""
+        hp = self.hp
+        Pt, S, hs, Qs = self._views()
+        eps = np.float32(hp.eps)
+        W = self.W
         for i in range(self.n_cov):
             B, lam = self.Bs[i], np.float32(hp.lam[i])
             if hp.loss_type == "kl-divergence":
@@ -104,6 +112,62 @@ class NumpyShardSolver:
         _, S2, _, _ = self._views()
         t2 = float(np.sum(T.astype(np.float64) * S2.astype(np.float64)))
         self.rows.append([t1, t2] + pred)
+
+    # ---- peer-exchange mode (same dataflow as csrc/peer_exchange.cuh, with gloo standing in for NVLink loads / stores):
+    # every rank sums the ranks' partials only for ITS gene slice (whole 64-gene tiles), updates that slice of W, and
+    # the slices are gathered; the small statistics are summed in rank order on every rank.
+    peer = False
+
+    def enable_peer_exchange(self, group=None):
+        import torch.distributed as dist
+
+        self.peer, self._group = True, group
+        self._rank, self._world = dist.get_rank(group), dist.get_world_size(group)
+        return True
+
+    def mu_apply_peer(self, it):
+        import torch.distributed as dist
+
+        bufs = [torch.empty_like(self._buf) for _ in range(self._world)]
+        dist.all_gather(bufs, self._buf, group=self._group)          # "peer loads" of every rank's exchange block
+        small0 = self.K * self.G
+        tiles = (self.G + 63) // 64
+        g0 = tiles * self._rank // self._world * 64
+        g1 = min(self.G, tiles * (self._rank + 1) // self._world * 64)
+        mine = self._buf.numpy()
+        small = np.zeros(mine.size - small0, dtype=np.float32)
+        for b in bufs:                                               # rank order: identical sums on every rank
+            small += b.numpy()[small0:]
+        P_slice = np.zeros((self.K, g1 - g0), dtype=np.float32)
+        for b in bufs:
+            P_slice += b.numpy()[:small0].reshape(self.K, self.G)[:, g0:g1]
+        local_small = mine[small0:].copy()
+        mine[small0:] = small                                        # the updates below read the summed statistics
+        Pt, S, hs, Qs = self._views()
+        hp = self.hp
+        eps = np.float32(hp.eps)
+        W = self.W
+        c1, c2 = np.float32((1 - hp.l1_ratio_W) * hp.alpha_W), np.float32(hp.l1_ratio_W * hp.alpha_W)
+        Ws = W[g0:g1]
+        den = 2 * (Ws @ S) + c1 * Ws + np.float32(hp.orth_W) * (Ws.sum(axis=1, keepdims=True) - Ws) + c2
+        new_slice = torch.from_numpy(np.ascontiguousarray(Ws * ((2 * P_slice.T) / np.maximum(den, eps))))
+        sizes = [min(self.G, tiles * (r + 1) // self._world * 64) - tiles * r // self._world * 64 for r in range(self._world)]
+        parts = [torch.empty((sz, self.K), dtype=torch.float32) for sz in sizes]
+        dist.all_gather(parts, new_slice, group=self._group) if len(set(sizes)) == 1 else self._gather_ragged(parts, new_slice)
+        W[...] = np.concatenate([p.numpy() for p in parts], axis=0)  # "peer stores" of every rank's new slice
+        Pt[...] = 0  # the numerator was consumed from the gathered blocks; mu_apply's W part must not run again
+        self._apply_after_w(it)
+        # like the CUDA path, the exchange block keeps THIS rank's partial statistics for the next iteration: they
+        # were refreshed by _apply_after_w (via _stats), nothing to restore
+        del local_small
+
+    def _gather_ragged(self, parts, mine):
+        import torch.distributed as dist
+
+        for r, p in enumerate(parts):
+            if r == self._rank:
+                p.copy_(mine)
+            dist.broadcast(p, src=r, group=self._group)
 
     # ---- block Gauss-Seidel sweep (same split as alpine_als_block / alpine_als_finish)
     @property

@@ -40,7 +40,7 @@ def _free_port():
     return port
 
 
-def _run_rank(rank, world, port, name, n_iter, out_dir):
+def _run_rank(rank, world, port, name, n_iter, out_dir, peer=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.set_num_threads(1)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -52,6 +52,8 @@ def _run_rank(rank, world, port, name, n_iter, out_dir):
         solver = NumpyShardSolver(np.ascontiguousarray(X[:, lo:hi]), [np.ascontiguousarray(y[:, lo:hi]) for y in Ys],
                                   st.W.copy(), np.ascontiguousarray(st.H[:, lo:hi]), [b.copy() for b in st.Bs],
                                   st.blocks, hp)
+        if peer:
+            assert solver.enable_peer_exchange()
         engine = MUEngine(solver, hp.lam, use_als=CASE_KW[name].get("use_als", False))
         assert (engine.rank, engine.world) == (rank, world)
         hist = engine.run(n_iter)
@@ -84,6 +86,26 @@ def test_two_rank_run_matches_oracle(name, tmp_path):
     assert abs(hist[-1, 1] - ref64[1]) / ref64[1] < 1e-4          # trace-identity reconstruction loss
     np.testing.assert_allclose(hist[-1, 2:], ref64[2:], rtol=1e-3, atol=1e-6 * X.shape[1])
     np.testing.assert_allclose(hist[-1, 0], hist[-1, 1] + sum(l * p for l, p in zip(hp.lam, hist[-1, 2:])), rtol=1e-12)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_peer_exchange_mode_matches_oracle(world, tmp_path):
+    """MUEngine's peer branch (mu_partials + mu_apply_peer, no all-reduce of the buffer) with the stand-in solver's
+    gene-slice exchange; 3 ranks make the 64-gene-tile slices ragged."""
+    name, n_iter = "kl_reg_nan", 4
+    mp.spawn(_run_rank, args=(world, _free_port(), name, n_iter, str(tmp_path), True), nprocs=world, join=True)
+    g = load_golden(name)
+    hp = hp_of(name)
+    X, Ys, st = inputs_of(g)
+    orc.fit_loop(X, Ys, st, hp, n_iter)
+    parts = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
+    assert rel_fro(np.concatenate([p["H"] for p in parts], axis=1), st.H) < 2e-5
+    for p in parts:
+        assert rel_fro(p["W"], st.W) < 2e-5
+        np.testing.assert_array_equal(p["W"], parts[0]["W"])     # bit-identical replicas
+        np.testing.assert_array_equal(p["hist"], parts[0]["hist"])
+    ref64 = orc.compute_loss(X, Ys, st, hp, dtype=np.float64)
+    assert abs(parts[0]["hist"][-1, 1] - ref64[1]) / ref64[1] < 1e-4
 
 
 def test_single_process_engine_matches_oracle():
