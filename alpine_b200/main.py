@@ -187,6 +187,7 @@ class ALPINE:
         # the non-negativity scan of a large dense X is done on the device after the upload (same ValueError)
         self._nonneg_pending = validation.check_fit_args(self, adata, covariate_keys, batch_size, max_iter,
                                                          sampling_method, verbose, defer_nonneg=True)
+        validation.check_native_limits(self)
         lap("validate")
         self.feature_names = adata.var_names.tolist()
         self.n_features = adata.shape[1]
@@ -232,6 +233,7 @@ class ALPINE:
                 m.solver.close()
                 m.solver = None
         self.matrices = m.to_numpy()
+        self._rng_publish()
         lap("scale_download")
         self.store_embeddings(adata, _dummy_matrices=Y)  # the encoders were fitted on this adata a moment ago
         lap("store_embeddings")
@@ -270,9 +272,13 @@ class ALPINE:
         if not sparse:
             Xd = _native.padded_rows(n_sample, G, dev)
             _native.upload_rows(Xd, Xcm)
-        # un-reseeded draw from the device generator, as the reference (main.py:687-689)
+        # un-reseeded draw from the device generator, as the reference (main.py:687-689): the process-wide one, which
+        # fit() left where the reference leaves it -- or this model's own stream when it was told to keep it private
         H = _native.padded_rows(K, n_sample, dev)
-        H.copy_(torch.rand((K, n_sample), dtype=torch.float32, device=dev))
+        gen = getattr(self, "_gen_dev", None) if getattr(self, "_rng_private", False) else None
+        if gen is not None and gen.device != dev:
+            gen = None
+        H.copy_(torch.rand((K, n_sample), dtype=torch.float32, device=dev, generator=gen))
         W = torch.cat([torch.tensor(w, dtype=torch.float32, device=dev) for w in self.matrices["Ws"]], dim=1).contiguous()
         solver = _native.Solver(dev, G, n_sample, [K], [])
         try:
@@ -382,6 +388,40 @@ class ALPINE:
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         return torch.device("cuda", idx)
 
+    def _rng_begin(self, dev: torch.device) -> torch.Generator:
+        """Fresh per-model generators with the seeds main.py:440-442 gives the process-wide ones."""
+        self._gen_dev = torch.Generator(device=dev)
+        self._gen_dev.manual_seed(self.random_state)
+        self._gen_cpu = torch.Generator()
+        self._gen_cpu.manual_seed(self.random_state)
+        return self._gen_dev
+
+    def _rng_skip_randperms(self, n: int, count: int) -> None:
+        """Advance the device generator as ``count`` calls of ``torch.randperm(n, device=...)`` would (the reference
+        draws one permutation per full-batch iteration, main.py:502-506, which only reorders fp32 sums there and is
+        not needed here).  One real draw measures the Philox offset a call consumes; the rest is arithmetic."""
+        g = getattr(self, "_gen_dev", None)
+        if g is None or count <= 0:
+            return
+        try:
+            o0 = g.get_offset()
+            torch.randperm(n, device=g.device, generator=g)
+            o1 = g.get_offset()
+            g.set_offset(o1 + (count - 1) * (o1 - o0))
+        except (AttributeError, RuntimeError):  # a torch without offset access: draw them all
+            for _ in range(count - 1):
+                torch.randperm(n, device=g.device, generator=g)
+
+    def _rng_publish(self) -> None:
+        """Leave the process-wide generators where the reference's ``fit`` leaves them (unless this model was told to
+        keep its streams private: ``_rng_private``, set by ComponentOptimizer's worker threads)."""
+        if getattr(self, "_rng_private", False) or getattr(self, "_gen_dev", None) is None:
+            return
+        idx = self._gen_dev.device.index
+        torch.cuda.default_generators[idx if idx is not None else torch.cuda.current_device()].set_state(
+            self._gen_dev.get_state())
+        torch.default_generator.set_state(self._gen_cpu.get_state())
+
     def _initialize_matrices(self, X_array: Float32Array, Y_list_array: List[Float32Array]) -> AlpineMatrices:
         """Seed, upload, draw W / H / B in the reference's order (main.py:436-472).
 
@@ -390,16 +430,17 @@ class ALPINE:
         devices) and keeps its own column block of X, Y and H.
         """
         dev = self._cuda_device()
-        torch.manual_seed(self.random_state)
-        torch.cuda.manual_seed(self.random_state)
-        # The draws below take an explicit generator of THIS device with the same seed: the same Philox stream as
-        # the freshly seeded default generator (so the factors equal the reference's on the same device type), but
-        # not shared with other threads -- ComponentOptimizer runs one fit per GPU from worker threads, and the
-        # global seeding calls above race between them.
-        gen = torch.Generator(device=dev)
-        gen.manual_seed(self.random_state)
+        # The reference seeds the process-wide generators here (torch.manual_seed / torch.cuda.manual_seed) and every
+        # later draw -- W, H, B below, one randperm per iteration, the weighted sampler, transform's H0 -- continues
+        # those streams.  The same streams are kept here in two per-model generators (same seed, same draw order =>
+        # same numbers), because ComponentOptimizer runs one fit per GPU from worker threads and the global seeding
+        # calls would race between them; ``fit`` publishes their final state to the process-wide generators, so a
+        # later ``transform`` (or any user draw) starts exactly where it starts after the reference's ``fit``.
+        gen = self._rng_begin(dev)
         G, n = X_array.shape
         rank, world = dist_info()
+        if world > n:
+            raise ValueError(f"cell sharding needs at least one cell per rank ({n} cells, {world} ranks)")
         lo, hi = shard_bounds(n, world, rank)
         n_loc = hi - lo
         K = self.total_components
@@ -466,8 +507,13 @@ class ALPINE:
         full_batch = self.batch_size >= m.n_total
         if self.sampling_method not in ("random", "weighted"):
             raise ValueError(f"Unknown sampling method: {self.sampling_method}. Only 'weighted', and 'random' are supported.")
+        colnames = ["total loss", "reconstruction loss"] + [f"prediction loss({k})" for k in self.covariate_keys]
+        if self.max_iter <= 0:  # the reference's loop body never runs: empty loss history, factors untouched
+            self.loss_history = pd.DataFrame([], columns=colnames)
+            return
         if not full_batch or self.sampling_method == "weighted":
             return self._fit_minibatch(m)
+        self._rng_skip_randperms(m.n_total, self.max_iter)  # main.py:502-506, one permutation per iteration
         solver = self._make_solver(m)
         try:
             if dist_info()[1] > 1 and not self.use_als and os.environ.get("ALPINE_B200_PEER", "0") == "1":
@@ -489,11 +535,12 @@ class ALPINE:
                 m.solver = solver
             else:
                 solver.close()
-        colnames = ["total loss", "reconstruction loss"] + [f"prediction loss({k})" for k in self.covariate_keys]
         self.loss_history = pd.DataFrame(history.tolist(), columns=colnames)
 
     def _fit_minibatch(self, m: AlpineMatrices) -> None:
-        """Epochs of mini-batch MU steps (main.py:500-521, 589-663) with the reference's index streams.
+        """Epochs of mini-batch MU steps (main.py:500-521, 589-663) with the reference's index streams: the epoch
+        indices come from the same generator calls in the same stream position as the reference's (``randperm`` on the
+        device generator after the W / H / B draws; the weighted sampler's ``multinomial`` on the CPU generator).
 
         Per batch the cells ``idx`` are gathered into contiguous buffers (rows of the cells-major X -- or of the CSR
         matrix --, columns of H and Y), one MU step runs on them with the same kernels as the full-batch path, and the H columns are
@@ -544,7 +591,9 @@ class ALPINE:
                     epoch_indices = torch.as_tensor(next(stream), dtype=torch.long, device=dev)
                 else:
                     epoch_indices = generate_epoch_indices(joint_labels=joint_labels,
-                                                           sampling_method=self.sampling_method, device=dev)
+                                                           sampling_method=self.sampling_method, device=dev,
+                                                           generator=getattr(self, "_gen_dev", None),
+                                                           cpu_generator=getattr(self, "_gen_cpu", None))
                 for b in range(get_num_batches(len(epoch_indices), bs)):
                     idx = get_batch_indices(epoch_indices, b, bs)
                     if len(idx) == 0:

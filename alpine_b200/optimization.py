@@ -135,6 +135,7 @@ class ComponentOptimizer:
         # scheduling: one fit per GPU (the reference runs the folds one after the other on one device)
         self.devices: List[str] = visible_devices(device)
         self._fold_cache: dict = {}
+        self.device_busy_s: dict = {}  # device -> seconds spent inside fold jobs, summed over the whole search
         self._fold_lock = threading.Lock()
         self.scorer: Callable = default_scorer
         self.model_factory: Callable[..., ALPINE] = ALPINE
@@ -260,6 +261,7 @@ class ComponentOptimizer:
         jobs = [(a, tr, va) for a in all_args if a is not None for tr, va in folds]
         self.last_scheduler = DeviceScheduler(self.devices)
         out = self.last_scheduler.map(self._fit_fold, jobs) if jobs else []
+        self._account_busy()
         results, pos = [], 0
         for a in all_args:
             if a is None:
@@ -295,7 +297,7 @@ class ComponentOptimizer:
         row subsets of X and obs are materialised once per fold and every job gets its own AnnData around them
         (fresh obsm / varm / layers, its own obs frame): fits never write to X, and concurrent trials must not share
         the slots they do write."""
-        key = (len(idx), int(idx[0]) if len(idx) else -1, int(np.sum(idx)))
+        key = np.ascontiguousarray(idx, dtype=np.int64).tobytes()  # the index content itself: no collisions
         with self._fold_lock:
             hit = self._fold_cache.get(key)
             if hit is None:
@@ -316,6 +318,9 @@ class ComponentOptimizer:
             lam=[float(v) for v in args["lam"]], orth_W=float(args["orth_W"]), alpha_W=float(args["alpha_W"]),
             l1_ratio_W=float(args["l1_ratio_W"]), use_als=self.use_als, random_state=self.random_state,
             loss_type=self.loss_type, device=device)
+        # worker threads run concurrently: the model keeps its random streams to itself instead of publishing them to
+        # the process-wide generators (same numbers as the reference's sequential fit -> transform on one device)
+        model._rng_private = True
         model.fit(adata=train_adata, covariate_keys=self.covariate_keys, max_iter=self.max_iter,
                   batch_size=self.batch_size, sampling_method=self.sampling_method, verbose=False)
         # (the reference stores the embeddings into train_adata again here, optimization.py:267; fit has just done
@@ -329,9 +334,14 @@ class ComponentOptimizer:
         jobs = [(args, tr, va) for tr, va in self._folds()]
         self.last_scheduler = DeviceScheduler(self.devices)
         out = self.last_scheduler.map(self._fit_fold, jobs)
+        self._account_busy()
         if self.max_iter_detect:
             self.iter_records.extend(m for _, m in out)
         return float(np.mean([s for s, _ in out]))
+
+    def _account_busy(self) -> None:
+        for d, t in self.last_scheduler.busy_s.items():
+            self.device_busy_s[d] = self.device_busy_s.get(d, 0.0) + t
 
     # ------------------------------------------------------------------------------------------- persistence
     def save_trials(self, filename: str):

@@ -12,6 +12,7 @@ from __future__ import annotations
 
 import queue
 import threading
+import time
 from typing import Any, Callable, List, Optional, Sequence
 
 
@@ -35,6 +36,7 @@ class DeviceScheduler:
             raise ValueError("at least one device is required")
         self.devices = list(devices)
         self.assignments: List[tuple] = []  # (job index, device) in completion order, for inspection / tests
+        self.busy_s = {d: 0.0 for d in self.devices}  # seconds every device spent inside jobs (bench.py's cfg5 block)
 
     def map(self, fn: Callable[[Any, str], Any], jobs: Sequence[Any]) -> List[Any]:
         results: List[Any] = [None] * len(jobs)
@@ -51,10 +53,13 @@ class DeviceScheduler:
                 except queue.Empty:
                     return
                 try:
+                    t0 = time.perf_counter()
                     out = fn(jobs[i], device)
+                    dt = time.perf_counter() - t0
                     with lock:
                         results[i] = out
                         self.assignments.append((i, device))
+                        self.busy_s[device] += dt
                 except BaseException as exc:  # propagate to the caller
                     with lock:
                         errors.append(exc)

@@ -28,15 +28,21 @@ def _balanced_sample_weight(labels: List[str]) -> np.ndarray:
 
 
 def generate_epoch_indices(joint_labels: List[str], sampling_method: str, device: torch.device, **kwargs) -> torch.Tensor:
+    """``kwargs`` (the reference's signature has them too, unused): ``generator`` = the device generator ``randperm``
+    draws from, ``cpu_generator`` = the CPU generator of the weighted sampler; ``None`` = the process-wide ones, which
+    is what the reference uses."""
     total_samples = len(joint_labels)
     if sampling_method == "weighted":
         from torch.utils.data import WeightedRandomSampler
 
         sampler = WeightedRandomSampler(weights=_balanced_sample_weight(joint_labels), num_samples=total_samples,
-                                        replacement=True)
+                                        replacement=True, generator=kwargs.get("cpu_generator"))
         return torch.tensor(list(sampler), device=device, dtype=torch.long)
     if sampling_method == "random":
-        return torch.randperm(total_samples, device=device)
+        gen = kwargs.get("generator")
+        if gen is not None and gen.device != torch.device(device):
+            gen = None
+        return torch.randperm(total_samples, device=device, generator=gen)
     raise ValueError(f"Unknown sampling method: {sampling_method}. Only 'weighted', and 'random' are supported.")
 
 

@@ -33,6 +33,17 @@ def make_counts(
     return X.astype(dtype)
 
 
+def make_poisson_counts(n_cells: int, n_genes: int, seed: int = 0, rank: int = 8, depth: float = 3.0) -> np.ndarray:
+    """cells x genes raw counts (uint16): Poisson draws around a low-rank Gamma mean, like UMI count matrices.
+    Every value is an integer < 2048, i.e. exactly representable in tf32 (the count-matrix kernel variant)."""
+    rng = np.random.default_rng(seed)
+    Hc = rng.gamma(0.6, 1.0, size=(n_cells, rank))
+    Wg = rng.gamma(0.4, 1.0, size=(rank, n_genes))
+    mean = Hc @ Wg
+    mean *= depth / mean.mean()
+    return np.minimum(rng.poisson(mean), 2047).astype(np.uint16)
+
+
 def make_labels(
     n_cells: int,
     n_categories: Sequence[int],

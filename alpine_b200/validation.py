@@ -116,6 +116,23 @@ def _check_fit_args(m, adata, covariate_keys, batch_size, max_iter, sampling_met
 _check_fit_args.last_deferred = False
 
 
+# limits of the native library (csrc/mu_small_kernels.cuh kMaxCov, csrc/mu_gemm_sm100.cuh kMaxK): reported here, by
+# name, before anything is uploaded -- the reference itself has no such limits
+MAX_TOTAL_COMPONENTS = 128
+MAX_COVARIATES = 8
+
+
+def check_native_limits(m) -> None:
+    """Inputs the reference accepts but the B200 library cannot run; raised by ``fit`` with an explicit message."""
+    _require(len(m.n_covariate_components) <= MAX_COVARIATES, ValueError,
+             f"alpine_b200 supports at most {MAX_COVARIATES} covariates (got {len(m.n_covariate_components)}).")
+    _require(all(k > 0 for k in m.n_covariate_components), ValueError,
+             "alpine_b200 needs at least one component per covariate block (an entry of n_covariate_components is 0).")
+    total = sum(m.n_covariate_components) + m.n_components
+    _require(total <= MAX_TOTAL_COMPONENTS, ValueError,
+             f"alpine_b200 supports at most {MAX_TOTAL_COMPONENTS} components in total (got {total}).")
+
+
 def check_trained(m) -> None:
     _require(hasattr(m, "matrices"), RuntimeError, "Model is not trained yet. Please fit the model first.")
 

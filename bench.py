@@ -168,7 +168,10 @@ class ClockSampler:
 
 # --------------------------------------------------------------------------------------------- synthetic data
 def synth_device_problem(dev, G, n_loc, col0, wl, seed=0):
-    """Device-resident shard: X (n_loc x G, cells-major), Ys, W, H, Bs.  Low-rank + noise, non-negative."""
+    """Device-resident shard [col0, col0 + n_loc) of the synthetic problem: X (n_loc x G, cells-major), Ys, W, H, Bs.
+    Low-rank + noise, non-negative.  Cells are generated in fixed GLOBAL chunks, each from its own seeded stream, so
+    the data of a cell does not depend on how the cells are sharded: every N sees the same problem and the final
+    loss must agree across N."""
     import torch
 
     from alpine_b200 import _native
@@ -177,62 +180,103 @@ def synth_device_problem(dev, G, n_loc, col0, wl, seed=0):
     g = torch.Generator(device=dev)
     g.manual_seed(1000 + seed)
     rank = 16
-    Wg = torch.rand((rank, G), device=dev, generator=g).pow_(3.0)         # shared across shards (same seed)
+    Wg = torch.rand((rank, G), device=dev, generator=g).pow_(3.0)
     X = _native.padded_rows(n_loc, G, dev)
+    H = _native.padded_rows(K, n_loc, dev)
+    Ys = [torch.empty((c, n_loc), dtype=torch.float32, device=dev) for c in wl["categories"]]
+    step = max(1, (1 << 26) // max(G, 64))
     gs = torch.Generator(device=dev)
-    gs.manual_seed(2000 + seed + 7919 * (col0 + 1))
-    step = max(1, (1 << 27) // G)
-    for r0 in range(0, n_loc, step):
-        r1 = min(n_loc, r0 + step)
-        Hc = torch.rand((r1 - r0, rank), device=dev, generator=gs).pow_(2.0)
+    for chunk in range(col0 // step, (col0 + n_loc + step - 1) // step if n_loc > 0 else 0):
+        c0 = chunk * step
+        gs.manual_seed(2000 + seed + 7919 * (chunk + 1))
+        Hc = torch.rand((step, rank), device=dev, generator=gs).pow_(2.0)
         blk = Hc @ Wg
-        blk.add_(torch.rand((r1 - r0, G), device=dev, generator=gs).pow_(4.0), alpha=0.5)
-        X[r0:r1] = blk
-    Ys = []
-    for c in wl["categories"]:
-        codes = torch.randint(0, c, (n_loc,), device=dev, generator=gs)
-        Ys.append(torch.nn.functional.one_hot(codes, c).T.contiguous().float())
+        blk.add_(torch.rand((step, G), device=dev, generator=gs).pow_(4.0), alpha=0.5)
+        h0 = torch.rand((K, step), device=dev, generator=gs).clamp_(min=wl["eps"])
+        codes = [torch.randint(0, c, (step,), device=dev, generator=gs) for c in wl["categories"]]
+        a, b = max(c0, col0), min(c0 + step, col0 + n_loc)  # global cells of this chunk that belong to the shard
+        X[a - col0:b - col0] = blk[a - c0:b - c0]
+        H[:, a - col0:b - col0] = h0[:, a - c0:b - c0]
+        for y, cd, c in zip(Ys, codes, wl["categories"]):
+            y[:, a - col0:b - col0] = torch.nn.functional.one_hot(cd[a - c0:b - c0], c).T.float()
+        del blk, Hc, h0
     gw = torch.Generator(device=dev)
     gw.manual_seed(42)
     W = torch.rand((G, K), device=dev, generator=gw).clamp_(min=wl["eps"])
-    H = _native.padded_rows(K, n_loc, dev)
-    H.copy_(torch.rand((K, n_loc), device=dev, generator=gs).clamp_(min=wl["eps"]))
     Bs = [torch.rand((c, k), device=dev, generator=gw).clamp_(min=wl["eps"]).contiguous()
           for c, k in zip(wl["categories"], wl["n_covariate_components"])]
     return X, Ys, W, H, Bs
 
 
 def synth_device_csr(dev, G, n_loc, col0, wl, seed=0):
-    """Device-resident CSR shard over cells: Bernoulli(density) mask x (1 + Poisson(1)) counts, built chunk-wise."""
+    """Device-resident CSR shard over cells: Bernoulli(density) mask x (1 + Poisson(1)) counts, built in fixed global
+    chunks of cells (shard-independent, as synth_device_problem)."""
     import torch
 
     gs = torch.Generator(device=dev)
-    gs.manual_seed(3000 + seed + 7919 * (col0 + 1))
-    step = max(1, (1 << 26) // G)
+    step = max(1, (1 << 28) // G)
     counts, cols, vals = [], [], []
-    for r0 in range(0, n_loc, step):
-        r1 = min(n_loc, r0 + step)
-        mask = torch.rand((r1 - r0, G), device=dev, generator=gs) < wl["density"]
-        counts.append(mask.sum(dim=1))
-        c = mask.nonzero()[:, 1].to(torch.int32)
-        cols.append(c)
-        vals.append(1.0 + torch.poisson(torch.ones(c.shape[0], device=dev), generator=gs))
+    for chunk in range(col0 // step, (col0 + n_loc + step - 1) // step if n_loc > 0 else 0):
+        c0 = chunk * step
+        gs.manual_seed(3000 + seed + 7919 * (chunk + 1))
+        mask = torch.rand((step, G), device=dev, generator=gs) < wl["density"]
+        nz = mask.nonzero()
         del mask
+        v = 1.0 + torch.poisson(torch.ones(nz.shape[0], device=dev), generator=gs)
+        a, b = max(c0, col0), min(c0 + step, col0 + n_loc)
+        if a != c0 or b != c0 + step:  # keep the rows of this chunk that belong to the shard
+            sel = (nz[:, 0] >= a - c0) & (nz[:, 0] < b - c0)
+            nz, v = nz[sel], v[sel]
+        counts.append(torch.bincount(nz[:, 0] - (a - c0), minlength=b - a))
+        cols.append(nz[:, 1].to(torch.int32))
+        vals.append(v)
+        del nz
     indptr = torch.zeros(n_loc + 1, dtype=torch.int64, device=dev)
     indptr[1:] = torch.cumsum(torch.cat(counts), 0)
     return indptr, torch.cat(cols), torch.cat(vals).float()
 
 
 # ------------------------------------------------------------------------------------------- CPU baseline
-def cpu_baseline(wl, sample_cells=8000, iters=2):
-    """The reference's step on the host CPU: oracle/torch_port.py restates main.py:589-663 and 726-753 with the same
-    torch operators the reference runs on device="cpu" (MKL GEMMs, torch threading, its per-iteration randperm and
-    X[:, perm] gather, its G x n temporaries), pinned on the reference-generated fixtures.  Timed on a column sample
-    of the workload with every host core; returns (iterations/s extrapolated linearly in cells to the full
-    workload, seconds/iteration on the sample, threads, sample cells)."""
+def _port_inputs(wl, n_cells, device="cpu", seed=0):
+    """Synthetic inputs of the torch port (oracle/torch_port.py) on `device`: X as the genes x cells view of a
+    cells-major buffer (main.py:104), labels, factors."""
     import torch
 
     from oracle import alpine_oracle as orc
+
+    G = wl["n_genes"]
+    g = torch.Generator(device=device).manual_seed(seed)
+    Xcm = torch.empty((n_cells, G), device=device)
+    step = max(1, (1 << 27) // G)
+    for r0 in range(0, n_cells, step):  # chunked: no second 8 GB temporary next to X
+        r1 = min(n_cells, r0 + step)
+        Xcm[r0:r1] = torch.rand((r1 - r0, G), generator=g, device=device).pow_(3)
+    Ys = []
+    for c in wl["categories"]:
+        codes = torch.randint(0, c, (n_cells,), generator=g, device=device)
+        Ys.append(torch.nn.functional.one_hot(codes, c).T.contiguous().float())
+    blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
+    K = sum(blocks)
+    W = torch.rand((G, K), generator=g, device=device).clamp_(min=1e-6)
+    H = torch.rand((K, n_cells), generator=g, device=device).clamp_(min=1e-6)
+    Bs = [torch.rand((c, k), generator=g, device=device).clamp_(min=1e-6)
+          for c, k in zip(wl["categories"], wl["n_covariate_components"])]
+    hp = orc.HyperParams(n_components=wl["n_components"], n_covariate_components=list(wl["n_covariate_components"]),
+                         lam=list(wl["lam"]), orth_W=wl["orth_W"], alpha_W=wl["alpha_W"],
+                         l1_ratio_W=wl["l1_ratio_W"], eps=wl["eps"])
+    return Xcm.T, Ys, W, H, Bs, blocks, hp
+
+
+def cpu_reference_run(wl, warmup, steps, budget_s=240.0):
+    """The reference's iteration on the host CPU, MEASURED: oracle/torch_port.py restates main.py:502-663 (step, with
+    its per-iteration randperm and X[:, perm] gather and its G x n temporaries) and main.py:726-753 (loss) with the
+    same torch-CPU operators the reference runs on device="cpu" (MKL GEMMs, all host threads); pinned on the
+    reference-generated fixtures.  Runs `warmup` + `steps` iterations on the FULL workload when host memory holds it
+    (X + gather + two G x n temporaries: ~4.5 x |X|) and the run fits `budget_s`; otherwise on the largest leading
+    block of cells that does, extrapolated linearly in cells (stated in "sample").  Returns a dict."""
+    import psutil
+    import torch
+
     from oracle import torch_port as tp
 
     threads = os.cpu_count() or 1
@@ -240,87 +284,121 @@ def cpu_baseline(wl, sample_cells=8000, iters=2):
     torch.set_num_threads(threads)  # torchrun exports OMP_NUM_THREADS=1
     try:
         G, n = wl["n_genes"], wl["n_cells"]
-        ns = min(sample_cells, n)
-        g = torch.Generator().manual_seed(0)
-        X = torch.rand((ns, G), generator=g).pow_(3).T   # genes x cells view of a cells-major buffer, as main.py:104
-        Ys = []
-        for c in wl["categories"]:
-            codes = torch.randint(0, c, (ns,), generator=g)
-            Ys.append(torch.nn.functional.one_hot(codes, c).T.contiguous().float())
-        blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
-        K = sum(blocks)
-        W = torch.rand((G, K), generator=g).clamp_(min=1e-6)
-        H = torch.rand((K, ns), generator=g).clamp_(min=1e-6)
-        Bs = [torch.rand((c, k), generator=g).clamp_(min=1e-6) for c, k in zip(wl["categories"], wl["n_covariate_components"])]
-        hp = orc.HyperParams(n_components=wl["n_components"], n_covariate_components=list(wl["n_covariate_components"]),
-                             lam=list(wl["lam"]), orth_W=wl["orth_W"], alpha_W=wl["alpha_W"],
-                             l1_ratio_W=wl["l1_ratio_W"], eps=wl["eps"])
-        tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(ns))  # warm-up (thread pools, page faults)
+        avail = psutil.virtual_memory().available
+        ns = n
+        per_cell = 4.6 * 4.0 * G  # bytes of host memory per cell the port needs at its peak
+        if per_cell * ns > 0.85 * avail:
+            ns = max(1000, int(0.85 * avail / per_cell))
+        # probe the cost per cell on a small block, then shrink the block if warmup + steps would overrun the budget
+        X, Ys, W, H, Bs, blocks, hp = _port_inputs(wl, min(ns, 4000))
+        tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(X.shape[1]))
         t0 = time.perf_counter()
-        for _ in range(iters):
+        tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(X.shape[1]))
+        tp.compute_loss(X, Ys, W, H, Bs, blocks, hp)
+        per_cell_s = (time.perf_counter() - t0) / X.shape[1]
+        del X, Ys, W, H, Bs
+        total_iters = max(1, warmup) + max(1, steps)
+        if per_cell_s * ns * total_iters > budget_s:
+            ns = max(1000, int(budget_s / (per_cell_s * total_iters)))
+        ns = min(ns, n)
+        X, Ys, W, H, Bs, blocks, hp = _port_inputs(wl, ns)
+        for _ in range(max(1, warmup)):
+            tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(ns))
+            tp.compute_loss(X, Ys, W, H, Bs, blocks, hp)
+        t0 = time.perf_counter()
+        for _ in range(max(1, steps)):
             tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(ns))  # main.py:502-663
             tp.compute_loss(X, Ys, W, H, Bs, blocks, hp)                      # main.py:666, 726-753
-        dt = (time.perf_counter() - t0) / iters
+        dt = (time.perf_counter() - t0) / max(1, steps)
     finally:
         torch.set_num_threads(old_threads)
-    return 1.0 / (dt * (n / ns)), dt, threads, ns
+    full = ns == n
+    value = 1.0 / (dt * (n / ns))
+    sample = (f"the full workload ({n} cells x {G} genes), {max(1, warmup)} warm-up + {max(1, steps)} timed iterations, "
+              f"{dt:.3f} s per iteration, nothing extrapolated" if full else
+              f"the first {ns} of {n} cells (all {G} genes; host memory / time budget), {max(1, warmup)} warm-up + "
+              f"{max(1, steps)} timed iterations, {dt:.3f} s per iteration on the sample, extrapolated linearly in cells")
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+            "seconds_per_iteration_measured": dt, "cells_measured": ns, "full_workload": full}
+
+
+def gpu_torch_baseline(wl, dev, iters=3):
+    """The reference's device="cuda" arithmetic on this B200 (the bar on the GPU): the same torch
+    port as the CPU leg, on CUDA tensors, fp32 cuBLAS GEMMs with TF32 off (torch's default, the reference never
+    switches it on), per-iteration randperm gather, G x n temporaries and the materialised-WH loss.  1 warm-up +
+    `iters` timed iterations on the full workload, CUDA events."""
+    import torch
+
+    from oracle import torch_port as tp
+
+    free, _ = torch.cuda.mem_get_info(dev)
+    need = 5.5 * 4.0 * wl["n_genes"] * wl["n_cells"]
+    if free < need:
+        return {"value": None, "unit": UNIT, "skipped": f"needs {need / 2**30:.0f} GiB of free HBM"}
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        n = wl["n_cells"]
+        X, Ys, W, H, Bs, blocks, hp = _port_inputs(wl, n, device=dev)
+
+        def one():
+            tp.mu_step(X, Ys, W, H, Bs, blocks, hp, perm=torch.randperm(n, device=dev))
+            return tp.compute_loss(X, Ys, W, H, Bs, blocks, hp)
+
+        one()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            one()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = e0.elapsed_time(e1) / iters
+        peak = torch.cuda.max_memory_allocated(dev)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+    del X, Ys, W, H, Bs
+    torch.cuda.empty_cache()
+    return {"value": 1000.0 / ms, "unit": UNIT, "ms_per_iteration": ms, "iterations": iters, "kind": "port",
+            "what": "oracle/torch_port.py (the reference's torch operators, main.py:502-663 + 726-753) on device=cuda, "
+                    "fp32 cuBLAS (allow_tf32=False), full workload, CUDA events",
+            "peak_hbm_gb": peak / 1e9}
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's algorithm on the host CPU.  The reference itself is pure Python over
     torch and needs anndata/scanpy/kneed (absent, no network), and /root/reference does not exist on the GPU box, so
-    the arm times the torch-CPU port of its step (oracle/torch_port.py, same operators and BLAS); rank 0 only."""
+    the arm times the torch-CPU port of its iteration (oracle/torch_port.py, same operators and BLAS); rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOAD
-    sample = 8000
-    # each step = one iteration on the sample; K steps + W warm-ups
-    vals = []
-    total_iters = max(1, args.warmup) + max(1, args.steps)
-    v, dt, threads, ns = cpu_baseline(wl, sample_cells=sample, iters=min(total_iters, 4))
+    cb = cpu_reference_run(wl, args.warmup, args.steps)
+    v = cb["value"]
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 / v, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "l2": "inputs larger than L2"},
-        "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                         "sample": f"{ns} of {wl['n_cells']} cells (all {wl['n_genes']} genes), {dt:.3f} s per "
-                                   f"iteration on the sample, extrapolated linearly in cells"},
+        "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
-def run_gpu_arm(args):
+def measure_resident(args, wl, sparse, dev, world, rank, local_rank, steps, warmup, sample_clocks=True):
+    """K timed full-batch iterations with everything resident in HBM (this rank's shard of `wl`); returns the fields
+    of the JSON line that describe them (rank 0) or None."""
     import torch
     import torch.distributed as dist
 
     from alpine_b200 import _native
     from alpine_b200.engine import MUEngine, shard_bounds
 
-    sparse = args.workload == "cfg4"
-    wl = dict(WORKLOAD_CFG4 if sparse else WORKLOAD)
-    if args.cells:
-        wl["n_cells"] = args.cells
-    if args.genes:
-        wl["n_genes"] = args.genes
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the MU loop has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if world != args.gpus and rank == 0:
-        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
     G, n = wl["n_genes"], wl["n_cells"]
     lo, hi = shard_bounds(n, world, rank)
     blocks = list(wl["n_covariate_components"]) + [wl["n_components"]]
-
     solver = _native.Solver(dev, G, hi - lo, blocks, wl["categories"])
     nnz = 0
     if sparse:
@@ -347,9 +425,9 @@ def run_gpu_arm(args):
         exchange = ("NVLink peer memory inside the W-update kernels (reduce-scatter + update + all-gather)" if peer
                     else "NCCL all-reduce of the packed buffer")
     engine = MUEngine(solver, wl["lam"], use_als=args.use_als)
-    total = args.warmup + args.steps
+    total = warmup + steps
     engine.begin(total)
-    for it in range(args.warmup):
+    for it in range(warmup):
         engine.step(it)
 
     def fence():
@@ -360,13 +438,13 @@ def run_gpu_arm(args):
 
     fence()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and sample_clocks:
         sampler.start()
     solver.profile(True)
     launches0 = _native.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for it in range(args.warmup, total):
+    for it in range(warmup, total):
         engine.step(it)
     e1.record()
     fence()
@@ -374,61 +452,97 @@ def run_gpu_arm(args):
     launches = _native.launch_count() - launches0
     solver.profile(False)
     gemm_ms, gemm_n = solver.profile_read()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
     t = torch.tensor([ms, gemm_ms / max(gemm_n, 1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, gemm_ms_avg = float(t[0]), float(t[1])
     hist = engine.collect_losses(total)  # also checks the kernels' error flag
-    value = args.steps / (ms / 1000.0)
+    value = steps / (ms / 1000.0)
 
     # ---- roofline of the contraction kernel (per launch, this rank's shard)
     peaks = load_peaks()
     K = sum(blocks)
     n_loc = hi - lo
-    flops = 3.0 * 2.0 * G * n_loc * K          # 3xTF32: three tf32 MMAs per fp32 product
+    # 3xTF32: three tf32 MMAs per fp32 product; tf32-exact integer counts (the CSR workload): two
+    mma_per_product = 2.0 if sparse else 3.0
+    flops = mma_per_product * 2.0 * G * n_loc * K
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     achieved = flops / (gemm_ms_avg * 1e-3) / 1e12 if gemm_ms_avg > 0 else 0.0
     x_bytes = 8.0 * nnz if sparse else 4.0 * G * n_loc
-    if sparse:
-        flops = 2.0 * 2.0 * G * n_loc * K      # integer counts are tf32-exact: two tf32 MMAs per fp32 product
     hbm_ms = x_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+    achieved_gbs = x_bytes / (gemm_ms_avg * 1e-3) / 1e9 if gemm_ms_avg > 0 else 0.0
     traffic, traffic_src = (None, None)
     if world == 1 and not args.cells and not args.genes:
-        traffic, traffic_src = load_traffic("cfg3_n1" if not sparse else "none")
+        traffic, traffic_src = load_traffic("cfg3_n1" if not sparse else "cfg4_n1")
     step_bound_ms = 2.0 * max(flops / (tf32_peak * 1e12), x_bytes / (peaks["hbm_gbs"] * 1e9)) * 1e3
     roofline = {
-        "kernel": "mu_gemm_kernel (X H^T and W^T X, %s tcgen05)" % ("2xTF32 on tf32-exact counts, CSR tile lists" if sparse else "3xTF32"),
+        "kernel": "mu_gemm_kernel (X H^T and W^T X, %s tcgen05)" % ("2xTF32 on tf32-exact counts, CSR tile lists expanded on chip" if sparse else "3xTF32"),
         "bound": "tensor",
         "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
         "traffic": traffic, "traffic_source": traffic_src,
         "iteration": {"what": "whole MU iteration against the slower of (two contractions at the tensor peak, two "
                               "sweeps of X at HBM bandwidth) -- BASELINE north_star's roofline",
-                      "bound_ms": step_bound_ms, "measured_ms": ms / args.steps,
-                      "frac": step_bound_ms / (ms / args.steps)},
+                      "bound_ms": step_bound_ms, "measured_ms": ms / steps,
+                      "frac": step_bound_ms / (ms / steps)},
         "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (no TF32 figure in MEASURED_PEAKS.json; the "
                        f"kernel is timed inside the step loop)",
         "avg_launch_ms": gemm_ms_avg, "launches_timed": gemm_n,
-        "hbm_bound_ms_per_launch": hbm_ms, "hbm_frac": hbm_ms / gemm_ms_avg if gemm_ms_avg > 0 else None,
-        "algorithmic": {"tf32_flop_per_launch": flops, "x_bytes_per_launch": x_bytes},
+        # the same launch against SURVEY.md 8 d3's HBM bound (dense: 4 B per X element; CSR: 8 B per nonzero)
+        "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved_gbs / peaks["hbm_gbs"], "bound_ms_per_launch": hbm_ms},
+        "algorithmic": {"tf32_flop_per_launch": flops, "tf32_mma_per_fp32_product": mma_per_product,
+                        "x_bytes_per_launch": x_bytes},
     }
-
-    line = None
+    out = None
     if rank == 0:
-        line = {
-            "metric": METRIC if not sparse else "MU iterations/sec at 30k genes x 1M cells CSR, k=100", "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
-            "config": {"workload": wl["name"] + (", use_als=True" if args.use_als else ""), "parallelism": f"cells sharded over {world} GPU(s)", "exchange": exchange,
+        out = {
+            "value": value, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup,
+            "config": {"workload": wl["name"] + (", use_als=True" if args.use_als else ""),
+                       "parallelism": f"cells sharded over {world} GPU(s)", "exchange": exchange,
                        "l2": "inputs larger than L2 (X is %.1f GB per GPU)" % (x_bytes / 1e9)},
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline,
             "final_loss": {"total": float(hist[-1, 0]), "reconstruction": float(hist[-1, 1])},
         }
     solver.close()
-    del X, H, W
+    del X, H, W, Ys, Bs, solver, engine
     torch.cuda.empty_cache()
+    return out
+
+
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    sparse = args.workload == "cfg4"
+    wl = dict(WORKLOAD_CFG4 if sparse else WORKLOAD)
+    if args.cells:
+        wl["n_cells"] = args.cells
+    if args.genes:
+        wl["n_genes"] = args.genes
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the MU loop has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    if world != args.gpus and rank == 0:
+        print(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE", file=sys.stderr)
+
+    res = measure_resident(args, wl, sparse, dev, world, rank, local_rank, args.steps, args.warmup)
+    line = None
+    if rank == 0:
+        line = {"metric": METRIC if not sparse else "MU iterations/sec at 30k genes x 1M cells CSR, k=100",
+                "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+                "config": res["config"], "clocks": res["clocks"], "gpu_launches": res["gpu_launches"],
+                "roofline": res["roofline"], "final_loss": res["final_loss"]}
     if sparse:  # the sparse scaling workload has no host-API / CPU legs (the reference rejects sparse input)
-        args.no_e2e = args.no_cpu = True
+        args.no_e2e = args.no_cpu = args.no_cfg4 = True
 
     # ---- e2e through the public API with host buffers (N = 1 process; each rank runs the sharded fit under torchrun)
     if not args.no_e2e:
@@ -442,21 +556,90 @@ def run_gpu_arm(args):
             e2e = run_e2e(args, wl, dev, world, rank)
         if rank == 0:
             line["e2e"] = e2e
+    # ---- N > 1: sharded == single-GPU, once, outside every timed region (the test of tests/test_gpu_multi.py)
+    if world > 1 and not args.no_parity:
+        from alpine_b200.utils.dist_selfcheck import sharded_vs_single
+
+        par = sharded_vs_single(dev)
+        if rank == 0:
+            line["parity_vs_n1"] = par
+    # ---- BASELINE configs[3] on the same ranks: the workload the >= 6x @ 8 GPUs target is stated on
+    if not args.no_cfg4 and not args.cells and not args.genes and not args.use_als:
+        wl4 = dict(WORKLOAD_CFG4)
+        free, _ = torch.cuda.mem_get_info(dev)
+        # per GPU: tile lists 16 B/nnz + CSR source 12 B/nnz + generator scratch
+        need4 = 30.0 * wl4["density"] * wl4["n_genes"] * (wl4["n_cells"] / world) + (6 << 30)
+        if free < need4:
+            c4 = {"skipped": "needs %.0f GiB of free HBM per GPU" % (need4 / 2**30)}
+        else:
+            r4 = measure_resident(args, wl4, True, dev, world, rank, local_rank, 30, 3, sample_clocks=False)
+            c4 = None
+            if rank == 0:
+                c4 = {"metric": "MU iterations/sec at 30k genes x 1M cells CSR (5% density), k=100", "value": r4["value"],
+                      "unit": UNIT, "ms_per_step": r4["ms_per_step"], "steps": 30, "warmup": 3, "scaling": "strong",
+                      "config": r4["config"], "gpu_launches": r4["gpu_launches"], "final_loss": r4["final_loss"],
+                      "roofline": {"tensor": {k: r4["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
+                                   "hbm": r4["roofline"]["hbm"], "avg_launch_ms": r4["roofline"]["avg_launch_ms"],
+                                   "algorithmic": r4["roofline"]["algorithmic"]}}
+        if rank == 0:
+            line["cfg4"] = c4
     if rank == 0 and world == 1 and not args.no_tf32_peak:
         # after every timed region, so that its heat does not touch them
         tf = cublas_tf32_peak(dev)
         line["roofline"]["cublas_tf32_tflops"] = tf
         line["roofline"]["frac_of_cublas_tf32_sustained"] = line["roofline"]["achieved"] / tf["sustained"]
+    if rank == 0 and world == 1 and not args.no_gpu_torch:
+        line["gpu_torch_baseline"] = gpu_torch_baseline(wl, dev)
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, dt, threads, ns = cpu_baseline(wl, sample_cells=8000, iters=2)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                                "sample": f"{ns} of {wl['n_cells']} cells (all {wl['n_genes']} genes), {dt:.3f} s per "
-                                          f"iteration on the sample, extrapolated linearly in cells"}
-    if rank == 0:
-        print(json.dumps(line), flush=True)
+        line["cpu_baseline"] = cpu_reference_run(wl, warmup=1, steps=2, budget_s=40.0)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    # ---- BASELINE configs[4]: 64 trials x 3 folds, one fit per GPU, from ONE process (rank 0) over all GPUs of the box
+    if rank == 0 and (args.cfg5 or (world == 8 and not args.no_cfg5)):
+        try:
+            line["cfg5"] = run_cfg5(args)
+        except Exception as exc:  # never lose the headline line to the auxiliary block
+            line["cfg5"] = {"error": repr(exc)[:300]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+def run_cfg5(args, trials=64, n_splits=3, max_iter=100):
+    """ComponentOptimizer.search_hyperparams on 5,000 HVG x 50,000 cells, `trials` trials x `n_splits` folds, one fit
+    per GPU over every visible GPU (worker threads of this process; the other ranks have exited)."""
+    import pandas as pd
+    import torch
+
+    from alpine_b200.optimization import ComponentOptimizer
+    from alpine_b200.utils.anndata_compat import AnnData
+    from alpine_b200.utils.synth import make_labels
+
+    n, G = 50_000, 5_000
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    Wg = torch.rand((12, G), device=dev, generator=g).pow_(3.0)
+    Hc = torch.rand((n, 12), device=dev, generator=g).pow_(2.0)
+    labels = make_labels(n, [3, 4], seed=5)
+    # cells of the same joint label share a bump in two latent factors, so that the embedding can be scored
+    codes = torch.from_numpy(np.stack([pd.factorize(l)[0] for l in labels], 1)).to(dev)
+    Hc[torch.arange(n, device=dev), codes[:, 0]] += 1.0
+    Hc[torch.arange(n, device=dev), 3 + codes[:, 1]] += 1.0
+    X = (Hc @ Wg + 0.25 * torch.rand((n, G), device=dev, generator=g).pow_(4.0)).cpu().numpy()
+    del Wg, Hc
+    torch.cuda.empty_cache()
+    obs = pd.DataFrame({f"cov{i}": pd.Series(l, dtype=object) for i, l in enumerate(labels)})
+    opt = ComponentOptimizer(AnnData(X, obs=obs), ["cov0", "cov1"], max_iter=max_iter, device="cuda")
+    t0 = time.perf_counter()
+    best = opt.search_hyperparams(n_total_components_range=(10, 100), max_evals=trials, n_splits=n_splits)
+    wall = time.perf_counter() - t0
+    busy = {d: round(t / wall, 3) for d, t in sorted(opt.device_busy_s.items())}
+    return {"what": f"ComponentOptimizer.search_hyperparams, {trials} trials x {n_splits} folds on {G} HVG x {n} cells, "
+                    f"max_iter={max_iter}, one fit per GPU (fit on 2/3 of the cells + transform of 1/3 + scoring per fold)",
+            "wall_s": wall, "s_per_trial": wall / trials, "gpus": len(opt.devices), "trials": trials,
+            "per_gpu_busy_fraction": busy,
+            "optimiser": "seeded random search stand-in (hyperopt is not installed); k-means scorer stand-in (scanpy absent)",
+            "best": {k: (v if not isinstance(v, float) else round(v, 4)) for k, v in best.items()}}
 
 
 def run_e2e(args, wl, dev, world, rank):
@@ -535,6 +718,11 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tf32-peak", action="store_true", help="skip the cuBLAS TF32 reference measurement")
+    ap.add_argument("--no-gpu-torch", action="store_true", help="skip the torch-CUDA (reference arithmetic) baseline leg")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the auxiliary cfg4 (CSR scaling workload) block")
+    ap.add_argument("--no-cfg5", action="store_true", help="skip the auxiliary cfg5 (hyper-parameter search) block at 8 GPUs")
+    ap.add_argument("--cfg5", action="store_true", help="run the cfg5 block at any GPU count")
+    ap.add_argument("--no-parity", action="store_true", help="skip the sharded == single-GPU self-check at N > 1")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -28,7 +28,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim  # noqa: E402
-from alpine_b200.utils.synth import make_counts, make_labels  # noqa: E402
+from alpine_b200.utils.synth import make_counts, make_labels, make_poisson_counts  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -78,12 +78,22 @@ CASES = {
         kw=dict(n_components=9, n_covariate_components=[3], lam=[1e3],
                 orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
     ),
+    # raw counts (tf32-exact: the 2-MMA kernel variant), 2,000 genes: top-100 rankings of W columns and of the
+    # per-category gene scores (main.py:246-273) after 60 iterations; X stored as uint16
+    "kl_scores2k": dict(
+        n_cells=500, n_genes=2000, cats=[3, 4], rank=8, n_iter=60, keep_every=60, counts=True,
+        kw=dict(n_components=10, n_covariate_components=[4, 3], lam=[1e3, 5e2],
+                orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
+    ),
 }
 
 
 def run_case(ref_main, name: str, spec: dict) -> dict:
     n, G = spec["n_cells"], spec["n_genes"]
-    Xcg = make_counts(n, G, seed=len(name) * 7 + n, rank=spec["rank"])
+    if spec.get("counts"):
+        Xcg = make_poisson_counts(n, G, seed=len(name) * 7 + n, rank=spec["rank"])
+    else:
+        Xcg = make_counts(n, G, seed=len(name) * 7 + n, rank=spec["rank"])
     labels = make_labels(n, spec["cats"], seed=G, nan_fraction=spec.get("nan_fraction", 0.0))
     keys = [f"cov{i}" for i in range(len(labels))]
     index = [str(i) for i in range(n)]

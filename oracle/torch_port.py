@@ -1,4 +1,5 @@
-"""Torch (CPU) restatement of the reference's simultaneous-update step, for the CPU timing legs of bench.py.
+"""Torch restatement of the reference's simultaneous-update step, for the timing legs of bench.py and, on
+``device="cuda"``, as the same-box fp32 trajectory the large-shape GPU parity tests compare against.
 
 TEST / MEASUREMENT INFRASTRUCTURE ONLY (see oracle/alpine_oracle.py for the rules).  The reference runs its loop
 with torch operators on ``device="cpu"`` (MKL GEMMs, torch's threading); the NumPy oracle computes the same numbers
@@ -6,7 +7,9 @@ but through NumPy's BLAS, which is about half as fast on these shapes.  A CPU ba
 the thing it stands for, so ``bench.py``'s ``cpu_baseline`` and ``--impl reference`` legs time THIS restatement:
 the same operators, operator precedence, temporaries and batch gather as ``alpine/main.py:589-663`` (step) and
 ``main.py:726-753`` (loss), on torch CPU tensors with all host threads.  Pinned by tests/test_oracle_golden.py
-against the same reference-generated fixtures as the NumPy oracle.
+against the same reference-generated fixtures as the NumPy oracle.  Every tensor it creates lives on the device of
+its inputs, so the same code is the reference's ``device="cuda"`` arithmetic (cuBLAS fp32 GEMMs; callers switch
+``allow_tf32`` off) when handed CUDA tensors: tests/test_gpu_bigshape.py and bench.py's ``gpu_torch_baseline``.
 """
 from __future__ import annotations
 
@@ -33,15 +36,17 @@ def mu_step(X: torch.Tensor, Ys: List[torch.Tensor], W: torch.Tensor, H: torch.T
     sls = block_slices(blocks)
     n_cov = len(hp.n_covariate_components)
     eps = hp.eps
-    if perm is None:
-        perm = torch.arange(X.shape[1])
-    X_b = X[:, perm]  # main.py:520
-    Ys_b = [Y[:, perm] for Y in Ys]  # main.py:521
-    H_b = H[:, perm]  # main.py:593-594
+    if perm is None:  # natural order without the gather copies (the permutation only reorders fp32 sums)
+        X_b, Ys_b, H_b = X, list(Ys), H
+    else:
+        X_b = X[:, perm]  # main.py:520
+        Ys_b = [Y[:, perm] for Y in Ys]  # main.py:521
+        H_b = H[:, perm]  # main.py:593-594
     K = W.shape[1]
     # === W === (main.py:592-612)
     numerator = (2 * X_b) @ H_b.T  # main.py:596
-    orth = hp.orth_W * (torch.ones((K, K), dtype=W.dtype) - torch.eye(K, dtype=W.dtype))  # main.py:474-484
+    orth = hp.orth_W * (torch.ones((K, K), dtype=W.dtype, device=W.device)
+                        - torch.eye(K, dtype=W.dtype, device=W.device))  # main.py:474-484
     denominator = ((2 * W) @ H_b) @ H_b.T + ((1 - hp.l1_ratio_W) * hp.alpha_W) * W + W @ orth  # main.py:599-601
     denominator += hp.l1_ratio_W * hp.alpha_W * torch.ones_like(denominator)  # main.py:603
     denominator = torch.clamp(denominator, min=eps)  # main.py:604
@@ -70,7 +75,10 @@ def mu_step(X: torch.Tensor, Ys: List[torch.Tensor], W: torch.Tensor, H: torch.T
     numerator += (2 * W.T) @ X_b  # main.py:653
     denominator += (2 * W.T) @ (W @ H_b)  # main.py:654
     denominator = torch.clamp(denominator, min=eps)  # main.py:655
-    H[:, perm] = H_b * (numerator / denominator)  # main.py:656-663
+    if perm is None:
+        H.copy_(H_b * (numerator / denominator))
+    else:
+        H[:, perm] = H_b * (numerator / denominator)  # main.py:656-663
 
 
 @torch.no_grad()

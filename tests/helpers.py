@@ -25,6 +25,8 @@ CASE_KW = {
     "mb_weighted": dict(n_components=6, n_covariate_components=[3], lam=[1e3], alpha_W=0.3),
     "mb_als": dict(n_components=6, n_covariate_components=[3, 2], lam=[1e2, 1e3],
                    orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5, use_als=True),
+    "kl_scores2k": dict(n_components=10, n_covariate_components=[4, 3], lam=[1e3, 5e2],
+                        orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
     "kl_long200": dict(n_components=9, n_covariate_components=[3], lam=[1e3],
                        orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5),
 }

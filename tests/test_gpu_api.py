@@ -256,3 +256,101 @@ def test_large_negative_matrix_is_rejected_after_the_deferred_device_check():
         model.fit(ad, ["cov0"], max_iter=2)
     X[4321, 1234] = 0.5
     assert model.fit(ad, ["cov0"], max_iter=2) is model
+
+
+# ------------------------------------------------------------------------------------------------- random streams
+def _reference_draw_sequence(model, G, n, cats, dev):
+    """The draws the reference makes on the process-wide generators, restated call by call: seeding
+    (main.py:440-442), then rand for every W block, every H block, every B (main.py:454-470)."""
+    torch.manual_seed(model.random_state)
+    torch.cuda.manual_seed(model.random_state)
+    for k in model.n_all_components:
+        torch.rand((G, k), dtype=torch.float32, device=dev)
+    for k in model.n_all_components:
+        torch.rand((k, n), dtype=torch.float32, device=dev)
+    for c, k in zip(cats, model.n_covariate_components):
+        torch.rand((c, k), dtype=torch.float32, device=dev)
+
+
+def test_generators_after_fit_are_where_the_reference_leaves_them():
+    """fit() draws W / H / B and one randperm per full-batch iteration from the seeded device generator
+    (main.py:440-470, 502-506); a following transform() continues that stream (main.py:687-689)."""
+    dev = torch.device("cuda:0")
+    ad = _adata()
+    keys = ["cov0", "cov1"]
+    n_iter = 7
+    model = ALPINE(device="cuda:0", random_state=11, **KW)
+    model.fit(ad, keys, max_iter=n_iter)
+    got_state = torch.cuda.get_rng_state(0).clone()
+    _reference_draw_sequence(model, 400, 600, [3, 4], dev)
+    for _ in range(n_iter):
+        torch.randperm(600, device=dev)  # main.py:502-506
+    assert torch.equal(torch.cuda.get_rng_state(0), got_state)
+    K = model.total_components
+    H0 = torch.rand((K, 200), dtype=torch.float32, device=dev).cpu().numpy()  # the reference's next draw (main.py:687)
+    torch.cuda.set_rng_state(got_state, 0)
+    val = _adata(n=200, seed=9)
+    model.transform(val, n_iter=4)
+    W = np.concatenate(model.get_decomposed_matrices()["Ws"], axis=1)
+    Ht = orc.transform_loop(np.ascontiguousarray(val.X).T, W, H0, 4, model.eps)
+    got = np.concatenate([val.obsm["cov0"].T, val.obsm["cov1"].T, val.obsm["ALPINE_embedding"].T], axis=0)
+    assert rel_fro(got, Ht) < 2e-5
+
+
+@pytest.mark.parametrize("method", ["random", "weighted"])
+def test_minibatch_index_stream_equals_the_reference_call_sequence(method, monkeypatch):
+    """Un-hooked mini-batch fit: the epoch index vectors equal what the reference's calls yield on freshly seeded
+    process-wide generators (device randperm after the init draws; CPU multinomial of the weighted sampler)."""
+    from alpine_b200.utils import sampling
+
+    dev = torch.device("cuda:0")
+    ad = _adata(n=500, G=300, cats=(3,), nan_fraction=0.0)
+    seen = []
+    real = sampling.generate_epoch_indices
+
+    def recording(*a, **k):
+        idx = real(*a, **k)
+        seen.append(idx.cpu().numpy().copy())
+        return idx
+
+    monkeypatch.setattr(sampling, "generate_epoch_indices", recording)
+    model = ALPINE(n_components=5, n_covariate_components=[3], lam=[1e2], device="cuda:0", random_state=5)
+    model.fit(ad, ["cov0"], max_iter=3, batch_size=128, sampling_method=method)
+    monkeypatch.setattr(sampling, "generate_epoch_indices", real)
+    assert len(seen) == 3
+    _reference_draw_sequence(model, 300, 500, [3], dev)
+    Y = model.fe.transform(ad.obs)
+    joint = sampling.create_joint_labels_from_dummy_matrices([torch.from_numpy(np.ascontiguousarray(y.T)) for y in Y])
+    for it in range(3):
+        want = real(joint_labels=joint, sampling_method=method, device=dev)  # process-wide generators, as the reference
+        np.testing.assert_array_equal(seen[it], want.cpu().numpy())
+
+
+def test_search_hyperparams_runs_real_fits_on_the_gpu():
+    """ComponentOptimizer.search_hyperparams (optimization.py:51-151) driving real fold fits + transforms through the
+    device scheduler (4 trials x 2 folds; random-search and k-means stand-ins, as hyperopt / scanpy are absent)."""
+    from alpine_b200 import ComponentOptimizer
+
+    ad = _adata(n=900, G=300, cats=(3, 2), nan_fraction=0.0)
+    opt = ComponentOptimizer(ad, ["cov0", "cov1"], max_iter=30, device="cuda", random_state=3)
+    best = opt.search_hyperparams(n_total_components_range=(10, 24), max_evals=4, n_splits=2)
+    assert set(best) == {"n_components", "n_covariate_components", "lam", "alpha_W", "orth_W", "l1_ratio_W", "random_state"}
+    hist = opt.get_train_history()
+    assert len(hist) >= 1 and np.isfinite(hist["score"]).all()
+    assert sum(t > 0 for t in opt.device_busy_s.values()) >= 1
+    model = ALPINE(**best, device="cuda")  # the returned dict constructs a model (optimization.py:141-151)
+    model.fit(ad, ["cov0", "cov1"], max_iter=5)
+    assert len(model.loss_history) == 5
+    # same seed, same data => same suggestions and scores (per-model random streams, no cross-thread seeding)
+    opt2 = ComponentOptimizer(ad, ["cov0", "cov1"], max_iter=30, device="cuda", random_state=3)
+    opt2.search_hyperparams(n_total_components_range=(10, 24), max_evals=4, n_splits=2)
+    np.testing.assert_allclose(opt2.get_train_history()["score"].to_numpy(), hist["score"].to_numpy(), rtol=1e-6)
+
+
+def test_max_iter_zero_and_limits_are_handled_on_the_host():
+    ad = _adata(n=200, G=100, cats=(3,), nan_fraction=0.0)
+    model = ALPINE(n_components=4, n_covariate_components=[3], lam=[1.0], device="cuda")
+    model.fit(ad, ["cov0"], max_iter=0)  # the reference's loop never runs: empty history, scaled initial factors
+    assert len(model.loss_history) == 0 and list(model.loss_history.columns)[:2] == ["total loss", "reconstruction loss"]
+    with pytest.raises(ValueError, match="at least one component per covariate"):
+        ALPINE(n_components=4, n_covariate_components=[0], lam=[1.0], device="cuda").fit(ad, ["cov0"], max_iter=2)
