@@ -51,6 +51,31 @@ int fail(int code, const char* fmt, ...) {
       return fail(ALPINE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
   } while (0)
 
+// Every entry point runs on its context's device and puts the caller's current device back on return (the host
+// side keeps using torch on whatever device it had selected).
+struct DeviceScope {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceScope(int dev) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) return;
+    if (cur == dev) {
+      ok = true;
+      return;
+    }
+    ok = cudaSetDevice(dev) == cudaSuccess;
+    if (ok) prev = cur;
+  }
+  ~DeviceScope() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceScope(const DeviceScope&) = delete;
+  DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define DEVICE_SCOPE(c)                                  \
+  DeviceScope dev_scope__((c)->device);                  \
+  if (!dev_scope__.ok) return fail(ALPINE_ERR_CUDA, "cannot select device %d", (c)->device)
+
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -266,25 +291,24 @@ inline void ws_free(const alpine_ctx* c, void* q) {
 
 int set_kernel_attrs();
 
-int ensure_flags(alpine_ctx* c) {
+// (initialisations below are issued on the caller's stream, the one the consuming kernels are launched on)
+int ensure_flags(alpine_ctx* c, cudaStream_t st) {
   if (c->flags != nullptr) return ALPINE_OK;
   AL_TRY(ws_alloc(c, &c->flags, 2));
-  const int init[2] = {1, 1};
-  CU_TRY(cudaMemcpy(c->flags, init, sizeof(init), cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemsetAsync(c->flags, 1, 2 * sizeof(int), st));  // any non-zero value = "not known to be tf32-exact"
   return ALPINE_OK;
 }
 
-int ensure_workspace(alpine_ctx* c) {
+int ensure_workspace(alpine_ctx* c, cudaStream_t st) {
   if (c->ws_ready) return ALPINE_OK;
-  CU_TRY(cudaSetDevice(c->device));
   AL_TRY(set_kernel_attrs());
   const size_t K = c->K;
   AL_TRY(ws_alloc(c, &c->WT, K * c->ldG));
   AL_TRY(ws_alloc(c, &c->A, K * c->ldN));
   AL_TRY(ws_alloc(c, &c->Hsplit, 2 * K * c->ldN));
   AL_TRY(ws_alloc(c, &c->Wsplit, 2 * K * c->ldG));
-  CU_TRY(cudaMemset(c->Hsplit, 0, 2 * K * c->ldN * sizeof(float)));
-  CU_TRY(cudaMemset(c->Wsplit, 0, 2 * K * c->ldG * sizeof(float)));
+  CU_TRY(cudaMemsetAsync(c->Hsplit, 0, 2 * K * c->ldN * sizeof(float), st));
+  CU_TRY(cudaMemsetAsync(c->Wsplit, 0, 2 * K * c->ldG * sizeof(float), st));
   AL_TRY(ws_alloc(c, &c->numG, static_cast<size_t>(c->Kg) * c->ldN));
   AL_TRY(ws_alloc(c, &c->denG, static_cast<size_t>(c->Kg) * c->ldN));
   AL_TRY(ws_alloc(c, &c->T, K * K));
@@ -298,9 +322,9 @@ int ensure_workspace(alpine_ctx* c) {
   AL_TRY(ws_alloc(c, &c->sumsq_partial, 1024));
   AL_TRY(ws_alloc(c, &c->xnorm2, 1));
   AL_TRY(ws_alloc(c, &c->err, 8));
-  CU_TRY(cudaMemset(c->err, 0, 8 * sizeof(int)));
-  AL_TRY(ensure_flags(c));
-  CU_TRY(cudaMemset(c->t1_partial, 0, sizeof(double) * c->sl_blocks_n));
+  CU_TRY(cudaMemsetAsync(c->err, 0, 8 * sizeof(int), st));
+  AL_TRY(ensure_flags(c, st));
+  CU_TRY(cudaMemsetAsync(c->t1_partial, 0, sizeof(double) * c->sl_blocks_n, st));
   if (c->reduce == nullptr) {
     AL_TRY(ws_alloc(c, &c->own_reduce, static_cast<size_t>(c->reduce_floats())));
     c->reduce = c->own_reduce;
@@ -359,10 +383,10 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
 
 // Work space, grid and slot count of one contraction; returns the floats its partial-sum slots need.
 size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p, int* grid_out);
-int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop);
+int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop, cudaStream_t st);
 
 // Build the plan of one contraction (see GemmOperands).
-int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
+int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, cudaStream_t st) {
   const long long R = (op.orient == ORIENT_XH) ? op.rows : op.cols;
   pl->op = op;
   GemmParams& p = pl->p;
@@ -396,7 +420,7 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op) {
       other.r.partial = c->partial;
     }
   }
-  return build_plan_tail(c, pl, op, R, Kop);
+  return build_plan_tail(c, pl, op, R, Kop, st);
 }
 
 size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p, int* grid_out) {
@@ -431,7 +455,7 @@ size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p,
   return static_cast<size_t>(grid) * p.max_segs * p.K * rows;
 }
 
-int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop) {
+int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop, cudaStream_t st) {
   const int rows = kRows;
   GemmParams& p = pl->p;
   p.partial = c->partial;
@@ -465,8 +489,11 @@ int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long lo
     pl->d_slot_ofs = pl->d_slots = nullptr;
     AL_TRY(ws_alloc(c, &pl->d_slot_ofs, ofs.size()));
     AL_TRY(ws_alloc(c, &pl->d_slots, slots.size() + 1));
-    CU_TRY(cudaMemcpy(pl->d_slot_ofs, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    CU_TRY(cudaMemcpy(pl->d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // on the launch stream (and complete before the host vectors go away): ordered before the reduce kernel even when
+    // the caller runs on a non-blocking side stream
+    CU_TRY(cudaMemcpyAsync(pl->d_slot_ofs, ofs.data(), ofs.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(pl->d_slots, slots.data(), slots.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaStreamSynchronize(st));
     r.slot_ofs = pl->d_slot_ofs;
     r.slots = pl->d_slots;
   }
@@ -517,8 +544,9 @@ int run_split(alpine_ctx* c, const float* src, long long ld_src, long long R, fl
 // out[k][m] (ld_out) = contraction `which`; its B operand must already be in the split workspace
 int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_t st) {
   GemmPlan* pl = &c->plans[which];
-  if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which)));
+  if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which), st));
   const GemmOperands& op = pl->op;
+#ifdef ALPINE_B200_DEBUG_SIMT  // A/B checking builds only: the shipped library has no CUDA-core contraction
   if (c->simt && op.sp_ofs == nullptr && which < PLAN_WX_BLOCK) {
     const float* Bsrc = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->H : c->WT;
     const long long ldB = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->ldH : c->ldG;
@@ -530,6 +558,7 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
     LAUNCH_CHECK();
     return ALPINE_OK;
   }
+#endif
   if (op.profiled) AL_TRY(prof_mark(c, st));
   // op.profiled marks the contractions whose A operand is X; only those can use the count-matrix variant
   if (op.profiled && c->x_exact) {
@@ -697,7 +726,9 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
   c->Kp = static_cast<int>(round_up(K, 16));
   c->Kg = Kg;
   c->q_total = q;
+#ifdef ALPINE_B200_DEBUG_SIMT
   if (const char* e = getenv("ALPINE_B200_GEMM")) c->simt = (strcmp(e, "simt") == 0);
+#endif
   c->ldG = round_up(n_genes, 4);
   c->ldN = round_up(n_cells, 4);
   *out = c;
@@ -706,7 +737,7 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
 
 int alpine_destroy(alpine_ctx* c) {
   if (c == nullptr) return ALPINE_OK;
-  cudaSetDevice(c->device);
+  DeviceScope dev_scope__(c->device);
   for (int q = 0; q < kMaxPeers; ++q)
     if (c->peer_opened[q]) cudaIpcCloseMemHandle(c->peer_base[q]);
   if (c->xchg != nullptr) {
@@ -787,8 +818,8 @@ int alpine_bind_csr(alpine_ctx* c, const int64_t* indptr, const int32_t* indices
   if (c == nullptr || indptr == nullptr || (nnz > 0 && (indices == nullptr || values == nullptr)))
     return fail(ALPINE_ERR_ARG, "null argument");
   if (nnz < 0) return fail(ALPINE_ERR_ARG, "negative nnz");
-  CU_TRY(cudaSetDevice(c->device));
-  AL_TRY(ensure_flags(c));
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_flags(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   for (int o = 0; o < 2; ++o) {
     if (c->sp_ofs[o]) cudaFree(c->sp_ofs[o]);
@@ -901,8 +932,8 @@ int alpine_bind_reduce_buffer(alpine_ctx* c, float* buf) {
 int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
   AL_TRY(check_bound(c, true));
   if (max_iter <= 0) return fail(ALPINE_ERR_ARG, "max_iter must be positive");
-  CU_TRY(cudaSetDevice(c->device));
-  AL_TRY(ensure_workspace(c));
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (max_iter > c->loss_cap) {
     ws_free(c, c->loss_hist);
@@ -939,8 +970,8 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
 
 int alpine_batch_begin(alpine_ctx* c, void* stream) {
   AL_TRY(check_bound(c, true));
-  CU_TRY(cudaSetDevice(c->device));
-  AL_TRY(ensure_workspace(c));
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (c->loss_cap < 1) {
     AL_TRY(ws_alloc(c, &c->loss_hist, static_cast<size_t>(2 + c->n_cov)));
@@ -960,7 +991,7 @@ int alpine_batch_begin(alpine_ctx* c, void* stream) {
 int alpine_mu_partials(alpine_ctx* c, void* stream) {
   AL_TRY(check_bound(c, true));
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   return run_gemm(c, PLAN_XH, c->red_Pt(), c->ldG, static_cast<cudaStream_t>(stream));  // Hsplit is current
 }
 
@@ -988,7 +1019,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   if (peer != c->peer_on())
     return fail(ALPINE_ERR_STATE, peer ? "alpine_peer_import has not been called"
                                        : "this context exchanges over peer memory: call alpine_mu_apply_peer");
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // ---- W update (main.py:592-612) on W^T, then refresh the caller's row-major W
   SymLongParams w{};
@@ -1101,9 +1132,10 @@ int alpine_peer_export(alpine_ctx* c, void* handle_out) {
   if (c == nullptr || handle_out == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
   if (c->ws_ready || c->reduce != nullptr)
     return fail(ALPINE_ERR_STATE, "alpine_peer_export must come before alpine_bind_reduce_buffer / alpine_fit_begin");
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   CU_TRY(cudaMalloc(reinterpret_cast<void**>(&c->xchg), c->xchg_floats() * sizeof(float)));
   CU_TRY(cudaMemset(c->xchg, 0, c->xchg_floats() * sizeof(float)));
+  CU_TRY(cudaDeviceSynchronize());  // the zero-fill is complete before any stream (or peer) touches the block
   AL_TRY(ws_alloc(c, &c->sum_small, static_cast<size_t>(c->small_floats())));
   AL_TRY(ws_alloc(c, &c->sum_P, static_cast<size_t>(c->K) * c->ldG));
   c->reduce = c->xchg;                          // [X H^T | H H^T | rowsum H | B statistics] partials of this rank
@@ -1120,7 +1152,7 @@ int alpine_peer_import(alpine_ctx* c, int rank, int world, const void* handles) 
   if (c->xchg == nullptr) return fail(ALPINE_ERR_STATE, "alpine_peer_export has not been called");
   if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
     return fail(ALPINE_ERR_ARG, "peer exchange needs 2..%d ranks (rank %d of %d)", kMaxPeers, rank, world);
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   for (int q = 0; q < world; ++q) {
     if (q == rank) {
       c->peer_base[q] = c->xchg;
@@ -1154,7 +1186,7 @@ int alpine_als_block(alpine_ctx* c, int b, void* stream) {
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   if (b < 0 || b >= c->n_blocks) return fail(ALPINE_ERR_ARG, "block %d outside [0, %d)", b, c->n_blocks);
   if (c->peer_on()) return fail(ALPINE_ERR_STATE, "the block-wise sweep exchanges through the caller's all-reduce, not peer memory");
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int r0 = 0;
   for (int i = 0; i < b; ++i) r0 += c->kblk[i];
@@ -1231,7 +1263,7 @@ int alpine_als_finish(alpine_ctx* c, int iter, void* stream) {
   AL_TRY(check_bound(c, true));
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   if (iter < 0 || iter >= c->loss_cap) return fail(ALPINE_ERR_ARG, "iteration %d outside [0, %d)", iter, c->loss_cap);
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
                                                                                        c->W, c->ldW);
@@ -1246,7 +1278,7 @@ int alpine_fit_losses(alpine_ctx* c, int n_iter, double* xnorm2, double* rows, v
   if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   if (n_iter < 0 || n_iter > c->loss_cap) return fail(ALPINE_ERR_ARG, "n_iter outside the loss history");
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   CU_TRY(cudaStreamSynchronize(st));
   AL_TRY(check_kernel_error(c));
@@ -1258,8 +1290,8 @@ int alpine_fit_losses(alpine_ctx* c, int n_iter, double* xnorm2, double* rows, v
 
 int alpine_scale(alpine_ctx* c, void* stream) {
   AL_TRY(check_bound(c, false));
-  CU_TRY(cudaSetDevice(c->device));
-  AL_TRY(ensure_workspace(c));
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
@@ -1282,8 +1314,8 @@ int alpine_scale(alpine_ctx* c, void* stream) {
 int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
   AL_TRY(check_bound(c, false));
   if (n_iter < 0) return fail(ALPINE_ERR_ARG, "n_iter must be >= 0");
-  CU_TRY(cudaSetDevice(c->device));
-  AL_TRY(ensure_workspace(c));
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
@@ -1310,8 +1342,8 @@ int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
 int alpine_xh_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
   AL_TRY(check_bound(c, false));
   if (out == nullptr || ld_out < c->G) return fail(ALPINE_ERR_ARG, "bad output");
-  CU_TRY(cudaSetDevice(c->device));
-  AL_TRY(ensure_workspace(c));
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   AL_TRY(run_split(c, c->H, c->ldH, c->n, c->Hsplit, c->ldN, st));
   AL_TRY(run_gemm(c, PLAN_XH, out, ld_out, st));
@@ -1322,8 +1354,8 @@ int alpine_xh_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
 int alpine_wx_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
   AL_TRY(check_bound(c, false));
   if (out == nullptr || ld_out < c->n) return fail(ALPINE_ERR_ARG, "bad output");
-  CU_TRY(cudaSetDevice(c->device));
-  AL_TRY(ensure_workspace(c));
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
@@ -1343,7 +1375,7 @@ int alpine_profile(alpine_ctx* c, int enable) {
 
 int alpine_profile_read(alpine_ctx* c, double* gemm_ms_total, long long* gemm_launches) {
   if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
-  CU_TRY(cudaSetDevice(c->device));
+  DEVICE_SCOPE(c);
   double total = 0.0;
   const size_t pairs = c->prof_used / 2;
   for (size_t i = 0; i < pairs; ++i) {

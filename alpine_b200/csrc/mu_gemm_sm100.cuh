@@ -721,7 +721,9 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Plain fp32 CUDA-core version of the same contractions (debug / A-B checking only: ALPINE_B200_GEMM=simt).
+#ifdef ALPINE_B200_DEBUG_SIMT
+// Plain fp32 CUDA-core version of the same contractions: compiled only into A/B-checking builds
+// (-DALPINE_B200_DEBUG_SIMT, then selected with ALPINE_B200_GEMM=simt); the shipped library does not contain it.
 // out[k][m] = sum_r A(m, r) * B[k][r];  XH: A(m, r) = X[r * ldX + m];  WX: A(m, r) = X[m * ldX + r].
 template <int ORIENT>
 __global__ void simt_gemm_kernel(const float* __restrict__ X, long long ldX, const float* __restrict__ B,
@@ -736,5 +738,6 @@ __global__ void simt_gemm_kernel(const float* __restrict__ X, long long ldX, con
   }
   out[static_cast<long long>(k) * ld_out + m] = acc;
 }
+#endif  // ALPINE_B200_DEBUG_SIMT
 
 }  // namespace alpine
