@@ -62,6 +62,8 @@ SIGNATURES = {
     "alpine_transform": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_xh_product": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, ctypes.c_void_p]),
     "alpine_wx_product": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "alpine_upload_rows": (ctypes.c_int, [ctypes.c_int, _f32p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                          ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]),
     "alpine_profile": (ctypes.c_int, [_c_ctx, ctypes.c_int]),
     "alpine_profile_read": (ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_longlong)]),
     "alpine_query": (ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
@@ -116,76 +118,39 @@ def padded_rows(rows: int, cols: int, device, dtype=torch.float32, fill: Optiona
     return buf[:, :cols]
 
 
-class _RingStore(threading.local):
-    """Per-thread pinned staging ring (ComponentOptimizer uploads from one worker thread per GPU)."""
-
-    def __init__(self):
-        self.rings: dict = {}
-
-
-_RING = _RingStore()
-
-
 def _host_copy_threads() -> int:
-    """Threads for the pageable -> pinned staging copy: the cores of the box shared between the ranks of this node
-    (torchrun exports OMP_NUM_THREADS=1, which would leave that copy single-threaded at ~10 GB/s)."""
+    """Staging threads of an upload: the cores of the box shared between the ranks of this node (torchrun exports
+    OMP_NUM_THREADS=1, which says nothing about how many cores are idle)."""
     cores = os.cpu_count() or 1
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", "1") or 1)
-    return max(1, min(16, cores // max(1, local_world)))
+    return max(2, min(16, cores // max(1, local_world)))
 
 
-def upload_rows(dst: torch.Tensor, src, chunk_bytes: int = 16 << 20, n_buffers: int = 4) -> None:
-    """dst[:] = src for a 2-D fp32 device tensor and a pageable host array, through a small ring of pinned staging
-    buffers: the (multi-threaded) host copy into pinned memory overlaps the DMA of the previous chunk.  Measured on
-    the B200 box (8 GB, 16 cores): 53 GB/s with 16 MB chunks, 43 GB/s with 64 MB chunks, ~11 GB/s for a direct copy
-    from pageable memory; allocating the pinned ring costs ~1 ms per MB once per process, hence the small ring."""
+def upload_rows(dst: torch.Tensor, src, threads: Optional[int] = None) -> None:
+    """dst[:] = src for a 2-D fp32 device tensor (unit column stride) and a host array, through the library's
+    uploader (csrc/host_upload.cuh): host threads stage row chunks of the pageable array into a process-wide ring of
+    pinned buffers and queue the DMAs; the call returns once everything is queued and the current stream waits for
+    the copies.  The GIL is released for the duration, so the caller's other threads keep running."""
     import numpy as np
 
     src = np.asarray(src)
     if src.dtype != np.float32:
         src = src.astype(np.float32)
     rows, cols = src.shape
-    assert tuple(dst.shape) == (rows, cols) and dst.dtype == torch.float32
+    assert tuple(dst.shape) == (rows, cols) and dst.dtype == torch.float32 and dst.is_cuda
     if rows == 0 or cols == 0:
         return
-    if src.nbytes < (8 << 20):
-        dst.copy_(torch.from_numpy(np.ascontiguousarray(src)))
-        return
-    chunk_rows = max(1, chunk_bytes // (cols * 4))
-    key = (chunk_rows * cols, n_buffers)
-    rings = _RING.rings
-    if key not in rings:
-        rings.clear()  # keep at most one ring alive per thread
-        rings[key] = [torch.empty(chunk_rows * cols, dtype=torch.float32, pin_memory=True) for _ in range(n_buffers)]
-    bufs = rings[key]
-    events = [None] * n_buffers
-    stream = torch.cuda.current_stream(dst.device)
-    old_threads = torch.get_num_threads()
-    want = _host_copy_threads()
-    if want != old_threads:
-        torch.set_num_threads(want)
-    try:
-        _upload_chunks(dst, src, rows, cols, chunk_rows, n_buffers, bufs, events, stream)
-    finally:
-        if want != old_threads:
-            torch.set_num_threads(old_threads)
-
-
-def _upload_chunks(dst, src, rows, cols, chunk_rows, n_buffers, bufs, events, stream) -> None:
-    for i, r0 in enumerate(range(0, rows, chunk_rows)):
-        r1 = min(rows, r0 + chunk_rows)
-        b = i % n_buffers
-        if events[b] is not None:
-            events[b].synchronize()
-        stage = bufs[b][: (r1 - r0) * cols].view(r1 - r0, cols)
-        stage.copy_(torch.from_numpy(src[r0:r1]))
-        dst[r0:r1].copy_(stage, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(stream)
-        events[b] = ev
-    for ev in events:
-        if ev is not None:
-            ev.synchronize()
+    assert dst.stride(1) == 1 or cols == 1
+    if src.strides[1] != 4 or src.strides[0] % 4 != 0 or src.strides[0] < cols * 4:
+        src = np.ascontiguousarray(src)
+    lib = load_library()
+    dev = dst.device.index if dst.device.index is not None else torch.cuda.current_device()
+    ld_dst = dst.stride(0) if rows > 1 else max(dst.stride(0), cols)
+    ld_src = src.strides[0] // 4 if rows > 1 else cols
+    _check(lib, lib.alpine_upload_rows(dev, dst.data_ptr(), ld_dst, src.ctypes.data, ld_src, rows, cols,
+                                       int(threads or _host_copy_threads()), _stream_ptr(dst.device)))
+    # `src` must stay alive until the staging threads are done: they are, the call returns after the last chunk was
+    # copied out of it (only the DMAs out of the pinned ring are still in flight)
 
 
 class Solver:

@@ -14,6 +14,7 @@
 #include "mu_small_kernels.cuh"
 #include "csr_tiles.cuh"
 #include "peer_exchange.cuh"
+#include "host_upload.cuh"
 
 using namespace alpine;
 
@@ -670,7 +671,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 7; }
+int alpine_abi_version(void) { return 8; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -1364,6 +1365,18 @@ int alpine_wx_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
   AL_TRY(run_gemm(c, PLAN_WX, out, ld_out, st));
   CU_TRY(cudaStreamSynchronize(st));
   return check_kernel_error(c);
+}
+
+int alpine_upload_rows(int device, float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows,
+                       int64_t cols, int threads, void* stream) {
+  if (rows < 0 || cols < 0 || (rows > 0 && cols > 0 && (dst == nullptr || src == nullptr)))
+    return fail(ALPINE_ERR_ARG, "null / negative argument");
+  if (ld_dst < cols || ld_src < cols) return fail(ALPINE_ERR_ARG, "leading dimension smaller than the row length");
+  DeviceScope scope(device);
+  if (!scope.ok) return fail(ALPINE_ERR_CUDA, "cannot select device %d", device);
+  const cudaError_t e = upload_rows_f32(device, dst, ld_dst, src, ld_src, rows, cols, threads, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(ALPINE_ERR_CUDA, "host -> device upload failed: %s", cudaGetErrorString(e));
+  return ALPINE_OK;
 }
 
 int alpine_profile(alpine_ctx* c, int enable) {

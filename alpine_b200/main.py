@@ -109,6 +109,30 @@ def _csr_take_rows(csr, idx: torch.Tensor):
     return new_indptr, indices[src].contiguous(), values[src].contiguous()
 
 
+class _Background:
+    """A callable running on its own thread (the native calls inside release the GIL); ``result()`` joins and
+    re-raises."""
+
+    def __init__(self, fn):
+        import threading
+
+        self._out, self._exc = None, None
+        self._thread = threading.Thread(target=self._run, args=(fn,), daemon=True)
+        self._thread.start()
+
+    def _run(self, fn):
+        try:
+            self._out = fn()
+        except BaseException as exc:  # re-raised by result()
+            self._exc = exc
+
+    def result(self):
+        self._thread.join()
+        if self._exc is not None:
+            raise self._exc
+        return self._out
+
+
 def _gather_cells(Hs: List[torch.Tensor], shard, n_total: int) -> List[torch.Tensor]:
     """All ranks' column blocks of every H block, concatenated along cells (identity without sharding)."""
     rank, world = dist_info()
@@ -203,6 +227,9 @@ class ALPINE:
         else:
             X = np.ascontiguousarray(adata.X, dtype=np.float32).T
         n_sample = X.shape[1]
+        # the upload of this rank's cells starts now, on host threads of the library, and overlaps the label encoding
+        # and the factor draws; a warm-up fit and the main fit share the one device copy of X (it is never written)
+        Xdev = self._start_upload(X)
         self.fe = FeatureEncoders(covariate_keys)
         Y = self.fe.fit_transform(adata.obs)
         self.batch_size = batch_size if batch_size is not None else n_sample
@@ -210,7 +237,7 @@ class ALPINE:
 
         if max_iter is None:
             # warm-up run + Kneedle elbow on log10(reconstruction loss) (main.py:116-131, 755-770)
-            m_warmup = self._initialize_matrices(X, Y)
+            m_warmup = self._initialize_matrices(X, Y, _Xdev=Xdev)
             self.max_iter = 200
             self._fit(m_warmup)
             self.max_iter = self._compute_best_iter(self.loss_history["reconstruction loss"].values)
@@ -221,7 +248,8 @@ class ALPINE:
         else:
             self.max_iter = max_iter
 
-        m = self._initialize_matrices(X, Y)
+        m = self._initialize_matrices(X, Y, _Xdev=Xdev)
+        del Xdev
         lap("upload_init")
         try:
             self._fit(m, keep_solver=True)
@@ -422,7 +450,29 @@ class ALPINE:
             self._gen_dev.get_state())
         torch.default_generator.set_state(self._gen_cpu.get_state())
 
-    def _initialize_matrices(self, X_array: Float32Array, Y_list_array: List[Float32Array]) -> AlpineMatrices:
+    def _start_upload(self, X_array):
+        """Begin the host -> device copy of this rank's block of cells on a background thread; the returned handle's
+        ``result()`` is what ``_initialize_matrices`` takes as ``_Xdev``: the cells-major device matrix, or the device
+        CSR triple for sparse input."""
+        dev = self._cuda_device()
+        G, n = X_array.shape
+        rank, world = dist_info()
+        if world > n:
+            raise ValueError(f"cell sharding needs at least one cell per rank ({n} cells, {world} ranks)")
+        lo, hi = shard_bounds(n, world, rank)
+        Xcm_host = X_array.T  # cells x genes; C-contiguous when X_array came from fit()
+
+        def work():
+            if is_sparse(X_array):
+                return _upload_csr(_as_csr_f32(Xcm_host), lo, hi, dev)
+            Xd = _native.padded_rows(hi - lo, G, dev)
+            _native.upload_rows(Xd, Xcm_host[lo:hi])
+            return Xd
+
+        return _Background(work)
+
+    def _initialize_matrices(self, X_array: Float32Array, Y_list_array: List[Float32Array],
+                             _Xdev=None) -> AlpineMatrices:
         """Seed, upload, draw W / H / B in the reference's order (main.py:436-472).
 
         ``X_array`` is genes x cells (a view of the cells-major buffer).  With torch.distributed initialised and
@@ -445,23 +495,8 @@ class ALPINE:
         n_loc = hi - lo
         K = self.total_components
 
-        Xcm_host = X_array.T  # cells x genes; C-contiguous when X_array came from fit()
-        X_csr = None
-        if is_sparse(X_array):
-            X_csr = _upload_csr(_as_csr_f32(Xcm_host), lo, hi, dev)
-            Xd = None
-        else:
-            Xd = _native.padded_rows(n_loc, G, dev)
-            _native.upload_rows(Xd, Xcm_host[lo:hi])
-            if getattr(self, "_nonneg_pending", False):
-                self._nonneg_pending = False
-                ok = torch.tensor([1.0 if (n_loc == 0 or bool(Xd.min() >= 0)) else 0.0], device=dev)  # NaN fails
-                if world > 1:
-                    import torch.distributed as dist
-
-                    dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank raises, or none
-                if float(ok.item()) != 1.0:
-                    raise ValueError(validation.NONNEG_MSG)
+        if _Xdev is None:
+            _Xdev = self._start_upload(X_array)
         Ys_host = [np.ascontiguousarray(y.T, dtype=np.float32) for y in Y_list_array]  # c_i x n (main.py:447)
         Ys = [torch.from_numpy(np.ascontiguousarray(y[:, lo:hi])).to(dev) for y in Ys_host]
 
@@ -484,6 +519,19 @@ class ALPINE:
             del full
         Bs = [torch.rand((y.shape[0], k), dtype=torch.float32, device=dev, generator=gen).clamp(min=eps).contiguous()
               for (y, k) in zip(Ys_host, self.n_covariate_components)]  # main.py:466-470
+
+        # X: uploaded by now, or still arriving while the draws above ran
+        uploaded = _Xdev.result() if isinstance(_Xdev, _Background) else _Xdev
+        X_csr, Xd = (uploaded, None) if isinstance(uploaded, tuple) else (None, uploaded)
+        if Xd is not None and getattr(self, "_nonneg_pending", False):
+            self._nonneg_pending = False
+            ok = torch.tensor([1.0 if (n_loc == 0 or bool(Xd.min() >= 0)) else 0.0], device=dev)  # NaN fails
+            if world > 1:
+                import torch.distributed as dist
+
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank raises, or none
+            if float(ok.item()) != 1.0:
+                raise ValueError(validation.NONNEG_MSG)
         return AlpineMatrices(X=Xd.T if Xd is not None else None, Ys=Ys, Ws=Ws, Hs=Hs, Bs=Bs, W=W, H=H,
                               X_cells_major=Xd, X_csr=X_csr, X_host=X_array, Ys_host=Ys_host, shard=(lo, hi), n_total=n)
 

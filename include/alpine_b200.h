@@ -53,6 +53,13 @@ int alpine_destroy(alpine_ctx* ctx);
  * allocates by itself.  Call right after alpine_create; `base` 256-byte aligned, alive until alpine_destroy.   */
 int64_t alpine_workspace_bytes(const alpine_ctx* ctx);
 int alpine_bind_workspace(alpine_ctx* ctx, void* base, int64_t bytes);
+/* Host -> device copy of a dense fp32 matrix held in PAGEABLE host memory (what `torch.tensor(X_array, device=...)`
+ * does in _initialize_matrices, main.py:445): dst[r * ld_dst + c] = src[r * ld_src + c].  `threads` host threads
+ * stage row chunks through a process-wide ring of pinned buffers and queue one DMA per chunk; on return all copies
+ * are queued and `stream` has been made to wait for them (no host-side wait for the GPU).  Context-free: can run
+ * before alpine_create.                                                                                          */
+int alpine_upload_rows(int device, float* dst, int64_t ld_dst, const float* src, int64_t ld_src, int64_t rows,
+                       int64_t cols, int threads, void* stream);
 /* Bind the expression matrix (AlpineMatrices.X, main.py:445). */
 int alpine_bind_dense(alpine_ctx* ctx, const float* X_cells_major, int64_t ldX);
 /* Bind a SPARSE expression matrix instead (north_star's optional CSR variant; the reference itself rejects sparse

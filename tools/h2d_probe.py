@@ -1,80 +1,57 @@
-"""Measure host->device upload strategies for a pageable numpy matrix (run under gpurun)."""
-import threading
+"""Host -> device upload rate of the library's uploader (csrc/host_upload.cuh) on this box.
+
+    python tools/h2d_probe.py [--gb 8] [--threads 16]
+
+Prints the first call (includes pinning the staging ring) and a second call, against a pinned-memory cudaMemcpy of the
+same size (the PCIe ceiling) and torch's pageable copy (what the reference's torch.tensor(..., device=) does).
+"""
+import argparse
+import os
+import sys
 import time
 
 import numpy as np
 import torch
 
-n, G = 25000, 20000
-X = np.random.default_rng(0).random((n, G), dtype=np.float32)
-dev = torch.device("cuda:0")
-dst = torch.empty((n, G), device=dev)
-torch.cuda.synchronize()
-gb = X.nbytes / 1e9
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from alpine_b200 import _native  # noqa: E402
 
 
-def t(fn, name):
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gb", type=float, default=8.0)
+    ap.add_argument("--genes", type=int, default=20000)
+    ap.add_argument("--threads", default="4,8,12,16")
+    a = ap.parse_args()
+    dev = torch.device("cuda:0")
+    rows = int(a.gb * 1e9 / 4 / a.genes)
+    src = np.ones((rows, a.genes), dtype=np.float32)
+    src[::1000] = 2.0
+    dst = _native.padded_rows(rows, a.genes, dev)
     torch.cuda.synchronize()
+    gb = src.nbytes / 1e9
+    for th in [int(v) for v in a.threads.split(",")] * 2:
+        t0 = time.perf_counter()
+        _native.upload_rows(dst, src, threads=th)
+        t1 = time.perf_counter()
+        torch.cuda.synchronize()
+        t2 = time.perf_counter()
+        print(f"uploader threads={th:2d}: {gb / (t2 - t0):6.1f} GB/s  (call returned after {t1 - t0:.3f} s, done after {t2 - t0:.3f} s)")
+    assert float(dst[::1000].sum()) == 2.0 * a.genes * len(range(0, rows, 1000))
     t0 = time.perf_counter()
-    fn()
+    pin = torch.empty((1 << 26,), dtype=torch.float32, pin_memory=True)
+    print(f"pinning 256 MB: {time.perf_counter() - t0:.3f} s")
+    flat = dst.reshape(-1) if dst.is_contiguous() else dst
+    t0 = time.perf_counter()
+    for i in range(8):
+        flat.view(-1)[i * (1 << 26):(i + 1) * (1 << 26)].copy_(pin, non_blocking=True)
     torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    print(f"{name:40s} {dt*1e3:8.1f} ms  {gb/dt:6.1f} GB/s")
+    print(f"pinned cudaMemcpy 2 GB: {2.147 / (time.perf_counter() - t0):.1f} GB/s")
+    t0 = time.perf_counter()
+    dst[: rows // 8].copy_(torch.from_numpy(src[: rows // 8]))
+    torch.cuda.synchronize()
+    print(f"torch pageable copy: {gb / 8 / (time.perf_counter() - t0):.1f} GB/s")
 
 
-t(lambda: dst.copy_(torch.from_numpy(X)), "direct pageable copy_ (cold)")
-t(lambda: dst.copy_(torch.from_numpy(X)), "direct pageable copy_")
-
-
-def ring(chunk_rows, nbuf):
-    bufs = [torch.empty((chunk_rows, G), dtype=torch.float32, pin_memory=True) for _ in range(nbuf)]
-    evs = [None] * nbuf
-
-    def run():
-        i = 0
-        for r0 in range(0, n, chunk_rows):
-            r1 = min(n, r0 + chunk_rows)
-            b = i % nbuf
-            if evs[b] is not None:
-                evs[b].synchronize()
-            bufs[b][: r1 - r0].copy_(torch.from_numpy(X[r0:r1]))
-            dst[r0:r1].copy_(bufs[b][: r1 - r0], non_blocking=True)
-            e = torch.cuda.Event()
-            e.record()
-            evs[b] = e
-            i += 1
-    return run
-
-
-t0 = time.perf_counter()
-r = ring(800, 3)
-print(f"pinned ring alloc (3 x 64 MB): {(time.perf_counter()-t0)*1e3:.1f} ms")
-t(r, "pinned ring 3x64MB, torch host copy")
-t(r, "pinned ring 3x64MB, torch host copy (2)")
-r = ring(3200, 3)
-t(r, "pinned ring 3x256MB")
-
-
-def threaded(nthreads):
-    def run():
-        def work(k):
-            s = torch.cuda.Stream()
-            rows = (n + nthreads - 1) // nthreads
-            r0, r1 = k * rows, min(n, (k + 1) * rows)
-            with torch.cuda.stream(s):
-                dst[r0:r1].copy_(torch.from_numpy(X[r0:r1]), non_blocking=True)
-            s.synchronize()
-        th = [threading.Thread(target=work, args=(k,)) for k in range(nthreads)]
-        [x.start() for x in th]
-        [x.join() for x in th]
-    return run
-
-
-for k in (2, 4, 8):
-    t(threaded(k), f"{k} threads, pageable copies on own streams")
-t0 = time.perf_counter()
-rc = torch.cuda.cudart().cudaHostRegister(X.ctypes.data, X.nbytes, 0)
-print(f"cudaHostRegister 2 GB: {(time.perf_counter()-t0)*1e3:.1f} ms rc={rc}")
-t(lambda: dst.copy_(torch.from_numpy(X), non_blocking=True), "copy from registered memory")
-torch.cuda.cudart().cudaHostUnregister(X.ctypes.data)
-print("threads", torch.get_num_threads())
+if __name__ == "__main__":
+    main()
