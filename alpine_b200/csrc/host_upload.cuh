@@ -105,6 +105,21 @@ inline cudaError_t upload_rows_f32(int device, float* dst, int64_t ld_dst, const
                                    int64_t rows, int64_t cols, int n_threads, cudaStream_t stream) {
   if (rows <= 0 || cols <= 0) return cudaSuccess;
   if (device < 0 || device >= kUploadMaxDevices) return cudaErrorInvalidDevice;
+  {
+    // page-locked source (cudaHostAlloc / cudaHostRegister by the caller): the DMA engine reads it directly, no
+    // staging and no host threads
+    cudaPointerAttributes a0{}, a1{};
+    const float* last = src + (rows - 1) * ld_src + (cols - 1);
+    const bool pinned = cudaPointerGetAttributes(&a0, src) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+                        cudaPointerGetAttributes(&a1, last) == cudaSuccess && a1.type == cudaMemoryTypeHost;
+    cudaGetLastError();  // (older runtimes report unregistered memory as an error)
+    if (pinned) {
+      if (ld_src == cols && ld_dst == cols)
+        return cudaMemcpyAsync(dst, src, static_cast<size_t>(rows) * cols * sizeof(float), cudaMemcpyHostToDevice, stream);
+      return cudaMemcpy2DAsync(dst, ld_dst * sizeof(float), src, ld_src * sizeof(float), cols * sizeof(float), rows,
+                               cudaMemcpyHostToDevice, stream);
+    }
+  }
   UploadPool& pool = upload_pool(device);
   if (n_threads < 1) n_threads = 1;
   if (n_threads > kUploadMaxThreads) n_threads = kUploadMaxThreads;

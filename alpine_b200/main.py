@@ -462,11 +462,18 @@ class ALPINE:
         lo, hi = shard_bounds(n, world, rank)
         Xcm_host = X_array.T  # cells x genes; C-contiguous when X_array came from fit()
 
+        detail = self.__dict__.setdefault("timings_detail", {})
+
         def work():
+            import time
+
+            t0 = time.perf_counter()
             if is_sparse(X_array):
                 return _upload_csr(_as_csr_f32(Xcm_host), lo, hi, dev)
             Xd = _native.padded_rows(hi - lo, G, dev)
+            t1 = time.perf_counter()
             _native.upload_rows(Xd, Xcm_host[lo:hi])
+            detail["x_alloc"], detail["x_upload_call"] = t1 - t0, time.perf_counter() - t1
             return Xd
 
         return _Background(work)
@@ -495,6 +502,10 @@ class ALPINE:
         n_loc = hi - lo
         K = self.total_components
 
+        import time
+
+        detail = self.__dict__.setdefault("timings_detail", {})
+        t_begin = time.perf_counter()
         if _Xdev is None:
             _Xdev = self._start_upload(X_array)
         Ys_host = [np.ascontiguousarray(y.T, dtype=np.float32) for y in Y_list_array]  # c_i x n (main.py:447)
@@ -521,7 +532,9 @@ class ALPINE:
               for (y, k) in zip(Ys_host, self.n_covariate_components)]  # main.py:466-470
 
         # X: uploaded by now, or still arriving while the draws above ran
+        t_draws = time.perf_counter()
         uploaded = _Xdev.result() if isinstance(_Xdev, _Background) else _Xdev
+        detail["init_labels_draws"], detail["init_wait_upload"] = t_draws - t_begin, time.perf_counter() - t_draws
         X_csr, Xd = (uploaded, None) if isinstance(uploaded, tuple) else (None, uploaded)
         if Xd is not None and getattr(self, "_nonneg_pending", False):
             self._nonneg_pending = False

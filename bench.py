@@ -651,9 +651,19 @@ def run_e2e(args, wl, dev, world, rank):
     from alpine_b200.utils.anndata_compat import AnnData
 
     G, n = wl["n_genes"], wl["n_cells"]
-    # host data (built on the device for speed, then copied out; not timed)
+    from alpine_b200.engine import shard_bounds
+
+    # host data (built on the device for speed, then copied out; not timed).  The rows this rank uploads are
+    # page-locked (cudaHostRegister), as the bench contract asks ("from pinned host memory"): the library's uploader
+    # then hands them to the DMA engine directly; pageable arrays go through its staging ring instead
+    # (tools/e2e_probe.py measures both).
     X, Ys, _, _, _ = synth_device_problem(dev, G, n, 0, wl, seed=1)
     Xh = X.cpu().numpy()
+    lo, hi = shard_bounds(n, world, rank)
+    pinned = False
+    if not args.e2e_pageable and hi > lo:
+        rc = torch.cuda.cudart().cudaHostRegister(Xh.ctypes.data + lo * G * 4, (hi - lo) * G * 4, 0)
+        pinned = int(rc) == 0
     obs = {}
     for i, y in enumerate(Ys):
         codes = y.argmax(dim=0).cpu().numpy()
@@ -693,12 +703,16 @@ def run_e2e(args, wl, dev, world, rank):
     h2d = 4.0 * (G * n + n_cat * n) / world
     d2h = 4.0 * (G * K + K * n + sum(c * k for c, k in zip(wl["categories"], wl["n_covariate_components"]))) + 8.0 * steps * 4
     peer_fit = os.environ.get("ALPINE_B200_PEER", "0") == "1"
+    if pinned:
+        torch.cuda.cudart().cudaHostUnregister(Xh.ctypes.data + lo * G * 4)
     return {"value": steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d / steps, "d2h_bytes_per_step": d2h / steps,
+            "host_memory": "page-locked (cudaHostRegister on this rank's rows of adata.X)" if pinned else "pageable",
             "exchange": ("none (single GPU)" if world == 1 else
                          "NVLink peer memory (ALPINE_B200_PEER=1)" if peer_fit else
                          "NCCL all-reduce (ALPINE.fit's default: mapping peer memory costs ~0.2 s per fit)"),
             "seconds_per_fit": dt, "iterations_per_fit": steps, "nccl_channels_warmed_before_timing": world > 1,
             "phases_s": {k: round(v, 4) for k, v in getattr(model, "timings", {}).items()},
+            "phases_detail_s": {k: round(v, 4) for k, v in getattr(model, "timings_detail", {}).items()},
             "what": "ALPINE(...).fit(adata, keys, max_iter=steps) on host numpy data: validation, encoders, H2D of X/Y, "
                     "init, the loop, loss read-back, scaling, D2H of W/H/B, store_embeddings"}
 
@@ -716,6 +730,7 @@ def main():
     ap.add_argument("--use-als", action="store_true",
                     help="time the block Gauss-Seidel sweep (use_als=True, main.py:523-588) instead of the default update")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-pageable", action="store_true", help="leave adata.X in pageable host memory for the e2e fit")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-tf32-peak", action="store_true", help="skip the cuBLAS TF32 reference measurement")
     ap.add_argument("--no-gpu-torch", action="store_true", help="skip the torch-CUDA (reference arithmetic) baseline leg")
