@@ -49,6 +49,7 @@ SIGNATURES = {
     "alpine_batch_begin": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_partials": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_apply": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
+    "alpine_sync_w": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_peer_export": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_peer_import": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "alpine_mu_apply_peer": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
@@ -309,6 +310,10 @@ class Solver:
 
     def mu_apply(self, it: int) -> None:
         _check(self.lib, self.lib.alpine_mu_apply(self._ctx, int(it), self._stream()))
+
+    def sync_w(self) -> None:
+        """Refresh the bound row-major W from the library's W^T master copy (the updates only touch the latter)."""
+        _check(self.lib, self.lib.alpine_sync_w(self._ctx, self._stream()))
 
     # -- block Gauss-Seidel sweep (use_als=True, main.py:523-588) ------------------------------------------
     @property

@@ -12,6 +12,7 @@
 
 #include "mu_gemm_sm100.cuh"
 #include "mu_small_kernels.cuh"
+#include "mu_update_kernels.cuh"
 #include "csr_tiles.cuh"
 #include "peer_exchange.cuh"
 #include "host_upload.cuh"
@@ -193,6 +194,17 @@ struct alpine_ctx {
   float* hsum_partial = nullptr;  // [sl_blocks_n][K]
   int sl_blocks_n = 0;
   double* sumsq_partial = nullptr;
+  // fused update kernels (csrc/mu_update_kernels.cuh): per-CTA partials, summed by the finish kernels
+  int upd_grid_w = 0, upd_grid_h = 0;
+  float* gram_part_w = nullptr;   // [upd_grid_w][gram_floats]
+  float* gram_part_h = nullptr;   // [upd_grid_h][gram_floats]
+  float* hsum_part = nullptr;     // [upd_grid_h][K]
+  float* q_part = nullptr;        // [upd_grid_h][q_total]
+  double* pred_part = nullptr;    // [upd_grid_h][n_cov]
+  double* t1_part = nullptr;      // [upd_grid_h]
+  unsigned int* finish_counter = nullptr;
+  bool xh_in_slots = false;       // the numerator of the pending W update is still in the contraction's slots
+  bool w_stale = false;           // W^T (the master copy) is ahead of the caller's row-major W
   double* xnorm2 = nullptr;
   double* loss_hist = nullptr;
   int loss_cap = 0;
@@ -321,6 +333,21 @@ int ensure_workspace(alpine_ctx* c, cudaStream_t st) {
   AL_TRY(ws_alloc(c, &c->t1_partial, static_cast<size_t>(c->sl_blocks_n)));
   AL_TRY(ws_alloc(c, &c->hsum_partial, static_cast<size_t>(c->sl_blocks_n) * K));
   AL_TRY(ws_alloc(c, &c->sumsq_partial, 1024));
+  {
+    const int nc = c->Kp / 16;
+    const size_t gram_floats = static_cast<size_t>((nc * (nc + 1) / 2 + kUpdWarps - 1) / kUpdWarps) * kUpdWarps * 2 * 32 * 4;
+    const int tiles_w = ceil_div(c->G, kUpdCols), tiles_h = ceil_div(c->n, kUpdCols);
+    c->upd_grid_w = tiles_w < c->num_sms ? tiles_w : c->num_sms;
+    c->upd_grid_h = tiles_h < c->num_sms ? tiles_h : c->num_sms;
+    AL_TRY(ws_alloc(c, &c->gram_part_w, gram_floats * c->upd_grid_w));
+    AL_TRY(ws_alloc(c, &c->gram_part_h, gram_floats * c->upd_grid_h));
+    AL_TRY(ws_alloc(c, &c->hsum_part, K * c->upd_grid_h));
+    AL_TRY(ws_alloc(c, &c->q_part, static_cast<size_t>(c->q_total > 0 ? c->q_total : 1) * c->upd_grid_h));
+    AL_TRY(ws_alloc(c, &c->pred_part, static_cast<size_t>(c->n_cov > 0 ? c->n_cov : 1) * c->upd_grid_h));
+    AL_TRY(ws_alloc(c, &c->t1_part, static_cast<size_t>(c->upd_grid_h)));
+    AL_TRY(ws_alloc(c, &c->finish_counter, 4));
+    CU_TRY(cudaMemsetAsync(c->finish_counter, 0, 4 * sizeof(unsigned int), st));
+  }
   AL_TRY(ws_alloc(c, &c->xnorm2, 1));
   AL_TRY(ws_alloc(c, &c->err, 8));
   CU_TRY(cudaMemsetAsync(c->err, 0, 8 * sizeof(int), st));
@@ -349,6 +376,13 @@ int set_kernel_attrs() {
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
+#define ALPINE_UPD_ATTR(NC)                                                                                            \
+  CU_TRY(cudaFuncSetAttribute(w_update_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));                 \
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));           \
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  ALPINE_UPD_ATTR(1) ALPINE_UPD_ATTR(2) ALPINE_UPD_ATTR(3) ALPINE_UPD_ATTR(4)
+  ALPINE_UPD_ATTR(5) ALPINE_UPD_ATTR(6) ALPINE_UPD_ATTR(7) ALPINE_UPD_ATTR(8)
+#undef ALPINE_UPD_ATTR
   CU_TRY(cudaFuncSetAttribute(cov_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU_TRY(cudaFuncSetAttribute(guided_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return ALPINE_OK;
@@ -543,6 +577,25 @@ int run_split(alpine_ctx* c, const float* src, long long ld_src, long long R, fl
 }
 
 // out[k][m] (ld_out) = contraction `which`; its B operand must already be in the split workspace
+// out[k][m] (ld_out) = sum of the partial-sum slots contraction `which` has just written
+int reduce_slots(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_t st) {
+  const GemmPlan* pl = &c->plans[which];
+  ReduceParams r = pl->r;
+  r.out = out;
+  r.ld = ld_out;
+  if (pl->p.ws.num_tiles * 8 >= 2 * c->num_sms) {
+    int gy = ceil_div(32 * c->num_sms, pl->p.ws.num_tiles * 8);
+    const int gy_max = ceil_div(pl->p.K, 8);
+    if (gy > gy_max) gy = gy_max;
+    reduce_partials_by_k_kernel<<<dim3(pl->p.ws.num_tiles * 8, gy), 256, 0, st>>>(r);
+  } else {
+    reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, pl->p.K), 256, 0, st>>>(r);
+  }
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+// (out == nullptr: leave the result in the partial-sum slots; the fused update kernels add them up themselves)
 int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_t st) {
   GemmPlan* pl = &c->plans[which];
   if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which), st));
@@ -573,19 +626,8 @@ int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_
     AL_TRY((launch_gemm_t<ORIENT_WX, false>(*pl, st)));
   }
   if (op.profiled) AL_TRY(prof_mark(c, st));
-  ReduceParams r = pl->r;
-  r.out = out;
-  r.ld = ld_out;
-  if (pl->p.ws.num_tiles * 8 >= 2 * c->num_sms) {
-    int gy = ceil_div(32 * c->num_sms, pl->p.ws.num_tiles * 8);
-    const int gy_max = ceil_div(pl->p.K, 8);
-    if (gy > gy_max) gy = gy_max;
-    reduce_partials_by_k_kernel<<<dim3(pl->p.ws.num_tiles * 8, gy), 256, 0, st>>>(r);
-  } else {
-    reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, pl->p.K), 256, 0, st>>>(r);
-  }
-  LAUNCH_CHECK();
-  return ALPINE_OK;
+  if (out == nullptr) return ALPINE_OK;
+  return reduce_slots(c, which, out, ld_out, st);
 }
 
 template <int EPI>
@@ -643,6 +685,75 @@ int run_stats(alpine_ctx* c, double* loss_row, bool fresh_h_update, cudaStream_t
   return ALPINE_OK;
 }
 
+// ---- fused update kernels (csrc/mu_update_kernels.cuh)
+UpdNumSrc num_from_slots(const GemmPlan& pl) {
+  UpdNumSrc s{};
+  s.direct = nullptr;
+  s.partial = pl.p.partial;
+  s.slot_ofs = pl.r.slot_ofs;
+  s.slots = pl.r.slots;
+  s.K = pl.p.K;
+  return s;
+}
+UpdNumSrc num_direct(const float* a, long long ld) {
+  UpdNumSrc s{};
+  s.direct = a;
+  s.ld = ld;
+  return s;
+}
+
+int launch_w_update(alpine_ctx* c, const WUpdParams& p, cudaStream_t st) {
+  const long long tiles = ceil_div(p.col1 - p.col0, kUpdCols);
+  if (tiles <= 0) return ALPINE_OK;
+  // with a Gram partial every CTA of the grid must write one: the grid is exactly the workspace's row count
+  const int grid = p.gram_partial != nullptr ? c->upd_grid_w : static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
+  switch (c->Kp / 16) {
+#define ALPINE_WUPD_CASE(NC)                                                                    \
+  case NC:                                                                                      \
+    w_update_kernel<NC><<<grid, kUpdThreads, w_update_smem_bytes<NC>(), st>>>(p);               \
+    break;
+    ALPINE_WUPD_CASE(1) ALPINE_WUPD_CASE(2) ALPINE_WUPD_CASE(3) ALPINE_WUPD_CASE(4)
+    ALPINE_WUPD_CASE(5) ALPINE_WUPD_CASE(6) ALPINE_WUPD_CASE(7) ALPINE_WUPD_CASE(8)
+#undef ALPINE_WUPD_CASE
+    default:
+      return fail(ALPINE_ERR_ARG, "unsupported padded component count %d", c->Kp);
+  }
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+template <bool FIT>
+int launch_h_update(alpine_ctx* c, const HUpdParams& p, cudaStream_t st) {
+  const int grid = c->upd_grid_h;
+  if (grid <= 0) return ALPINE_OK;
+  size_t smem = 0;
+  switch (c->Kp / 16) {
+#define ALPINE_HUPD_CASE(NC)                                                                    \
+  case NC:                                                                                      \
+    smem = h_update_smem_bytes<NC>(c->K, p.Kg, p.c_total, p.q_total);                           \
+    if (smem > 227 * 1024) return fail(ALPINE_ERR_ARG, "covariate blocks too large for the H update kernel (%zu bytes of shared memory)", smem); \
+    h_update_kernel<NC, FIT><<<grid, kUpdThreads, smem, st>>>(p);                               \
+    break;
+    ALPINE_HUPD_CASE(1) ALPINE_HUPD_CASE(2) ALPINE_HUPD_CASE(3) ALPINE_HUPD_CASE(4)
+    ALPINE_HUPD_CASE(5) ALPINE_HUPD_CASE(6) ALPINE_HUPD_CASE(7) ALPINE_HUPD_CASE(8)
+#undef ALPINE_HUPD_CASE
+    default:
+      return fail(ALPINE_ERR_ARG, "unsupported padded component count %d", c->Kp);
+  }
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+// the caller's row-major W from the W^T master copy, when an update has run since the last export
+int export_w(alpine_ctx* c, cudaStream_t st) {
+  if (!c->w_stale) return ALPINE_OK;
+  transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
+                                                                                       c->W, c->ldW);
+  LAUNCH_CHECK();
+  c->w_stale = false;
+  return ALPINE_OK;
+}
+
 int check_bound(const alpine_ctx* c, bool need_labels) {
   if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
   if (c->X == nullptr && !c->sparse) return fail(ALPINE_ERR_STATE, "alpine_bind_dense / alpine_bind_csr has not been called");
@@ -671,7 +782,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 8; }
+int alpine_abi_version(void) { return 9; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -749,7 +860,8 @@ int alpine_destroy(alpine_ctx* c) {
   ws_free(c, c->sum_P);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
                   c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
-                  c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags};
+                  c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags,
+                  c->gram_part_w, c->gram_part_h, c->hsum_part, c->q_part, c->pred_part, c->t1_part, c->finish_counter};
   for (void* p : ptrs) ws_free(c, p);
   for (auto& pl : c->plans) {
     ws_free(c, pl.d_slot_ofs);
@@ -772,6 +884,15 @@ int64_t alpine_workspace_bytes(const alpine_ctx* c) {
   b += ws_bytes(stat_blocks * (c->q_total > 0 ? c->q_total : 1), f) + ws_bytes(stat_blocks * (c->n_cov > 0 ? c->n_cov : 1), 8);
   b += ws_bytes(sl_blocks, 8) + ws_bytes(sl_blocks * K, f) + ws_bytes(1024, 8) + 4 * kWsAlign;
   b += ws_bytes(static_cast<size_t>(c->reduce_floats()), f);
+  {
+    const int nc = c->Kp / 16, sms = c->num_sms;
+    const size_t gram_floats = static_cast<size_t>((nc * (nc + 1) / 2 + kUpdWarps - 1) / kUpdWarps) * kUpdWarps * 2 * 32 * 4;
+    const size_t gw = ceil_div(c->G, kUpdCols) < sms ? ceil_div(c->G, kUpdCols) : sms;
+    const size_t gh = ceil_div(c->n, kUpdCols) < sms ? ceil_div(c->n, kUpdCols) : sms;
+    b += ws_bytes(gram_floats * gw, f) + ws_bytes(gram_floats * gh, f) + ws_bytes(K * gh, f);
+    b += ws_bytes((c->q_total > 0 ? c->q_total : 1) * gh, f) + ws_bytes((c->n_cov > 0 ? c->n_cov : 1) * gh, 8);
+    b += ws_bytes(gh, 8) + kWsAlign;
+  }
   // partial-sum slots of the largest standard plan, and the slot lists of all of them
   size_t hint = 0;
   for (int which = 0; which < PLAN_WX_BLOCK; ++which) {
@@ -907,6 +1028,7 @@ int alpine_bind_factors(alpine_ctx* c, float* W, int64_t ldW, float* H, int64_t 
   c->ldH = ldH;
   for (int i = 0; i < c->n_cov; ++i) c->B[i] = Bs[i];
   for (auto& pl : c->plans) pl.valid = false;
+  c->w_stale = false;  // the bound W is the truth until an update runs
   return ALPINE_OK;
 }
 
@@ -958,6 +1080,7 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
     c->x_exact = (h_inexact == 0);
   }
   // W^T master copy for the gene-side kernels
+  AL_TRY(export_w(c, st));
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
@@ -978,6 +1101,7 @@ int alpine_batch_begin(alpine_ctx* c, void* stream) {
     AL_TRY(ws_alloc(c, &c->loss_hist, static_cast<size_t>(2 + c->n_cov)));
     c->loss_cap = 1;
   }
+  AL_TRY(export_w(c, st));
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
@@ -993,7 +1117,10 @@ int alpine_mu_partials(alpine_ctx* c, void* stream) {
   AL_TRY(check_bound(c, true));
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   DEVICE_SCOPE(c);
-  return run_gemm(c, PLAN_XH, c->red_Pt(), c->ldG, static_cast<cudaStream_t>(stream));  // Hsplit is current
+  // Single GPU (no caller-owned reduce buffer, no peers): nobody else needs the numerator as an array, the W update
+  // sums it straight from the contraction's partial slots.  Otherwise it goes into the exchange buffer.
+  c->xh_in_slots = !c->peer_on() && c->reduce == c->own_reduce;
+  return run_gemm(c, PLAN_XH, c->xh_in_slots ? nullptr : c->red_Pt(), c->ldG, static_cast<cudaStream_t>(stream));  // Hsplit is current
 }
 
 }  // extern "C"
@@ -1022,103 +1149,133 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
                                        : "this context exchanges over peer memory: call alpine_mu_apply_peer");
   DEVICE_SCOPE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  // ---- W update (main.py:592-612) on W^T, then refresh the caller's row-major W
-  SymLongParams w{};
-  w.Sym = c->use_S();
+  const CovTable tab = make_cov_table(c);
+  int ckmax = 1, c_total = 0;
+  for (int i = 0; i < c->n_cov; ++i) {
+    ckmax = c->ccov[i] * c->kblk[i] > ckmax ? c->ccov[i] * c->kblk[i] : ckmax;
+    c_total += c->ccov[i];
+  }
+  // ---- W update (main.py:592-612) on W^T (the caller's row-major W is refreshed on demand: export_w)
+  WUpdParams w{};
+  w.S = c->use_S();
   w.ldS = c->K;
-  w.Mat = c->WT;
-  w.ldM = c->ldG;
+  w.WT = c->WT;
+  w.ldG = c->ldG;
   w.K = c->K;
-  w.r0 = 0, w.r1 = c->K;
-  w.L = c->G;
-  w.Num = c->red_Pt();
-  w.ldNum = c->ldG;
+  w.col0 = 0, w.col1 = c->G;
   w.c1 = static_cast<float>((1.0 - c->l1) * c->alpha);
   w.c2 = static_cast<float>(c->l1 * c->alpha);
   w.orth = static_cast<float>(c->orth);
   w.eps = static_cast<float>(c->eps);
-  w.split_hi = c->Wsplit;  // B operand of W^T W and W^T X below
+  w.split_hi = c->Wsplit;  // B operand of W^T X below
   w.split_lo = c->Wsplit + static_cast<size_t>(c->K) * c->ldG;
-  w.ld_split = c->ldG;
+  WFinishParams wf{};
+  wf.cov = tab;
+  wf.loss_type = c->loss_type;
+  wf.stats_q = c->use_Q();
+  wf.hsum = c->use_hsum();
+  wf.S = c->use_S();
+  wf.ldS = c->K;
+  wf.eps = static_cast<float>(c->eps);
+  wf.gram.NC = c->Kp / 16;
+  wf.gram.K = c->K;
+  wf.gram.out = c->T;
+  wf.gram.ld = c->K;
   if (!peer) {
-    AL_TRY(run_sym_long<EPI_W>(c, w, st));
+    w.num = c->xh_in_slots ? num_from_slots(c->plans[PLAN_XH]) : num_direct(c->red_Pt(), c->ldG);
+    w.gram_partial = c->gram_part_w;
+    AL_TRY(launch_w_update(c, w, st));
+    // ---- T = W^T W of the new W (sum of the update kernel's Gram partials) and the B updates (main.py:615-628)
+    wf.gram.partial = c->gram_part_w;
+    wf.gram.n_parts = c->upd_grid_w;
+    wf.gram_blocks = ceil_div(gram_reduce_threads(c->Kp / 16), 256);
+    if (wf.gram_blocks + (c->n_cov > 0 ? 1 : 0) > 0) {
+      w_finish_kernel<<<wf.gram_blocks + (c->n_cov > 0 ? 1 : 0), 256, ckmax * sizeof(float), st>>>(wf);
+      LAUNCH_CHECK();
+    }
   } else {
     const int epoch = ++c->peer_epoch;
     const PeerTable pt = make_peer_table(c);
     // this rank's gene slice, in whole 64-column tiles
-    const long long tiles = ceil_div(c->G, kSLCols);
-    const long long g0 = tiles * c->peer_rank / c->peer_world * kSLCols;
-    long long g1 = tiles * (c->peer_rank + 1) / c->peer_world * kSLCols;
+    const long long tiles = ceil_div(c->G, kUpdCols);
+    const long long g0 = tiles * c->peer_rank / c->peer_world * kUpdCols;
+    long long g1 = tiles * (c->peer_rank + 1) / c->peer_world * kUpdCols;
     if (g1 > c->G) g1 = c->G;
     const int n_small = static_cast<int>(c->small_floats());
     peer_gather_reduce_kernel<<<2 * c->num_sms, 256, 0, st>>>(pt, epoch, n_small, c->sum_small, c->K, c->ldG, g0, g1,
                                                               c->sum_P, c->err);
     LAUNCH_CHECK();
     w.col0 = g0;
-    w.L = g1;
-    w.Num = c->sum_P;
+    w.col1 = g1;
+    w.num = num_direct(c->sum_P, c->ldG);
     w.n_peers = c->peer_world;
     for (int q = 0; q < c->peer_world; ++q)
-      w.mat_peer[q] = (q == c->peer_rank) ? nullptr : c->peer_base[q] + c->xchg_wt_off();
+      w.wt_peer[q] = (q == c->peer_rank) ? nullptr : c->peer_base[q] + c->xchg_wt_off();
     w.split_hi = w.split_lo = nullptr;  // taken from the gathered W^T below
-    AL_TRY(run_sym_long<EPI_W>(c, w, st));
+    w.gram_partial = nullptr;           // T needs every rank's slice: taken from the gathered W^T below
+    AL_TRY(launch_w_update(c, w, st));
     peer_signal_wait_kernel<<<1, 32, 0, st>>>(pt, 1, epoch, c->err);  // every slice of the new W^T is in every block
     LAUNCH_CHECK();
     AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
-  }
-  transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
-                                                                                       c->W, c->ldW);
-  LAUNCH_CHECK();
-  // ---- B updates (main.py:615-628) from the statistics of the old H / old B
-  const CovTable tab = make_cov_table(c);
-  if (c->n_cov > 0) {
-    int ckmax = 0;
-    for (int i = 0; i < c->n_cov; ++i) ckmax = c->ccov[i] * c->kblk[i] > ckmax ? c->ccov[i] * c->kblk[i] : ckmax;
-    b_update_kernel<<<c->n_cov, 128, ckmax * sizeof(float), st>>>(tab, c->loss_type, c->use_Q(), c->use_hsum(),
-                                                                  c->use_S(), c->K, (float)c->eps);
-    LAUNCH_CHECK();
-  }
-  // ---- T = W^T W of the new W
-  AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));
-  // ---- A = W^T X (main.py:653)
-  AL_TRY(run_gemm(c, PLAN_WX, c->A, c->ldN, st));
-  // ---- guided terms (main.py:637-650) with the old H and the new B
-  if (c->n_cov > 0) {
-    int kmax = 0, ckmax = 0;
-    for (int i = 0; i < c->n_cov; ++i) {
-      kmax = c->kblk[i] > kmax ? c->kblk[i] : kmax;
-      ckmax = c->ccov[i] * c->kblk[i] > ckmax ? c->ccov[i] * c->kblk[i] : ckmax;
+    AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));
+    if (c->n_cov > 0) {
+      wf.gram.n_parts = 0;
+      wf.gram_blocks = 0;
+      w_finish_kernel<<<1, 256, ckmax * sizeof(float), st>>>(wf);
+      LAUNCH_CHECK();
     }
-    const size_t smem = (static_cast<size_t>(ckmax) + 3ull * kmax * 128) * sizeof(float);
-    if (smem > 200 * 1024) return fail(ALPINE_ERR_ARG, "covariate block too large for the guided-terms kernel");
-    guided_terms_kernel<<<dim3(ceil_div(c->n, 128), c->n_cov), 128, smem, st>>>(tab, c->loss_type, c->H, c->ldH, (int)c->n,
-                                                                               (float)c->eps, c->numG, c->denG, c->ldN);
-    LAUNCH_CHECK();
   }
-  // ---- H update (main.py:652-663)
-  SymLongParams h{};
-  h.Sym = c->T;
-  h.ldS = c->K;
-  h.Mat = c->H;
-  h.ldM = c->ldH;
+  c->w_stale = true;
+  // ---- A = W^T X (main.py:653), left in the contraction's partial slots
+  AL_TRY(run_gemm(c, PLAN_WX, nullptr, c->ldN, st));
+  // ---- H update (main.py:631-663) with the guided terms of (old H, new B), statistics of (new H, new B)
+  HUpdParams h{};
+  h.T = c->T;
+  h.ldT = c->K;
+  h.H = c->H;
+  h.ldH = c->ldH;
   h.K = c->K;
-  h.r0 = 0, h.r1 = c->K;
-  h.L = c->n;
-  h.Num = c->A;
-  h.ldNum = c->ldN;
-  h.numG = c->numG;
-  h.denG = c->denG;
-  h.ldD = c->ldN;
-  h.Kg = c->Kg;
+  h.n = c->n;
+  h.num = num_from_slots(c->plans[PLAN_WX]);
   h.eps = static_cast<float>(c->eps);
-  h.t1_partial = c->t1_partial;
-  h.rowsum_partial = c->hsum_partial;
-  h.split_hi = c->Hsplit;  // B operand of H H^T below and of the next iteration's X H^T
+  h.cov = tab;
+  h.loss_type = c->loss_type;
+  h.Kg = c->Kg;
+  h.c_total = c_total;
+  h.q_total = c->q_total;
+  h.split_hi = c->Hsplit;  // B operand of the next iteration's X H^T
   h.split_lo = c->Hsplit + static_cast<size_t>(c->K) * c->ldN;
   h.ld_split = c->ldN;
-  AL_TRY(run_sym_long<EPI_H>(c, h, st));
+  h.gram_partial = c->gram_part_h;
+  h.hsum_partial = c->hsum_part;
+  h.q_partial = c->q_part;
+  h.pred_partial = c->pred_part;
+  h.t1_partial = c->t1_part;
+  AL_TRY(launch_h_update<true>(c, h, st));
   // ---- statistics of the new H for the next iteration + loss terms of this one (main.py:666, 726-753)
-  AL_TRY(run_stats(c, c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov), true, st));
+  HFinishParams hf{};
+  hf.gram.partial = c->gram_part_h;
+  hf.gram.n_parts = c->upd_grid_h;
+  hf.gram.NC = c->Kp / 16;
+  hf.gram.K = c->K;
+  hf.gram.out = c->red_S();
+  hf.gram.ld = c->K;
+  hf.gram_blocks = ceil_div(gram_reduce_threads(c->Kp / 16), 256);
+  hf.n_parts = c->upd_grid_h;
+  hf.hsum_partial = c->hsum_part;
+  hf.hsum = c->red_hsum();
+  hf.q_partial = c->q_part;
+  hf.stats_q = c->red_Q();
+  hf.q_total = c->q_total;
+  hf.pred_partial = c->pred_part;
+  hf.n_cov = c->n_cov;
+  hf.t1_partial = c->t1_part;
+  hf.T = c->T;
+  hf.ldT = c->K;
+  hf.loss_row = c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov);
+  hf.counter = c->finish_counter;
+  h_finish_kernel<<<hf.gram_blocks + 1, 256, 0, st>>>(hf);
+  LAUNCH_CHECK();
   return ALPINE_OK;
 }
 
@@ -1192,6 +1349,10 @@ int alpine_als_block(alpine_ctx* c, int b, void* stream) {
   int r0 = 0;
   for (int i = 0; i < b; ++i) r0 += c->kblk[i];
   const int r1 = r0 + c->kblk[b];
+  if (c->xh_in_slots) {  // single GPU: alpine_mu_partials left the numerator in the contraction's slots
+    AL_TRY(reduce_slots(c, PLAN_XH, c->red_Pt(), c->ldG, st));
+    c->xh_in_slots = false;
+  }
   // ---- W_b update (main.py:527-545): den = 2 W_cat (H_cat H_b^T) + (1-l1) alpha W_b + W_b orth(k_b) + l1 alpha
   SymLongParams w{};
   w.Sym = c->red_S();
@@ -1269,6 +1430,7 @@ int alpine_als_finish(alpine_ctx* c, int iter, void* stream) {
   transpose_kernel<<<dim3(ceil_div(c->G, 32), ceil_div(c->K, 32)), dim3(32, 8), 0, st>>>(c->WT, c->ldG, c->K, (int)c->G,
                                                                                        c->W, c->ldW);
   LAUNCH_CHECK();
+  c->w_stale = false;
   // every A_b was formed with its final W_b, every H_b is final: t1 = sum A .* H (main.py:666 via the trace identity)
   dot_partial_kernel<<<c->sl_blocks_n, 256, 0, st>>>(c->A, c->ldN, c->H, c->ldH, c->K, c->n, c->t1_partial);
   LAUNCH_CHECK();
@@ -1281,6 +1443,7 @@ int alpine_fit_losses(alpine_ctx* c, int n_iter, double* xnorm2, double* rows, v
   if (n_iter < 0 || n_iter > c->loss_cap) return fail(ALPINE_ERR_ARG, "n_iter outside the loss history");
   DEVICE_SCOPE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AL_TRY(export_w(c, st));  // the caller reads W next
   CU_TRY(cudaStreamSynchronize(st));
   AL_TRY(check_kernel_error(c));
   if (xnorm2) CU_TRY(cudaMemcpy(xnorm2, c->xnorm2, sizeof(double), cudaMemcpyDeviceToHost));
@@ -1294,6 +1457,7 @@ int alpine_scale(alpine_ctx* c, void* stream) {
   DEVICE_SCOPE(c);
   AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AL_TRY(export_w(c, st));
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
@@ -1318,26 +1482,32 @@ int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
   DEVICE_SCOPE(c);
   AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AL_TRY(export_w(c, st));
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();
   AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));  // T = W^T W, loop-invariant
   AL_TRY(run_gemm(c, PLAN_WX, c->A, c->ldN, st));    // A = W^T X, loop-invariant (main.py:706)
-  SymLongParams h{};
-  h.Sym = c->T;
-  h.ldS = c->K;
-  h.Mat = c->H;
-  h.ldM = c->ldH;
+  HUpdParams h{};
+  h.T = c->T;
+  h.ldT = c->K;
+  h.H = c->H;
+  h.ldH = c->ldH;
   h.K = c->K;
-  h.r0 = 0, h.r1 = c->K;
-  h.L = c->n;
-  h.Num = c->A;
-  h.ldNum = c->ldN;
+  h.n = c->n;
+  h.num = num_direct(c->A, c->ldN);
   h.eps = static_cast<float>(c->eps);
-  for (int it = 0; it < n_iter; ++it) AL_TRY(run_sym_long<EPI_TRANSFORM>(c, h, st));
+  for (int it = 0; it < n_iter; ++it) AL_TRY(launch_h_update<false>(c, h, st));  // main.py:705-709
   CU_TRY(cudaStreamSynchronize(st));
   return check_kernel_error(c);
+}
+
+int alpine_sync_w(alpine_ctx* c, void* stream) {
+  if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
+  if (c->W == nullptr) return fail(ALPINE_ERR_STATE, "alpine_bind_factors has not been called");
+  DEVICE_SCOPE(c);
+  return export_w(c, static_cast<cudaStream_t>(stream));
 }
 
 int alpine_xh_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
@@ -1358,6 +1528,7 @@ int alpine_wx_product(alpine_ctx* c, float* out, int64_t ld_out, void* stream) {
   DEVICE_SCOPE(c);
   AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AL_TRY(export_w(c, st));
   transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
                                                                                        c->WT, c->ldG);
   LAUNCH_CHECK();

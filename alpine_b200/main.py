@@ -675,6 +675,7 @@ class ALPINE:
                         s.als_finish(0)
                     else:
                         s.mu_apply(0)
+                        s.sync_w()  # the next batch's context (and the per-epoch loss) read the shared row-major W
                     m.H[:, idx] = Hb  # main.py:662; duplicates of the weighted sampler carry identical columns
                 history.append(self._compute_loss(m, solver=full, xnorm2=xnorm2))
                 if pbar is not None:

@@ -28,7 +28,8 @@ def csr_to_dev(X_cells_by_genes, device):
 class DeviceProblem:
     """X (cells x genes), Ys (c_i x n), W0 (G x K), H0 (K x n), Bs0 on the GPU, bound to a native Solver."""
 
-    def __init__(self, X_cells_by_genes, Ys, W0, H0, Bs0, blocks, kw, device="cuda:0", sparse=False):
+    def __init__(self, X_cells_by_genes, Ys, W0, H0, Bs0, blocks, kw, device="cuda:0", sparse=False,
+                 exchange_buffer=False):
         self.device = torch.device(device)
         n, G = X_cells_by_genes.shape
         self.X = None if sparse else to_dev_padded(X_cells_by_genes, self.device)
@@ -46,7 +47,12 @@ class DeviceProblem:
         self.solver.bind_factors(self.W, self.H, self.Bs)
         self.solver.set_hparams(kw.get("lam", []), kw.get("alpha_W", 0.0), kw.get("l1_ratio_W", 0.0),
                                 kw.get("orth_W", 0.0), kw.get("eps", 1e-6))
-        self.solver.reduce_buffer()
+        # exchange_buffer=True binds a caller-owned reduce buffer as the multi-GPU engine does: the numerator of the
+        # W update then goes through it (alpine_mu_partials reduces the partial sums into it) instead of being summed
+        # from the contraction's slots inside the update kernel; the block Gauss-Seidel sweep always uses it
+        self.exchange_buffer = exchange_buffer
+        if exchange_buffer:
+            self.solver.reduce_buffer()
 
     def run(self, n_iter, on_iter=None, use_als=False):
         s = self.solver
@@ -64,13 +70,14 @@ class DeviceProblem:
         return s.losses(n_iter)
 
     def host(self):
+        self.solver.sync_w()  # the updates keep W^T; the bound row-major W is refreshed on demand
         return self.W.cpu().numpy(), self.H.cpu().numpy(), [b.cpu().numpy() for b in self.Bs]
 
 
-def problem_from_golden(name, g, device="cuda:0", sparse=False) -> DeviceProblem:
+def problem_from_golden(name, g, device="cuda:0", sparse=False, exchange_buffer=False) -> DeviceProblem:
     n_cov = int(g["n_cov"])
     Ys = [np.ascontiguousarray(g[f"Y{i}_cells_by_cat"].T) for i in range(n_cov)]
     kw = dict(CASE_KW[name])
     kw.pop("use_als", None)
     return DeviceProblem(g["X_cells_by_genes"], Ys, g["W0"], g["H0"], [g[f"B0_{i}"] for i in range(n_cov)],
-                         [int(b) for b in g["blocks"]], kw, device, sparse=sparse)
+                         [int(b) for b in g["blocks"]], kw, device, sparse=sparse, exchange_buffer=exchange_buffer)

@@ -152,6 +152,7 @@ def test_named_config_trajectory_matches_torch_cuda_port(case):
         for it in range(n_iter):
             s.mu_partials()
             s.mu_apply(it)
+            s.sync_w()
             tp.mu_step(Xg, Ys, Wp, Hp, Bp, blocks, hp)
             eW = float(torch.linalg.norm((W - Wp).double()) / torch.linalg.norm(Wp.double()))
             eH = float(torch.linalg.norm((H - Hp).double()) / torch.linalg.norm(Hp.double()))

@@ -75,15 +75,18 @@ def test_contraction_is_deterministic():
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("exchange_buffer", [False, True])
 @pytest.mark.parametrize("name", full_batch_mu_names())
-def test_trajectory_matches_reference_golden(name):
-    """Per-iteration W/H/B against the unmodified reference's trajectory (tests/golden, oracle/gen_golden.py)."""
+def test_trajectory_matches_reference_golden(name, exchange_buffer):
+    """Per-iteration W/H/B against the unmodified reference's trajectory (tests/golden, oracle/gen_golden.py); with
+    the W update's numerator summed from the contraction's partial slots (single GPU) and read from the exchange
+    buffer (what the multi-GPU engine all-reduces)."""
     gu = _gpu_utils()
     g = load_golden(name)
     kept = [int(i) for i in g["kept_iters"]]
     n_iter = max(kept)
     n_cov = int(g["n_cov"])
-    prob = gu.problem_from_golden(name, g)
+    prob = gu.problem_from_golden(name, g, exchange_buffer=exchange_buffer)
     tol = PARITY_TOL
     seen = {}
 
