@@ -90,14 +90,15 @@ struct UpdGeom {
   static constexpr int KS = 2 * NC;                  // k-steps of 8 over the padded K
   static constexpr int NB = NC * (NC + 1) / 2;       // Gram blocks
   static constexpr int NBW = (NB + kUpdWarps - 1) / kUpdWarps;  // Gram blocks per warp
-  static constexpr int afrag_floats = NC * KS * 32 * 8;
+  static constexpr int afrag_floats = NC * KS * 32 * 4;  // fp32 A fragments (split into hi / lo when loaded)
   static constexpr int tile_floats = Kp * kUpdPitch;
+  static constexpr int n_tile_bufs = 4;                  // two cp.async targets + tf32 hi / lo of the current tile
   static constexpr int gram_floats = NBW * kUpdWarps * 2 * 32 * 4;  // per CTA, fragment order
 };
 
-// Stage Sym [K][K] (global) through `scratch` (>= K*K floats of shared memory) and write its 3xTF32 A fragments:
-// afrag[((mt * KS + ks) * 32 + lane) * 8 + {hi a0..a3, lo a0..a3}],  a0 = (16 mt + g, 8 ks + t), a1 = (+8, .),
-// a2 = (., +4), a3 = (+8, +4), g = lane / 4, t = lane % 4; entries outside K are zero.
+// Stage Sym [K][K] (global) through `scratch` (>= K*K floats of shared memory) and write it in A-fragment order:
+// afrag[((mt * KS + ks) * 32 + lane) * 4 + {a0..a3}],  a0 = (16 mt + g, 8 ks + t), a1 = (+8, .), a2 = (., +4),
+// a3 = (+8, +4), g = lane / 4, t = lane % 4; entries outside K are zero.
 template <int NC>
 __device__ void build_afrag(float* afrag, float* scratch, const float* __restrict__ Sym, int ldS, int K) {
   constexpr int KS = 2 * NC;
@@ -114,16 +115,26 @@ __device__ void build_afrag(float* afrag, float* scratch, const float* __restric
     const float v1 = (r1 < K && k0 < K) ? scratch[r1 * K + k0] : 0.f;
     const float v2 = (r0 < K && k1 < K) ? scratch[r0 * K + k1] : 0.f;
     const float v3 = (r1 < K && k1 < K) ? scratch[r1 * K + k1] : 0.f;
-    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-    ptx::split_tf32(v0, h0, l0);
-    ptx::split_tf32(v1, h1, l1);
-    ptx::split_tf32(v2, h2, l2);
-    ptx::split_tf32(v3, h3, l3);
-    float4* dst = reinterpret_cast<float4*>(afrag) + 2 * e;
-    dst[0] = make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-    dst[1] = make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+    reinterpret_cast<float4*>(afrag)[e] = make_float4(v0, v1, v2, v3);
   }
   __syncthreads();
+}
+
+// tf32 hi / lo copies of the rows [0, K) of a tile (same pitch)
+__device__ __forceinline__ void split_tile(const float* tile, float* thi, float* tlo, int K) {
+  for (int e = threadIdx.x; e < K * 16; e += kUpdThreads) {
+    const int o = (e >> 4) * kUpdPitch + 4 * (e & 15);
+    const float4 v = *reinterpret_cast<const float4*>(tile + o);
+    uint32_t h[4], l[4];
+    ptx::split_tf32(v.x, h[0], l[0]);
+    ptx::split_tf32(v.y, h[1], l[1]);
+    ptx::split_tf32(v.z, h[2], l[2]);
+    ptx::split_tf32(v.w, h[3], l[3]);
+    *reinterpret_cast<float4*>(thi + o) =
+        make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
+    *reinterpret_cast<float4*>(tlo + o) =
+        make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+  }
 }
 
 // rows [0, K) x 64 columns [c0, c0 + 64) of Mat [K][ld] -> tile [Kp][72]; columns >= L arrive as zeros
@@ -141,83 +152,129 @@ __device__ __forceinline__ void load_tile_async(float* tile, const float* __rest
   cp_async_commit();
 }
 
-// Z accumulators of warp `mt` (rows 16 mt ..): acc[nt][0..3] over the 8 column groups of the tile
+// Z accumulators of warp `mt` (rows 16 mt ..): acc[nt][0..3] over the 8 column groups of the tile.  The three
+// products of a k-step are issued product-major (eight independent accumulators between two MMAs on the same one),
+// and even / odd k-steps go to two accumulator sets that are added at the end: twice the independent work for the
+// tensor pipe and half the length of every round-toward-zero accumulation chain.
 template <int NC>
-__device__ __forceinline__ void z_product(float (&acc)[8][4], const float* afrag, const float* tile, int mt, int ks_used,
-                                          int lane) {
+__device__ __forceinline__ void z_product(float (&acc)[8][4], const float* afrag, const float* thi, const float* tlo,
+                                          int mt, int ks_used, int lane) {
   constexpr int KS = 2 * NC;
   const int g = lane >> 2, t = lane & 3;
+  float acc2[8][4];
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) acc[nt][i] = 0.f;
-  const float4* af = reinterpret_cast<const float4*>(afrag) + (static_cast<size_t>(mt) * KS * 32 + lane) * 2;
-  for (int ks = 0; ks < ks_used; ++ks) {
-    const float4 h = af[ks * 64], l = af[ks * 64 + 1];
-    const uint32_t ahi[4] = {__float_as_uint(h.x), __float_as_uint(h.y), __float_as_uint(h.z), __float_as_uint(h.w)};
-    const uint32_t alo[4] = {__float_as_uint(l.x), __float_as_uint(l.y), __float_as_uint(l.z), __float_as_uint(l.w)};
-    const float* b0p = tile + (8 * ks + t) * kUpdPitch + g;
-    const float* b1p = b0p + 4 * kUpdPitch;
+    for (int i = 0; i < 4; ++i) acc[nt][i] = acc2[nt][i] = 0.f;
+  const float4* af = reinterpret_cast<const float4*>(afrag) + static_cast<size_t>(mt) * KS * 32 + lane;
+  auto step = [&](int ks, float (&d)[8][4]) {
+    const float4 a = af[ks * 32];
+    uint32_t ahi[4], alo[4];
+    ptx::split_tf32(a.x, ahi[0], alo[0]);
+    ptx::split_tf32(a.y, ahi[1], alo[1]);
+    ptx::split_tf32(a.z, ahi[2], alo[2]);
+    ptx::split_tf32(a.w, ahi[3], alo[3]);
+    const int o = (8 * ks + t) * kUpdPitch + g;
+    uint32_t bh0[8], bh1[8], bl0[8], bl1[8];
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt) {
-      uint32_t bh0, bl0, bh1, bl1;
-      ptx::split_tf32(b0p[8 * nt], bh0, bl0);
-      ptx::split_tf32(b1p[8 * nt], bh1, bl1);
-      mma3(acc[nt], ahi, alo, bh0, bh1, bl0, bl1);
+      bh0[nt] = __float_as_uint(thi[o + 8 * nt]);
+      bh1[nt] = __float_as_uint(thi[o + 4 * kUpdPitch + 8 * nt]);
+      bl0[nt] = __float_as_uint(tlo[o + 8 * nt]);
+      bl1[nt] = __float_as_uint(tlo[o + 4 * kUpdPitch + 8 * nt]);
     }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) mma_tf32_m16n8k8(d[nt], alo, bh0[nt], bh1[nt]);  // small terms first
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) mma_tf32_m16n8k8(d[nt], ahi, bl0[nt], bl1[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) mma_tf32_m16n8k8(d[nt], ahi, bh0[nt], bh1[nt]);
+  };
+  int ks = 0;
+  for (; ks + 1 < ks_used; ks += 2) {
+    step(ks, acc);
+    step(ks + 1, acc2);
   }
+  if (ks < ks_used) step(ks, acc);
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[nt][i] += acc2[nt][i];
 }
 
-// Gram accumulation of one tile: gacc[i] (+)= block (mt_i, nt_i) of tile * tile^T over the 64 columns
+// Gram of one tile, added (round-to-nearest) to this CTA's running partial in global memory: block (mt_i, nt_i) of
+// tile * tile^T over the 64 columns, from the tile's tf32 hi / lo copies.  Fresh accumulators per tile keep the
+// tensor core's round-toward-zero chains short (12 MMAs); every thread owns its float4 slots of the partial, so the
+// read-modify-write needs no synchronisation.  Fragment order: [(i * 8 + warp) * 2 + j][lane] float4.
 template <int NBW>
-__device__ __forceinline__ void gram_accumulate(float (&gacc)[NBW][2][4], const float* tile, const int (&bmt)[NBW],
-                                                const int (&bnt)[NBW], int lane) {
+__device__ __forceinline__ void gram_tile(float* gram_partial, int gram_floats, bool first, const float* thi,
+                                          const float* tlo, const int (&bmt)[NBW], const int (&bnt)[NBW], int warp,
+                                          int lane) {
   const int g = lane >> 2, t = lane & 3;
+  float4* out = reinterpret_cast<float4*>(gram_partial + static_cast<size_t>(blockIdx.x) * gram_floats);
 #pragma unroll
   for (int i = 0; i < NBW; ++i) {
     if (bmt[i] < 0) continue;
-    const float* arow0 = tile + (16 * bmt[i] + g) * kUpdPitch + t;
-    const float* arow1 = arow0 + 8 * kUpdPitch;
-    const float* brow0 = tile + (16 * bnt[i] + g) * kUpdPitch + t;
-    const float* brow1 = brow0 + 8 * kUpdPitch;
-#pragma unroll 2
+    float d[2][2][4];  // [j][k-step parity][c0..c3]
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 2; ++q)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) d[j][q][x] = 0.f;
+    const int ao = (16 * bmt[i] + g) * kUpdPitch + t, bo = (16 * bnt[i] + g) * kUpdPitch + t;
+#pragma unroll
     for (int ks = 0; ks < kUpdCols / 8; ++ks) {
-      uint32_t ahi[4], alo[4];
-      ptx::split_tf32(arow0[8 * ks], ahi[0], alo[0]);
-      ptx::split_tf32(arow1[8 * ks], ahi[1], alo[1]);
-      ptx::split_tf32(arow0[8 * ks + 4], ahi[2], alo[2]);
-      ptx::split_tf32(arow1[8 * ks + 4], ahi[3], alo[3]);
-      uint32_t bh0, bl0, bh1, bl1;
-      ptx::split_tf32(brow0[8 * ks], bh0, bl0);
-      ptx::split_tf32(brow0[8 * ks + 4], bh1, bl1);
-      mma3(gacc[i][0], ahi, alo, bh0, bh1, bl0, bl1);
-      ptx::split_tf32(brow1[8 * ks], bh0, bl0);
-      ptx::split_tf32(brow1[8 * ks + 4], bh1, bl1);
-      mma3(gacc[i][1], ahi, alo, bh0, bh1, bl0, bl1);
+      const int q = ks & 1;
+      uint32_t ahi[4], alo[4], bh[2][2], bl[2][2];
+      ahi[0] = __float_as_uint(thi[ao + 8 * ks]);
+      ahi[1] = __float_as_uint(thi[ao + 8 * kUpdPitch + 8 * ks]);
+      ahi[2] = __float_as_uint(thi[ao + 8 * ks + 4]);
+      ahi[3] = __float_as_uint(thi[ao + 8 * kUpdPitch + 8 * ks + 4]);
+      alo[0] = __float_as_uint(tlo[ao + 8 * ks]);
+      alo[1] = __float_as_uint(tlo[ao + 8 * kUpdPitch + 8 * ks]);
+      alo[2] = __float_as_uint(tlo[ao + 8 * ks + 4]);
+      alo[3] = __float_as_uint(tlo[ao + 8 * kUpdPitch + 8 * ks + 4]);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        bh[j][0] = __float_as_uint(thi[bo + 8 * j * kUpdPitch + 8 * ks]);
+        bh[j][1] = __float_as_uint(thi[bo + 8 * j * kUpdPitch + 8 * ks + 4]);
+        bl[j][0] = __float_as_uint(tlo[bo + 8 * j * kUpdPitch + 8 * ks]);
+        bl[j][1] = __float_as_uint(tlo[bo + 8 * j * kUpdPitch + 8 * ks + 4]);
+      }
+      mma_tf32_m16n8k8(d[0][q], alo, bh[0][0], bh[0][1]);
+      mma_tf32_m16n8k8(d[1][q], alo, bh[1][0], bh[1][1]);
+      mma_tf32_m16n8k8(d[0][q], ahi, bl[0][0], bl[0][1]);
+      mma_tf32_m16n8k8(d[1][q], ahi, bl[1][0], bl[1][1]);
+      mma_tf32_m16n8k8(d[0][q], ahi, bh[0][0], bh[0][1]);
+      mma_tf32_m16n8k8(d[1][q], ahi, bh[1][0], bh[1][1]);
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      float4* slot = out + ((i * kUpdWarps + warp) * 2 + j) * 32 + lane;
+      float4 v = make_float4(d[j][0][0] + d[j][1][0], d[j][0][1] + d[j][1][1], d[j][0][2] + d[j][1][2],
+                             d[j][0][3] + d[j][1][3]);
+      if (!first) {
+        const float4 old = *slot;
+        v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
+      }
+      *slot = v;
     }
   }
 }
 
-template <int NBW>
-__device__ __forceinline__ void gram_store(const float (&gacc)[NBW][2][4], float* gram_partial, int gram_floats, int warp,
-                                           int lane) {
-  float4* out = reinterpret_cast<float4*>(gram_partial + static_cast<size_t>(blockIdx.x) * gram_floats);
-#pragma unroll
-  for (int i = 0; i < NBW; ++i)
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-      out[((i * kUpdWarps + warp) * 2 + j) * 32 + lane] = make_float4(gacc[i][j][0], gacc[i][j][1], gacc[i][j][2], gacc[i][j][3]);
-}
-
-// tile rows [0, K) -> Mat (and its hi / lo copies, and the peers' copies); columns >= L are skipped (Mat) / zero (split)
-__device__ __forceinline__ void store_tile(const float* tile, float* __restrict__ Mat, long long ld, int K, long long c0,
-                                           long long L, float* __restrict__ split_hi, float* __restrict__ split_lo,
-                                           long long ld_split, int n_peers, float* const* mat_peer) {
+// tile rows [0, K) -> Mat, its tf32 hi / lo copies (from the tile's own hi / lo copies) and the peers' copies;
+// columns >= L are skipped (Mat) / zero (split: pitches are multiples of 4, whole float4 groups are written)
+__device__ __forceinline__ void store_tile(const float* tile, const float* thi, const float* tlo, float* __restrict__ Mat,
+                                           long long ld, int K, long long c0, long long L, float* __restrict__ split_hi,
+                                           float* __restrict__ split_lo, long long ld_split, int n_peers,
+                                           float* const* mat_peer) {
   for (int e = threadIdx.x; e < K * 16; e += kUpdThreads) {
     const int k = e >> 4, c4 = e & 15;
     const long long col = c0 + 4 * c4;
     if (col >= L) continue;
-    const float4 v = *reinterpret_cast<const float4*>(tile + k * kUpdPitch + 4 * c4);
+    const int o = k * kUpdPitch + 4 * c4;
+    const float4 v = *reinterpret_cast<const float4*>(tile + o);
     const bool full = col + 4 <= L;
     float* dst = Mat + static_cast<long long>(k) * ld + col;
     if (full) {
@@ -239,19 +296,21 @@ __device__ __forceinline__ void store_tile(const float* tile, float* __restrict_
       }
     }
     if (split_hi != nullptr) {
-      // (values at columns >= L are zero in the tile; pitches are multiples of 4, so whole float4 groups are written)
-      uint32_t h[4], l[4];
-      ptx::split_tf32(v.x, h[0], l[0]);
-      ptx::split_tf32(v.y, h[1], l[1]);
-      ptx::split_tf32(v.z, h[2], l[2]);
-      ptx::split_tf32(v.w, h[3], l[3]);
-      const long long o = static_cast<long long>(k) * ld_split + col;
-      *reinterpret_cast<float4*>(split_hi + o) =
-          make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
-      *reinterpret_cast<float4*>(split_lo + o) =
-          make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+      const long long so = static_cast<long long>(k) * ld_split + col;
+      *reinterpret_cast<float4*>(split_hi + so) = *reinterpret_cast<const float4*>(thi + o);
+      *reinterpret_cast<float4*>(split_lo + so) = *reinterpret_cast<const float4*>(tlo + o);
     }
   }
+}
+
+// new value of two adjacent tile entries: fp32 into the tile, tf32 hi / lo into its copies
+__device__ __forceinline__ void put2(float* tile, float* thi, float* tlo, int o, float v0, float v1) {
+  uint32_t h0, l0, h1, l1;
+  ptx::split_tf32(v0, h0, l0);
+  ptx::split_tf32(v1, h1, l1);
+  *reinterpret_cast<float2*>(tile + o) = make_float2(v0, v1);
+  *reinterpret_cast<float2*>(thi + o) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
+  *reinterpret_cast<float2*>(tlo + o) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -275,7 +334,8 @@ struct WUpdParams {
 template <int NC>
 inline size_t w_update_smem_bytes() {
   using G = UpdGeom<NC>;
-  return (static_cast<size_t>(G::afrag_floats) + 2 * G::tile_floats) * sizeof(float) + kUpdCols * sizeof(double) + 16;
+  return (static_cast<size_t>(G::afrag_floats) + G::n_tile_bufs * G::tile_floats) * sizeof(float) +
+         kUpdCols * sizeof(double) + 16;
 }
 
 template <int NC>
@@ -283,34 +343,32 @@ __global__ void __launch_bounds__(kUpdThreads, 1) w_update_kernel(const WUpdPara
   using G = UpdGeom<NC>;
   extern __shared__ __align__(16) uint8_t upd_smem[];
   float* afrag = reinterpret_cast<float*>(upd_smem);
-  float* tiles = afrag + G::afrag_floats;
-  double* cs = reinterpret_cast<double*>(tiles + 2 * G::tile_floats);
+  float* tiles = afrag + G::afrag_floats;   // [2][Kp][72] cp.async targets; the current one receives the new values
+  float* thi = tiles + 2 * G::tile_floats;  // [Kp][72] tf32 hi of the current tile (old values, then new)
+  float* tlo = thi + G::tile_floats;
+  double* cs = reinterpret_cast<double*>(tlo + G::tile_floats);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int K = p.K;
   const int ks_used = (K + 7) >> 3;
   const long long n_tiles = (p.col1 - p.col0 + kUpdCols - 1) / kUpdCols;
 
   build_afrag<NC>(afrag, tiles, p.S, p.ldS, K);
-  for (int e = tid; e < 2 * G::tile_floats; e += kUpdThreads) tiles[e] = 0.f;  // pad rows stay zero
+  for (int e = tid; e < G::n_tile_bufs * G::tile_floats; e += kUpdThreads) tiles[e] = 0.f;  // pad rows stay zero
   __syncthreads();
 
   int bmt[G::NBW], bnt[G::NBW];
-  float gacc[G::NBW][2][4];
 #pragma unroll
   for (int i = 0; i < G::NBW; ++i) {
     const int b = warp + kUpdWarps * i;
     bmt[i] = bnt[i] = -1;
     if (b < G::NB) gram_block_decode(b, NC, bmt[i], bnt[i]);
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int x = 0; x < 4; ++x) gacc[i][j][x] = 0.f;
   }
 
   long long tile_i = blockIdx.x;
   int buf = 0;
+  bool first = true;
   if (tile_i < n_tiles) load_tile_async(tiles, p.WT, p.ldG, K, p.col0 + tile_i * kUpdCols, p.col1);
-  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1) {
+  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1, first = false) {
     float* tile = tiles + buf * G::tile_floats;
     const long long c0 = p.col0 + tile_i * kUpdCols;
     // numerator fragments of this warp's rows (issued before anything waits)
@@ -331,19 +389,21 @@ __global__ void __launch_bounds__(kUpdThreads, 1) w_update_kernel(const WUpdPara
         }
     }
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();  // the tile has landed; everybody is done with the previous tile's buffers
     const long long next = tile_i + gridDim.x;
     if (next < n_tiles)
       load_tile_async(tiles + (buf ^ 1) * G::tile_floats, p.WT, p.ldG, K, p.col0 + next * kUpdCols, p.col1);
+    split_tile(tile, thi, tlo, K);
     // rowsum_K W[g][:] per gene, fp64 so that (rowsum - w) does not cancel (the reference sums the other K-1 entries)
     if (tid < kUpdCols) {
       double sacc = 0.0;
       for (int k = 0; k < K; ++k) sacc += static_cast<double>(tile[k * kUpdPitch + tid]);
       cs[tid] = sacc;
     }
+    __syncthreads();
     float acc[8][4];
-    if (warp < NC) z_product<NC>(acc, afrag, tile, warp, ks_used, lane);
-    __syncthreads();  // every warp has read the old tile; cs is complete
+    if (warp < NC) z_product<NC>(acc, afrag, thi, tlo, warp, ks_used, lane);
+    __syncthreads();  // every warp has read the old hi / lo copies
     if (warp < NC) {
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
@@ -352,8 +412,8 @@ __global__ void __launch_bounds__(kUpdThreads, 1) w_update_kernel(const WUpdPara
           const int k = 16 * warp + g + 8 * h;
           if (k >= K) continue;
           const int cl = 8 * nt + 2 * t;
-          float2* cell = reinterpret_cast<float2*>(tile + k * kUpdPitch + cl);
-          const float2 old = *cell;
+          const int o = k * kUpdPitch + cl;
+          const float2 old = *reinterpret_cast<const float2*>(tile + o);
           const float oldv[2] = {old.x, old.y}, numv[2] = {nu[nt][h].x, nu[nt][h].y};
           float outv[2];
 #pragma unroll
@@ -364,16 +424,15 @@ __global__ void __launch_bounds__(kUpdThreads, 1) w_update_kernel(const WUpdPara
             den = fmaxf(den, p.eps);                                                    // main.py:604
             outv[x] = (c0 + cl + x < p.col1) ? oldv[x] * ((2.0f * numv[x]) / den) : 0.f;  // main.py:596, 605
           }
-          *cell = make_float2(outv[0], outv[1]);
+          put2(tile, thi, tlo, o, outv[0], outv[1]);
         }
     }
-    __syncthreads();  // the tile holds the new values
-    store_tile(tile, p.WT, p.ldG, K, c0, p.col1, p.split_hi, p.split_lo, p.ldG, p.n_peers, p.wt_peer);
-    if (p.gram_partial != nullptr) gram_accumulate<G::NBW>(gacc, tile, bmt, bnt, lane);
-    // (the next iteration's first barrier separates these reads from the prefetch into this buffer two tiles on)
+    __syncthreads();  // the tile and its hi / lo copies hold the new values
+    store_tile(tile, thi, tlo, p.WT, p.ldG, K, c0, p.col1, p.split_hi, p.split_lo, p.ldG, p.n_peers, p.wt_peer);
+    if (p.gram_partial != nullptr) gram_tile<G::NBW>(p.gram_partial, G::gram_floats, first, thi, tlo, bmt, bnt, warp, lane);
+    // (the next iteration's first barrier separates these reads from the next split / prefetch)
   }
   cp_async_wait_all();
-  if (p.gram_partial != nullptr) gram_store<G::NBW>(gacc, p.gram_partial, G::gram_floats, warp, lane);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -404,7 +463,7 @@ template <int NC>
 inline size_t h_update_smem_bytes(int K, int Kg, int c_total, int q_total) {
   using G = UpdGeom<NC>;
   const size_t q_pad = (static_cast<size_t>(q_total) + 3) & ~size_t(3);
-  size_t f = static_cast<size_t>(G::afrag_floats) + 2 * G::tile_floats;
+  size_t f = static_cast<size_t>(G::afrag_floats) + G::n_tile_bufs * G::tile_floats;
   f += q_pad * 2 + 2 * static_cast<size_t>(c_total) * kUpdCols + Kg + K;  // Bs, qacc, rn, rd, dcol, hacc
   return f * sizeof(float) + (kUpdThreads / 32) * sizeof(double) + static_cast<size_t>(Kg + 1 + kMaxCov) * sizeof(int) + 32;
 }
@@ -417,7 +476,9 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
   float* afrag = reinterpret_cast<float*>(upd_smem);
   float* tiles = afrag + G::afrag_floats;
   const int q_pad = (p.q_total + 3) & ~3;           // keeps rn / rd 16-byte aligned
-  float* Bs = tiles + 2 * G::tile_floats;           // [q_total]  all B_i, row-major [c][k] at q_off
+  float* thi = tiles + 2 * G::tile_floats;          // tf32 hi / lo of the current tile (old values, then new)
+  float* tlo = thi + G::tile_floats;
+  float* Bs = tlo + G::tile_floats;                 // [q_total]  all B_i, row-major [c][k] at q_off
   float* qacc = Bs + q_pad;                         // [q_total]  running Q partial of this CTA
   float* rn = qacc + q_pad;                         // [c_total][64]  per-cell numerator ratios (rho / Y)
   float* rd = rn + static_cast<size_t>(p.c_total) * kUpdCols;  // [c_total][64]  Frobenius: B H_i
@@ -433,7 +494,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
   const float scale_kl = 1.0f, scale_fr = 2.0f;
 
   build_afrag<NC>(afrag, tiles, p.T, p.ldT, K);
-  for (int e = tid; e < 2 * G::tile_floats; e += kUpdThreads) tiles[e] = 0.f;
+  for (int e = tid; e < G::n_tile_bufs * G::tile_floats; e += kUpdThreads) tiles[e] = 0.f;
   if (FIT) {
     int coff = 0;
     for (int i = 0; i < p.cov.n_cov; ++i) {
@@ -458,23 +519,19 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
   }
 
   int bmt[G::NBW], bnt[G::NBW];
-  float gacc[G::NBW][2][4];
 #pragma unroll
   for (int i = 0; i < G::NBW; ++i) {
     const int b = warp + kUpdWarps * i;
     bmt[i] = bnt[i] = -1;
     if (b < G::NB) gram_block_decode(b, NC, bmt[i], bnt[i]);
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int x = 0; x < 4; ++x) gacc[i][j][x] = 0.f;
   }
   double t1 = 0.0, pl0 = 0.0, pl1 = 0.0;  // pred loss of covariates (tid / 64) and (tid / 64 + 4)
 
   long long tile_i = blockIdx.x;
   int buf = 0;
+  bool first = true;
   if (tile_i < n_tiles) load_tile_async(tiles, p.H, p.ldH, K, tile_i * kUpdCols, p.n);
-  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1) {
+  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1, first = false) {
     float* tile = tiles + buf * G::tile_floats;
     const long long c0 = tile_i * kUpdCols;
     float2 nu[8][2];
@@ -497,6 +554,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
     __syncthreads();
     const long long next = tile_i + gridDim.x;
     if (next < n_tiles) load_tile_async(tiles + (buf ^ 1) * G::tile_floats, p.H, p.ldH, K, next * kUpdCols, p.n);
+    split_tile(tile, thi, tlo, K);
     if (FIT) {
       // guided terms of the OLD H with the NEW B, per cell (main.py:637-650): thread (i, j) = (tid / 64 [+4], tid % 64)
       const int j = tid & 63;
@@ -513,9 +571,10 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
         }
       }
     }
+    __syncthreads();  // hi / lo copies and rn / rd are complete
     float acc[8][4];
-    if (warp < NC) z_product<NC>(acc, afrag, tile, warp, ks_used, lane);
-    __syncthreads();  // every warp has read the old tile; rn / rd are complete
+    if (warp < NC) z_product<NC>(acc, afrag, thi, tlo, warp, ks_used, lane);
+    __syncthreads();  // every warp has read the old hi / lo copies
     if (warp < NC) {
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
@@ -524,8 +583,8 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
           const int k = 16 * warp + g + 8 * h;
           if (k >= K) continue;
           const int cl = 8 * nt + 2 * t;
-          float2* cell = reinterpret_cast<float2*>(tile + k * kUpdPitch + cl);
-          const float2 old = *cell;
+          const int o = k * kUpdPitch + cl;
+          const float2 old = *reinterpret_cast<const float2*>(tile + o);
           const float oldv[2] = {old.x, old.y}, numv[2] = {nu[nt][h].x, nu[nt][h].y};
           float gn[2] = {0.f, 0.f}, gd[2] = {0.f, 0.f};
           if (FIT && k < p.Kg) {
@@ -551,11 +610,11 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
             outv[x] = (c0 + cl + x < p.n) ? oldv[x] * (num / den) : 0.f;     // main.py:656 / 709
             if (FIT) t1 += static_cast<double>(numv[x]) * static_cast<double>(outv[x]);
           }
-          *cell = make_float2(outv[0], outv[1]);
+          put2(tile, thi, tlo, o, outv[0], outv[1]);
         }
     }
-    __syncthreads();  // the tile holds the new H
-    store_tile(tile, p.H, p.ldH, K, c0, p.n, p.split_hi, p.split_lo, p.ld_split, 0, nullptr);
+    __syncthreads();  // the tile and its hi / lo copies hold the new H
+    store_tile(tile, thi, tlo, p.H, p.ldH, K, c0, p.n, p.split_hi, p.split_lo, p.ld_split, 0, nullptr);
     if (FIT) {
       // statistics of (new H, new B): rho' = Y / max(B H_i, eps) per cell, prediction loss (main.py:727-748)
       const int j = tid & 63;
@@ -604,12 +663,11 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
           hacc[k] += a;
         }
       }
-      gram_accumulate<G::NBW>(gacc, tile, bmt, bnt, lane);
+      gram_tile<G::NBW>(p.gram_partial, G::gram_floats, first, thi, tlo, bmt, bnt, warp, lane);
     }
   }
   cp_async_wait_all();
   if (!FIT) return;
-  gram_store<G::NBW>(gacc, p.gram_partial, G::gram_floats, warp, lane);
   __syncthreads();
   for (int e = tid; e < p.q_total; e += kUpdThreads) p.q_partial[static_cast<size_t>(blockIdx.x) * p.q_total + e] = qacc[e];
   for (int k = tid; k < K; k += kUpdThreads) p.hsum_partial[static_cast<size_t>(blockIdx.x) * K + k] = hacc[k];
