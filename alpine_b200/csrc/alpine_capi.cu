@@ -125,12 +125,15 @@ struct GemmOperands {
   long long ldS = 0;
   int k0 = 0, Kop = 0;            // component rows [k0, k0 + Kop) of the B operand take part (Kop = 0: all K)
   bool profiled = false;  // counted by alpine_profile (the two contractions over X)
+  bool z_slots = false;   // partial sums go to the second slot buffer (they are consumed together with another plan's)
   // sparse X: tile lists instead of Xmem (csr_tiles.cuh)
   const long long* sp_ofs = nullptr;
   const uint2* sp_ent = nullptr;
 };
 // PLAN_WX_BLOCK + b: W_b^T X of component block b alone (block Gauss-Seidel sweep, main.py:567)
-enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_WX_BLOCK = 4, PLAN_COUNT = 4 + kMaxCov + 1 };
+// PLAN_ZW / PLAN_ZH: the K x K-deep products of the Gram reformulation, Z_W = (H H^T) W^T and Z_H = (W^T W) H
+enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_ZW = 4, PLAN_ZH = 5, PLAN_WX_BLOCK = 6,
+       PLAN_COUNT = 6 + kMaxCov + 1 };
 
 struct GemmPlan {
   bool valid = false;
@@ -195,9 +198,12 @@ struct alpine_ctx {
   int sl_blocks_n = 0;
   double* sumsq_partial = nullptr;
   // fused update kernels (csrc/mu_update_kernels.cuh): per-CTA partials, summed by the finish kernels
-  int upd_grid_w = 0, upd_grid_h = 0;
-  float* gram_part_w = nullptr;   // [upd_grid_w][gram_floats]
-  float* gram_part_h = nullptr;   // [upd_grid_h][gram_floats]
+  int upd_grid_h = 0;
+  long long ldK = 0;
+  float* Ssplit = nullptr;        // [2][K][ldK]  tf32 hi / lo of the complete H H^T (B operand of Z_W)
+  float* Tsplit = nullptr;        // [2][K][ldK]  tf32 hi / lo of W^T W             (B operand of Z_H)
+  float* partial_z = nullptr;     // slots of the Z plans
+  size_t partial_z_floats = 0;
   float* hsum_part = nullptr;     // [upd_grid_h][K]
   float* q_part = nullptr;        // [upd_grid_h][q_total]
   double* pred_part = nullptr;    // [upd_grid_h][n_cov]
@@ -222,6 +228,13 @@ struct alpine_ctx {
   float* sum_small = nullptr;       // [S | hsum | Q] summed over the ranks (peer mode)
   float* sum_P = nullptr;           // [K][ldG]: this rank's gene slice of the summed numerator (peer mode)
   bool peer_on() const { return peer_world > 1; }
+  // this rank's gene slice of the W update under peer exchange, in whole 64-column tiles
+  void peer_slice(long long* g0, long long* g1) const {
+    const long long tiles = (G + 63) / 64;
+    *g0 = tiles * peer_rank / peer_world * 64;
+    *g1 = tiles * (peer_rank + 1) / peer_world * 64;
+    if (*g1 > G) *g1 = G;
+  }
   long long xchg_wt_off() const { return round_up_ll(reduce_floats(), 64); }
   long long xchg_flag_off() const { return xchg_wt_off() + round_up_ll(static_cast<long long>(K) * ldG, 64); }
   long long xchg_floats() const { return xchg_flag_off() + kPeerFlagInts; }
@@ -334,13 +347,13 @@ int ensure_workspace(alpine_ctx* c, cudaStream_t st) {
   AL_TRY(ws_alloc(c, &c->hsum_partial, static_cast<size_t>(c->sl_blocks_n) * K));
   AL_TRY(ws_alloc(c, &c->sumsq_partial, 1024));
   {
-    const int nc = c->Kp / 16;
-    const size_t gram_floats = static_cast<size_t>((nc * (nc + 1) / 2 + kUpdWarps - 1) / kUpdWarps) * kUpdWarps * 2 * 32 * 4;
-    const int tiles_w = ceil_div(c->G, kUpdCols), tiles_h = ceil_div(c->n, kUpdCols);
-    c->upd_grid_w = tiles_w < c->num_sms ? tiles_w : c->num_sms;
-    c->upd_grid_h = tiles_h < c->num_sms ? tiles_h : c->num_sms;
-    AL_TRY(ws_alloc(c, &c->gram_part_w, gram_floats * c->upd_grid_w));
-    AL_TRY(ws_alloc(c, &c->gram_part_h, gram_floats * c->upd_grid_h));
+    const int tiles_h = ceil_div(c->n, kUpdCols);
+    c->upd_grid_h = tiles_h < 2 * c->num_sms ? tiles_h : 2 * c->num_sms;
+    c->ldK = round_up(c->K, 4);
+    AL_TRY(ws_alloc(c, &c->Ssplit, 2 * K * c->ldK));
+    AL_TRY(ws_alloc(c, &c->Tsplit, 2 * K * c->ldK));
+    CU_TRY(cudaMemsetAsync(c->Ssplit, 0, 2 * K * c->ldK * sizeof(float), st));
+    CU_TRY(cudaMemsetAsync(c->Tsplit, 0, 2 * K * c->ldK * sizeof(float), st));
     AL_TRY(ws_alloc(c, &c->hsum_part, K * c->upd_grid_h));
     AL_TRY(ws_alloc(c, &c->q_part, static_cast<size_t>(c->q_total > 0 ? c->q_total : 1) * c->upd_grid_h));
     AL_TRY(ws_alloc(c, &c->pred_part, static_cast<size_t>(c->n_cov > 0 ? c->n_cov : 1) * c->upd_grid_h));
@@ -376,13 +389,9 @@ int set_kernel_attrs() {
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
-#define ALPINE_UPD_ATTR(NC)                                                                                            \
-  CU_TRY(cudaFuncSetAttribute(w_update_kernel<NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));                 \
-  CU_TRY(cudaFuncSetAttribute(h_update_kernel<NC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));           \
-  CU_TRY(cudaFuncSetAttribute(h_update_kernel<NC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  ALPINE_UPD_ATTR(1) ALPINE_UPD_ATTR(2) ALPINE_UPD_ATTR(3) ALPINE_UPD_ATTR(4)
-  ALPINE_UPD_ATTR(5) ALPINE_UPD_ATTR(6) ALPINE_UPD_ATTR(7) ALPINE_UPD_ATTR(8)
-#undef ALPINE_UPD_ATTR
+  CU_TRY(cudaFuncSetAttribute(w_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
   CU_TRY(cudaFuncSetAttribute(cov_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU_TRY(cudaFuncSetAttribute(guided_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return ALPINE_OK;
@@ -441,8 +450,18 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, cudaStream_t
   p.sx = sx;
   p.sb = sb;
   pl->smem = gemm_smem_layout(p.Kp, sx, sb).total + 1024;
-  // partial-sum slots (one buffer shared by all plans: contractions run one after the other on the stream)
-  if (need > c->partial_floats) {
+  // partial-sum slots: one buffer shared by the plans whose results are consumed before the next contraction runs,
+  // a second one for the Z plans (their slots are read together with the preceding contraction's)
+  if (op.z_slots) {
+    if (need > c->partial_z_floats) {
+      ws_free(c, c->partial_z);
+      c->partial_z = nullptr;
+      AL_TRY(ws_alloc(c, &c->partial_z, need));
+      c->partial_z_floats = need;
+      for (auto& other : c->plans)
+        if (other.op.z_slots) other.p.partial = c->partial_z, other.r.partial = c->partial_z;
+    }
+  } else if (need > c->partial_floats) {
     ws_free(c, c->partial);
     c->partial = nullptr;
     // with an arena, size the buffer for the largest of this context's standard plans at once (a bump allocator
@@ -450,10 +469,8 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, cudaStream_t
     const size_t want = (c->arena != nullptr && c->partial_hint > need) ? c->partial_hint : need;
     AL_TRY(ws_alloc(c, &c->partial, want));
     c->partial_floats = want;
-    for (auto& other : c->plans) {
-      other.p.partial = c->partial;
-      other.r.partial = c->partial;
-    }
+    for (auto& other : c->plans)
+      if (!other.op.z_slots) other.p.partial = c->partial, other.r.partial = c->partial;
   }
   return build_plan_tail(c, pl, op, R, Kop, st);
 }
@@ -493,7 +510,7 @@ size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p,
 int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop, cudaStream_t st) {
   const int rows = kRows;
   GemmParams& p = pl->p;
-  p.partial = c->partial;
+  p.partial = op.z_slots ? c->partial_z : c->partial;
   p.err = c->err;
   p.sp_ofs = op.sp_ofs;
   p.sp_ent = op.sp_ent;
@@ -509,7 +526,7 @@ int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long lo
   AL_TRY(make_map(&pl->tmBhi, b_hi, R, Kop, op.ldS, kBK, p.Kp, true));
   AL_TRY(make_map(&pl->tmBlo, b_hi + static_cast<size_t>(c->K) * op.ldS, R, Kop, op.ldS, kBK, p.Kp, true));
   ReduceParams& r = pl->r;
-  r.partial = c->partial;
+  r.partial = p.partial;
   r.rows = rows;
   r.M = p.M;
   r.K = p.K;
@@ -556,6 +573,21 @@ GemmOperands plan_operands(const alpine_ctx* c, int which) {
     case PLAN_GRAM_W:  // T[b][a] = sum_g W^T[a][g] W^T[b][g]        (W^T W of main.py:654 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
       op.Bsplit = c->Wsplit, op.ldS = c->ldG;
+      break;
+    case PLAN_ZW:      // Z[k][g] = sum_k' S[k][k'] W^T[k'][g]      ((2W) @ H @ H^T of main.py:599 after the reformulation)
+      op.orient = ORIENT_XH, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
+      op.Bsplit = c->Ssplit, op.ldS = c->ldK, op.z_slots = true;
+      if (c->peer_on()) {
+        // only this rank's gene slice: the peers store their new slices into the other columns of W^T while this
+        // product may still be running
+        long long g0, g1;
+        c->peer_slice(&g0, &g1);
+        op.Xmem = c->WT + g0, op.cols = g1 - g0;
+      }
+      break;
+    case PLAN_ZH:      // Z[k][j] = sum_k' T[k][k'] H[k'][j]        ((2W^T) @ (W @ H) of main.py:654 after the reformulation)
+      op.orient = ORIENT_XH, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
+      op.Bsplit = c->Tsplit, op.ldS = c->ldK, op.z_slots = true;
       break;
     default: {         // A[k][j] = sum_g X[j][g] W^T[k][g] for the rows k of one component block     (main.py:567)
       op = plan_operands(c, PLAN_WX);
@@ -686,8 +718,8 @@ int run_stats(alpine_ctx* c, double* loss_row, bool fresh_h_update, cudaStream_t
 }
 
 // ---- fused update kernels (csrc/mu_update_kernels.cuh)
-UpdNumSrc num_from_slots(const GemmPlan& pl) {
-  UpdNumSrc s{};
+SlotSrc src_slots(const GemmPlan& pl) {
+  SlotSrc s{};
   s.direct = nullptr;
   s.partial = pl.p.partial;
   s.slot_ofs = pl.r.slot_ofs;
@@ -695,8 +727,8 @@ UpdNumSrc num_from_slots(const GemmPlan& pl) {
   s.K = pl.p.K;
   return s;
 }
-UpdNumSrc num_direct(const float* a, long long ld) {
-  UpdNumSrc s{};
+SlotSrc src_direct(const float* a, long long ld) {
+  SlotSrc s{};
   s.direct = a;
   s.ld = ld;
   return s;
@@ -705,19 +737,8 @@ UpdNumSrc num_direct(const float* a, long long ld) {
 int launch_w_update(alpine_ctx* c, const WUpdParams& p, cudaStream_t st) {
   const long long tiles = ceil_div(p.col1 - p.col0, kUpdCols);
   if (tiles <= 0) return ALPINE_OK;
-  // with a Gram partial every CTA of the grid must write one: the grid is exactly the workspace's row count
-  const int grid = p.gram_partial != nullptr ? c->upd_grid_w : static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
-  switch (c->Kp / 16) {
-#define ALPINE_WUPD_CASE(NC)                                                                    \
-  case NC:                                                                                      \
-    w_update_kernel<NC><<<grid, kUpdThreads, w_update_smem_bytes<NC>(), st>>>(p);               \
-    break;
-    ALPINE_WUPD_CASE(1) ALPINE_WUPD_CASE(2) ALPINE_WUPD_CASE(3) ALPINE_WUPD_CASE(4)
-    ALPINE_WUPD_CASE(5) ALPINE_WUPD_CASE(6) ALPINE_WUPD_CASE(7) ALPINE_WUPD_CASE(8)
-#undef ALPINE_WUPD_CASE
-    default:
-      return fail(ALPINE_ERR_ARG, "unsupported padded component count %d", c->Kp);
-  }
+  const int grid = static_cast<int>(tiles < 2 * c->num_sms ? tiles : 2 * c->num_sms);
+  w_update_kernel<<<grid, kUpdThreads, w_update_smem_bytes(c->K), st>>>(p);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
@@ -726,20 +747,18 @@ template <bool FIT>
 int launch_h_update(alpine_ctx* c, const HUpdParams& p, cudaStream_t st) {
   const int grid = c->upd_grid_h;
   if (grid <= 0) return ALPINE_OK;
-  size_t smem = 0;
-  switch (c->Kp / 16) {
-#define ALPINE_HUPD_CASE(NC)                                                                    \
-  case NC:                                                                                      \
-    smem = h_update_smem_bytes<NC>(c->K, p.Kg, p.c_total, p.q_total);                           \
-    if (smem > 227 * 1024) return fail(ALPINE_ERR_ARG, "covariate blocks too large for the H update kernel (%zu bytes of shared memory)", smem); \
-    h_update_kernel<NC, FIT><<<grid, kUpdThreads, smem, st>>>(p);                               \
-    break;
-    ALPINE_HUPD_CASE(1) ALPINE_HUPD_CASE(2) ALPINE_HUPD_CASE(3) ALPINE_HUPD_CASE(4)
-    ALPINE_HUPD_CASE(5) ALPINE_HUPD_CASE(6) ALPINE_HUPD_CASE(7) ALPINE_HUPD_CASE(8)
-#undef ALPINE_HUPD_CASE
-    default:
-      return fail(ALPINE_ERR_ARG, "unsupported padded component count %d", c->Kp);
-  }
+  const size_t smem = h_update_smem_bytes(c->K, p.Kg, p.c_total, p.q_total);
+  if (smem > 227 * 1024)
+    return fail(ALPINE_ERR_ARG, "covariate blocks too large for the H update kernel (%zu bytes of shared memory)", smem);
+  h_update_kernel<FIT><<<grid, kUpdThreads, smem, st>>>(p);
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+// tf32 hi / lo copies of a K x K matrix (pitch ld_src, any alignment) into a [2][K][ldK] operand buffer
+int run_split_small(alpine_ctx* c, const float* src, int ld_src, float* dst, cudaStream_t st) {
+  split_small_kernel<<<ceil_div(static_cast<long long>(c->K) * c->K, 256), 256, 0, st>>>(
+      src, ld_src, c->K, dst, dst + static_cast<size_t>(c->K) * c->ldK, static_cast<int>(c->ldK));
   LAUNCH_CHECK();
   return ALPINE_OK;
 }
@@ -861,7 +880,7 @@ int alpine_destroy(alpine_ctx* c) {
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
                   c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
                   c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags,
-                  c->gram_part_w, c->gram_part_h, c->hsum_part, c->q_part, c->pred_part, c->t1_part, c->finish_counter};
+                  c->Ssplit, c->Tsplit, c->partial_z, c->hsum_part, c->q_part, c->pred_part, c->t1_part, c->finish_counter};
   for (void* p : ptrs) ws_free(c, p);
   for (auto& pl : c->plans) {
     ws_free(c, pl.d_slot_ofs);
@@ -885,24 +904,24 @@ int64_t alpine_workspace_bytes(const alpine_ctx* c) {
   b += ws_bytes(sl_blocks, 8) + ws_bytes(sl_blocks * K, f) + ws_bytes(1024, 8) + 4 * kWsAlign;
   b += ws_bytes(static_cast<size_t>(c->reduce_floats()), f);
   {
-    const int nc = c->Kp / 16, sms = c->num_sms;
-    const size_t gram_floats = static_cast<size_t>((nc * (nc + 1) / 2 + kUpdWarps - 1) / kUpdWarps) * kUpdWarps * 2 * 32 * 4;
-    const size_t gw = ceil_div(c->G, kUpdCols) < sms ? ceil_div(c->G, kUpdCols) : sms;
-    const size_t gh = ceil_div(c->n, kUpdCols) < sms ? ceil_div(c->n, kUpdCols) : sms;
-    b += ws_bytes(gram_floats * gw, f) + ws_bytes(gram_floats * gh, f) + ws_bytes(K * gh, f);
+    const size_t gh = ceil_div(c->n, kUpdCols) < 2 * c->num_sms ? ceil_div(c->n, kUpdCols) : 2 * c->num_sms;
+    b += 2 * ws_bytes(2 * K * round_up(c->K, 4), f) + ws_bytes(K * gh, f);
     b += ws_bytes((c->q_total > 0 ? c->q_total : 1) * gh, f) + ws_bytes((c->n_cov > 0 ? c->n_cov : 1) * gh, 8);
     b += ws_bytes(gh, 8) + kWsAlign;
   }
   // partial-sum slots of the largest standard plan, and the slot lists of all of them
-  size_t hint = 0;
+  size_t hint = 0, hint_z = 0;
   for (int which = 0; which < PLAN_WX_BLOCK; ++which) {
     GemmParams p{};
     int grid = 0;
     const size_t need = plan_geometry(c, plan_operands(c, which), p, &grid);
-    hint = need > hint ? need : hint;
+    if (which == PLAN_ZW || which == PLAN_ZH)
+      hint_z = need > hint_z ? need : hint_z;
+    else
+      hint = need > hint ? need : hint;
     b += ws_bytes(p.ws.num_tiles + 1, 4) + ws_bytes(static_cast<size_t>(p.ws.num_tiles) * p.ws.pieces * 3 + grid + 1, 4);
   }
-  b += ws_bytes(hint, f);
+  b += ws_bytes(hint, f) + ws_bytes(hint_z, f);
   return static_cast<int64_t>(b + (2u << 20));  // + loss history, flags, alignment slack
 }
 
@@ -915,6 +934,7 @@ int alpine_bind_workspace(alpine_ctx* c, void* base, int64_t bytes) {
   c->arena_used = 0;
   size_t hint = 0;
   for (int which = 0; which < PLAN_WX_BLOCK; ++which) {
+    if (which == PLAN_ZW || which == PLAN_ZH) continue;  // their slots live in a buffer of their own
     GemmParams p{};
     const size_t need = plan_geometry(c, plan_operands(c, which), p, nullptr);
     hint = need > hint ? need : hint;
@@ -1088,6 +1108,7 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
   // block-wise sweep (alpine_als_block) only the rows of the block it has just updated
   AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_stats(c, nullptr, false, st));
+  AL_TRY(run_split_small(c, c->red_S(), c->K, c->Ssplit, st));  // (re-done after the exchange under cell sharding)
   c->fit_active = true;
   return ALPINE_OK;
 }
@@ -1109,6 +1130,7 @@ int alpine_batch_begin(alpine_ctx* c, void* stream) {
   // block-wise sweep (alpine_als_block) only the rows of the block it has just updated
   AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_stats(c, nullptr, false, st));
+  AL_TRY(run_split_small(c, c->red_S(), c->K, c->Ssplit, st));
   c->fit_active = true;
   return ALPINE_OK;
 }
@@ -1155,10 +1177,9 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     ckmax = c->ccov[i] * c->kblk[i] > ckmax ? c->ccov[i] * c->kblk[i] : ckmax;
     c_total += c->ccov[i];
   }
+  const bool single = !peer && c->reduce == c->own_reduce;  // no exchange: S is this GPU's own, already split
   // ---- W update (main.py:592-612) on W^T (the caller's row-major W is refreshed on demand: export_w)
   WUpdParams w{};
-  w.S = c->use_S();
-  w.ldS = c->K;
   w.WT = c->WT;
   w.ldG = c->ldG;
   w.K = c->K;
@@ -1167,100 +1188,102 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   w.c2 = static_cast<float>(c->l1 * c->alpha);
   w.orth = static_cast<float>(c->orth);
   w.eps = static_cast<float>(c->eps);
-  w.split_hi = c->Wsplit;  // B operand of W^T X below
+  w.split_hi = c->Wsplit;  // B operand of W^T W and W^T X below
   w.split_lo = c->Wsplit + static_cast<size_t>(c->K) * c->ldG;
-  WFinishParams wf{};
-  wf.cov = tab;
-  wf.loss_type = c->loss_type;
-  wf.stats_q = c->use_Q();
-  wf.hsum = c->use_hsum();
-  wf.S = c->use_S();
-  wf.ldS = c->K;
-  wf.eps = static_cast<float>(c->eps);
-  wf.gram.NC = c->Kp / 16;
-  wf.gram.K = c->K;
-  wf.gram.out = c->T;
-  wf.gram.ld = c->K;
   if (!peer) {
-    w.num = c->xh_in_slots ? num_from_slots(c->plans[PLAN_XH]) : num_direct(c->red_Pt(), c->ldG);
-    w.gram_partial = c->gram_part_w;
+    w.num = c->xh_in_slots ? src_slots(c->plans[PLAN_XH]) : src_direct(c->red_Pt(), c->ldG);
+    if (!single) AL_TRY(run_split_small(c, c->use_S(), c->K, c->Ssplit, st));  // the all-reduced H H^T
+    AL_TRY(run_gemm(c, PLAN_ZW, nullptr, 0, st));   // Z_W = (H H^T) W^T, into the second slot buffer
+    w.z = src_slots(c->plans[PLAN_ZW]);
     AL_TRY(launch_w_update(c, w, st));
-    // ---- T = W^T W of the new W (sum of the update kernel's Gram partials) and the B updates (main.py:615-628)
-    wf.gram.partial = c->gram_part_w;
-    wf.gram.n_parts = c->upd_grid_w;
-    wf.gram_blocks = ceil_div(gram_reduce_threads(c->Kp / 16), 256);
-    if (wf.gram_blocks + (c->n_cov > 0 ? 1 : 0) > 0) {
-      w_finish_kernel<<<wf.gram_blocks + (c->n_cov > 0 ? 1 : 0), 256, ckmax * sizeof(float), st>>>(wf);
-      LAUNCH_CHECK();
-    }
   } else {
     const int epoch = ++c->peer_epoch;
     const PeerTable pt = make_peer_table(c);
-    // this rank's gene slice, in whole 64-column tiles
-    const long long tiles = ceil_div(c->G, kUpdCols);
-    const long long g0 = tiles * c->peer_rank / c->peer_world * kUpdCols;
-    long long g1 = tiles * (c->peer_rank + 1) / c->peer_world * kUpdCols;
-    if (g1 > c->G) g1 = c->G;
+    long long g0, g1;
+    c->peer_slice(&g0, &g1);
     const int n_small = static_cast<int>(c->small_floats());
     peer_gather_reduce_kernel<<<2 * c->num_sms, 256, 0, st>>>(pt, epoch, n_small, c->sum_small, c->K, c->ldG, g0, g1,
                                                               c->sum_P, c->err);
     LAUNCH_CHECK();
+    AL_TRY(run_split_small(c, c->use_S(), c->K, c->Ssplit, st));
+    AL_TRY(run_gemm(c, PLAN_ZW, nullptr, 0, st));  // (this rank's gene slice only, see plan_operands)
+    w.z = src_slots(c->plans[PLAN_ZW]);
+    w.z.origin = g0;
     w.col0 = g0;
     w.col1 = g1;
-    w.num = num_direct(c->sum_P, c->ldG);
+    w.num = src_direct(c->sum_P, c->ldG);
     w.n_peers = c->peer_world;
     for (int q = 0; q < c->peer_world; ++q)
       w.wt_peer[q] = (q == c->peer_rank) ? nullptr : c->peer_base[q] + c->xchg_wt_off();
     w.split_hi = w.split_lo = nullptr;  // taken from the gathered W^T below
-    w.gram_partial = nullptr;           // T needs every rank's slice: taken from the gathered W^T below
     AL_TRY(launch_w_update(c, w, st));
     peer_signal_wait_kernel<<<1, 32, 0, st>>>(pt, 1, epoch, c->err);  // every slice of the new W^T is in every block
     LAUNCH_CHECK();
     AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
-    AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));
-    if (c->n_cov > 0) {
-      wf.gram.n_parts = 0;
-      wf.gram_blocks = 0;
-      w_finish_kernel<<<1, 256, ckmax * sizeof(float), st>>>(wf);
-      LAUNCH_CHECK();
-    }
   }
   c->w_stale = true;
-  // ---- A = W^T X (main.py:653), left in the contraction's partial slots
-  AL_TRY(run_gemm(c, PLAN_WX, nullptr, c->ldN, st));
+  // ---- T = W^T W of the new W (tcgen05 Gram plan; its slots are summed by the finish kernel, which also writes the
+  //      hi / lo copies Z_H needs) and the B updates (main.py:615-628)
+  AL_TRY(run_gemm(c, PLAN_GRAM_W, nullptr, 0, st));
+  {
+    WFinishParams wf{};
+    wf.gram.src = src_slots(c->plans[PLAN_GRAM_W]);
+    wf.gram.K = c->K;
+    wf.gram.out = c->T;
+    wf.gram.ld = c->K;
+    wf.gram.split_hi = c->Tsplit;
+    wf.gram.split_lo = c->Tsplit + static_cast<size_t>(c->K) * c->ldK;
+    wf.gram.ld_split = static_cast<int>(c->ldK);
+    wf.gram_blocks = ceil_div(static_cast<long long>(c->K) * c->K, 8);
+    wf.cov = tab;
+    wf.loss_type = c->loss_type;
+    wf.stats_q = c->use_Q();
+    wf.hsum = c->use_hsum();
+    wf.S = c->use_S();
+    wf.ldS = c->K;
+    wf.eps = static_cast<float>(c->eps);
+    w_finish_kernel<<<wf.gram_blocks + (c->n_cov > 0 ? 1 : 0), 256, ckmax * sizeof(float), st>>>(wf);
+    LAUNCH_CHECK();
+  }
+  // ---- A = W^T X (main.py:653) and Z_H = (W^T W) H, both left in their slots
+  AL_TRY(run_gemm(c, PLAN_WX, nullptr, 0, st));
+  AL_TRY(run_gemm(c, PLAN_ZH, nullptr, 0, st));
   // ---- H update (main.py:631-663) with the guided terms of (old H, new B), statistics of (new H, new B)
   HUpdParams h{};
-  h.T = c->T;
-  h.ldT = c->K;
   h.H = c->H;
   h.ldH = c->ldH;
   h.K = c->K;
   h.n = c->n;
-  h.num = num_from_slots(c->plans[PLAN_WX]);
+  h.num = src_slots(c->plans[PLAN_WX]);
+  h.z = src_slots(c->plans[PLAN_ZH]);
   h.eps = static_cast<float>(c->eps);
   h.cov = tab;
   h.loss_type = c->loss_type;
   h.Kg = c->Kg;
   h.c_total = c_total;
   h.q_total = c->q_total;
-  h.split_hi = c->Hsplit;  // B operand of the next iteration's X H^T
+  h.split_hi = c->Hsplit;  // B operand of H H^T below and of the next iteration's X H^T
   h.split_lo = c->Hsplit + static_cast<size_t>(c->K) * c->ldN;
   h.ld_split = c->ldN;
-  h.gram_partial = c->gram_part_h;
   h.hsum_partial = c->hsum_part;
   h.q_partial = c->q_part;
   h.pred_partial = c->pred_part;
   h.t1_partial = c->t1_part;
   AL_TRY(launch_h_update<true>(c, h, st));
-  // ---- statistics of the new H for the next iteration + loss terms of this one (main.py:666, 726-753)
+  // ---- S = H H^T of the new H (Gram plan), statistics for the next iteration, loss terms of this one
+  //      (main.py:666, 726-753)
+  AL_TRY(run_gemm(c, PLAN_GRAM_H, nullptr, 0, st));
   HFinishParams hf{};
-  hf.gram.partial = c->gram_part_h;
-  hf.gram.n_parts = c->upd_grid_h;
-  hf.gram.NC = c->Kp / 16;
+  hf.gram.src = src_slots(c->plans[PLAN_GRAM_H]);
   hf.gram.K = c->K;
   hf.gram.out = c->red_S();
   hf.gram.ld = c->K;
-  hf.gram_blocks = ceil_div(gram_reduce_threads(c->Kp / 16), 256);
+  if (single) {  // S stays this GPU's own: its hi / lo copies can be written right away
+    hf.gram.split_hi = c->Ssplit;
+    hf.gram.split_lo = c->Ssplit + static_cast<size_t>(c->K) * c->ldK;
+    hf.gram.ld_split = static_cast<int>(c->ldK);
+  }
+  hf.gram_blocks = ceil_div(static_cast<long long>(c->K) * c->K, 8);
   hf.n_parts = c->upd_grid_h;
   hf.hsum_partial = c->hsum_part;
   hf.hsum = c->red_hsum();
@@ -1488,17 +1511,20 @@ int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
   LAUNCH_CHECK();
   AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));  // T = W^T W, loop-invariant
+  AL_TRY(run_split_small(c, c->T, c->K, c->Tsplit, st));
   AL_TRY(run_gemm(c, PLAN_WX, c->A, c->ldN, st));    // A = W^T X, loop-invariant (main.py:706)
   HUpdParams h{};
-  h.T = c->T;
-  h.ldT = c->K;
   h.H = c->H;
   h.ldH = c->ldH;
   h.K = c->K;
   h.n = c->n;
-  h.num = num_direct(c->A, c->ldN);
+  h.num = src_direct(c->A, c->ldN);
   h.eps = static_cast<float>(c->eps);
-  for (int it = 0; it < n_iter; ++it) AL_TRY(launch_h_update<false>(c, h, st));  // main.py:705-709
+  for (int it = 0; it < n_iter; ++it) {  // main.py:705-709
+    AL_TRY(run_gemm(c, PLAN_ZH, nullptr, 0, st));  // Z = T H
+    h.z = src_slots(c->plans[PLAN_ZH]);
+    AL_TRY(launch_h_update<false>(c, h, st));
+  }
   CU_TRY(cudaStreamSynchronize(st));
   return check_kernel_error(c);
 }

@@ -259,6 +259,18 @@ __global__ void split_operand_kernel(const float* __restrict__ src, long long ld
   }
 }
 
+// the same for a small K x K matrix of any pitch / alignment (H H^T, W^T W): scalar accesses
+__global__ void split_small_kernel(const float* __restrict__ src, int ld_src, int K, float* __restrict__ hi,
+                                   float* __restrict__ lo, int ld_dst) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= K * K) return;
+  const int r = e / K, c = e - r * K;
+  uint32_t h, l;
+  ptx::split_tf32(src[r * ld_src + c], h, l);
+  hi[r * ld_dst + c] = __uint_as_float(h);
+  lo[r * ld_dst + c] = __uint_as_float(l);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // out[c][r] = in[r][c]  (W <-> W^T), 32x32 tiles through shared memory, both sides coalesced
 __global__ void transpose_kernel(const float* __restrict__ in, long long ld_in, int rows, int cols,

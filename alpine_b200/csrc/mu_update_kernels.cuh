@@ -1,23 +1,25 @@
-// The multiplicative updates of one MU iteration as two fused, persistent kernels (+ two small finish kernels), so
-// that an iteration is six launches: X H^T contraction, W update, W finish, W^T X contraction, H update, H finish.
+// The multiplicative updates of one MU iteration as two fused epilogue kernels (+ two small finish kernels).
+//
+// All four K x K-sized products of the Gram reformulation run on the tcgen05 contraction kernel
+// (csrc/mu_gemm_sm100.cuh) as small plans -- Z_W = (H H^T) W^T, T = W^T W, Z_H = T H, S = H H^T -- and leave their
+// results in stream-K partial-sum slots; the kernels here consume those slots directly:
 //
 //   w_update_kernel  (main.py:596-612)  per 64-gene tile of W^T [K][G]:
-//       numerator P = X H^T  (summed from the contraction's stream-K partial slots, or read from the reduce buffer)
-//       Z = (H H^T) W^T      (K x K by K x 64, 3xTF32 mma.sync, fp32 accumulate)
-//       W *= 2P / max(2Z + (1-l1) a W + orth (rowsum_K(W) - W) + l1 a, eps)
-//       tf32 hi/lo copies of the new tile (B operand of the next contraction), peer stores (cell sharding),
-//       and this CTA's running Gram partial  W_new^T W_new  (upper 16x16 blocks, 3xTF32 mma.sync)
-//   w_finish_kernel  sums the Gram partials in a fixed order -> T = W^T W, and applies the B updates (main.py:615-628)
+//       P = X H^T (slots of the big contraction, or the all-reduced exchange buffer), Z_W (slots)
+//       W *= 2P / max(2 Z_W + (1-l1) a W + orth (rowsum_K(W) - W) + l1 a, eps);  tf32 hi/lo copies of the new tile
+//       (B operand of the next contraction);  peer stores under cell sharding
+//   w_finish_kernel  T = W^T W from the Gram plan's slots (+ its hi/lo copies, B operand of Z_H) and the B updates
+//       (main.py:615-628)
 //   h_update_kernel  (main.py:631-663)  per 64-cell tile of H [K][n]:
-//       numerator A = W^T X  (from the partial slots),  Z = T H,  guided terms from (old H, new B) per cell,
-//       H *= (numG + 2A) / max(denG + 2Z, eps),  hi/lo copies,  t1 = sum A .* H_new (fp64),
-//       statistics of (new H, new B) for the next iteration: rowsum(H), Q_i, prediction loss, Gram partial H H^T
-//   h_finish_kernel  sums the partials -> S = H H^T, rowsum(H), Q_i into the reduce buffer, and the loss row
-//       [t1, t2 = sum T .* S, pred_i] (main.py:666, 726-753 through the trace identity)
+//       A = W^T X (slots), Z_H (slots), guided terms from (old H, new B) per cell,
+//       H *= (numG + 2A) / max(denG + 2 Z_H, eps);  hi/lo copies;  t1 = sum A .* H_new (fp64);
+//       statistics of (new H, new B) for the next iteration: rowsum(H), Q_i, prediction loss
+//   h_finish_kernel  S = H H^T from the Gram plan's slots (+ hi/lo copies, B operand of Z_W), rowsum(H), Q_i into
+//       the exchange buffer, and the loss row [t1, t2 = sum T .* S, pred_i] (main.py:666, 726-753, trace identity)
 //
-// The K x K products are < 1 % of the iteration's FLOPs; they run on the tensor cores through mma.sync.m16n8k8
-// (tf32 operands split hi/lo, three products per term as in the big contractions) because the CUDA-core version of
-// the same products was what bounded the update kernels (125 us of a 4.06 ms iteration at cfg 3, round 1).
+// Measured dead end (round 2, kept in the history): the same products on mma.sync.m16n8k8.tf32 inside these kernels.
+// Parity was green, but the legacy tensor path of sm_100 issues one such MMA per ~100 cycles per SM sub-partition
+// (h_update 470 us at cfg 3, slower than the CUDA-core version it replaced), so the products moved to tcgen05.
 // Everything is deterministic: fixed tile -> CTA assignment, fixed summation orders, no atomics on data.
 #pragma once
 #include "mu_small_kernels.cuh"
@@ -25,24 +27,8 @@
 namespace alpine {
 
 constexpr int kUpdCols = 64;       // columns (cells or genes) per tile
-constexpr int kUpdPitch = 72;      // shared-memory row pitch of a tile (floats): conflict-free fragment loads
-constexpr int kUpdThreads = 256;   // 8 warps
-constexpr int kUpdWarps = 8;
-
-// D (16x8, fp32) += A (16x8, tf32, row) * B (8x8, tf32, col)
-__device__ __forceinline__ void mma_tf32_m16n8k8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
-      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-// 3xTF32: small terms first
-__device__ __forceinline__ void mma3(float (&d)[4], const uint32_t (&ahi)[4], const uint32_t (&alo)[4], uint32_t bhi0,
-                                     uint32_t bhi1, uint32_t blo0, uint32_t blo1) {
-  mma_tf32_m16n8k8(d, alo, bhi0, bhi1);
-  mma_tf32_m16n8k8(d, ahi, blo0, blo1);
-  mma_tf32_m16n8k8(d, ahi, bhi0, bhi1);
-}
+constexpr int kUpdPitch = 68;      // shared-memory row pitch of a tile (floats)
+constexpr int kUpdThreads = 256;
 
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
@@ -50,94 +36,39 @@ __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// Where the numerator of a tile comes from: a finished [K][ld] array, or the stream-K partial-sum slots of the
-// contraction that has just run (slot s holds [K][256] sums of one segment of a 256-row super-tile).
-struct UpdNumSrc {
-  const float* direct;
+// A [K][L] operand of an update: a finished array, or the stream-K partial-sum slots of the contraction that has
+// just produced it (slot s holds [K][256] sums of one segment of a 256-row super-tile; the slots of a super-tile
+// are added in the fixed order of its list).
+struct SlotSrc {
+  const float* direct;  // [K][ld] or nullptr
   long long ld;
   const float* partial;
   const int* slot_ofs;  // [super-tiles + 1]
   const int* slots;
-  int K;                // row pitch of a slot is K * 256
+  int K;                // components per slot
+  long long origin;     // column of the caller's matrix that is row 0 of the plan's first super-tile
 };
-// the two adjacent columns (col, col + 1) of row k; col is even
-__device__ __forceinline__ float2 num_load2(const UpdNumSrc& s, int k, long long col, int s0, int s1) {
-  if (s.direct != nullptr) return __ldg(reinterpret_cast<const float2*>(s.direct + static_cast<long long>(k) * s.ld + col));
-  const int r = static_cast<int>(col & 255);
-  float2 acc = make_float2(0.f, 0.f);
+// four adjacent columns (col .. col + 3) of row k; col % 4 == 0
+__device__ __forceinline__ float4 slot_load4(const SlotSrc& s, int k, long long col, int s0, int s1) {
+  if (s.direct != nullptr) return __ldg(reinterpret_cast<const float4*>(s.direct + static_cast<long long>(k) * s.ld + col));
+  const int r = static_cast<int>((col - s.origin) & 255);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (int q = s0; q < s1; ++q) {
-    const float2 v = __ldcg(reinterpret_cast<const float2*>(
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(
         s.partial + (static_cast<size_t>(__ldg(s.slots + q)) * s.K + k) * 256 + r));
-    acc.x += v.x, acc.y += v.y;
+    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
   }
   return acc;
 }
-
-// Upper-triangular 16x16 blocks (mt <= nt) of a (16 NC)^2 Gram matrix, enumerated row by row.
-__device__ __forceinline__ void gram_block_decode(int b, int NC, int& mt, int& nt) {
-  mt = 0;
-  int rem = b;
-  while (rem >= NC - mt) {
-    rem -= NC - mt;
-    ++mt;
-  }
-  nt = mt + rem;
-}
-
-template <int NC>
-struct UpdGeom {
-  static constexpr int Kp = 16 * NC;
-  static constexpr int KS = 2 * NC;                  // k-steps of 8 over the padded K
-  static constexpr int NB = NC * (NC + 1) / 2;       // Gram blocks
-  static constexpr int NBW = (NB + kUpdWarps - 1) / kUpdWarps;  // Gram blocks per warp
-  static constexpr int afrag_floats = NC * KS * 32 * 4;  // fp32 A fragments (split into hi / lo when loaded)
-  static constexpr int tile_floats = Kp * kUpdPitch;
-  static constexpr int n_tile_bufs = 4;                  // two cp.async targets + tf32 hi / lo of the current tile
-  static constexpr int gram_floats = NBW * kUpdWarps * 2 * 32 * 4;  // per CTA, fragment order
-};
-
-// Stage Sym [K][K] (global) through `scratch` (>= K*K floats of shared memory) and write it in A-fragment order:
-// afrag[((mt * KS + ks) * 32 + lane) * 4 + {a0..a3}],  a0 = (16 mt + g, 8 ks + t), a1 = (+8, .), a2 = (., +4),
-// a3 = (+8, +4), g = lane / 4, t = lane % 4; entries outside K are zero.
-template <int NC>
-__device__ void build_afrag(float* afrag, float* scratch, const float* __restrict__ Sym, int ldS, int K) {
-  constexpr int KS = 2 * NC;
-  for (int e = threadIdx.x; e < K * K; e += kUpdThreads) {
-    const int r = e / K, c = e - r * K;
-    scratch[e] = __ldcg(Sym + static_cast<long long>(r) * ldS + c);
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < NC * KS * 32; e += kUpdThreads) {
-    const int lane = e & 31, ks = (e >> 5) % KS, mt = (e >> 5) / KS;
-    const int g = lane >> 2, t = lane & 3;
-    const int r0 = 16 * mt + g, r1 = r0 + 8, k0 = 8 * ks + t, k1 = k0 + 4;
-    const float v0 = (r0 < K && k0 < K) ? scratch[r0 * K + k0] : 0.f;
-    const float v1 = (r1 < K && k0 < K) ? scratch[r1 * K + k0] : 0.f;
-    const float v2 = (r0 < K && k1 < K) ? scratch[r0 * K + k1] : 0.f;
-    const float v3 = (r1 < K && k1 < K) ? scratch[r1 * K + k1] : 0.f;
-    reinterpret_cast<float4*>(afrag)[e] = make_float4(v0, v1, v2, v3);
-  }
-  __syncthreads();
-}
-
-// tf32 hi / lo copies of the rows [0, K) of a tile (same pitch)
-__device__ __forceinline__ void split_tile(const float* tile, float* thi, float* tlo, int K) {
-  for (int e = threadIdx.x; e < K * 16; e += kUpdThreads) {
-    const int o = (e >> 4) * kUpdPitch + 4 * (e & 15);
-    const float4 v = *reinterpret_cast<const float4*>(tile + o);
-    uint32_t h[4], l[4];
-    ptx::split_tf32(v.x, h[0], l[0]);
-    ptx::split_tf32(v.y, h[1], l[1]);
-    ptx::split_tf32(v.z, h[2], l[2]);
-    ptx::split_tf32(v.w, h[3], l[3]);
-    *reinterpret_cast<float4*>(thi + o) =
-        make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
-    *reinterpret_cast<float4*>(tlo + o) =
-        make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+__device__ __forceinline__ void slot_range(const SlotSrc& s, long long c0, int& s0, int& s1) {
+  s0 = s1 = 0;
+  if (s.direct == nullptr) {
+    s0 = __ldg(s.slot_ofs + ((c0 - s.origin) >> 8));
+    s1 = __ldg(s.slot_ofs + ((c0 - s.origin) >> 8) + 1);
   }
 }
 
-// rows [0, K) x 64 columns [c0, c0 + 64) of Mat [K][ld] -> tile [Kp][72]; columns >= L arrive as zeros
+// rows [0, K) x 64 columns [c0, c0 + 64) of Mat [K][ld] -> tile [K][68]; columns >= L arrive as zeros
 __device__ __forceinline__ void load_tile_async(float* tile, const float* __restrict__ Mat, long long ld, int K,
                                                 long long c0, long long L) {
   const uint32_t base = ptx::smem_u32(tile);
@@ -152,248 +83,82 @@ __device__ __forceinline__ void load_tile_async(float* tile, const float* __rest
   cp_async_commit();
 }
 
-// Z accumulators of warp `mt` (rows 16 mt ..): acc[nt][0..3] over the 8 column groups of the tile.  The three
-// products of a k-step are issued product-major (eight independent accumulators between two MMAs on the same one),
-// and even / odd k-steps go to two accumulator sets that are added at the end: twice the independent work for the
-// tensor pipe and half the length of every round-toward-zero accumulation chain.
-template <int NC>
-__device__ __forceinline__ void z_product(float (&acc)[8][4], const float* afrag, const float* thi, const float* tlo,
-                                          int mt, int ks_used, int lane) {
-  constexpr int KS = 2 * NC;
-  const int g = lane >> 2, t = lane & 3;
-  float acc2[8][4];
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[nt][i] = acc2[nt][i] = 0.f;
-  const float4* af = reinterpret_cast<const float4*>(afrag) + static_cast<size_t>(mt) * KS * 32 + lane;
-  auto step = [&](int ks, float (&d)[8][4]) {
-    const float4 a = af[ks * 32];
-    uint32_t ahi[4], alo[4];
-    ptx::split_tf32(a.x, ahi[0], alo[0]);
-    ptx::split_tf32(a.y, ahi[1], alo[1]);
-    ptx::split_tf32(a.z, ahi[2], alo[2]);
-    ptx::split_tf32(a.w, ahi[3], alo[3]);
-    const int o = (8 * ks + t) * kUpdPitch + g;
-    uint32_t bh0[8], bh1[8], bl0[8], bl1[8];
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) {
-      bh0[nt] = __float_as_uint(thi[o + 8 * nt]);
-      bh1[nt] = __float_as_uint(thi[o + 4 * kUpdPitch + 8 * nt]);
-      bl0[nt] = __float_as_uint(tlo[o + 8 * nt]);
-      bl1[nt] = __float_as_uint(tlo[o + 4 * kUpdPitch + 8 * nt]);
-    }
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) mma_tf32_m16n8k8(d[nt], alo, bh0[nt], bh1[nt]);  // small terms first
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) mma_tf32_m16n8k8(d[nt], ahi, bl0[nt], bl1[nt]);
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt) mma_tf32_m16n8k8(d[nt], ahi, bh0[nt], bh1[nt]);
-  };
-  int ks = 0;
-  for (; ks + 1 < ks_used; ks += 2) {
-    step(ks, acc);
-    step(ks + 1, acc2);
+// one float4 of new values -> Mat (masked at L), its tf32 hi / lo copies (whole float4 groups: pitches are
+// multiples of 4 and the values at columns >= L are zero) and the peers' copies of Mat
+__device__ __forceinline__ void store4(float4 v, int k, long long col, long long L, float* __restrict__ Mat, long long ld,
+                                       float* __restrict__ split_hi, float* __restrict__ split_lo, long long ld_split,
+                                       int n_peers, float* const* mat_peer) {
+  const bool full = col + 4 <= L;
+  const float vv[4] = {v.x, v.y, v.z, v.w};
+  float* dst = Mat + static_cast<long long>(k) * ld + col;
+  if (full) {
+    *reinterpret_cast<float4*>(dst) = v;
+  } else {
+    for (int x = 0; x < 4; ++x)
+      if (col + x < L) dst[x] = vv[x];
   }
-  if (ks < ks_used) step(ks, acc);
-#pragma unroll
-  for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-    for (int i = 0; i < 4; ++i) acc[nt][i] += acc2[nt][i];
-}
-
-// Gram of one tile, added (round-to-nearest) to this CTA's running partial in global memory: block (mt_i, nt_i) of
-// tile * tile^T over the 64 columns, from the tile's tf32 hi / lo copies.  Fresh accumulators per tile keep the
-// tensor core's round-toward-zero chains short (12 MMAs); every thread owns its float4 slots of the partial, so the
-// read-modify-write needs no synchronisation.  Fragment order: [(i * 8 + warp) * 2 + j][lane] float4.
-template <int NBW>
-__device__ __forceinline__ void gram_tile(float* gram_partial, int gram_floats, bool first, const float* thi,
-                                          const float* tlo, const int (&bmt)[NBW], const int (&bnt)[NBW], int warp,
-                                          int lane) {
-  const int g = lane >> 2, t = lane & 3;
-  float4* out = reinterpret_cast<float4*>(gram_partial + static_cast<size_t>(blockIdx.x) * gram_floats);
-#pragma unroll
-  for (int i = 0; i < NBW; ++i) {
-    if (bmt[i] < 0) continue;
-    float d[2][2][4];  // [j][k-step parity][c0..c3]
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int q = 0; q < 2; ++q)
-#pragma unroll
-        for (int x = 0; x < 4; ++x) d[j][q][x] = 0.f;
-    const int ao = (16 * bmt[i] + g) * kUpdPitch + t, bo = (16 * bnt[i] + g) * kUpdPitch + t;
-#pragma unroll
-    for (int ks = 0; ks < kUpdCols / 8; ++ks) {
-      const int q = ks & 1;
-      uint32_t ahi[4], alo[4], bh[2][2], bl[2][2];
-      ahi[0] = __float_as_uint(thi[ao + 8 * ks]);
-      ahi[1] = __float_as_uint(thi[ao + 8 * kUpdPitch + 8 * ks]);
-      ahi[2] = __float_as_uint(thi[ao + 8 * ks + 4]);
-      ahi[3] = __float_as_uint(thi[ao + 8 * kUpdPitch + 8 * ks + 4]);
-      alo[0] = __float_as_uint(tlo[ao + 8 * ks]);
-      alo[1] = __float_as_uint(tlo[ao + 8 * kUpdPitch + 8 * ks]);
-      alo[2] = __float_as_uint(tlo[ao + 8 * ks + 4]);
-      alo[3] = __float_as_uint(tlo[ao + 8 * kUpdPitch + 8 * ks + 4]);
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        bh[j][0] = __float_as_uint(thi[bo + 8 * j * kUpdPitch + 8 * ks]);
-        bh[j][1] = __float_as_uint(thi[bo + 8 * j * kUpdPitch + 8 * ks + 4]);
-        bl[j][0] = __float_as_uint(tlo[bo + 8 * j * kUpdPitch + 8 * ks]);
-        bl[j][1] = __float_as_uint(tlo[bo + 8 * j * kUpdPitch + 8 * ks + 4]);
-      }
-      mma_tf32_m16n8k8(d[0][q], alo, bh[0][0], bh[0][1]);
-      mma_tf32_m16n8k8(d[1][q], alo, bh[1][0], bh[1][1]);
-      mma_tf32_m16n8k8(d[0][q], ahi, bl[0][0], bl[0][1]);
-      mma_tf32_m16n8k8(d[1][q], ahi, bl[1][0], bl[1][1]);
-      mma_tf32_m16n8k8(d[0][q], ahi, bh[0][0], bh[0][1]);
-      mma_tf32_m16n8k8(d[1][q], ahi, bh[1][0], bh[1][1]);
-    }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      float4* slot = out + ((i * kUpdWarps + warp) * 2 + j) * 32 + lane;
-      float4 v = make_float4(d[j][0][0] + d[j][1][0], d[j][0][1] + d[j][1][1], d[j][0][2] + d[j][1][2],
-                             d[j][0][3] + d[j][1][3]);
-      if (!first) {
-        const float4 old = *slot;
-        v.x += old.x, v.y += old.y, v.z += old.z, v.w += old.w;
-      }
-      *slot = v;
-    }
-  }
-}
-
-// tile rows [0, K) -> Mat, its tf32 hi / lo copies (from the tile's own hi / lo copies) and the peers' copies;
-// columns >= L are skipped (Mat) / zero (split: pitches are multiples of 4, whole float4 groups are written)
-__device__ __forceinline__ void store_tile(const float* tile, const float* thi, const float* tlo, float* __restrict__ Mat,
-                                           long long ld, int K, long long c0, long long L, float* __restrict__ split_hi,
-                                           float* __restrict__ split_lo, long long ld_split, int n_peers,
-                                           float* const* mat_peer) {
-  for (int e = threadIdx.x; e < K * 16; e += kUpdThreads) {
-    const int k = e >> 4, c4 = e & 15;
-    const long long col = c0 + 4 * c4;
-    if (col >= L) continue;
-    const int o = k * kUpdPitch + 4 * c4;
-    const float4 v = *reinterpret_cast<const float4*>(tile + o);
-    const bool full = col + 4 <= L;
-    float* dst = Mat + static_cast<long long>(k) * ld + col;
+  for (int q = 0; q < n_peers; ++q) {
+    if (mat_peer[q] == nullptr) continue;
+    float* pd = mat_peer[q] + static_cast<long long>(k) * ld + col;
     if (full) {
-      *reinterpret_cast<float4*>(dst) = v;
+      *reinterpret_cast<float4*>(pd) = v;
     } else {
-      const float vv[4] = {v.x, v.y, v.z, v.w};
       for (int x = 0; x < 4; ++x)
-        if (col + x < L) dst[x] = vv[x];
-    }
-    for (int q = 0; q < n_peers; ++q) {
-      if (mat_peer[q] == nullptr) continue;
-      float* pd = mat_peer[q] + static_cast<long long>(k) * ld + col;
-      if (full) {
-        *reinterpret_cast<float4*>(pd) = v;
-      } else {
-        const float vv[4] = {v.x, v.y, v.z, v.w};
-        for (int x = 0; x < 4; ++x)
-          if (col + x < L) pd[x] = vv[x];
-      }
-    }
-    if (split_hi != nullptr) {
-      const long long so = static_cast<long long>(k) * ld_split + col;
-      *reinterpret_cast<float4*>(split_hi + so) = *reinterpret_cast<const float4*>(thi + o);
-      *reinterpret_cast<float4*>(split_lo + so) = *reinterpret_cast<const float4*>(tlo + o);
+        if (col + x < L) pd[x] = vv[x];
     }
   }
-}
-
-// new value of two adjacent tile entries: fp32 into the tile, tf32 hi / lo into its copies
-__device__ __forceinline__ void put2(float* tile, float* thi, float* tlo, int o, float v0, float v1) {
-  uint32_t h0, l0, h1, l1;
-  ptx::split_tf32(v0, h0, l0);
-  ptx::split_tf32(v1, h1, l1);
-  *reinterpret_cast<float2*>(tile + o) = make_float2(v0, v1);
-  *reinterpret_cast<float2*>(thi + o) = make_float2(__uint_as_float(h0), __uint_as_float(h1));
-  *reinterpret_cast<float2*>(tlo + o) = make_float2(__uint_as_float(l0), __uint_as_float(l1));
+  if (split_hi != nullptr) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int x = 0; x < 4; ++x) ptx::split_tf32(vv[x], h[x], l[x]);
+    const long long o = static_cast<long long>(k) * ld_split + col;
+    *reinterpret_cast<float4*>(split_hi + o) =
+        make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
+    *reinterpret_cast<float4*>(split_lo + o) =
+        make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // W update
 struct WUpdParams {
-  const float* S;       // [K][ldS]  H H^T (complete: all-reduced / summed over the peers)
-  int ldS;
   float* WT;            // [K][ldG]  updated in place
   long long ldG;
   int K;
   long long col0, col1; // genes [col0, col1) are updated by this launch (col0 % 64 == 0)
-  UpdNumSrc num;        // X H^T
+  SlotSrc num;          // X H^T
+  SlotSrc z;            // (H H^T) W^T
   float c1, c2, orth, eps;
   float* split_hi;      // [K][ldG] tf32 copies of the new W^T, or nullptr
   float* split_lo;
   int n_peers;
   float* wt_peer[kMaxPeers];
-  float* gram_partial;  // [gridDim.x][UpdGeom::gram_floats] or nullptr
 };
-
-template <int NC>
-inline size_t w_update_smem_bytes() {
-  using G = UpdGeom<NC>;
-  return (static_cast<size_t>(G::afrag_floats) + G::n_tile_bufs * G::tile_floats) * sizeof(float) +
-         kUpdCols * sizeof(double) + 16;
+inline size_t w_update_smem_bytes(int K) {
+  return static_cast<size_t>(2) * K * kUpdPitch * sizeof(float) + kUpdCols * sizeof(double) + 16;
 }
 
-template <int NC>
-__global__ void __launch_bounds__(kUpdThreads, 1) w_update_kernel(const WUpdParams p) {
-  using G = UpdGeom<NC>;
+__global__ void __launch_bounds__(kUpdThreads) w_update_kernel(const WUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
-  float* afrag = reinterpret_cast<float*>(upd_smem);
-  float* tiles = afrag + G::afrag_floats;   // [2][Kp][72] cp.async targets; the current one receives the new values
-  float* thi = tiles + 2 * G::tile_floats;  // [Kp][72] tf32 hi of the current tile (old values, then new)
-  float* tlo = thi + G::tile_floats;
-  double* cs = reinterpret_cast<double*>(tlo + G::tile_floats);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int K = p.K;
-  const int ks_used = (K + 7) >> 3;
+  float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]
+  double* cs = reinterpret_cast<double*>(tiles + 2 * K * kUpdPitch);
+  const int tid = threadIdx.x;
   const long long n_tiles = (p.col1 - p.col0 + kUpdCols - 1) / kUpdCols;
-
-  build_afrag<NC>(afrag, tiles, p.S, p.ldS, K);
-  for (int e = tid; e < G::n_tile_bufs * G::tile_floats; e += kUpdThreads) tiles[e] = 0.f;  // pad rows stay zero
-  __syncthreads();
-
-  int bmt[G::NBW], bnt[G::NBW];
-#pragma unroll
-  for (int i = 0; i < G::NBW; ++i) {
-    const int b = warp + kUpdWarps * i;
-    bmt[i] = bnt[i] = -1;
-    if (b < G::NB) gram_block_decode(b, NC, bmt[i], bnt[i]);
-  }
-
   long long tile_i = blockIdx.x;
   int buf = 0;
-  bool first = true;
   if (tile_i < n_tiles) load_tile_async(tiles, p.WT, p.ldG, K, p.col0 + tile_i * kUpdCols, p.col1);
-  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1, first = false) {
-    float* tile = tiles + buf * G::tile_floats;
+  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1) {
+    const float* tile = tiles + buf * K * kUpdPitch;
     const long long c0 = p.col0 + tile_i * kUpdCols;
-    // numerator fragments of this warp's rows (issued before anything waits)
-    float2 nu[8][2];
-    {
-      int s0 = 0, s1 = 0;
-      if (p.num.direct == nullptr) {
-        s0 = __ldg(p.num.slot_ofs + (c0 >> 8));
-        s1 = __ldg(p.num.slot_ofs + (c0 >> 8) + 1);
-      }
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = 16 * warp + g + 8 * h;
-          const long long col = c0 + 8 * nt + 2 * t;
-          nu[nt][h] = (warp < NC && k < K && col < p.col1) ? num_load2(p.num, k, col, s0, s1) : make_float2(0.f, 0.f);
-        }
-    }
+    int n0, n1, z0, z1;
+    slot_range(p.num, c0, n0, n1);
+    slot_range(p.z, c0, z0, z1);
     cp_async_wait_all();
-    __syncthreads();  // the tile has landed; everybody is done with the previous tile's buffers
+    __syncthreads();  // the tile has landed; everybody is done with the other buffer
     const long long next = tile_i + gridDim.x;
     if (next < n_tiles)
-      load_tile_async(tiles + (buf ^ 1) * G::tile_floats, p.WT, p.ldG, K, p.col0 + next * kUpdCols, p.col1);
-    split_tile(tile, thi, tlo, K);
+      load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.WT, p.ldG, K, p.col0 + next * kUpdCols, p.col1);
     // rowsum_K W[g][:] per gene, fp64 so that (rowsum - w) does not cancel (the reference sums the other K-1 entries)
     if (tid < kUpdCols) {
       double sacc = 0.0;
@@ -401,36 +166,28 @@ __global__ void __launch_bounds__(kUpdThreads, 1) w_update_kernel(const WUpdPara
       cs[tid] = sacc;
     }
     __syncthreads();
-    float acc[8][4];
-    if (warp < NC) z_product<NC>(acc, afrag, thi, tlo, warp, ks_used, lane);
-    __syncthreads();  // every warp has read the old hi / lo copies
-    if (warp < NC) {
+    for (int e = tid; e < K * 16; e += kUpdThreads) {
+      const int k = e >> 4, c4 = e & 15;
+      const long long col = c0 + 4 * c4;
+      if (col >= p.col1) continue;
+      const float4 num4 = slot_load4(p.num, k, col, n0, n1);
+      const float4 z4 = slot_load4(p.z, k, col, z0, z1);
+      const float4 old4 = *reinterpret_cast<const float4*>(tile + k * kUpdPitch + 4 * c4);
+      const float oldv[4] = {old4.x, old4.y, old4.z, old4.w}, numv[4] = {num4.x, num4.y, num4.z, num4.w};
+      const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+      float outv[4];
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = 16 * warp + g + 8 * h;
-          if (k >= K) continue;
-          const int cl = 8 * nt + 2 * t;
-          const int o = k * kUpdPitch + cl;
-          const float2 old = *reinterpret_cast<const float2*>(tile + o);
-          const float oldv[2] = {old.x, old.y}, numv[2] = {nu[nt][h].x, nu[nt][h].y};
-          float outv[2];
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const float others = static_cast<float>(cs[cl + x] - static_cast<double>(oldv[x]));
-            float den = (2.0f * acc[nt][2 * h + x] + p.c1 * oldv[x]) + p.orth * others;  // main.py:599-601
-            den += p.c2;                                                                // main.py:603
-            den = fmaxf(den, p.eps);                                                    // main.py:604
-            outv[x] = (c0 + cl + x < p.col1) ? oldv[x] * ((2.0f * numv[x]) / den) : 0.f;  // main.py:596, 605
-          }
-          put2(tile, thi, tlo, o, outv[0], outv[1]);
-        }
+      for (int x = 0; x < 4; ++x) {
+        const float others = static_cast<float>(cs[4 * c4 + x] - static_cast<double>(oldv[x]));
+        float den = (2.0f * zv[x] + p.c1 * oldv[x]) + p.orth * others;  // main.py:599-601
+        den += p.c2;                                                   // main.py:603
+        den = fmaxf(den, p.eps);                                       // main.py:604
+        outv[x] = (col + x < p.col1) ? oldv[x] * ((2.0f * numv[x]) / den) : 0.f;  // main.py:596, 605
+      }
+      store4(make_float4(outv[0], outv[1], outv[2], outv[3]), k, col, p.col1, p.WT, p.ldG, p.split_hi, p.split_lo, p.ldG,
+             p.n_peers, p.wt_peer);
     }
-    __syncthreads();  // the tile and its hi / lo copies hold the new values
-    store_tile(tile, thi, tlo, p.WT, p.ldG, K, c0, p.col1, p.split_hi, p.split_lo, p.ldG, p.n_peers, p.wt_peer);
-    if (p.gram_partial != nullptr) gram_tile<G::NBW>(p.gram_partial, G::gram_floats, first, thi, tlo, bmt, bnt, warp, lane);
-    // (the next iteration's first barrier separates these reads from the next split / prefetch)
+    // (the next iteration's first barrier separates these reads from the prefetch into this buffer two tiles on)
   }
   cp_async_wait_all();
 }
@@ -438,13 +195,12 @@ __global__ void __launch_bounds__(kUpdThreads, 1) w_update_kernel(const WUpdPara
 // ---------------------------------------------------------------------------------------------------------------
 // H update
 struct HUpdParams {
-  const float* T;  // [K][ldT]  W^T W (transform: of the fixed W)
-  int ldT;
   float* H;        // [K][ldH]  updated in place
   long long ldH;
   int K;
   long long n;
-  UpdNumSrc num;   // W^T X
+  SlotSrc num;     // W^T X
+  SlotSrc z;       // (W^T W) H
   float eps;
   CovTable cov;
   int loss_type;
@@ -452,49 +208,37 @@ struct HUpdParams {
   float* split_hi;  // [K][ld_split] or nullptr
   float* split_lo;
   long long ld_split;
-  float* gram_partial;    // [gridDim.x][gram_floats]
   float* hsum_partial;    // [gridDim.x][K]
   float* q_partial;       // [gridDim.x][q_total]
   double* pred_partial;   // [gridDim.x][n_cov]
   double* t1_partial;     // [gridDim.x]
 };
-
-template <int NC>
 inline size_t h_update_smem_bytes(int K, int Kg, int c_total, int q_total) {
-  using G = UpdGeom<NC>;
   const size_t q_pad = (static_cast<size_t>(q_total) + 3) & ~size_t(3);
-  size_t f = static_cast<size_t>(G::afrag_floats) + G::n_tile_bufs * G::tile_floats;
-  f += q_pad * 2 + 2 * static_cast<size_t>(c_total) * kUpdCols + Kg + K;  // Bs, qacc, rn, rd, dcol, hacc
+  size_t f = static_cast<size_t>(2) * K * kUpdPitch;
+  f += q_pad * 2 + 2 * static_cast<size_t>(c_total) * kUpdCols + ((Kg + 3) & ~3) + ((K + 3) & ~3);  // Bs, qacc, rn, rd, dcol, hacc
   return f * sizeof(float) + (kUpdThreads / 32) * sizeof(double) + static_cast<size_t>(Kg + 1 + kMaxCov) * sizeof(int) + 32;
 }
 
 // FIT: the full update with statistics; otherwise the transform update H *= 2A / max(2 T H, eps) (main.py:705-709)
-template <int NC, bool FIT>
-__global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdParams p) {
-  using G = UpdGeom<NC>;
+template <bool FIT>
+__global__ void __launch_bounds__(kUpdThreads) h_update_kernel(const HUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
-  float* afrag = reinterpret_cast<float*>(upd_smem);
-  float* tiles = afrag + G::afrag_floats;
-  const int q_pad = (p.q_total + 3) & ~3;           // keeps rn / rd 16-byte aligned
-  float* thi = tiles + 2 * G::tile_floats;          // tf32 hi / lo of the current tile (old values, then new)
-  float* tlo = thi + G::tile_floats;
-  float* Bs = tlo + G::tile_floats;                 // [q_total]  all B_i, row-major [c][k] at q_off
+  const int K = p.K;
+  const int q_pad = (p.q_total + 3) & ~3;           // keeps the arrays behind 16-byte aligned
+  float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]: old H, overwritten with the new H
+  float* Bs = tiles + 2 * K * kUpdPitch;            // [q_total]  all B_i, row-major [c][k] at q_off
   float* qacc = Bs + q_pad;                         // [q_total]  running Q partial of this CTA
   float* rn = qacc + q_pad;                         // [c_total][64]  per-cell numerator ratios (rho / Y)
   float* rd = rn + static_cast<size_t>(p.c_total) * kUpdCols;  // [c_total][64]  Frobenius: B H_i
-  float* dcol = rd + static_cast<size_t>(p.c_total) * kUpdCols;  // [Kg]  KL: scale * colsum(B) per guided row
-  float* hacc = dcol + p.Kg;                        // [K]  running row sums of the new H
-  double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(hacc + p.K) + 7) & ~uintptr_t(7));  // [8]
+  float* dcol = rd + static_cast<size_t>(p.c_total) * kUpdCols;  // [Kg]  KL: lam * colsum(B) per guided row
+  float* hacc = dcol + ((p.Kg + 3) & ~3);           // [K]  running row sums of the new H
+  double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(hacc + ((K + 3) & ~3)) + 7) & ~uintptr_t(7));  // [8]
   int* rowcov = reinterpret_cast<int*>(red + kUpdThreads / 32);  // [Kg]  covariate of guided row k
-  int* rowc0 = rowcov + p.Kg + 1;                   // [n_cov]-indexed by covariate: first row of rn / rd (category offset)
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
-  const int K = p.K;
-  const int ks_used = (K + 7) >> 3;
+  int* rowc0 = rowcov + p.Kg + 1;                   // [n_cov]  first row of rn / rd of a covariate
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long n_tiles = (p.n + kUpdCols - 1) / kUpdCols;
-  const float scale_kl = 1.0f, scale_fr = 2.0f;
 
-  build_afrag<NC>(afrag, tiles, p.T, p.ldT, K);
-  for (int e = tid; e < G::n_tile_bufs * G::tile_floats; e += kUpdThreads) tiles[e] = 0.f;
   if (FIT) {
     int coff = 0;
     for (int i = 0; i < p.cov.n_cov; ++i) {
@@ -506,55 +250,30 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
     }
     for (int e = tid; e < p.q_total; e += kUpdThreads) qacc[e] = 0.f;
     for (int k = tid; k < K; k += kUpdThreads) hacc[k] = 0.f;
-  }
-  __syncthreads();
-  if (FIT) {
+    __syncthreads();
     // KL: denG = (lam B^T) 1 = lam * colsum(B), the same for every cell (main.py:644)
     for (int k = tid; k < p.Kg; k += kUpdThreads) {
       const CovDesc d = p.cov.d[rowcov[k]];
       float s = 0.f;
-      for (int c = 0; c < d.c; ++c) s += (scale_kl * d.lam * Bs[d.q_off + c * d.k + (k - d.row0)]) * 1.0f;
+      for (int c = 0; c < d.c; ++c) s += (d.lam * Bs[d.q_off + c * d.k + (k - d.row0)]) * 1.0f;
       dcol[k] = s;
     }
-  }
-
-  int bmt[G::NBW], bnt[G::NBW];
-#pragma unroll
-  for (int i = 0; i < G::NBW; ++i) {
-    const int b = warp + kUpdWarps * i;
-    bmt[i] = bnt[i] = -1;
-    if (b < G::NB) gram_block_decode(b, NC, bmt[i], bnt[i]);
   }
   double t1 = 0.0, pl0 = 0.0, pl1 = 0.0;  // pred loss of covariates (tid / 64) and (tid / 64 + 4)
 
   long long tile_i = blockIdx.x;
   int buf = 0;
-  bool first = true;
   if (tile_i < n_tiles) load_tile_async(tiles, p.H, p.ldH, K, tile_i * kUpdCols, p.n);
-  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1, first = false) {
-    float* tile = tiles + buf * G::tile_floats;
+  for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1) {
+    float* tile = tiles + buf * K * kUpdPitch;
     const long long c0 = tile_i * kUpdCols;
-    float2 nu[8][2];
-    {
-      int s0 = 0, s1 = 0;
-      if (p.num.direct == nullptr) {
-        s0 = __ldg(p.num.slot_ofs + (c0 >> 8));
-        s1 = __ldg(p.num.slot_ofs + (c0 >> 8) + 1);
-      }
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = 16 * warp + g + 8 * h;
-          const long long col = c0 + 8 * nt + 2 * t;
-          nu[nt][h] = (warp < NC && k < K && col < p.n) ? num_load2(p.num, k, col, s0, s1) : make_float2(0.f, 0.f);
-        }
-    }
+    int n0, n1, z0, z1;
+    slot_range(p.num, c0, n0, n1);
+    slot_range(p.z, c0, z0, z1);
     cp_async_wait_all();
-    __syncthreads();
+    __syncthreads();  // the tile has landed (also orders the set-up above); everybody is done with the other buffer
     const long long next = tile_i + gridDim.x;
-    if (next < n_tiles) load_tile_async(tiles + (buf ^ 1) * G::tile_floats, p.H, p.ldH, K, next * kUpdCols, p.n);
-    split_tile(tile, thi, tlo, K);
+    if (next < n_tiles) load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.H, p.ldH, K, next * kUpdCols, p.n);
     if (FIT) {
       // guided terms of the OLD H with the NEW B, per cell (main.py:637-650): thread (i, j) = (tid / 64 [+4], tid % 64)
       const int j = tid & 63;
@@ -570,52 +289,51 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
           rd[(cbase + c) * kUpdCols + j] = yhat;
         }
       }
+      __syncthreads();  // rn / rd are complete
     }
-    __syncthreads();  // hi / lo copies and rn / rd are complete
-    float acc[8][4];
-    if (warp < NC) z_product<NC>(acc, afrag, thi, tlo, warp, ks_used, lane);
-    __syncthreads();  // every warp has read the old hi / lo copies
-    if (warp < NC) {
-#pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          const int k = 16 * warp + g + 8 * h;
-          if (k >= K) continue;
-          const int cl = 8 * nt + 2 * t;
-          const int o = k * kUpdPitch + cl;
-          const float2 old = *reinterpret_cast<const float2*>(tile + o);
-          const float oldv[2] = {old.x, old.y}, numv[2] = {nu[nt][h].x, nu[nt][h].y};
-          float gn[2] = {0.f, 0.f}, gd[2] = {0.f, 0.f};
-          if (FIT && k < p.Kg) {
-            const CovDesc d = p.cov.d[rowcov[k]];
-            const int cbase = rowc0[rowcov[k]];
-            const float scale = (p.loss_type == LOSS_KL) ? scale_kl * d.lam : scale_fr * d.lam;
-            for (int c = 0; c < d.c; ++c) {
-              const float lb = scale * Bs[d.q_off + c * d.k + (k - d.row0)];
-              const float2 r = *reinterpret_cast<const float2*>(rn + (cbase + c) * kUpdCols + cl);
-              gn[0] += lb * r.x, gn[1] += lb * r.y;
-              if (p.loss_type != LOSS_KL) {
-                const float2 q = *reinterpret_cast<const float2*>(rd + (cbase + c) * kUpdCols + cl);
-                gd[0] += lb * q.x, gd[1] += lb * q.y;
-              }
-            }
-            if (p.loss_type == LOSS_KL) gd[0] = gd[1] = dcol[k];
+    for (int e = tid; e < K * 16; e += kUpdThreads) {
+      const int k = e >> 4, c4 = e & 15;
+      const long long col = c0 + 4 * c4;
+      float* cell = tile + k * kUpdPitch + 4 * c4;
+      if (col >= p.n) {
+        *reinterpret_cast<float4*>(cell) = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      const float4 num4 = slot_load4(p.num, k, col, n0, n1);
+      const float4 z4 = slot_load4(p.z, k, col, z0, z1);
+      const float4 old4 = *reinterpret_cast<const float4*>(cell);
+      const float oldv[4] = {old4.x, old4.y, old4.z, old4.w}, numv[4] = {num4.x, num4.y, num4.z, num4.w};
+      const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
+      float gn[4] = {0.f, 0.f, 0.f, 0.f}, gd[4] = {0.f, 0.f, 0.f, 0.f};
+      if (FIT && k < p.Kg) {
+        const CovDesc d = p.cov.d[rowcov[k]];
+        const int cbase = rowc0[rowcov[k]];
+        const float scale = (p.loss_type == LOSS_KL) ? d.lam : 2.0f * d.lam;
+        for (int c = 0; c < d.c; ++c) {
+          const float lb = scale * Bs[d.q_off + c * d.k + (k - d.row0)];
+          const float4 r = *reinterpret_cast<const float4*>(rn + (cbase + c) * kUpdCols + 4 * c4);
+          gn[0] += lb * r.x, gn[1] += lb * r.y, gn[2] += lb * r.z, gn[3] += lb * r.w;
+          if (p.loss_type != LOSS_KL) {
+            const float4 q = *reinterpret_cast<const float4*>(rd + (cbase + c) * kUpdCols + 4 * c4);
+            gd[0] += lb * q.x, gd[1] += lb * q.y, gd[2] += lb * q.z, gd[3] += lb * q.w;
           }
-          float outv[2];
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const float num = gn[x] + 2.0f * numv[x];                        // main.py:648, 653 / 706
-            const float den = fmaxf(gd[x] + 2.0f * acc[nt][2 * h + x], p.eps);  // main.py:649, 654-655 / 707-708
-            outv[x] = (c0 + cl + x < p.n) ? oldv[x] * (num / den) : 0.f;     // main.py:656 / 709
-            if (FIT) t1 += static_cast<double>(numv[x]) * static_cast<double>(outv[x]);
-          }
-          put2(tile, thi, tlo, o, outv[0], outv[1]);
         }
+        if (p.loss_type == LOSS_KL) gd[0] = gd[1] = gd[2] = gd[3] = dcol[k];
+      }
+      float outv[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) {
+        const float num = gn[x] + 2.0f * numv[x];               // main.py:648, 653 / 706
+        const float den = fmaxf(gd[x] + 2.0f * zv[x], p.eps);   // main.py:649, 654-655 / 707-708
+        outv[x] = (col + x < p.n) ? oldv[x] * (num / den) : 0.f;  // main.py:656 / 709
+        if (FIT) t1 += static_cast<double>(numv[x]) * static_cast<double>(outv[x]);
+      }
+      const float4 out4 = make_float4(outv[0], outv[1], outv[2], outv[3]);
+      if (FIT) *reinterpret_cast<float4*>(cell) = out4;  // the statistics below read the new tile
+      store4(out4, k, col, p.n, p.H, p.ldH, p.split_hi, p.split_lo, p.ld_split, 0, nullptr);
     }
-    __syncthreads();  // the tile and its hi / lo copies hold the new H
-    store_tile(tile, thi, tlo, p.H, p.ldH, K, c0, p.n, p.split_hi, p.split_lo, p.ld_split, 0, nullptr);
     if (FIT) {
+      __syncthreads();  // the tile holds the new H
       // statistics of (new H, new B): rho' = Y / max(B H_i, eps) per cell, prediction loss (main.py:727-748)
       const int j = tid & 63;
       const bool live = c0 + j < p.n;
@@ -643,27 +361,38 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
         if (slot == 0) pl0 += pl; else pl1 += pl;
       }
       __syncthreads();  // rn now holds rho' of the new H
-      // Q_i += rho' H_i^T over this tile's cells; row sums of the new H  (one owner thread per entry: fixed order)
-      for (int e = tid; e < p.q_total + K; e += kUpdThreads) {
-        if (e < p.q_total) {
-          int i = 0;
-          while (i + 1 < p.cov.n_cov && e >= p.cov.d[i + 1].q_off) ++i;
-          const CovDesc d = p.cov.d[i];
-          const int c = (e - d.q_off) / d.k, k = (e - d.q_off) - c * d.k;
-          const float* rrow = rn + (rowc0[i] + c) * kUpdCols;
-          const float* hrow = tile + (d.row0 + k) * kUpdPitch;
-          float a = 0.f;
-          for (int u = 0; u < kUpdCols; ++u) a += rrow[u] * hrow[u];
-          qacc[e] += a;
-        } else {
-          const int k = e - p.q_total;
-          const float* hrow = tile + k * kUpdPitch;
-          float a = 0.f;
-          for (int u = 0; u < kUpdCols; ++u) a += hrow[u];
-          hacc[k] += a;
+      // Q_i += rho' H_i^T over this tile's cells; row sums of the new H.  One (entry, quarter) per thread, the four
+      // quarters of an entry are combined in a fixed order by the owner lane.
+      const int n_items = 4 * (p.q_total + K);
+      for (int e0 = 0; e0 < n_items; e0 += kUpdThreads) {  // (warp-uniform trip count: the shuffles below are full-warp)
+        const int e = e0 + tid;
+        const int ent = e >> 2, quarter = e & 3;
+        float a = 0.f;
+        if (e < n_items) {
+          if (ent < p.q_total) {
+            int i = 0;
+            while (i + 1 < p.cov.n_cov && ent >= p.cov.d[i + 1].q_off) ++i;
+            const CovDesc d = p.cov.d[i];
+            const int c = (ent - d.q_off) / d.k, k = (ent - d.q_off) - c * d.k;
+            const float* rrow = rn + (rowc0[i] + c) * kUpdCols + 16 * quarter;
+            const float* hrow = tile + (d.row0 + k) * kUpdPitch + 16 * quarter;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) a += rrow[u] * hrow[u];
+          } else {
+            const float* hrow = tile + (ent - p.q_total) * kUpdPitch + 16 * quarter;
+#pragma unroll
+            for (int u = 0; u < 16; ++u) a += hrow[u];
+          }
+        }
+        // the four quarters of an entry sit in adjacent lanes (e is a multiple of 4 at quarter 0)
+        const float a1 = __shfl_down_sync(0xffffffffu, a, 1);
+        const float a2 = __shfl_down_sync(0xffffffffu, a, 2);
+        const float a3 = __shfl_down_sync(0xffffffffu, a, 3);
+        if (e < n_items && quarter == 0) {
+          const float s = (a + a1) + (a2 + a3);
+          if (ent < p.q_total) qacc[ent] += s; else hacc[ent - p.q_total] += s;
         }
       }
-      gram_tile<G::NBW>(p.gram_partial, G::gram_floats, first, thi, tlo, bmt, bnt, warp, lane);
     }
   }
   cp_async_wait_all();
@@ -677,7 +406,7 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
   __syncthreads();
   if (tid == 0) {
     double s = 0.0;
-    for (int w = 0; w < kUpdWarps; ++w) s += red[w];
+    for (int w = 0; w < kUpdThreads / 32; ++w) s += red[w];
     p.t1_partial[blockIdx.x] = s;
   }
   // prediction loss: warps (2i, 2i+1) hold covariate i in pl0 and covariate i + 4 in pl1
@@ -695,52 +424,43 @@ __global__ void __launch_bounds__(kUpdThreads, 1) h_update_kernel(const HUpdPara
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// Finish kernels: fixed-order sums of the per-CTA partials
-struct GramReduce {
-  const float* partial;  // [n_parts][gram_floats]
-  int n_parts, NC, K;
-  float* out;            // [K][ld]
+// Finish kernels
+// K x K Gram matrix from the slots of its contraction (one super-tile: rows = components): out[k][r] = sum over the
+// slots, in list order.  32 lanes share an output element's slots (strided) and are combined by a fixed shuffle
+// tree, so that the many small loads overlap.  Also writes the tf32 hi / lo copies (B operand of the next Z plan).
+struct GramFromSlots {
+  SlotSrc src;       // slots [K][256] of the Gram plan (rows r < K are meaningful)
+  int K;
+  float* out;        // [K][ld]
   int ld;
+  float* split_hi;   // [K][ld_split] or nullptr
+  float* split_lo;
+  int ld_split;
 };
-// one thread per float4 of the fragment layout; off-diagonal blocks are mirrored
-__device__ __forceinline__ void gram_reduce_thread(const GramReduce& r, int idx) {
-  const int NB = r.NC * (r.NC + 1) / 2;
-  const int NBW = (NB + kUpdWarps - 1) / kUpdWarps;
-  const int gram_floats = NBW * kUpdWarps * 2 * 32 * 4;
-  if (idx >= NBW * kUpdWarps * 2 * 32) return;
-  const int lane = idx & 31, j = (idx >> 5) & 1, w = (idx >> 6) % kUpdWarps, i = (idx >> 6) / kUpdWarps;
-  const int b = w + kUpdWarps * i;
-  if (b >= NB) return;
-  int mt, nt;
-  gram_block_decode(b, r.NC, mt, nt);
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* src = reinterpret_cast<const float4*>(r.partial) + idx;
-#pragma unroll 4
-  for (int q = 0; q < r.n_parts; ++q) {
-    const float4 v = __ldcg(src + static_cast<size_t>(q) * (gram_floats / 4));
-    acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
-  }
-  const int g = lane >> 2, t = lane & 3;
-  const int row = 16 * mt + g, col = 16 * nt + 8 * j + 2 * t;
-  const float v[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll
-  for (int x = 0; x < 4; ++x) {
-    const int rr = row + 8 * (x >> 1), cc = col + (x & 1);
-    if (rr < r.K && cc < r.K) {
-      r.out[rr * r.ld + cc] = v[x];
-      if (mt != nt) r.out[cc * r.ld + rr] = v[x];
+// one warp per output element; blockDim.x = 256 -> 8 elements per block
+__device__ __forceinline__ void gram_from_slots_warp(const GramFromSlots& g, int elem, int lane) {
+  if (elem >= g.K * g.K) return;
+  const int k = elem / g.K, r = elem - k * g.K;
+  const int s0 = __ldg(g.src.slot_ofs), s1 = __ldg(g.src.slot_ofs + 1);
+  float a = 0.f;
+  for (int q = s0 + lane; q < s1; q += 32)
+    a += __ldcg(g.src.partial + (static_cast<size_t>(__ldg(g.src.slots + q)) * g.src.K + k) * 256 + r);
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+  if (lane == 0) {
+    g.out[k * g.ld + r] = a;
+    if (g.split_hi != nullptr) {
+      uint32_t h, l;
+      ptx::split_tf32(a, h, l);
+      g.split_hi[k * g.ld_split + r] = __uint_as_float(h);
+      g.split_lo[k * g.ld_split + r] = __uint_as_float(l);
     }
   }
 }
-inline int gram_reduce_threads(int NC) {
-  const int NB = NC * (NC + 1) / 2;
-  return ((NB + kUpdWarps - 1) / kUpdWarps) * kUpdWarps * 2 * 32;
-}
 
 struct WFinishParams {
-  GramReduce gram;   // -> T = W^T W  (n_parts == 0: T comes from elsewhere)
-  int gram_blocks;
-  CovTable cov;      // B updates (main.py:615-628)
+  GramFromSlots gram;   // -> T = W^T W
+  int gram_blocks;      // 0: T comes from elsewhere
+  CovTable cov;         // B updates (main.py:615-628)
   int loss_type;
   const float* stats_q;
   const float* hsum;
@@ -750,7 +470,7 @@ struct WFinishParams {
 };
 __global__ void __launch_bounds__(256) w_finish_kernel(const WFinishParams p) {
   if (static_cast<int>(blockIdx.x) < p.gram_blocks) {
-    gram_reduce_thread(p.gram, blockIdx.x * 256 + threadIdx.x);
+    gram_from_slots_warp(p.gram, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
     return;
   }
   // the last block: every B_i, from the statistics of the old H / old B
@@ -780,7 +500,7 @@ __global__ void __launch_bounds__(256) w_finish_kernel(const WFinishParams p) {
 }
 
 struct HFinishParams {
-  GramReduce gram;   // -> S = H H^T of this shard
+  GramFromSlots gram;   // -> S = H H^T of this shard
   int gram_blocks;
   int n_parts;
   const float* hsum_partial;  // [n_parts][K]
@@ -802,18 +522,23 @@ __global__ void __launch_bounds__(256) h_finish_kernel(const HFinishParams p) {
   __shared__ double red[256];
   __shared__ unsigned int last;
   const int K = p.gram.K;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (static_cast<int>(blockIdx.x) < p.gram_blocks) {
-    gram_reduce_thread(p.gram, blockIdx.x * 256 + threadIdx.x);
+    gram_from_slots_warp(p.gram, blockIdx.x * 8 + warp, lane);
   } else {
-    for (int k = threadIdx.x; k < K; k += 256) {
+    // one warp per entry, lanes stride over the CTAs' partials, fixed shuffle tree
+    for (int e = warp; e < K + p.q_total; e += 8) {
       double a = 0.0;
-      for (int q = 0; q < p.n_parts; ++q) a += static_cast<double>(p.hsum_partial[static_cast<size_t>(q) * K + k]);
-      p.hsum[k] = static_cast<float>(a);
-    }
-    for (int e = threadIdx.x; e < p.q_total; e += 256) {
-      double a = 0.0;
-      for (int q = 0; q < p.n_parts; ++q) a += static_cast<double>(p.q_partial[static_cast<size_t>(q) * p.q_total + e]);
-      p.stats_q[e] = static_cast<float>(a);
+      if (e < K) {
+        for (int q = lane; q < p.n_parts; q += 32) a += static_cast<double>(p.hsum_partial[static_cast<size_t>(q) * K + e]);
+      } else {
+        for (int q = lane; q < p.n_parts; q += 32)
+          a += static_cast<double>(p.q_partial[static_cast<size_t>(q) * p.q_total + (e - K)]);
+      }
+      for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
+      if (lane == 0) {
+        if (e < K) p.hsum[e] = static_cast<float>(a); else p.stats_q[e - K] = static_cast<float>(a);
+      }
     }
     if (p.loss_row != nullptr) {
       for (int which = 0; which < 1 + p.n_cov; ++which) {  // t1, pred_0 ..
