@@ -126,6 +126,7 @@ struct GemmOperands {
   int k0 = 0, Kop = 0;            // component rows [k0, k0 + Kop) of the B operand take part (Kop = 0: all K)
   bool profiled = false;  // counted by alpine_profile (the two contractions over X)
   bool z_slots = false;   // partial sums go to the second slot buffer (they are consumed together with another plan's)
+  int chunk_log2 = kChunkLog2;  // TMEM accumulation chain between two fp32 flushes, in k-blocks (log2)
   // sparse X: tile lists instead of Xmem (csr_tiles.cuh)
   const long long* sp_ofs = nullptr;
   const uint2* sp_ent = nullptr;
@@ -348,7 +349,7 @@ int ensure_workspace(alpine_ctx* c, cudaStream_t st) {
   AL_TRY(ws_alloc(c, &c->sumsq_partial, 1024));
   {
     const int tiles_h = ceil_div(c->n, kUpdCols);
-    c->upd_grid_h = tiles_h < 2 * c->num_sms ? tiles_h : 2 * c->num_sms;
+    c->upd_grid_h = tiles_h < 3 * c->num_sms ? tiles_h : 3 * c->num_sms;
     c->ldK = round_up(c->K, 4);
     AL_TRY(ws_alloc(c, &c->Ssplit, 2 * K * c->ldK));
     AL_TRY(ws_alloc(c, &c->Tsplit, 2 * K * c->ldK));
@@ -510,6 +511,7 @@ size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p,
 int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop, cudaStream_t st) {
   const int rows = kRows;
   GemmParams& p = pl->p;
+  p.chunk_log2 = op.chunk_log2;
   p.partial = op.z_slots ? c->partial_z : c->partial;
   p.err = c->err;
   p.sp_ofs = op.sp_ofs;
@@ -568,15 +570,15 @@ GemmOperands plan_operands(const alpine_ctx* c, int which) {
       break;
     case PLAN_GRAM_H:  // S[b][a] = sum_j H[a][j] H[b][j]            (H H^T of main.py:599 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
-      op.Bsplit = c->Hsplit, op.ldS = c->ldN;
+      op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.chunk_log2 = 1;
       break;
     case PLAN_GRAM_W:  // T[b][a] = sum_g W^T[a][g] W^T[b][g]        (W^T W of main.py:654 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
-      op.Bsplit = c->Wsplit, op.ldS = c->ldG;
+      op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.chunk_log2 = 1;
       break;
     case PLAN_ZW:      // Z[k][g] = sum_k' S[k][k'] W^T[k'][g]      ((2W) @ H @ H^T of main.py:599 after the reformulation)
       op.orient = ORIENT_XH, op.Xmem = c->WT, op.ldX = c->ldG, op.rows = c->K, op.cols = c->G;
-      op.Bsplit = c->Ssplit, op.ldS = c->ldK, op.z_slots = true;
+      op.Bsplit = c->Ssplit, op.ldS = c->ldK, op.z_slots = true, op.chunk_log2 = 0;
       if (c->peer_on()) {
         // only this rank's gene slice: the peers store their new slices into the other columns of W^T while this
         // product may still be running
@@ -587,7 +589,7 @@ GemmOperands plan_operands(const alpine_ctx* c, int which) {
       break;
     case PLAN_ZH:      // Z[k][j] = sum_k' T[k][k'] H[k'][j]        ((2W^T) @ (W @ H) of main.py:654 after the reformulation)
       op.orient = ORIENT_XH, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
-      op.Bsplit = c->Tsplit, op.ldS = c->ldK, op.z_slots = true;
+      op.Bsplit = c->Tsplit, op.ldS = c->ldK, op.z_slots = true, op.chunk_log2 = 0;
       break;
     default: {         // A[k][j] = sum_g X[j][g] W^T[k][g] for the rows k of one component block     (main.py:567)
       op = plan_operands(c, PLAN_WX);
@@ -737,7 +739,7 @@ SlotSrc src_direct(const float* a, long long ld) {
 int launch_w_update(alpine_ctx* c, const WUpdParams& p, cudaStream_t st) {
   const long long tiles = ceil_div(p.col1 - p.col0, kUpdCols);
   if (tiles <= 0) return ALPINE_OK;
-  const int grid = static_cast<int>(tiles < 2 * c->num_sms ? tiles : 2 * c->num_sms);
+  const int grid = static_cast<int>(tiles < 3 * c->num_sms ? tiles : 3 * c->num_sms);
   w_update_kernel<<<grid, kUpdThreads, w_update_smem_bytes(c->K), st>>>(p);
   LAUNCH_CHECK();
   return ALPINE_OK;
@@ -904,7 +906,7 @@ int64_t alpine_workspace_bytes(const alpine_ctx* c) {
   b += ws_bytes(sl_blocks, 8) + ws_bytes(sl_blocks * K, f) + ws_bytes(1024, 8) + 4 * kWsAlign;
   b += ws_bytes(static_cast<size_t>(c->reduce_floats()), f);
   {
-    const size_t gh = ceil_div(c->n, kUpdCols) < 2 * c->num_sms ? ceil_div(c->n, kUpdCols) : 2 * c->num_sms;
+    const size_t gh = ceil_div(c->n, kUpdCols) < 3 * c->num_sms ? ceil_div(c->n, kUpdCols) : 3 * c->num_sms;
     b += 2 * ws_bytes(2 * K * round_up(c->K, 4), f) + ws_bytes(K * gh, f);
     b += ws_bytes((c->q_total > 0 ? c->q_total : 1) * gh, f) + ws_bytes((c->n_cov > 0 ? c->n_cov : 1) * gh, 8);
     b += ws_bytes(gh, 8) + kWsAlign;
@@ -1234,7 +1236,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     wf.gram.split_hi = c->Tsplit;
     wf.gram.split_lo = c->Tsplit + static_cast<size_t>(c->K) * c->ldK;
     wf.gram.ld_split = static_cast<int>(c->ldK);
-    wf.gram_blocks = ceil_div(static_cast<long long>(c->K) * c->K, 8);
+    wf.gram_blocks = gram_blocks_for(c->K);
     wf.cov = tab;
     wf.loss_type = c->loss_type;
     wf.stats_q = c->use_Q();
@@ -1283,7 +1285,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     hf.gram.split_lo = c->Ssplit + static_cast<size_t>(c->K) * c->ldK;
     hf.gram.ld_split = static_cast<int>(c->ldK);
   }
-  hf.gram_blocks = ceil_div(static_cast<long long>(c->K) * c->K, 8);
+  hf.gram_blocks = gram_blocks_for(c->K);
   hf.n_parts = c->upd_grid_h;
   hf.hsum_partial = c->hsum_part;
   hf.hsum = c->red_hsum();

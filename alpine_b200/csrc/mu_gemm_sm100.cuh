@@ -138,6 +138,9 @@ struct GemmParams {
   int sx;           // X ring depth
   int sb;           // B ring depth
   int max_segs;     // partial slots per CTA
+  int chunk_log2;   // k-blocks (2^chunk_log2) accumulated in TMEM between two round-to-nearest flushes: every MMA
+                    // adds into the accumulator with round-toward-zero, so shorter chains mean less bias (the small
+                    // K x K-deep plans use 1 or 2 k-blocks: their flushes cost nothing next to their launch)
   float* partial;   // [gridDim.x * max_segs][K][256]
   int* err;         // [8]
   // SRC_TILES: nonzeros of X grouped by (super-tile, k-block); entry = {x_tile_offset, fp32 bits}
@@ -226,7 +229,7 @@ struct RingPos {
     }
   }
 };
-constexpr int kChunk = 8;  // k-blocks accumulated in TMEM between two round-to-nearest flushes (power of two)
+constexpr int kChunkLog2 = 3;  // default: 8 k-blocks accumulated in TMEM between two round-to-nearest flushes
 
 // Fixed geometry: a super-tile is 2 MMA tiles (256 rows of X); 8 converter/epilogue warps, one thread per row.
 constexpr int kMT = 2;
@@ -266,7 +269,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int SX = p.sx, SB = p.sb;
-  constexpr int C = kChunk;
+  const int CL = p.chunk_log2, C = 1 << CL, CM = C - 1;
   const GemmSmemLayout lay = gemm_smem_layout(Kp, SX, SB);
   uint8_t* smem_x = smem + lay.x_off;
   uint8_t* smem_b = smem + lay.b_off;
@@ -484,8 +487,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       for (int li = 0; li < len; ++li, ++it, rb.advance(SB)) {
         const int t = it % kAStages;
         const int sbi = rb.s;
-        const bool c_first = (li % C) == 0;
-        const bool c_last = (li % C) == C - 1 || li == len - 1;
+        const bool c_first = (li & CM) == 0;
+        const bool c_last = (li & CM) == CM || li == len - 1;
         if (!warp_wait_bar(&bfull_bar[sbi], rb.ph, actx, ERR_MMA_BFULL, it, sbi) ||
             !warp_wait_bar(&cfull_bar[t], (it / kAStages) & 1, actx, ERR_MMA_CFULL, it, t)) {
           ok = false;
@@ -571,7 +574,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         const int t = it % kAStages;
         // ---- lagged flush: the chunk that ended kAStages k-blocks ago (its MMAs are the ones the aempty wait
         //      below waits for anyway), overlapped with the other tile's MMAs
-        if (li >= kAStages && ((li - kAStages) % C) == C - 1) {
+        if (li >= kAStages && ((li - kAStages) & CM) == CM) {
           if (!flush()) {
             ok = false;
             break;
@@ -621,8 +624,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       }
       if (!ok) break;
       // ---- remaining chunks of this segment, then the segment's sum -> partial-sum slot [K][256]
-      const int n_chunks = (len + C - 1) / C;
-      const int flushed = (len >= kAStages) ? (len - kAStages) / C : 0;
+      const int n_chunks = (len + C - 1) >> CL;
+      const int flushed = (len >= kAStages) ? (len - kAStages) >> CL : 0;
       for (int r = flushed; r < n_chunks && ok; ++r) ok = flush();
       if (!ok) break;
       float* dst = p.partial + (static_cast<size_t>(cta) * p.max_segs + seg) * p.K * kRows + row;

@@ -48,24 +48,42 @@ struct SlotSrc {
   int K;                // components per slot
   long long origin;     // column of the caller's matrix that is row 0 of the plan's first super-tile
 };
+// The slot ids of the tile's super-tile are staged in shared memory once per tile (ids[0 .. n)), so the loads of an
+// element are independent of each other; they are issued four at a time and added in list order.
+constexpr int kMaxTileSlots = 96;
+// (a super-tile with more slots than the staging array -- very long reductions cut into many pieces -- is read
+// through the global list instead)
+__device__ __forceinline__ int stage_slot_ids(const SlotSrc& s, long long c0, int* ids, const int** idp) {
+  *idp = ids;
+  if (s.direct != nullptr) return 0;
+  const long long t = (c0 - s.origin) >> 8;
+  const int s0 = __ldg(s.slot_ofs + t), n = __ldg(s.slot_ofs + t + 1) - s0;
+  if (n > kMaxTileSlots) {
+    *idp = s.slots + s0;
+    return n;
+  }
+  for (int q = threadIdx.x; q < n; q += kUpdThreads) ids[q] = __ldg(s.slots + s0 + q);
+  return n;
+}
 // four adjacent columns (col .. col + 3) of row k; col % 4 == 0
-__device__ __forceinline__ float4 slot_load4(const SlotSrc& s, int k, long long col, int s0, int s1) {
+__device__ __forceinline__ float4 slot_load4(const SlotSrc& s, int k, long long col, const int* ids, int n) {
   if (s.direct != nullptr) return __ldg(reinterpret_cast<const float4*>(s.direct + static_cast<long long>(k) * s.ld + col));
-  const int r = static_cast<int>((col - s.origin) & 255);
+  const float* base = s.partial + static_cast<size_t>(k) * 256 + static_cast<int>((col - s.origin) & 255);
+  const size_t stride = static_cast<size_t>(s.K) * 256;
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int q = s0; q < s1; ++q) {
-    const float4 v = __ldcg(reinterpret_cast<const float4*>(
-        s.partial + (static_cast<size_t>(__ldg(s.slots + q)) * s.K + k) * 256 + r));
+  int q = 0;
+  for (; q + 4 <= n; q += 4) {
+    float4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldcg(reinterpret_cast<const float4*>(base + ids[q + u] * stride));
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc.x += v[u].x, acc.y += v[u].y, acc.z += v[u].z, acc.w += v[u].w;
+  }
+  for (; q < n; ++q) {
+    const float4 v = __ldcg(reinterpret_cast<const float4*>(base + ids[q] * stride));
     acc.x += v.x, acc.y += v.y, acc.z += v.z, acc.w += v.w;
   }
   return acc;
-}
-__device__ __forceinline__ void slot_range(const SlotSrc& s, long long c0, int& s0, int& s1) {
-  s0 = s1 = 0;
-  if (s.direct == nullptr) {
-    s0 = __ldg(s.slot_ofs + ((c0 - s.origin) >> 8));
-    s1 = __ldg(s.slot_ofs + ((c0 - s.origin) >> 8) + 1);
-  }
 }
 
 // rows [0, K) x 64 columns [c0, c0 + 64) of Mat [K][ld] -> tile [K][68]; columns >= L arrive as zeros
@@ -138,8 +156,9 @@ inline size_t w_update_smem_bytes(int K) {
   return static_cast<size_t>(2) * K * kUpdPitch * sizeof(float) + kUpdCols * sizeof(double) + 16;
 }
 
-__global__ void __launch_bounds__(kUpdThreads) w_update_kernel(const WUpdParams p) {
+__global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
+  __shared__ int ids_num[kMaxTileSlots], ids_z[kMaxTileSlots];
   const int K = p.K;
   float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]
   double* cs = reinterpret_cast<double*>(tiles + 2 * K * kUpdPitch);
@@ -151,11 +170,10 @@ __global__ void __launch_bounds__(kUpdThreads) w_update_kernel(const WUpdParams 
   for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1) {
     const float* tile = tiles + buf * K * kUpdPitch;
     const long long c0 = p.col0 + tile_i * kUpdCols;
-    int n0, n1, z0, z1;
-    slot_range(p.num, c0, n0, n1);
-    slot_range(p.z, c0, z0, z1);
     cp_async_wait_all();
-    __syncthreads();  // the tile has landed; everybody is done with the other buffer
+    __syncthreads();  // the tile has landed; everybody is done with the other buffer and the slot ids
+    const int *idn, *idz;
+    const int nn = stage_slot_ids(p.num, c0, ids_num, &idn), nz = stage_slot_ids(p.z, c0, ids_z, &idz);
     const long long next = tile_i + gridDim.x;
     if (next < n_tiles)
       load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.WT, p.ldG, K, p.col0 + next * kUpdCols, p.col1);
@@ -170,8 +188,8 @@ __global__ void __launch_bounds__(kUpdThreads) w_update_kernel(const WUpdParams 
       const int k = e >> 4, c4 = e & 15;
       const long long col = c0 + 4 * c4;
       if (col >= p.col1) continue;
-      const float4 num4 = slot_load4(p.num, k, col, n0, n1);
-      const float4 z4 = slot_load4(p.z, k, col, z0, z1);
+      const float4 num4 = slot_load4(p.num, k, col, idn, nn);
+      const float4 z4 = slot_load4(p.z, k, col, idz, nz);
       const float4 old4 = *reinterpret_cast<const float4*>(tile + k * kUpdPitch + 4 * c4);
       const float oldv[4] = {old4.x, old4.y, old4.z, old4.w}, numv[4] = {num4.x, num4.y, num4.z, num4.w};
       const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -222,8 +240,9 @@ inline size_t h_update_smem_bytes(int K, int Kg, int c_total, int q_total) {
 
 // FIT: the full update with statistics; otherwise the transform update H *= 2A / max(2 T H, eps) (main.py:705-709)
 template <bool FIT>
-__global__ void __launch_bounds__(kUpdThreads) h_update_kernel(const HUpdParams p) {
+__global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
+  __shared__ int ids_num[kMaxTileSlots], ids_z[kMaxTileSlots];
   const int K = p.K;
   const int q_pad = (p.q_total + 3) & ~3;           // keeps the arrays behind 16-byte aligned
   float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]: old H, overwritten with the new H
@@ -267,11 +286,11 @@ __global__ void __launch_bounds__(kUpdThreads) h_update_kernel(const HUpdParams 
   for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1) {
     float* tile = tiles + buf * K * kUpdPitch;
     const long long c0 = tile_i * kUpdCols;
-    int n0, n1, z0, z1;
-    slot_range(p.num, c0, n0, n1);
-    slot_range(p.z, c0, z0, z1);
     cp_async_wait_all();
     __syncthreads();  // the tile has landed (also orders the set-up above); everybody is done with the other buffer
+    const int *idn, *idz;
+    const int nn = stage_slot_ids(p.num, c0, ids_num, &idn), nz = stage_slot_ids(p.z, c0, ids_z, &idz);
+    if (!FIT) __syncthreads();  // (FIT: the barrier after the guided terms publishes the ids)
     const long long next = tile_i + gridDim.x;
     if (next < n_tiles) load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.H, p.ldH, K, next * kUpdCols, p.n);
     if (FIT) {
@@ -299,8 +318,8 @@ __global__ void __launch_bounds__(kUpdThreads) h_update_kernel(const HUpdParams 
         *reinterpret_cast<float4*>(cell) = make_float4(0.f, 0.f, 0.f, 0.f);
         continue;
       }
-      const float4 num4 = slot_load4(p.num, k, col, n0, n1);
-      const float4 z4 = slot_load4(p.z, k, col, z0, z1);
+      const float4 num4 = slot_load4(p.num, k, col, idn, nn);
+      const float4 z4 = slot_load4(p.z, k, col, idz, nz);
       const float4 old4 = *reinterpret_cast<const float4*>(cell);
       const float oldv[4] = {old4.x, old4.y, old4.z, old4.w}, numv[4] = {num4.x, num4.y, num4.z, num4.w};
       const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -437,20 +456,29 @@ struct GramFromSlots {
   float* split_lo;
   int ld_split;
 };
-// one warp per output element; blockDim.x = 256 -> 8 elements per block
-__device__ __forceinline__ void gram_from_slots_warp(const GramFromSlots& g, int elem, int lane) {
-  if (elem >= g.K * g.K) return;
-  const int k = elem / g.K, r = elem - k * g.K;
+// one block per (component k, group of 32 rows r): lanes = 32 consecutive r (128-byte coalesced reads of a slot row),
+// the 8 warps take the slots round-robin and are combined in a fixed order
+inline int gram_blocks_for(int K) { return K * ((K + 31) / 32); }
+__device__ __forceinline__ void gram_from_slots_block(const GramFromSlots& g, int b, float (*red)[32]) {
+  const int RG = (g.K + 31) >> 5;
+  const int k = b / RG, rg = b - k * RG;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r = rg * 32 + lane;
   const int s0 = __ldg(g.src.slot_ofs), s1 = __ldg(g.src.slot_ofs + 1);
   float a = 0.f;
-  for (int q = s0 + lane; q < s1; q += 32)
-    a += __ldcg(g.src.partial + (static_cast<size_t>(__ldg(g.src.slots + q)) * g.src.K + k) * 256 + r);
-  for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-  if (lane == 0) {
-    g.out[k * g.ld + r] = a;
+  if (r < g.K)
+    for (int q = s0 + w; q < s1; q += 8)
+      a += __ldcg(g.src.partial + (static_cast<size_t>(__ldg(g.src.slots + q)) * g.src.K + k) * 256 + r);
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && r < g.K) {
+    float t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][lane];
+    g.out[k * g.ld + r] = t;
     if (g.split_hi != nullptr) {
       uint32_t h, l;
-      ptx::split_tf32(a, h, l);
+      ptx::split_tf32(t, h, l);
       g.split_hi[k * g.ld_split + r] = __uint_as_float(h);
       g.split_lo[k * g.ld_split + r] = __uint_as_float(l);
     }
@@ -469,8 +497,9 @@ struct WFinishParams {
   float eps;
 };
 __global__ void __launch_bounds__(256) w_finish_kernel(const WFinishParams p) {
+  __shared__ float gred[8][32];
   if (static_cast<int>(blockIdx.x) < p.gram_blocks) {
-    gram_from_slots_warp(p.gram, blockIdx.x * 8 + (threadIdx.x >> 5), threadIdx.x & 31);
+    gram_from_slots_block(p.gram, blockIdx.x, gred);
     return;
   }
   // the last block: every B_i, from the statistics of the old H / old B
@@ -520,11 +549,12 @@ struct HFinishParams {
 // then in memory) takes t2 = sum T .* S in a fixed order.
 __global__ void __launch_bounds__(256) h_finish_kernel(const HFinishParams p) {
   __shared__ double red[256];
+  __shared__ float gred[8][32];
   __shared__ unsigned int last;
   const int K = p.gram.K;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (static_cast<int>(blockIdx.x) < p.gram_blocks) {
-    gram_from_slots_warp(p.gram, blockIdx.x * 8 + warp, lane);
+    gram_from_slots_block(p.gram, blockIdx.x, gred);
   } else {
     // one warp per entry, lanes stride over the CTAs' partials, fixed shuffle tree
     for (int e = warp; e < K + p.q_total; e += 8) {
