@@ -390,9 +390,10 @@ int set_kernel_attrs() {
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_H>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
-  CU_TRY(cudaFuncSetAttribute(w_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CU_TRY(cudaFuncSetAttribute(h_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
-  CU_TRY(cudaFuncSetAttribute(h_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+  const int upd = big - 2048;  // (these kernels also hold a little static shared memory)
+  CU_TRY(cudaFuncSetAttribute(w_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
   CU_TRY(cudaFuncSetAttribute(cov_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU_TRY(cudaFuncSetAttribute(guided_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return ALPINE_OK;
@@ -750,7 +751,7 @@ int launch_h_update(alpine_ctx* c, const HUpdParams& p, cudaStream_t st) {
   const int grid = c->upd_grid_h;
   if (grid <= 0) return ALPINE_OK;
   const size_t smem = h_update_smem_bytes(c->K, p.Kg, p.c_total, p.q_total);
-  if (smem > 227 * 1024)
+  if (smem > 225 * 1024)
     return fail(ALPINE_ERR_ARG, "covariate blocks too large for the H update kernel (%zu bytes of shared memory)", smem);
   h_update_kernel<FIT><<<grid, kUpdThreads, smem, st>>>(p);
   LAUNCH_CHECK();
