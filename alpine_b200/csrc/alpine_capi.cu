@@ -1300,7 +1300,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   hf.ldT = c->K;
   hf.loss_row = c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov);
   hf.counter = c->finish_counter;
-  h_finish_kernel<<<hf.gram_blocks + 1, 256, 0, st>>>(hf);
+  h_finish_kernel<<<hf.gram_blocks + h_finish_stat_blocks(c->K, c->q_total), 256, 0, st>>>(hf);
   LAUNCH_CHECK();
   return ALPINE_OK;
 }

@@ -86,6 +86,28 @@ __device__ __forceinline__ float4 slot_load4(const SlotSrc& s, int k, long long 
   return acc;
 }
 
+// the common case of at most two slots (or a finished array): both loads are issued without being consumed, so that
+// a thread can have the loads of several elements in flight; sum = a + b
+struct SlotPair {
+  float4 a, b;
+};
+__device__ __forceinline__ SlotPair slot_load_pair(const SlotSrc& s, int k, long long col, const int* ids, int n) {
+  SlotPair r;
+  r.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.direct != nullptr) {
+    r.a = __ldg(reinterpret_cast<const float4*>(s.direct + static_cast<long long>(k) * s.ld + col));
+    return r;
+  }
+  const float* base = s.partial + static_cast<size_t>(k) * 256 + static_cast<int>((col - s.origin) & 255);
+  const size_t stride = static_cast<size_t>(s.K) * 256;
+  r.a = n > 0 ? __ldcg(reinterpret_cast<const float4*>(base + ids[0] * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n > 1) r.b = __ldcg(reinterpret_cast<const float4*>(base + ids[1] * stride));
+  return r;
+}
+__device__ __forceinline__ float4 pair_sum(const SlotPair& p) {
+  return make_float4(p.a.x + p.b.x, p.a.y + p.b.y, p.a.z + p.b.z, p.a.w + p.b.w);
+}
+
 // rows [0, K) x 64 columns [c0, c0 + 64) of Mat [K][ld] -> tile [K][68]; columns >= L arrive as zeros
 __device__ __forceinline__ void load_tile_async(float* tile, const float* __restrict__ Mat, long long ld, int K,
                                                 long long c0, long long L) {
@@ -184,12 +206,9 @@ __global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdPara
       cs[tid] = sacc;
     }
     __syncthreads();
-    for (int e = tid; e < K * 16; e += kUpdThreads) {
+    auto update = [&](int e, float4 num4, float4 z4) {
       const int k = e >> 4, c4 = e & 15;
       const long long col = c0 + 4 * c4;
-      if (col >= p.col1) continue;
-      const float4 num4 = slot_load4(p.num, k, col, idn, nn);
-      const float4 z4 = slot_load4(p.z, k, col, idz, nz);
       const float4 old4 = *reinterpret_cast<const float4*>(tile + k * kUpdPitch + 4 * c4);
       const float oldv[4] = {old4.x, old4.y, old4.z, old4.w}, numv[4] = {num4.x, num4.y, num4.z, num4.w};
       const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -204,6 +223,25 @@ __global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdPara
       }
       store4(make_float4(outv[0], outv[1], outv[2], outv[3]), k, col, p.col1, p.WT, p.ldG, p.split_hi, p.split_lo, p.ldG,
              p.n_peers, p.wt_peer);
+    };
+    const int n_items = K * 16;
+    if (nn <= 2 && nz <= 2) {
+      // two elements per thread and round: their (up to eight) loads are in flight together
+      for (int e = tid; e < n_items; e += 2 * kUpdThreads) {
+        const int e2 = e + kUpdThreads;
+        const bool v1 = c0 + 4 * (e & 15) < p.col1, v2 = e2 < n_items && c0 + 4 * (e2 & 15) < p.col1;
+        SlotPair n1{}, z1{}, n2{}, z2{};
+        if (v1) n1 = slot_load_pair(p.num, e >> 4, c0 + 4 * (e & 15), idn, nn), z1 = slot_load_pair(p.z, e >> 4, c0 + 4 * (e & 15), idz, nz);
+        if (v2) n2 = slot_load_pair(p.num, e2 >> 4, c0 + 4 * (e2 & 15), idn, nn), z2 = slot_load_pair(p.z, e2 >> 4, c0 + 4 * (e2 & 15), idz, nz);
+        if (v1) update(e, pair_sum(n1), pair_sum(z1));
+        if (v2) update(e2, pair_sum(n2), pair_sum(z2));
+      }
+    } else {
+      for (int e = tid; e < n_items; e += kUpdThreads) {
+        const long long col = c0 + 4 * (e & 15);
+        if (col >= p.col1) continue;
+        update(e, slot_load4(p.num, e >> 4, col, idn, nn), slot_load4(p.z, e >> 4, col, idz, nz));
+      }
     }
     // (the next iteration's first barrier separates these reads from the prefetch into this buffer two tiles on)
   }
@@ -310,16 +348,10 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
       }
       __syncthreads();  // rn / rd are complete
     }
-    for (int e = tid; e < K * 16; e += kUpdThreads) {
+    auto update = [&](int e, float4 num4, float4 z4) {
       const int k = e >> 4, c4 = e & 15;
       const long long col = c0 + 4 * c4;
       float* cell = tile + k * kUpdPitch + 4 * c4;
-      if (col >= p.n) {
-        *reinterpret_cast<float4*>(cell) = make_float4(0.f, 0.f, 0.f, 0.f);
-        continue;
-      }
-      const float4 num4 = slot_load4(p.num, k, col, idn, nn);
-      const float4 z4 = slot_load4(p.z, k, col, idz, nz);
       const float4 old4 = *reinterpret_cast<const float4*>(cell);
       const float oldv[4] = {old4.x, old4.y, old4.z, old4.w}, numv[4] = {num4.x, num4.y, num4.z, num4.w};
       const float zv[4] = {z4.x, z4.y, z4.z, z4.w};
@@ -350,6 +382,24 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
       const float4 out4 = make_float4(outv[0], outv[1], outv[2], outv[3]);
       if (FIT) *reinterpret_cast<float4*>(cell) = out4;  // the statistics below read the new tile
       store4(out4, k, col, p.n, p.H, p.ldH, p.split_hi, p.split_lo, p.ld_split, 0, nullptr);
+    };
+    const int n_items = K * 16;
+    if (nn <= 2 && nz <= 2) {
+      // two elements per thread and round: their (up to eight) loads are in flight together
+      for (int e = tid; e < n_items; e += 2 * kUpdThreads) {
+        const int e2 = e + kUpdThreads;
+        const bool v1 = c0 + 4 * (e & 15) < p.n, v2 = e2 < n_items && c0 + 4 * (e2 & 15) < p.n;
+        SlotPair n1{}, z1{}, n2{}, z2{};
+        if (v1) n1 = slot_load_pair(p.num, e >> 4, c0 + 4 * (e & 15), idn, nn), z1 = slot_load_pair(p.z, e >> 4, c0 + 4 * (e & 15), idz, nz);
+        if (v2) n2 = slot_load_pair(p.num, e2 >> 4, c0 + 4 * (e2 & 15), idn, nn), z2 = slot_load_pair(p.z, e2 >> 4, c0 + 4 * (e2 & 15), idz, nz);
+        if (v1) update(e, pair_sum(n1), pair_sum(z1));
+        if (v2) update(e2, pair_sum(n2), pair_sum(z2));
+      }
+    } else {
+      for (int e = tid; e < n_items; e += kUpdThreads) {
+        if (c0 + 4 * (e & 15) >= p.n) continue;
+        update(e, slot_load4(p.num, e >> 4, c0 + 4 * (e & 15), idn, nn), slot_load4(p.z, e >> 4, c0 + 4 * (e & 15), idz, nz));
+      }
     }
     if (FIT) {
       __syncthreads();  // the tile holds the new H
@@ -545,39 +595,49 @@ struct HFinishParams {
   double* loss_row;            // [2 + n_cov] or nullptr
   unsigned int* counter;       // zero before the first launch; left zero
 };
-// blocks [0, gram_blocks): Gram; block gram_blocks: hsum, Q, pred, t1.  The block that finishes last (all of S is
-// then in memory) takes t2 = sum T .* S in a fixed order.
+// fp64 column sums of 32 adjacent columns of a [n_parts][L] array of per-CTA partials: lanes = columns (coalesced), the
+// 8 warps stride over the parts and are combined in a fixed order
+__device__ __forceinline__ void colsum32_block(const float* __restrict__ part, int n_parts, int L, int c0,
+                                               float* __restrict__ out, double (*red)[32]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = c0 + lane;
+  double a = 0.0;
+  if (col < L)
+    for (int q = w; q < n_parts; q += 8) a += static_cast<double>(__ldcg(part + static_cast<size_t>(q) * L + col));
+  red[w][lane] = a;
+  __syncthreads();
+  if (w == 0 && col < L) {
+    double t = red[0][lane];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += red[i][lane];
+    out[col] = static_cast<float>(t);
+  }
+}
+inline int h_finish_stat_blocks(int K, int q_total) { return (K + 31) / 32 + (q_total + 31) / 32 + 1; }
+// blocks [0, gram_blocks): Gram; then ceil(K / 32) blocks of rowsum(H), ceil(q_total / 32) blocks of Q, one block of
+// scalars (t1, pred_i).  The block that finishes last (all of S is then in memory) takes t2 = sum T .* S in a fixed
+// order.
 __global__ void __launch_bounds__(256) h_finish_kernel(const HFinishParams p) {
   __shared__ double red[256];
   __shared__ float gred[8][32];
   __shared__ unsigned int last;
   const int K = p.gram.K;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (static_cast<int>(blockIdx.x) < p.gram_blocks) {
+  double (*red2)[32] = reinterpret_cast<double (*)[32]>(red);
+  const int hb = (K + 31) / 32, qb = (p.q_total + 31) / 32;
+  const int b2 = static_cast<int>(blockIdx.x) - p.gram_blocks;
+  if (b2 < 0) {
     gram_from_slots_block(p.gram, blockIdx.x, gred);
-  } else {
-    // one warp per entry, lanes stride over the CTAs' partials, fixed shuffle tree
-    for (int e = warp; e < K + p.q_total; e += 8) {
+  } else if (b2 < hb) {
+    colsum32_block(p.hsum_partial, p.n_parts, K, 32 * b2, p.hsum, red2);
+  } else if (b2 < hb + qb) {
+    colsum32_block(p.q_partial, p.n_parts, p.q_total, 32 * (b2 - hb), p.stats_q, red2);
+  } else if (p.loss_row != nullptr) {
+    for (int which = 0; which < 1 + p.n_cov; ++which) {  // t1, pred_0 ..
       double a = 0.0;
-      if (e < K) {
-        for (int q = lane; q < p.n_parts; q += 32) a += static_cast<double>(p.hsum_partial[static_cast<size_t>(q) * K + e]);
-      } else {
-        for (int q = lane; q < p.n_parts; q += 32)
-          a += static_cast<double>(p.q_partial[static_cast<size_t>(q) * p.q_total + (e - K)]);
-      }
-      for (int o = 16; o > 0; o >>= 1) a += __shfl_down_sync(0xffffffffu, a, o);
-      if (lane == 0) {
-        if (e < K) p.hsum[e] = static_cast<float>(a); else p.stats_q[e - K] = static_cast<float>(a);
-      }
-    }
-    if (p.loss_row != nullptr) {
-      for (int which = 0; which < 1 + p.n_cov; ++which) {  // t1, pred_0 ..
-        double a = 0.0;
-        for (int q = threadIdx.x; q < p.n_parts; q += 256)
-          a += which == 0 ? p.t1_partial[q] : p.pred_partial[static_cast<size_t>(q) * p.n_cov + (which - 1)];
-        const double s = block_sum_256(a, red);
-        if (threadIdx.x == 0) p.loss_row[which == 0 ? 0 : 1 + which] = s;
-      }
+      for (int q = threadIdx.x; q < p.n_parts; q += 256)
+        a += which == 0 ? p.t1_partial[q] : p.pred_partial[static_cast<size_t>(q) * p.n_cov + (which - 1)];
+      const double s = block_sum_256(a, red);
+      if (threadIdx.x == 0) p.loss_row[which == 0 ? 0 : 1 + which] = s;
     }
   }
   if (p.loss_row == nullptr) return;
@@ -587,12 +647,26 @@ __global__ void __launch_bounds__(256) h_finish_kernel(const HFinishParams p) {
   __syncthreads();
   if (last == 0u) return;
   __threadfence();
-  double a = 0.0;
-  for (int e = threadIdx.x; e < K * K; e += 256) {
-    const int r = e / K, c = e - r * K;
-    a += static_cast<double>(__ldcg(p.T + r * p.ldT + c)) * static_cast<double>(__ldcg(p.gram.out + r * p.gram.ld + c));
+  // (T and S are both K x K with pitch K here: walk them linearly, four independent loads in flight per thread)
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  const int KK = K * K;
+  if (p.ldT == K && p.gram.ld == K) {
+    int e = threadIdx.x;
+    for (; e + 768 < KK; e += 1024) {
+      const float t0 = __ldcg(p.T + e), t1 = __ldcg(p.T + e + 256), t2 = __ldcg(p.T + e + 512), t3 = __ldcg(p.T + e + 768);
+      const float s0 = __ldcg(p.gram.out + e), s1 = __ldcg(p.gram.out + e + 256), s2 = __ldcg(p.gram.out + e + 512),
+                  s3 = __ldcg(p.gram.out + e + 768);
+      a0 += static_cast<double>(t0) * s0, a1 += static_cast<double>(t1) * s1;
+      a2 += static_cast<double>(t2) * s2, a3 += static_cast<double>(t3) * s3;
+    }
+    for (; e < KK; e += 256) a0 += static_cast<double>(__ldcg(p.T + e)) * __ldcg(p.gram.out + e);
+  } else {
+    for (int e = threadIdx.x; e < KK; e += 256) {
+      const int r = e / K, c = e - r * K;
+      a0 += static_cast<double>(__ldcg(p.T + r * p.ldT + c)) * static_cast<double>(__ldcg(p.gram.out + r * p.gram.ld + c));
+    }
   }
-  const double s = block_sum_256(a, red);
+  const double s = block_sum_256((a0 + a1) + (a2 + a3), red);
   if (threadIdx.x == 0) {
     p.loss_row[1] = s;
     *p.counter = 0u;

@@ -21,7 +21,7 @@ import torch
 
 from oracle import alpine_oracle as orc
 from oracle import torch_port as tp
-from tests.helpers import CASE_KW, load_golden, rel_fro
+from tests.helpers import CASE_KW, assert_same_top_ranking, load_golden, rel_fro
 
 pytestmark = pytest.mark.gpu
 
@@ -191,8 +191,7 @@ def test_top100_rankings_of_W_and_gene_scores_match_reference_golden():
     W, H, Bs = prob.host()
     assert rel_fro(W, g[f"W_it{it}"]) < 2e-4 and rel_fro(H, g[f"H_it{it}"]) < 2e-4
     for k in range(W.shape[1]):
-        np.testing.assert_array_equal(np.argsort(-W[:, k], kind="stable")[:100],
-                                      np.argsort(-g[f"W_it{it}"][:, k], kind="stable")[:100])
+        assert_same_top_ranking(W[:, k], g[f"W_it{it}"][:, k], what=("W column", k))
     prob.solver.scale()
     W, H, Bs = prob.host()
     assert rel_fro(W, g["W_scaled"]) < 2e-4 and rel_fro(H, g["H_scaled"]) < 2e-4
@@ -217,5 +216,4 @@ def test_top100_rankings_of_W_and_gene_scores_match_reference_golden():
         assert got.shape == ref.shape
         assert rel_fro(got, ref) < 2e-4
         for c in range(ref.shape[1]):
-            np.testing.assert_array_equal(np.argsort(-got[:, c], kind="stable")[:100],
-                                          np.argsort(-ref[:, c], kind="stable")[:100])
+            assert_same_top_ranking(got[:, c], ref[:, c], what=(key, c))

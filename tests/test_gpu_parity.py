@@ -11,7 +11,8 @@ import pytest
 import torch
 
 from oracle import alpine_oracle as orc
-from tests.helpers import CASE_KW, full_batch_mu_names, golden_names, hp_of, inputs_of, load_golden, rel_fro
+from tests.helpers import (CASE_KW, assert_same_top_ranking, full_batch_mu_names, golden_names, hp_of, inputs_of,
+                           load_golden, rel_fro)
 
 pytestmark = pytest.mark.gpu
 
@@ -223,8 +224,7 @@ def test_long_run_top100_rankings_match_reference():
     Wref = g["W_it200"]
     assert rel_fro(W, Wref) < 2e-4
     for k in range(W.shape[1]):
-        np.testing.assert_array_equal(np.argsort(-W[:, k], kind="stable")[:100],
-                                      np.argsort(-Wref[:, k], kind="stable")[:100])
+        assert_same_top_ranking(W[:, k], Wref[:, k], what=("W column", k))
 
 
 @pytest.mark.parametrize("name", full_batch_mu_names())

@@ -8,7 +8,8 @@ import numpy as np
 import pytest
 
 from oracle import alpine_oracle as orc
-from tests.helpers import CASE_KW, epoch_batches, golden_names, hp_of, inputs_of, load_golden, rel_fro
+from tests.helpers import (CASE_KW, assert_same_top_ranking, epoch_batches, golden_names, hp_of, inputs_of,
+                           load_golden, rel_fro)
 
 def full_batch_mu_names_for_torch():
     from tests.helpers import full_batch_mu_names
@@ -98,9 +99,7 @@ def test_long_run_top100_rankings_match_reference():
         orc.mu_step(X, Ys, st, hp)
     Wref = g["W_it200"]
     for k in range(st.W.shape[1]):
-        top_ref = np.argsort(-Wref[:, k], kind="stable")[:100]
-        top_got = np.argsort(-st.W[:, k], kind="stable")[:100]
-        np.testing.assert_array_equal(top_got, top_ref)
+        assert_same_top_ranking(st.W[:, k], Wref[:, k], what=("W column", k))
 
 
 @pytest.mark.parametrize("name", full_batch_mu_names_for_torch())
