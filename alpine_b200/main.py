@@ -604,21 +604,30 @@ class ALPINE:
         device generator after the W / H / B draws; the weighted sampler's ``multinomial`` on the CPU generator).
 
         Per batch the cells ``idx`` are gathered into contiguous buffers (rows of the cells-major X -- or of the CSR
-        matrix --, columns of H and Y), one MU step runs on them with the same kernels as the full-batch path, and the H columns are
-        scattered back (``Hs[j][:, idx] = ...``, main.py:662; duplicate indices of the weighted sampler resolve as
-        torch's ``index_put`` does).  The loss of every epoch is evaluated on the full data (main.py:666).
+        matrix --, columns of H and Y), one MU step runs on them with the same kernels as the full-batch path, and the H
+        columns are scattered back (``Hs[j][:, idx] = ...``, main.py:662; duplicate indices of the weighted sampler
+        resolve as torch's ``index_put`` does).  The loss of every epoch is evaluated on the full data (main.py:666).
+        Under cell sharding every rank draws the same epoch indices, takes the batch's cells that fall into its own
+        column block and the batch's partial sums are all-reduced exactly like a full-batch iteration's.
         """
         from .utils.sampling import (create_joint_labels_from_dummy_matrices, generate_epoch_indices,
                                      get_batch_indices, get_num_batches)
 
-        if dist_info()[1] > 1:
-            raise NotImplementedError("mini-batch fitting is single-GPU; cell sharding covers the full-batch path")
+        rank, world = dist_info()
+        sharded = world > 1
+        lo, hi = m.shard if sharded else (0, m.H.shape[1])
+        n_total = m.n_total if sharded else m.H.shape[1]
         dev = m.W.device
         n, G = m.H.shape[1], m.W.shape[0]
         sparse = m.X_csr is not None
         K = self.total_components
-        joint_labels = create_joint_labels_from_dummy_matrices(m.Ys) if m.Ys else [""] * n
-        bs = int(min(self.batch_size, n))
+        if not m.Ys:
+            joint_labels = [""] * n_total
+        elif sharded:  # the sampler works on all cells: every rank draws the same epoch indices from the same stream
+            joint_labels = create_joint_labels_from_dummy_matrices([torch.from_numpy(y) for y in m.Ys_host])
+        else:
+            joint_labels = create_joint_labels_from_dummy_matrices(m.Ys)
+        bs = int(min(self.batch_size, n_total))
         solvers: dict = {}
 
         def batch_solver(size: int):
@@ -632,8 +641,15 @@ class ALPINE:
                 s.bind_labels(Yb)
                 s.bind_factors(m.W, Hb, m.Bs)
                 s.set_hparams(self.lam, self.alpha_W, self.l1_ratio_W, self.orth_W, self.eps)
+                if sharded:
+                    s.reduce_buffer()  # the batch's [X H^T | H H^T | ...] partials are all-reduced over the ranks
                 solvers[size] = (s, Xb, Hb, Yb)
             return solvers[size]
+
+        def all_reduce(t):
+            import torch.distributed as dist
+
+            dist.all_reduce(t)
 
         history = []
         pbar = None
@@ -659,24 +675,43 @@ class ALPINE:
                     idx = get_batch_indices(epoch_indices, b, bs)
                     if len(idx) == 0:
                         break
-                    s, Xb, Hb, Yb = batch_solver(len(idx))
-                    if sparse:  # the batch's cells as their own CSR matrix -> tile lists (once per batch)
-                        s.bind_csr(*_csr_take_rows(m.X_csr, idx))
+                    if sharded:
+                        # this rank's cells of the batch, padded with empty cells (zero rows of X, zero columns of H
+                        # and Y contribute nothing to any sum and stay zero) up to a multiple of 256, so that a handful
+                        # of contexts serves every batch; the exchange buffers have the same size on every rank
+                        loc = idx[(idx >= lo) & (idx < hi)] - lo
+                        cnt = int(loc.numel())
+                        size = max(256, (cnt + 255) // 256 * 256)
                     else:
-                        Xb.copy_(m.X_cells_major.index_select(0, idx))
-                    Hb.copy_(m.H.index_select(1, idx))
+                        loc, cnt, size = idx, len(idx), len(idx)
+                    s, Xb, Hb, Yb = batch_solver(size)
+                    if sparse:  # the batch's cells as their own CSR matrix -> tile lists (once per batch)
+                        indptr, indices, values = _csr_take_rows(m.X_csr, loc)
+                        if cnt < size:
+                            indptr = torch.cat([indptr, indptr[-1:].expand(size - cnt)])
+                        s.bind_csr(indptr.contiguous(), indices, values)
+                    else:
+                        Xb[:cnt].copy_(m.X_cells_major.index_select(0, loc))
+                        Xb[cnt:].zero_()
+                    Hb[:, :cnt].copy_(m.H.index_select(1, loc))
+                    Hb[:, cnt:].zero_()
                     for yb, y in zip(Yb, m.Ys):
-                        yb.copy_(y.index_select(1, idx))
+                        yb[:, :cnt].copy_(y.index_select(1, loc))
+                        yb[:, cnt:].zero_()
                     s.batch_begin()
                     s.mu_partials()
+                    if sharded:
+                        all_reduce(s.reduce_buffer())
                     if self.use_als:  # main.py:523-588 on the batch
                         for blk in range(s.n_blocks):
                             s.als_block(blk)
+                            if sharded and blk + 1 < s.n_blocks:
+                                all_reduce(s.gram_view())
                         s.als_finish(0)
                     else:
                         s.mu_apply(0)
                         s.sync_w()  # the next batch's context (and the per-epoch loss) read the shared row-major W
-                    m.H[:, idx] = Hb  # main.py:662; duplicates of the weighted sampler carry identical columns
+                    m.H[:, loc] = Hb[:, :cnt]  # main.py:662; duplicates of the weighted sampler carry identical columns
                 history.append(self._compute_loss(m, solver=full, xnorm2=xnorm2))
                 if pbar is not None:
                     pbar.set_postfix({"objective loss": history[-1][0]})

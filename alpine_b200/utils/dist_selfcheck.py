@@ -85,3 +85,45 @@ def sharded_vs_single(dev: torch.device, n: int = 6001, G: int = 1500, blocks: S
         ok = ok and max(eW, eH, eB, eL) < 1e-5 and eP < 1e-6 and same_w and (peer_on or not use_peer)
     res["ok"] = bool(ok)
     return res
+
+
+def minibatch_sharded_vs_single(dev: torch.device, n: int = 3001, G: int = 700, batch_size: int = 512, epochs: int = 3,
+                                sampling_method: str = "random", use_als: bool = False) -> Dict:
+    """Mini-batch ``ALPINE.fit`` under cell sharding == the same fit on one GPU (same epoch index stream: every rank
+    draws it from the same seeded generators).  Collective over the default process group."""
+    import pandas as pd
+    import torch.distributed as dist
+
+    from .. import engine as engine_mod
+    from .. import main as main_mod
+    from ..utils.anndata_compat import AnnData
+    from ..utils.synth import make_counts, make_labels
+
+    X = make_counts(n, G, seed=3, rank=6)
+    labels = make_labels(n, [3, 2], seed=3, nan_fraction=0.02)
+    obs = pd.DataFrame({f"cov{i}": pd.Series(l, dtype=object) for i, l in enumerate(labels)})
+    kw = dict(n_components=8, n_covariate_components=[3, 2], lam=[1e2, 5e1], orth_W=0.1, alpha_W=0.3, l1_ratio_W=0.5,
+              use_als=use_als, device=str(dev), random_state=7)
+
+    def fit():
+        model = main_mod.ALPINE(**kw)
+        model.fit(AnnData(X.copy(), obs=obs.copy()), ["cov0", "cov1"], batch_size=batch_size, max_iter=epochs,
+                  sampling_method=sampling_method)
+        mats = model.get_decomposed_matrices()
+        return (np.concatenate(mats["Ws"], axis=1), np.concatenate(mats["Hs"], axis=0), mats["Bs"],
+                model.loss_history.to_numpy())
+
+    Wd, Hd, Bd, hist_d = fit()
+    real_main, real_eng = main_mod.dist_info, engine_mod.dist_info
+    main_mod.dist_info = engine_mod.dist_info = lambda group=None: (0, 1)  # the same fit, unsharded, on this GPU
+    try:
+        W1, H1, B1, hist_1 = fit()
+    finally:
+        main_mod.dist_info, engine_mod.dist_info = real_main, real_eng
+    errs = np.array([_rel(Wd, W1), _rel(Hd, H1), max(_rel(a, b) for a, b in zip(Bd, B1)),
+                     float(np.max(np.abs(hist_d[:, 1] - hist_1[:, 1]) / np.abs(hist_1[:, 1])))])
+    t = torch.from_numpy(errs).to(dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    eW, eH, eB, eL = [float(v) for v in t.cpu()]
+    return {"world": dist.get_world_size(), "sampling_method": sampling_method, "use_als": use_als, "W": eW, "H": eH,
+            "B": eB, "recon_loss": eL, "ok": bool(max(eW, eH, eB, eL) < 2e-5)}

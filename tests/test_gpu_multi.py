@@ -41,3 +41,13 @@ def test_cell_sharded_fit_equals_single_gpu_fit(shape):
         assert res[mode]["W_bit_identical_across_ranks"], res
         assert max(res[mode][k] for k in ("W", "H", "B", "recon_loss")) < 1e-5, res
     assert res["peer"]["peer_exchange_active"], res
+
+
+def test_minibatch_epochs_under_cell_sharding_equal_single_gpu():
+    """batch_size < n_cells with the cells sharded (main.py:509-521 on every rank's part of the batch + the usual
+    all-reduce): random and weighted samplers and the block-wise sweep, against the same fit on one GPU."""
+    n_gpus = torch.cuda.device_count()
+    if n_gpus < 2:
+        pytest.skip("needs >= 2 GPUs (one process per GPU)")
+    res = _launch(n_gpus, ["--minibatch"])
+    assert res["ok"] and res["world"] == n_gpus, res

@@ -13,7 +13,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from alpine_b200.utils.dist_selfcheck import sharded_vs_single  # noqa: E402
+from alpine_b200.utils.dist_selfcheck import minibatch_sharded_vs_single, sharded_vs_single  # noqa: E402
 
 
 def main():
@@ -23,13 +23,19 @@ def main():
     ap.add_argument("--iters", type=int, default=8)
     ap.add_argument("--blocks", default="5,5,90")
     ap.add_argument("--cats", default="3,4")
+    ap.add_argument("--minibatch", action="store_true", help="check mini-batch epochs under cell sharding instead")
     args = ap.parse_args()
     rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    res = sharded_vs_single(dev, n=args.cells, G=args.genes, blocks=[int(v) for v in args.blocks.split(",")],
-                            cats=[int(v) for v in args.cats.split(",")], n_iter=args.iters)
+    if args.minibatch:
+        parts = [minibatch_sharded_vs_single(dev, sampling_method=m, use_als=a)
+                 for m, a in (("random", False), ("weighted", False), ("random", True))]
+        res = {"world": parts[0]["world"], "cases": parts, "ok": all(p["ok"] for p in parts)}
+    else:
+        res = sharded_vs_single(dev, n=args.cells, G=args.genes, blocks=[int(v) for v in args.blocks.split(",")],
+                                cats=[int(v) for v in args.cats.split(",")], n_iter=args.iters)
     if rank == 0:
         print("dist_check " + json.dumps(res), flush=True)
     dist.barrier()
