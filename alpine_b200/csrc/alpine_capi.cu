@@ -127,6 +127,7 @@ struct GemmOperands {
   bool profiled = false;  // counted by alpine_profile (the two contractions over X)
   bool z_slots = false;   // partial sums go to the second slot buffer (they are consumed together with another plan's)
   int chunk_log2 = kChunkLog2;  // TMEM accumulation chain between two fp32 flushes, in k-blocks (log2)
+  int group = 0;          // component group of this launch (K > 128 runs as two launches per contraction)
   // sparse X: tile lists instead of Xmem (csr_tiles.cuh)
   const long long* sp_ofs = nullptr;
   const uint2* sp_ent = nullptr;
@@ -203,8 +204,6 @@ struct alpine_ctx {
   long long ldK = 0;
   float* Ssplit = nullptr;        // [2][K][ldK]  tf32 hi / lo of the complete H H^T (B operand of Z_W)
   float* Tsplit = nullptr;        // [2][K][ldK]  tf32 hi / lo of W^T W             (B operand of Z_H)
-  float* partial_z = nullptr;     // slots of the Z plans
-  size_t partial_z_floats = 0;
   float* hsum_part = nullptr;     // [upd_grid_h][K]
   float* q_part = nullptr;        // [upd_grid_h][q_total]
   double* pred_part = nullptr;    // [upd_grid_h][n_cov]
@@ -216,8 +215,14 @@ struct alpine_ctx {
   double* loss_hist = nullptr;
   int loss_cap = 0;
   int* err = nullptr;
-  float* partial = nullptr;
-  size_t partial_floats = 0, partial_hint = 0;
+  // partial-sum slot buffers, by class = 2 * (Z plan) + component group: a Z plan's slots are consumed together
+  // with the preceding contraction's, and the two groups of one contraction together
+  float* pbuf[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t pbuf_floats[4] = {0, 0, 0, 0}, pbuf_hint[4] = {0, 0, 0, 0};
+  // component groups: the tcgen05 kernel accumulates at most 128 columns per launch
+  int n_groups = 1;
+  int gk0[2] = {0, 0}, gK[2] = {0, 0};
+  int split() const { return n_groups > 1 ? gk0[1] : 0x3fffffff; }
   float* own_reduce = nullptr;
   float* reduce = nullptr;  // [Pt K*ldG | S K*K | hsum K | Q q_total]
 
@@ -255,7 +260,7 @@ struct alpine_ctx {
     return arena != nullptr && b >= arena && b < arena + arena_size;
   }
 
-  GemmPlan plans[PLAN_COUNT];
+  GemmPlan plans[PLAN_COUNT][2];
   bool prof = false;
   std::vector<cudaEvent_t> prof_ev;  // pairs (start, stop)
   size_t prof_used = 0;
@@ -429,6 +434,7 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
 
 // Work space, grid and slot count of one contraction; returns the floats its partial-sum slots need.
 size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p, int* grid_out);
+GemmOperands plan_operands(const alpine_ctx* c, int which, int group);
 int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long long R, int Kop, cudaStream_t st);
 
 // Build the plan of one contraction (see GemmOperands).
@@ -452,27 +458,20 @@ int build_plan(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, cudaStream_t
   p.sx = sx;
   p.sb = sb;
   pl->smem = gemm_smem_layout(p.Kp, sx, sb).total + 1024;
-  // partial-sum slots: one buffer shared by the plans whose results are consumed before the next contraction runs,
-  // a second one for the Z plans (their slots are read together with the preceding contraction's)
-  if (op.z_slots) {
-    if (need > c->partial_z_floats) {
-      ws_free(c, c->partial_z);
-      c->partial_z = nullptr;
-      AL_TRY(ws_alloc(c, &c->partial_z, need));
-      c->partial_z_floats = need;
-      for (auto& other : c->plans)
-        if (other.op.z_slots) other.p.partial = c->partial_z, other.r.partial = c->partial_z;
-    }
-  } else if (need > c->partial_floats) {
-    ws_free(c, c->partial);
-    c->partial = nullptr;
+  // partial-sum slots: per class, one buffer shared by the plans whose results are consumed before the next
+  // contraction of that class runs
+  const int cls = (op.z_slots ? 2 : 0) + op.group;
+  if (need > c->pbuf_floats[cls]) {
+    ws_free(c, c->pbuf[cls]);
+    c->pbuf[cls] = nullptr;
     // with an arena, size the buffer for the largest of this context's standard plans at once (a bump allocator
     // cannot give memory back)
-    const size_t want = (c->arena != nullptr && c->partial_hint > need) ? c->partial_hint : need;
-    AL_TRY(ws_alloc(c, &c->partial, want));
-    c->partial_floats = want;
-    for (auto& other : c->plans)
-      if (!other.op.z_slots) other.p.partial = c->partial, other.r.partial = c->partial;
+    const size_t want = (c->arena != nullptr && c->pbuf_hint[cls] > need) ? c->pbuf_hint[cls] : need;
+    AL_TRY(ws_alloc(c, &c->pbuf[cls], want));
+    c->pbuf_floats[cls] = want;
+    for (auto& kind : c->plans)
+      for (auto& other : kind)
+        if ((other.op.z_slots ? 2 : 0) + other.op.group == cls) other.p.partial = c->pbuf[cls], other.r.partial = c->pbuf[cls];
   }
   return build_plan_tail(c, pl, op, R, Kop, st);
 }
@@ -513,7 +512,7 @@ int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long lo
   const int rows = kRows;
   GemmParams& p = pl->p;
   p.chunk_log2 = op.chunk_log2;
-  p.partial = op.z_slots ? c->partial_z : c->partial;
+  p.partial = c->pbuf[(op.z_slots ? 2 : 0) + op.group];
   p.err = c->err;
   p.sp_ofs = op.sp_ofs;
   p.sp_ent = op.sp_ent;
@@ -556,7 +555,7 @@ int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long lo
   return ALPINE_OK;
 }
 
-GemmOperands plan_operands(const alpine_ctx* c, int which) {
+GemmOperands plan_operands(const alpine_ctx* c, int which, int group = 0) {
   GemmOperands op;
   switch (which) {
     case PLAN_XH:  // P^T[k][g] = sum_j X[j][g] H[k][j]                                   (main.py:596)
@@ -594,11 +593,17 @@ GemmOperands plan_operands(const alpine_ctx* c, int which) {
       break;
     default: {         // A[k][j] = sum_g X[j][g] W^T[k][g] for the rows k of one component block     (main.py:567)
       op = plan_operands(c, PLAN_WX);
+      op.k0 = 0;
       const int b = which - PLAN_WX_BLOCK;
       for (int i = 0; i < b; ++i) op.k0 += c->kblk[i];
       op.Kop = c->kblk[b];
-      break;
+      return op;
     }
+  }
+  if (c->n_groups > 1) {  // this launch produces the components [gk0, gk0 + gK) of the result
+    op.group = group;
+    op.k0 = c->gk0[group];
+    op.Kop = c->gK[group];
   }
   return op;
 }
@@ -612,55 +617,62 @@ int run_split(alpine_ctx* c, const float* src, long long ld_src, long long R, fl
 }
 
 // out[k][m] (ld_out) = contraction `which`; its B operand must already be in the split workspace
-// out[k][m] (ld_out) = sum of the partial-sum slots contraction `which` has just written
+// out[k][m] (ld_out) = sum of the partial-sum slots contraction `which` has just written (all component groups)
 int reduce_slots(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_t st) {
-  const GemmPlan* pl = &c->plans[which];
-  ReduceParams r = pl->r;
-  r.out = out;
-  r.ld = ld_out;
-  if (pl->p.ws.num_tiles * 8 >= 2 * c->num_sms) {
-    int gy = ceil_div(32 * c->num_sms, pl->p.ws.num_tiles * 8);
-    const int gy_max = ceil_div(pl->p.K, 8);
-    if (gy > gy_max) gy = gy_max;
-    reduce_partials_by_k_kernel<<<dim3(pl->p.ws.num_tiles * 8, gy), 256, 0, st>>>(r);
-  } else {
-    reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, pl->p.K), 256, 0, st>>>(r);
+  const int groups = which < PLAN_WX_BLOCK ? c->n_groups : 1;
+  for (int g = 0; g < groups; ++g) {
+    const GemmPlan* pl = &c->plans[which][g];
+    ReduceParams r = pl->r;
+    r.out = out + static_cast<long long>(groups > 1 ? c->gk0[g] : 0) * ld_out;
+    r.ld = ld_out;
+    if (pl->p.ws.num_tiles * 8 >= 2 * c->num_sms) {
+      int gy = ceil_div(32 * c->num_sms, pl->p.ws.num_tiles * 8);
+      const int gy_max = ceil_div(pl->p.K, 8);
+      if (gy > gy_max) gy = gy_max;
+      reduce_partials_by_k_kernel<<<dim3(pl->p.ws.num_tiles * 8, gy), 256, 0, st>>>(r);
+    } else {
+      reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, pl->p.K), 256, 0, st>>>(r);
+    }
+    LAUNCH_CHECK();
   }
-  LAUNCH_CHECK();
   return ALPINE_OK;
 }
 
-// (out == nullptr: leave the result in the partial-sum slots; the fused update kernels add them up themselves)
+// Contraction `which` (one launch per component group).  out == nullptr: leave the result in the partial-sum slots;
+// the fused update kernels add them up themselves.  Its B operand must already be in the split workspace.
 int run_gemm(alpine_ctx* c, int which, float* out, long long ld_out, cudaStream_t st) {
-  GemmPlan* pl = &c->plans[which];
-  if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which), st));
-  const GemmOperands& op = pl->op;
+  const int groups = which < PLAN_WX_BLOCK ? c->n_groups : 1;
+  for (int g = 0; g < groups; ++g) {
+    GemmPlan* pl = &c->plans[which][g];
+    if (!pl->valid) AL_TRY(build_plan(c, pl, plan_operands(c, which, g), st));
+    const GemmOperands& op = pl->op;
 #ifdef ALPINE_B200_DEBUG_SIMT  // A/B checking builds only: the shipped library has no CUDA-core contraction
-  if (c->simt && op.sp_ofs == nullptr && which < PLAN_WX_BLOCK) {
-    const float* Bsrc = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->H : c->WT;
-    const long long ldB = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->ldH : c->ldG;
-    dim3 grid(ceil_div(pl->p.M, 128), c->K);
-    if (op.orient == ORIENT_XH)
-      simt_gemm_kernel<ORIENT_XH><<<grid, 128, 0, st>>>(op.Xmem, op.ldX, Bsrc, ldB, pl->p.M, pl->p.R, c->K, out, ld_out);
-    else
-      simt_gemm_kernel<ORIENT_WX><<<grid, 128, 0, st>>>(op.Xmem, op.ldX, Bsrc, ldB, pl->p.M, pl->p.R, c->K, out, ld_out);
-    LAUNCH_CHECK();
-    return ALPINE_OK;
-  }
+    if (c->simt && op.sp_ofs == nullptr && which < PLAN_ZW && out != nullptr && groups == 1) {
+      const float* Bsrc = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->H : c->WT;
+      const long long ldB = (which == PLAN_XH || which == PLAN_GRAM_H) ? c->ldH : c->ldG;
+      dim3 grid(ceil_div(pl->p.M, 128), c->K);
+      if (op.orient == ORIENT_XH)
+        simt_gemm_kernel<ORIENT_XH><<<grid, 128, 0, st>>>(op.Xmem, op.ldX, Bsrc, ldB, pl->p.M, pl->p.R, c->K, out, ld_out);
+      else
+        simt_gemm_kernel<ORIENT_WX><<<grid, 128, 0, st>>>(op.Xmem, op.ldX, Bsrc, ldB, pl->p.M, pl->p.R, c->K, out, ld_out);
+      LAUNCH_CHECK();
+      return ALPINE_OK;
+    }
 #endif
-  if (op.profiled) AL_TRY(prof_mark(c, st));
-  // op.profiled marks the contractions whose A operand is X; only those can use the count-matrix variant
-  if (op.profiled && c->x_exact) {
-    if (op.orient == ORIENT_XH)
-      AL_TRY((launch_gemm_t<ORIENT_XH, true>(*pl, st)));
-    else
-      AL_TRY((launch_gemm_t<ORIENT_WX, true>(*pl, st)));
-  } else if (op.orient == ORIENT_XH) {
-    AL_TRY((launch_gemm_t<ORIENT_XH, false>(*pl, st)));
-  } else {
-    AL_TRY((launch_gemm_t<ORIENT_WX, false>(*pl, st)));
+    if (op.profiled) AL_TRY(prof_mark(c, st));
+    // op.profiled marks the contractions whose A operand is X; only those can use the count-matrix variant
+    if (op.profiled && c->x_exact) {
+      if (op.orient == ORIENT_XH)
+        AL_TRY((launch_gemm_t<ORIENT_XH, true>(*pl, st)));
+      else
+        AL_TRY((launch_gemm_t<ORIENT_WX, true>(*pl, st)));
+    } else if (op.orient == ORIENT_XH) {
+      AL_TRY((launch_gemm_t<ORIENT_XH, false>(*pl, st)));
+    } else {
+      AL_TRY((launch_gemm_t<ORIENT_WX, false>(*pl, st)));
+    }
+    if (op.profiled) AL_TRY(prof_mark(c, st));
   }
-  if (op.profiled) AL_TRY(prof_mark(c, st));
   if (out == nullptr) return ALPINE_OK;
   return reduce_slots(c, which, out, ld_out, st);
 }
@@ -721,20 +733,26 @@ int run_stats(alpine_ctx* c, double* loss_row, bool fresh_h_update, cudaStream_t
 }
 
 // ---- fused update kernels (csrc/mu_update_kernels.cuh)
-SlotSrc src_slots(const GemmPlan& pl) {
-  SlotSrc s{};
-  s.direct = nullptr;
-  s.partial = pl.p.partial;
-  s.slot_ofs = pl.r.slot_ofs;
-  s.slots = pl.r.slots;
-  s.K = pl.p.K;
-  return s;
+SlotSrc2 src_slots(const alpine_ctx* c, int which) {
+  SlotSrc2 s2{};
+  s2.split = c->split();
+  for (int g = 0; g < c->n_groups; ++g) {
+    const GemmPlan& pl = c->plans[which][g];
+    SlotSrc& s = s2.g[g];
+    s.direct = nullptr;
+    s.partial = pl.p.partial;
+    s.slot_ofs = pl.r.slot_ofs;
+    s.slots = pl.r.slots;
+    s.K = pl.p.K;
+  }
+  return s2;
 }
-SlotSrc src_direct(const float* a, long long ld) {
-  SlotSrc s{};
-  s.direct = a;
-  s.ld = ld;
-  return s;
+SlotSrc2 src_direct(const float* a, long long ld) {
+  SlotSrc2 s2{};
+  s2.split = 0x3fffffff;
+  s2.g[0].direct = a;
+  s2.g[0].ld = ld;
+  return s2;
 }
 
 int launch_w_update(alpine_ctx* c, const WUpdParams& p, cudaStream_t st) {
@@ -851,12 +869,20 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
       q += c_cov[i] * k_blocks[i];
     }
   }
-  if (K > kAccStride) {
+  if (K > 2 * kAccStride) {
     delete c;
-    return fail(ALPINE_ERR_ARG, "total components %d > %d is not supported (two fp32 accumulators per CTA in TMEM)", K,
-                kAccStride);
+    return fail(ALPINE_ERR_ARG, "total components %d > %d is not supported (two launches of at most %d accumulator "
+                "columns per contraction)", K, 2 * kAccStride, kAccStride);
   }
   c->K = K;
+  if (K > kAccStride) {  // two balanced component groups, the first a multiple of 16
+    c->n_groups = 2;
+    c->gK[0] = static_cast<int>(round_up((K + 1) / 2, 16));
+    c->gK[1] = K - c->gK[0];
+    c->gk0[1] = c->gK[0];
+  } else {
+    c->gK[0] = K;
+  }
   c->Kp = static_cast<int>(round_up(K, 16));
   c->Kg = Kg;
   c->q_total = q;
@@ -881,14 +907,15 @@ int alpine_destroy(alpine_ctx* c) {
   ws_free(c, c->sum_small);
   ws_free(c, c->sum_P);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
-                  c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->partial,
+                  c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->pbuf[0], c->pbuf[1], c->pbuf[2], c->pbuf[3],
                   c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags,
-                  c->Ssplit, c->Tsplit, c->partial_z, c->hsum_part, c->q_part, c->pred_part, c->t1_part, c->finish_counter};
+                  c->Ssplit, c->Tsplit, c->hsum_part, c->q_part, c->pred_part, c->t1_part, c->finish_counter};
   for (void* p : ptrs) ws_free(c, p);
-  for (auto& pl : c->plans) {
-    ws_free(c, pl.d_slot_ofs);
-    ws_free(c, pl.d_slots);
-  }
+  for (auto& kind : c->plans)
+    for (auto& pl : kind) {
+      ws_free(c, pl.d_slot_ofs);
+      ws_free(c, pl.d_slots);
+    }
   for (cudaEvent_t e : c->prof_ev) cudaEventDestroy(e);
   delete c;
   return ALPINE_OK;
@@ -913,18 +940,18 @@ int64_t alpine_workspace_bytes(const alpine_ctx* c) {
     b += ws_bytes(gh, 8) + kWsAlign;
   }
   // partial-sum slots of the largest standard plan, and the slot lists of all of them
-  size_t hint = 0, hint_z = 0;
-  for (int which = 0; which < PLAN_WX_BLOCK; ++which) {
-    GemmParams p{};
-    int grid = 0;
-    const size_t need = plan_geometry(c, plan_operands(c, which), p, &grid);
-    if (which == PLAN_ZW || which == PLAN_ZH)
-      hint_z = need > hint_z ? need : hint_z;
-    else
-      hint = need > hint ? need : hint;
-    b += ws_bytes(p.ws.num_tiles + 1, 4) + ws_bytes(static_cast<size_t>(p.ws.num_tiles) * p.ws.pieces * 3 + grid + 1, 4);
-  }
-  b += ws_bytes(hint, f) + ws_bytes(hint_z, f);
+  size_t hint[4] = {0, 0, 0, 0};
+  for (int which = 0; which < PLAN_WX_BLOCK; ++which)
+    for (int g = 0; g < c->n_groups; ++g) {
+      GemmParams p{};
+      int grid = 0;
+      const GemmOperands op = plan_operands(c, which, g);
+      const size_t need = plan_geometry(c, op, p, &grid);
+      const int cls = (op.z_slots ? 2 : 0) + op.group;
+      hint[cls] = need > hint[cls] ? need : hint[cls];
+      b += ws_bytes(p.ws.num_tiles + 1, 4) + ws_bytes(static_cast<size_t>(p.ws.num_tiles) * p.ws.pieces * 3 + grid + 1, 4);
+    }
+  for (size_t h : hint) b += ws_bytes(h, f);
   return static_cast<int64_t>(b + (2u << 20));  // + loss history, flags, alignment slack
 }
 
@@ -935,14 +962,14 @@ int alpine_bind_workspace(alpine_ctx* c, void* base, int64_t bytes) {
   c->arena = static_cast<char*>(base);
   c->arena_size = static_cast<size_t>(bytes);
   c->arena_used = 0;
-  size_t hint = 0;
-  for (int which = 0; which < PLAN_WX_BLOCK; ++which) {
-    if (which == PLAN_ZW || which == PLAN_ZH) continue;  // their slots live in a buffer of their own
-    GemmParams p{};
-    const size_t need = plan_geometry(c, plan_operands(c, which), p, nullptr);
-    hint = need > hint ? need : hint;
-  }
-  c->partial_hint = hint;
+  for (int which = 0; which < PLAN_WX_BLOCK; ++which)
+    for (int g = 0; g < c->n_groups; ++g) {
+      GemmParams p{};
+      const GemmOperands op = plan_operands(c, which, g);
+      const size_t need = plan_geometry(c, op, p, nullptr);
+      const int cls = (op.z_slots ? 2 : 0) + op.group;
+      c->pbuf_hint[cls] = need > c->pbuf_hint[cls] ? need : c->pbuf_hint[cls];
+    }
   return ALPINE_OK;
 }
 
@@ -954,7 +981,8 @@ int alpine_bind_dense(alpine_ctx* c, const float* X, int64_t ldX) {
   c->ldX = ldX;
   c->sparse = false;
   c->x_exact = false;  // until alpine_fit_begin has looked at the values
-  for (auto& pl : c->plans) pl.valid = false;
+  for (auto& kind : c->plans)
+    for (auto& pl : kind) pl.valid = false;
   return ALPINE_OK;
 }
 
@@ -1029,7 +1057,8 @@ int alpine_bind_csr(alpine_ctx* c, const int64_t* indptr, const int32_t* indices
   c->sparse = true;
   c->x_exact = (h_inexact == 0);
   c->nnz = nnz;
-  for (auto& pl : c->plans) pl.valid = false;
+  for (auto& kind : c->plans)
+    for (auto& pl : kind) pl.valid = false;
   return ALPINE_OK;
 }
 
@@ -1050,7 +1079,8 @@ int alpine_bind_factors(alpine_ctx* c, float* W, int64_t ldW, float* H, int64_t 
   c->H = H;
   c->ldH = ldH;
   for (int i = 0; i < c->n_cov; ++i) c->B[i] = Bs[i];
-  for (auto& pl : c->plans) pl.valid = false;
+  for (auto& kind : c->plans)
+    for (auto& pl : kind) pl.valid = false;
   c->w_stale = false;  // the bound W is the truth until an update runs
   return ALPINE_OK;
 }
@@ -1194,10 +1224,10 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   w.split_hi = c->Wsplit;  // B operand of W^T W and W^T X below
   w.split_lo = c->Wsplit + static_cast<size_t>(c->K) * c->ldG;
   if (!peer) {
-    w.num = c->xh_in_slots ? src_slots(c->plans[PLAN_XH]) : src_direct(c->red_Pt(), c->ldG);
+    w.num = c->xh_in_slots ? src_slots(c, PLAN_XH) : src_direct(c->red_Pt(), c->ldG);
     if (!single) AL_TRY(run_split_small(c, c->use_S(), c->K, c->Ssplit, st));  // the all-reduced H H^T
     AL_TRY(run_gemm(c, PLAN_ZW, nullptr, 0, st));   // Z_W = (H H^T) W^T, into the second slot buffer
-    w.z = src_slots(c->plans[PLAN_ZW]);
+    w.z = src_slots(c, PLAN_ZW);
     AL_TRY(launch_w_update(c, w, st));
   } else {
     const int epoch = ++c->peer_epoch;
@@ -1210,8 +1240,8 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     LAUNCH_CHECK();
     AL_TRY(run_split_small(c, c->use_S(), c->K, c->Ssplit, st));
     AL_TRY(run_gemm(c, PLAN_ZW, nullptr, 0, st));  // (this rank's gene slice only, see plan_operands)
-    w.z = src_slots(c->plans[PLAN_ZW]);
-    w.z.origin = g0;
+    w.z = src_slots(c, PLAN_ZW);
+    w.z.g[0].origin = w.z.g[1].origin = g0;
     w.col0 = g0;
     w.col1 = g1;
     w.num = src_direct(c->sum_P, c->ldG);
@@ -1230,7 +1260,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   AL_TRY(run_gemm(c, PLAN_GRAM_W, nullptr, 0, st));
   {
     WFinishParams wf{};
-    wf.gram.src = src_slots(c->plans[PLAN_GRAM_W]);
+    wf.gram.src = src_slots(c, PLAN_GRAM_W);
     wf.gram.K = c->K;
     wf.gram.out = c->T;
     wf.gram.ld = c->K;
@@ -1257,8 +1287,8 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   h.ldH = c->ldH;
   h.K = c->K;
   h.n = c->n;
-  h.num = src_slots(c->plans[PLAN_WX]);
-  h.z = src_slots(c->plans[PLAN_ZH]);
+  h.num = src_slots(c, PLAN_WX);
+  h.z = src_slots(c, PLAN_ZH);
   h.eps = static_cast<float>(c->eps);
   h.cov = tab;
   h.loss_type = c->loss_type;
@@ -1277,7 +1307,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   //      (main.py:666, 726-753)
   AL_TRY(run_gemm(c, PLAN_GRAM_H, nullptr, 0, st));
   HFinishParams hf{};
-  hf.gram.src = src_slots(c->plans[PLAN_GRAM_H]);
+  hf.gram.src = src_slots(c, PLAN_GRAM_H);
   hf.gram.K = c->K;
   hf.gram.out = c->red_S();
   hf.gram.ld = c->K;
@@ -1370,6 +1400,7 @@ int alpine_als_block(alpine_ctx* c, int b, void* stream) {
   if (!c->fit_active) return fail(ALPINE_ERR_STATE, "alpine_fit_begin has not been called");
   if (b < 0 || b >= c->n_blocks) return fail(ALPINE_ERR_ARG, "block %d outside [0, %d)", b, c->n_blocks);
   if (c->peer_on()) return fail(ALPINE_ERR_STATE, "the block-wise sweep exchanges through the caller's all-reduce, not peer memory");
+  if (c->n_groups > 1) return fail(ALPINE_ERR_ARG, "the block-wise sweep (use_als) supports at most %d components in total", kAccStride);
   DEVICE_SCOPE(c);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int r0 = 0;
@@ -1525,7 +1556,7 @@ int alpine_transform(alpine_ctx* c, int n_iter, void* stream) {
   h.eps = static_cast<float>(c->eps);
   for (int it = 0; it < n_iter; ++it) {  // main.py:705-709
     AL_TRY(run_gemm(c, PLAN_ZH, nullptr, 0, st));  // Z = T H
-    h.z = src_slots(c->plans[PLAN_ZH]);
+    h.z = src_slots(c, PLAN_ZH);
     AL_TRY(launch_h_update<false>(c, h, st));
   }
   CU_TRY(cudaStreamSynchronize(st));
@@ -1605,8 +1636,8 @@ int alpine_profile_read(alpine_ctx* c, double* gemm_ms_total, long long* gemm_la
 int alpine_query(const alpine_ctx* c, int* num_sms, int* gemm_grid, int* smem_stages, int* k_padded) {
   if (c == nullptr) return fail(ALPINE_ERR_ARG, "null context");
   if (num_sms) *num_sms = c->num_sms;
-  if (gemm_grid) *gemm_grid = c->plans[PLAN_XH].valid ? c->plans[PLAN_XH].grid : 0;
-  if (smem_stages) *smem_stages = c->plans[PLAN_XH].valid ? c->plans[PLAN_XH].p.sx : 0;
+  if (gemm_grid) *gemm_grid = c->plans[PLAN_XH][0].valid ? c->plans[PLAN_XH][0].grid : 0;
+  if (smem_stages) *smem_stages = c->plans[PLAN_XH][0].valid ? c->plans[PLAN_XH][0].p.sx : 0;
   if (k_padded) *k_padded = c->Kp;
   return ALPINE_OK;
 }

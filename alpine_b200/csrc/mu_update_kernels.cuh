@@ -48,6 +48,13 @@ struct SlotSrc {
   int K;                // components per slot
   long long origin;     // column of the caller's matrix that is row 0 of the plan's first super-tile
 };
+// Up to 256 components run as two contraction launches over component groups [0, split) and [split, K) (the tcgen05
+// kernel accumulates at most 128 columns per launch): an operand is then two slot sets, selected by the row.
+struct SlotSrc2 {
+  SlotSrc g[2];
+  int split;  // first row of the second group (>= K: one group)
+};
+
 // The slot ids of the tile's super-tile are staged in shared memory once per tile (ids[0 .. n)), so the loads of an
 // element are independent of each other; they are issued four at a time and added in list order.
 constexpr int kMaxTileSlots = 96;
@@ -166,8 +173,8 @@ struct WUpdParams {
   long long ldG;
   int K;
   long long col0, col1; // genes [col0, col1) are updated by this launch (col0 % 64 == 0)
-  SlotSrc num;          // X H^T
-  SlotSrc z;            // (H H^T) W^T
+  SlotSrc2 num;         // X H^T
+  SlotSrc2 z;           // (H H^T) W^T
   float c1, c2, orth, eps;
   float* split_hi;      // [K][ldG] tf32 copies of the new W^T, or nullptr
   float* split_lo;
@@ -180,7 +187,7 @@ inline size_t w_update_smem_bytes(int K) {
 
 __global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
-  __shared__ int ids_num[kMaxTileSlots], ids_z[kMaxTileSlots];
+  __shared__ int ids_num[2][kMaxTileSlots], ids_z[2][kMaxTileSlots];
   const int K = p.K;
   float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]
   double* cs = reinterpret_cast<double*>(tiles + 2 * K * kUpdPitch);
@@ -194,8 +201,15 @@ __global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdPara
     const long long c0 = p.col0 + tile_i * kUpdCols;
     cp_async_wait_all();
     __syncthreads();  // the tile has landed; everybody is done with the other buffer and the slot ids
-    const int *idn, *idz;
-    const int nn = stage_slot_ids(p.num, c0, ids_num, &idn), nz = stage_slot_ids(p.z, c0, ids_z, &idz);
+    const int *idn[2], *idz[2];
+    int nn[2], nz[2];
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      idn[gi] = idz[gi] = ids_num[0];
+      nn[gi] = (gi == 0 || p.num.split < K) ? stage_slot_ids(p.num.g[gi], c0, ids_num[gi], &idn[gi]) : 0;
+      nz[gi] = (gi == 0 || p.z.split < K) ? stage_slot_ids(p.z.g[gi], c0, ids_z[gi], &idz[gi]) : 0;
+    }
+    const bool few_slots = nn[0] <= 2 && nn[1] <= 2 && nz[0] <= 2 && nz[1] <= 2;
     const long long next = tile_i + gridDim.x;
     if (next < n_tiles)
       load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.WT, p.ldG, K, p.col0 + next * kUpdCols, p.col1);
@@ -225,14 +239,22 @@ __global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdPara
              p.n_peers, p.wt_peer);
     };
     const int n_items = K * 16;
-    if (nn <= 2 && nz <= 2) {
+    if (few_slots) {
       // two elements per thread and round: their (up to eight) loads are in flight together
       for (int e = tid; e < n_items; e += 2 * kUpdThreads) {
         const int e2 = e + kUpdThreads;
         const bool v1 = c0 + 4 * (e & 15) < p.col1, v2 = e2 < n_items && c0 + 4 * (e2 & 15) < p.col1;
         SlotPair n1{}, z1{}, n2{}, z2{};
-        if (v1) n1 = slot_load_pair(p.num, e >> 4, c0 + 4 * (e & 15), idn, nn), z1 = slot_load_pair(p.z, e >> 4, c0 + 4 * (e & 15), idz, nz);
-        if (v2) n2 = slot_load_pair(p.num, e2 >> 4, c0 + 4 * (e2 & 15), idn, nn), z2 = slot_load_pair(p.z, e2 >> 4, c0 + 4 * (e2 & 15), idz, nz);
+        if (v1) {
+          const int k = e >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
+          n1 = slot_load_pair(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e & 15), idn[gn], nn[gn]);
+          z1 = slot_load_pair(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e & 15), idz[gz], nz[gz]);
+        }
+        if (v2) {
+          const int k = e2 >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
+          n2 = slot_load_pair(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e2 & 15), idn[gn], nn[gn]);
+          z2 = slot_load_pair(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e2 & 15), idz[gz], nz[gz]);
+        }
         if (v1) update(e, pair_sum(n1), pair_sum(z1));
         if (v2) update(e2, pair_sum(n2), pair_sum(z2));
       }
@@ -240,7 +262,9 @@ __global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdPara
       for (int e = tid; e < n_items; e += kUpdThreads) {
         const long long col = c0 + 4 * (e & 15);
         if (col >= p.col1) continue;
-        update(e, slot_load4(p.num, e >> 4, col, idn, nn), slot_load4(p.z, e >> 4, col, idz, nz));
+        const int k = e >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
+        update(e, slot_load4(p.num.g[gn], k - gn * p.num.split, col, idn[gn], nn[gn]),
+               slot_load4(p.z.g[gz], k - gz * p.z.split, col, idz[gz], nz[gz]));
       }
     }
     // (the next iteration's first barrier separates these reads from the prefetch into this buffer two tiles on)
@@ -255,8 +279,8 @@ struct HUpdParams {
   long long ldH;
   int K;
   long long n;
-  SlotSrc num;     // W^T X
-  SlotSrc z;       // (W^T W) H
+  SlotSrc2 num;    // W^T X
+  SlotSrc2 z;      // (W^T W) H
   float eps;
   CovTable cov;
   int loss_type;
@@ -280,7 +304,7 @@ inline size_t h_update_smem_bytes(int K, int Kg, int c_total, int q_total) {
 template <bool FIT>
 __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
-  __shared__ int ids_num[kMaxTileSlots], ids_z[kMaxTileSlots];
+  __shared__ int ids_num[2][kMaxTileSlots], ids_z[2][kMaxTileSlots];
   const int K = p.K;
   const int q_pad = (p.q_total + 3) & ~3;           // keeps the arrays behind 16-byte aligned
   float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]: old H, overwritten with the new H
@@ -326,8 +350,15 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
     const long long c0 = tile_i * kUpdCols;
     cp_async_wait_all();
     __syncthreads();  // the tile has landed (also orders the set-up above); everybody is done with the other buffer
-    const int *idn, *idz;
-    const int nn = stage_slot_ids(p.num, c0, ids_num, &idn), nz = stage_slot_ids(p.z, c0, ids_z, &idz);
+    const int *idn[2], *idz[2];
+    int nn[2], nz[2];
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      idn[gi] = idz[gi] = ids_num[0];
+      nn[gi] = (gi == 0 || p.num.split < K) ? stage_slot_ids(p.num.g[gi], c0, ids_num[gi], &idn[gi]) : 0;
+      nz[gi] = (gi == 0 || p.z.split < K) ? stage_slot_ids(p.z.g[gi], c0, ids_z[gi], &idz[gi]) : 0;
+    }
+    const bool few_slots = nn[0] <= 2 && nn[1] <= 2 && nz[0] <= 2 && nz[1] <= 2;
     if (!FIT) __syncthreads();  // (FIT: the barrier after the guided terms publishes the ids)
     const long long next = tile_i + gridDim.x;
     if (next < n_tiles) load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.H, p.ldH, K, next * kUpdCols, p.n);
@@ -384,21 +415,31 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
       store4(out4, k, col, p.n, p.H, p.ldH, p.split_hi, p.split_lo, p.ld_split, 0, nullptr);
     };
     const int n_items = K * 16;
-    if (nn <= 2 && nz <= 2) {
+    if (few_slots) {
       // two elements per thread and round: their (up to eight) loads are in flight together
       for (int e = tid; e < n_items; e += 2 * kUpdThreads) {
         const int e2 = e + kUpdThreads;
         const bool v1 = c0 + 4 * (e & 15) < p.n, v2 = e2 < n_items && c0 + 4 * (e2 & 15) < p.n;
         SlotPair n1{}, z1{}, n2{}, z2{};
-        if (v1) n1 = slot_load_pair(p.num, e >> 4, c0 + 4 * (e & 15), idn, nn), z1 = slot_load_pair(p.z, e >> 4, c0 + 4 * (e & 15), idz, nz);
-        if (v2) n2 = slot_load_pair(p.num, e2 >> 4, c0 + 4 * (e2 & 15), idn, nn), z2 = slot_load_pair(p.z, e2 >> 4, c0 + 4 * (e2 & 15), idz, nz);
+        if (v1) {
+          const int k = e >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
+          n1 = slot_load_pair(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e & 15), idn[gn], nn[gn]);
+          z1 = slot_load_pair(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e & 15), idz[gz], nz[gz]);
+        }
+        if (v2) {
+          const int k = e2 >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
+          n2 = slot_load_pair(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e2 & 15), idn[gn], nn[gn]);
+          z2 = slot_load_pair(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e2 & 15), idz[gz], nz[gz]);
+        }
         if (v1) update(e, pair_sum(n1), pair_sum(z1));
         if (v2) update(e2, pair_sum(n2), pair_sum(z2));
       }
     } else {
       for (int e = tid; e < n_items; e += kUpdThreads) {
         if (c0 + 4 * (e & 15) >= p.n) continue;
-        update(e, slot_load4(p.num, e >> 4, c0 + 4 * (e & 15), idn, nn), slot_load4(p.z, e >> 4, c0 + 4 * (e & 15), idz, nz));
+        const int k = e >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
+        update(e, slot_load4(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e & 15), idn[gn], nn[gn]),
+               slot_load4(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e & 15), idz[gz], nz[gz]));
       }
     }
     if (FIT) {
@@ -498,7 +539,7 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
 // slots, in list order.  32 lanes share an output element's slots (strided) and are combined by a fixed shuffle
 // tree, so that the many small loads overlap.  Also writes the tf32 hi / lo copies (B operand of the next Z plan).
 struct GramFromSlots {
-  SlotSrc src;       // slots [K][256] of the Gram plan (rows r < K are meaningful)
+  SlotSrc2 src;      // slots [K][256] of the Gram plan (rows r < K are meaningful), per component group
   int K;
   float* out;        // [K][ld]
   int ld;
@@ -514,11 +555,14 @@ __device__ __forceinline__ void gram_from_slots_block(const GramFromSlots& g, in
   const int k = b / RG, rg = b - k * RG;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int r = rg * 32 + lane;
-  const int s0 = __ldg(g.src.slot_ofs), s1 = __ldg(g.src.slot_ofs + 1);
+  const int gi = k >= g.src.split;
+  const SlotSrc& src = g.src.g[gi];
+  const int kl = k - gi * g.src.split;
+  const int s0 = __ldg(src.slot_ofs), s1 = __ldg(src.slot_ofs + 1);
   float a = 0.f;
   if (r < g.K)
     for (int q = s0 + w; q < s1; q += 8)
-      a += __ldcg(g.src.partial + (static_cast<size_t>(__ldg(g.src.slots + q)) * g.src.K + k) * 256 + r);
+      a += __ldcg(src.partial + (static_cast<size_t>(__ldg(src.slots + q)) * src.K + kl) * 256 + r);
   red[w][lane] = a;
   __syncthreads();
   if (w == 0 && r < g.K) {

@@ -574,8 +574,13 @@ class ALPINE:
             return
         if not full_batch or self.sampling_method == "weighted":
             return self._fit_minibatch(m)
+        import time
+
+        detail = self.__dict__.setdefault("timings_detail", {})
+        t0 = time.perf_counter()
         self._rng_skip_randperms(m.n_total, self.max_iter)  # main.py:502-506, one permutation per iteration
         solver = self._make_solver(m)
+        detail["loop_make_solver"] = time.perf_counter() - t0
         try:
             if dist_info()[1] > 1 and not self.use_als and os.environ.get("ALPINE_B200_PEER", "0") == "1":
                 # Opt-in: exchange over NVLink peer memory inside the W-update kernels instead of the NCCL
@@ -590,7 +595,16 @@ class ALPINE:
 
                 pbar = tqdm(total=self.max_iter, desc="Iteration", ncols=100)
             with (pbar if pbar is not None else nullcontext()):
-                history = engine.run(self.max_iter, on_iter=(lambda it: pbar.update(1)) if pbar is not None else None)
+                t1 = time.perf_counter()
+                engine.begin(self.max_iter)
+                t2 = time.perf_counter()
+                for it in range(self.max_iter):
+                    engine.step(it)
+                    if pbar is not None:
+                        pbar.update(1)
+                t3 = time.perf_counter()
+                history = engine.collect_losses(self.max_iter)
+                detail["loop_begin"], detail["loop_enqueue"], detail["loop_collect"] = t2 - t1, t3 - t2, time.perf_counter() - t3
         finally:
             if keep_solver:
                 m.solver = solver

@@ -118,7 +118,8 @@ _check_fit_args.last_deferred = False
 
 # limits of the native library (csrc/mu_small_kernels.cuh kMaxCov, csrc/mu_gemm_sm100.cuh kMaxK): reported here, by
 # name, before anything is uploaded -- the reference itself has no such limits
-MAX_TOTAL_COMPONENTS = 128
+MAX_TOTAL_COMPONENTS = 256
+MAX_TOTAL_COMPONENTS_ALS = 128
 MAX_COVARIATES = 8
 
 
@@ -131,6 +132,8 @@ def check_native_limits(m) -> None:
     total = sum(m.n_covariate_components) + m.n_components
     _require(total <= MAX_TOTAL_COMPONENTS, ValueError,
              f"alpine_b200 supports at most {MAX_TOTAL_COMPONENTS} components in total (got {total}).")
+    _require(not (m.use_als and total > MAX_TOTAL_COMPONENTS_ALS), ValueError,
+             f"alpine_b200 supports at most {MAX_TOTAL_COMPONENTS_ALS} components in total with use_als=True (got {total}).")
 
 
 def check_trained(m) -> None:

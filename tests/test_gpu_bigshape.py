@@ -72,6 +72,43 @@ def test_k100_simultaneous_update_matches_oracle_over_many_tiles():
         assert abs(rows[-1, 2 + i] - ref[2 + i]) <= 1e-3 * abs(ref[2 + i]) + 1e-6 * n
 
 
+@pytest.mark.parametrize("exchange_buffer", [False, True])
+def test_two_hundred_components_match_oracle(exchange_buffer):
+    """K = 200 (> 128: every contraction runs as two launches over component groups of 112 + 88, the update kernels
+    read both groups' slots) against the NumPy oracle; the reference has no limit on K (main.py:47-80)."""
+    gu = _gpu_utils()
+    from alpine_b200.utils.synth import labels_to_dummies, make_counts, make_labels
+
+    n, G, blocks, cats = 2050, 1300, [6, 4, 190], [3, 4]
+    kw = dict(n_components=190, n_covariate_components=[6, 4], lam=[1e3, 5e2], orth_W=0.2, alpha_W=0.5, l1_ratio_W=0.5)
+    X = make_counts(n, G, seed=21, rank=12)
+    Ycg, _ = labels_to_dummies(make_labels(n, cats, seed=21, nan_fraction=0.02))
+    Ys = [np.ascontiguousarray(y.T) for y in Ycg]
+    rng = np.random.default_rng(7)
+    K = sum(blocks)
+    W0 = np.maximum(rng.random((G, K), dtype=np.float32), 1e-6)
+    H0 = np.maximum(rng.random((K, n), dtype=np.float32), 1e-6)
+    B0 = [np.maximum(rng.random((c, k), dtype=np.float32), 1e-6) for c, k in zip(cats, blocks)]
+    hp = orc.HyperParams(**kw)
+    st = orc.State(W0.copy(), H0.copy(), [b.copy() for b in B0], blocks)
+    prob = gu.DeviceProblem(X, Ys, W0, H0, B0, blocks, kw, exchange_buffer=exchange_buffer)
+
+    def check(it):
+        orc.mu_step(X.T, Ys, st, hp)
+        W, H, Bs = prob.host()
+        e = max(rel_fro(W, st.W), rel_fro(H, st.H), max(rel_fro(a, b) for a, b in zip(Bs, st.Bs)))
+        assert e < EXPECTED_TOL, (it, e)
+
+    xn, rows = prob.run(5, on_iter=check)
+    ref = orc.compute_loss(X.T, Ys, st, hp, dtype=np.float64)
+    assert abs((xn - 2.0 * rows[-1, 0] + rows[-1, 1]) - ref[1]) / ref[1] < PARITY_TOL
+    # the H-only transform with the same component groups
+    prob2 = gu.DeviceProblem(X, [], st.W, H0, [], [K], {})
+    prob2.solver.transform(3)
+    Ht = orc.transform_loop(X.T, st.W, H0, 3, 1e-6)
+    assert rel_fro(prob2.H.cpu().numpy(), Ht) < EXPECTED_TOL
+
+
 def _recon_fp64(Xcm: torch.Tensor, W: torch.Tensor, H: torch.Tensor, chunk: int = 8192) -> float:
     """||X - W H||_F^2 in fp64, over chunks of cells (X is cells-major: Xcm[j][g])."""
     Wd = W.double()

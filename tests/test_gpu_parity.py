@@ -37,6 +37,8 @@ PRODUCT_SHAPES = [
     (3001, 2600, 100),
     (1200, 640, 128),
     (40000, 512, 100),
+    (1200, 640, 160),    # > 128 components: two launches per contraction (component groups of 80 + 80)
+    (900, 500, 256),     # the maximum: 128 + 128
 ]
 
 
@@ -253,7 +255,7 @@ def test_argument_errors_are_reported():
     from alpine_b200 import _native
 
     with pytest.raises(_native.AlpineNativeError):
-        _native.Solver("cuda:0", 10, 10, [129], [])  # K > 128
+        _native.Solver("cuda:0", 10, 10, [257], [])  # K > 256
     s = _native.Solver("cuda:0", 64, 64, [4], [])
     with pytest.raises(_native.AlpineNativeError):
         s.fit_begin(3)  # nothing bound
@@ -266,6 +268,7 @@ TINY_SHAPES = [
     (33, 257, [3, 14], [4]),
     (64, 1, [2, 2], [3]),
     (300, 40, [64, 64], [5]),       # K = 128: both TMEM accumulators full width, widest guided block
+    (300, 40, [70, 130], [5]),      # K = 200: two component groups per contraction (no block-wise sweep above 128)
 ]
 
 
@@ -275,6 +278,8 @@ def test_degenerate_and_maximal_shapes_match_oracle(shape, mode):
     """Shapes far below one tile (TMA boxes mostly out of bounds), a single cell / gene, and the K = 128 limit."""
     gu = _gpu_utils()
     n, G, blocks, cats = shape
+    if mode == "als" and sum(blocks) > 128:
+        pytest.skip("use_als supports at most 128 components in total")
     rng = np.random.default_rng(n * 1000 + G)
     X = rng.gamma(0.5, 2.0, size=(n, G)).astype(np.float32)
     X[rng.random((n, G)) < 0.3] = 0.0
