@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mu_gemm_sm100.cuh"
@@ -77,6 +78,37 @@ struct DeviceScope {
 #define DEVICE_SCOPE(c)                                  \
   DeviceScope dev_scope__((c)->device);                  \
   if (!dev_scope__.ok) return fail(ALPINE_ERR_CUDA, "cannot select device %d", (c)->device)
+
+// Launch with programmatic stream serialization (see ptx::pdl_enter): only for kernels that execute the wait in
+// every CTA.  ALPINE_B200_PDL=0 launches them as ordinary stream-ordered kernels.
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("ALPINE_B200_PDL");
+    return e == nullptr || strcmp(e, "0") != 0;
+  }();
+  return on;
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+#define PDL_LAUNCH(...)                                                                                     \
+  do {                                                                                                      \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                                     \
+    cudaError_t e__ = launch_pdl(__VA_ARGS__);                                                              \
+    if (e__ != cudaSuccess)                                                                                 \
+      return fail(ALPINE_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
 
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -420,7 +452,8 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
   switch (pl.p.Kp / 16) {
 #define ALPINE_GEMM_CASE(NC)                                                                     \
   case NC:                                                                                       \
-    mu_gemm_kernel<ORIENT, NC, EXACT><<<pl.grid, kGemmThreads, pl.smem, st>>>(pl.tmX, pl.tmBhi, pl.tmBlo, pl.p); \
+    PDL_LAUNCH(mu_gemm_kernel<ORIENT, NC, EXACT>, dim3(pl.grid), dim3(kGemmThreads), pl.smem, st, pl.tmX, pl.tmBhi,  \
+               pl.tmBlo, pl.p);                                                                  \
     break;
     ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
     ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
@@ -428,7 +461,6 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
     default:
       return fail(ALPINE_ERR_ARG, "unsupported padded component count %d", pl.p.Kp);
   }
-  LAUNCH_CHECK();
   return ALPINE_OK;
 }
 
@@ -611,8 +643,8 @@ GemmOperands plan_operands(const alpine_ctx* c, int which, int group = 0) {
 // tf32 hi / lo copies of a small operand [K][R]
 int run_split(alpine_ctx* c, const float* src, long long ld_src, long long R, float* dst, long long ldS,
               cudaStream_t st) {
-  split_operand_kernel<<<2 * c->num_sms, 256, 0, st>>>(src, ld_src, c->K, R, dst, dst + static_cast<size_t>(c->K) * ldS, ldS);
-  LAUNCH_CHECK();
+  PDL_LAUNCH(split_operand_kernel, dim3(2 * c->num_sms), dim3(256), 0, st, src, ld_src, c->K, R, dst,
+             dst + static_cast<size_t>(c->K) * ldS, ldS);
   return ALPINE_OK;
 }
 
@@ -629,11 +661,10 @@ int reduce_slots(alpine_ctx* c, int which, float* out, long long ld_out, cudaStr
       int gy = ceil_div(32 * c->num_sms, pl->p.ws.num_tiles * 8);
       const int gy_max = ceil_div(pl->p.K, 8);
       if (gy > gy_max) gy = gy_max;
-      reduce_partials_by_k_kernel<<<dim3(pl->p.ws.num_tiles * 8, gy), 256, 0, st>>>(r);
+      PDL_LAUNCH(reduce_partials_by_k_kernel, dim3(pl->p.ws.num_tiles * 8, gy), dim3(256), 0, st, r);
     } else {
-      reduce_partials_kernel<<<dim3(pl->p.ws.num_tiles * 8, pl->p.K), 256, 0, st>>>(r);
+      PDL_LAUNCH(reduce_partials_kernel, dim3(pl->p.ws.num_tiles * 8, pl->p.K), dim3(256), 0, st, r);
     }
-    LAUNCH_CHECK();
   }
   return ALPINE_OK;
 }
@@ -759,8 +790,7 @@ int launch_w_update(alpine_ctx* c, const WUpdParams& p, cudaStream_t st) {
   const long long tiles = ceil_div(p.col1 - p.col0, kUpdCols);
   if (tiles <= 0) return ALPINE_OK;
   const int grid = static_cast<int>(tiles < 3 * c->num_sms ? tiles : 3 * c->num_sms);
-  w_update_kernel<<<grid, kUpdThreads, w_update_smem_bytes(c->K), st>>>(p);
-  LAUNCH_CHECK();
+  PDL_LAUNCH(w_update_kernel, dim3(grid), dim3(kUpdThreads), w_update_smem_bytes(c->K), st, p);
   return ALPINE_OK;
 }
 
@@ -771,16 +801,14 @@ int launch_h_update(alpine_ctx* c, const HUpdParams& p, cudaStream_t st) {
   const size_t smem = h_update_smem_bytes(c->K, p.Kg, p.c_total, p.q_total);
   if (smem > 225 * 1024)
     return fail(ALPINE_ERR_ARG, "covariate blocks too large for the H update kernel (%zu bytes of shared memory)", smem);
-  h_update_kernel<FIT><<<grid, kUpdThreads, smem, st>>>(p);
-  LAUNCH_CHECK();
+  PDL_LAUNCH(h_update_kernel<FIT>, dim3(grid), dim3(kUpdThreads), smem, st, p);
   return ALPINE_OK;
 }
 
 // tf32 hi / lo copies of a K x K matrix (pitch ld_src, any alignment) into a [2][K][ldK] operand buffer
 int run_split_small(alpine_ctx* c, const float* src, int ld_src, float* dst, cudaStream_t st) {
-  split_small_kernel<<<ceil_div(static_cast<long long>(c->K) * c->K, 256), 256, 0, st>>>(
-      src, ld_src, c->K, dst, dst + static_cast<size_t>(c->K) * c->ldK, static_cast<int>(c->ldK));
-  LAUNCH_CHECK();
+  PDL_LAUNCH(split_small_kernel, dim3(ceil_div(static_cast<long long>(c->K) * c->K, 256)), dim3(256), 0, st, src, ld_src,
+             c->K, dst, dst + static_cast<size_t>(c->K) * c->ldK, static_cast<int>(c->ldK));
   return ALPINE_OK;
 }
 
@@ -1235,10 +1263,9 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     long long g0, g1;
     c->peer_slice(&g0, &g1);
     const int n_small = static_cast<int>(c->small_floats());
-    peer_gather_reduce_kernel<<<2 * c->num_sms, 256, 0, st>>>(pt, epoch, n_small, c->sum_small, c->K, c->ldG, g0, g1,
-                                                              c->sum_P, c->err);
-    LAUNCH_CHECK();
-    AL_TRY(run_split_small(c, c->use_S(), c->K, c->Ssplit, st));
+    PDL_LAUNCH(peer_gather_reduce_kernel, dim3(2 * c->num_sms), dim3(256), 0, st, pt, epoch, n_small, c->sum_small, c->K,
+               c->ldG, g0, g1, c->sum_P, c->err, c->Ssplit, c->Ssplit + static_cast<size_t>(c->K) * c->ldK,
+               static_cast<int>(c->ldK));
     AL_TRY(run_gemm(c, PLAN_ZW, nullptr, 0, st));  // (this rank's gene slice only, see plan_operands)
     w.z = src_slots(c, PLAN_ZW);
     w.z.g[0].origin = w.z.g[1].origin = g0;
@@ -1250,8 +1277,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
       w.wt_peer[q] = (q == c->peer_rank) ? nullptr : c->peer_base[q] + c->xchg_wt_off();
     w.split_hi = w.split_lo = nullptr;  // taken from the gathered W^T below
     AL_TRY(launch_w_update(c, w, st));
-    peer_signal_wait_kernel<<<1, 32, 0, st>>>(pt, 1, epoch, c->err);  // every slice of the new W^T is in every block
-    LAUNCH_CHECK();
+    PDL_LAUNCH(peer_signal_wait_kernel, dim3(1), dim3(32), 0, st, pt, 1, epoch, c->err);  // every slice of the new W^T is in every block
     AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   }
   c->w_stale = true;
@@ -1275,8 +1301,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     wf.S = c->use_S();
     wf.ldS = c->K;
     wf.eps = static_cast<float>(c->eps);
-    w_finish_kernel<<<wf.gram_blocks + (c->n_cov > 0 ? 1 : 0), 256, ckmax * sizeof(float), st>>>(wf);
-    LAUNCH_CHECK();
+    PDL_LAUNCH(w_finish_kernel, dim3(wf.gram_blocks + (c->n_cov > 0 ? 1 : 0)), dim3(256), ckmax * sizeof(float), st, wf);
   }
   // ---- A = W^T X (main.py:653) and Z_H = (W^T W) H, both left in their slots
   AL_TRY(run_gemm(c, PLAN_WX, nullptr, 0, st));
@@ -1330,8 +1355,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   hf.ldT = c->K;
   hf.loss_row = c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov);
   hf.counter = c->finish_counter;
-  h_finish_kernel<<<hf.gram_blocks + h_finish_stat_blocks(c->K, c->q_total), 256, 0, st>>>(hf);
-  LAUNCH_CHECK();
+  PDL_LAUNCH(h_finish_kernel, dim3(hf.gram_blocks + h_finish_stat_blocks(c->K, c->q_total)), dim3(256), 0, st, hf);
   return ALPINE_OK;
 }
 

@@ -265,6 +265,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  ptx::pdl_launch_dependents();  // the set-up below (barriers, TMEM) overlaps the predecessor's tail
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -325,6 +326,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  ptx::pdl_wait();  // from here on global memory written by the predecessor is read
   const uint32_t tmem_base = *tmem_slot;
   const WorkSpace ws = p.ws;
   const int cta = blockIdx.x;
@@ -687,6 +689,7 @@ inline int max_segments_per_cta(const WorkSpace& ws, int grid) {
 // Few slots per tile (the X contractions): grid = (num_tiles * 8, gy); block = (tile, 32-row group); lane = row
 // (coalesced 128-byte reads), each warp owns a strided set of components and adds the tile's slots in order.
 __global__ void __launch_bounds__(256) reduce_partials_by_k_kernel(const ReduceParams p) {
+  ptx::pdl_enter();
   const int tile = blockIdx.x >> 3, rg = blockIdx.x & 7;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int r = rg * 32 + lane;
@@ -703,6 +706,7 @@ __global__ void __launch_bounds__(256) reduce_partials_by_k_kernel(const ReduceP
 // Many slots per tile (the Gram contractions: one tile, one slot per CTA): grid = (num_tiles * 8, K); one block
 // per (tile, 32-row group, component); the 8 warps take the slots round-robin and are combined in a fixed order.
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
+  ptx::pdl_enter();
   __shared__ float red[8][32];
   const int tile = blockIdx.x >> 3, rg = blockIdx.x & 7, k = blockIdx.y;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -241,6 +241,7 @@ __global__ void scale_b_kernel(const CovTable tab, const float* __restrict__ s) 
 // Pitches are multiples of 4 floats and bases 16-byte aligned, so whole float4 groups are always in bounds.
 __global__ void split_operand_kernel(const float* __restrict__ src, long long ld_src, int rows, long long cols,
                                      float* __restrict__ hi, float* __restrict__ lo, long long ld_dst) {
+  ptx::pdl_enter();
   const long long c4n = (cols + 3) >> 2;
   const long long total = static_cast<long long>(rows) * c4n;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -262,6 +263,7 @@ __global__ void split_operand_kernel(const float* __restrict__ src, long long ld
 // the same for a small K x K matrix of any pitch / alignment (H H^T, W^T W): scalar accesses
 __global__ void split_small_kernel(const float* __restrict__ src, int ld_src, int K, float* __restrict__ hi,
                                    float* __restrict__ lo, int ld_dst) {
+  ptx::pdl_enter();
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= K * K) return;
   const int r = e / K, c = e - r * K;

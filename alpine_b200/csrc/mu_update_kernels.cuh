@@ -188,6 +188,7 @@ inline size_t w_update_smem_bytes(int K) {
 __global__ void __launch_bounds__(kUpdThreads, 3) w_update_kernel(const WUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
   __shared__ int ids_num[2][kMaxTileSlots], ids_z[2][kMaxTileSlots];
+  ptx::pdl_enter();
   const int K = p.K;
   float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]
   double* cs = reinterpret_cast<double*>(tiles + 2 * K * kUpdPitch);
@@ -305,6 +306,7 @@ template <bool FIT>
 __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
   __shared__ int ids_num[2][kMaxTileSlots], ids_z[2][kMaxTileSlots];
+  ptx::pdl_enter();
   const int K = p.K;
   const int q_pad = (p.q_total + 3) & ~3;           // keeps the arrays behind 16-byte aligned
   float* tiles = reinterpret_cast<float*>(upd_smem);  // [2][K][68]: old H, overwritten with the new H
@@ -592,6 +594,7 @@ struct WFinishParams {
 };
 __global__ void __launch_bounds__(256) w_finish_kernel(const WFinishParams p) {
   __shared__ float gred[8][32];
+  ptx::pdl_enter();
   if (static_cast<int>(blockIdx.x) < p.gram_blocks) {
     gram_from_slots_block(p.gram, blockIdx.x, gred);
     return;
@@ -665,6 +668,7 @@ __global__ void __launch_bounds__(256) h_finish_kernel(const HFinishParams p) {
   __shared__ double red[256];
   __shared__ float gred[8][32];
   __shared__ unsigned int last;
+  ptx::pdl_enter();
   const int K = p.gram.K;
   double (*red2)[32] = reinterpret_cast<double (*)[32]>(red);
   const int hb = (K + 31) / 32, qb = (p.q_total + 31) / 32;

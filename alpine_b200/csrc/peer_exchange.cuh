@@ -61,6 +61,7 @@ __device__ __forceinline__ bool peer_wait_all(const PeerTable& t, int which, int
 // done[r] = epoch on every rank, then wait until every rank has said so: one launch between the W-update kernel
 // (whose stores into the peers' W^T precede the fence in stream order) and the first consumer of the gathered W^T
 __global__ void __launch_bounds__(32) peer_signal_wait_kernel(const PeerTable t, int which, int epoch, int* err) {
+  ptx::pdl_enter();
   __threadfence_system();
   if (threadIdx.x < t.world) {
     volatile int* f = t.flags[threadIdx.x] + which * kMaxPeers + t.rank;
@@ -72,13 +73,17 @@ __global__ void __launch_bounds__(32) peer_signal_wait_kernel(const PeerTable t,
 
 // "Reduce-scatter" by peer loads: block 0 first publishes ready[r] = epoch (this rank's partials are complete: the
 // kernels that wrote them precede this one in the stream); every block then waits for all ranks and sums, in rank
-// order,  (a) the small statistics [S | hsum | Q] of all ranks -> small_out  and  (b) the columns [g0, g1) of the
+// order,  (a) the small statistics [S | hsum | Q] of all ranks -> small_out (and the tf32 hi / lo copies of the summed
+// S)  and  (b) the columns [g0, g1) of the
 // partial numerators (K x ldG at the head of every exchange block) -> p_out (same pitch).  One thread per float4,
 // all peers' loads in flight together, so the NVLink latency is paid once, not per peer.
 __global__ void __launch_bounds__(256) peer_gather_reduce_kernel(const PeerTable t, int epoch, int n_small,
                                                                  float* __restrict__ small_out, int K, long long ldG,
                                                                  long long g0, long long g1,
-                                                                 float* __restrict__ p_out, int* err) {
+                                                                 float* __restrict__ p_out, int* err,
+                                                                 float* __restrict__ s_hi, float* __restrict__ s_lo,
+                                                                 int ld_split) {
+  ptx::pdl_enter();
   if (blockIdx.x == 0) {
     __threadfence_system();
     if (threadIdx.x < t.world) {
@@ -98,6 +103,14 @@ __global__ void __launch_bounds__(256) peer_gather_reduce_kernel(const PeerTable
 #pragma unroll
     for (int q = 0; q < kMaxPeers; ++q) acc += v[q];
     small_out[e] = acc;
+    if (s_hi != nullptr && e < static_cast<long long>(K) * K) {
+      // the first K * K entries are the summed H H^T: its tf32 hi / lo copies are the B operand of (H H^T) W^T
+      const int r = static_cast<int>(e / K), c = static_cast<int>(e - static_cast<long long>(r) * K);
+      uint32_t h, l;
+      ptx::split_tf32(acc, h, l);
+      s_hi[r * ld_split + c] = __uint_as_float(h);
+      s_lo[r * ld_split + c] = __uint_as_float(l);
+    }
   }
   const long long w4 = (g1 - g0 + 3) >> 2;  // g0 is a multiple of 64 and ldG of 4: whole float4 groups stay in the pitch
   for (long long e = tid; e < static_cast<long long>(K) * w4; e += nth) {

@@ -12,6 +12,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Kernels of the iteration are launched with cudaLaunchAttributeProgrammaticStreamSerialization: a kernel lets its
+// successor in the stream be scheduled as soon as all of its own CTAs have started (launch_dependents), and waits
+// for the complete, flushed predecessor grid before it touches global memory (wait).  Both are no-ops in a kernel
+// that was launched without the attribute.  EVERY CTA of such a kernel must execute the wait (grid completion is
+// what the successor waits for, so a CTA that skipped it could let the successor overtake the predecessor).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
