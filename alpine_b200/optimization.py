@@ -198,12 +198,12 @@ class ComponentOptimizer:
                                   max_evals=n_new + len(self.trials.trials), trials=self.trials,
                                   rstate=np.random.default_rng(self.random_state))
         else:
-            # Random search: the suggestions do not depend on earlier results, so floor(n_gpus / n_splits) trials
-            # are evaluated at a time and all their fold fits go through ONE device queue (8 GPUs: 2 trials x 3
-            # folds in flight, the queue keeps every GPU busy).  Same suggestions, same scores and the same trial
+            # Random search: the suggestions do not depend on earlier results, so one trial per GPU is evaluated at
+            # a time and all their fold fits go through ONE device queue (8 GPUs: 8 trials x 3 folds = 24 jobs, the
+            # queue keeps every GPU busy until the batch drains).  Same suggestions, same scores and the same trial
             # order as evaluating them one by one.
             rng = np.random.default_rng(self.random_state + len(self.trials.trials))
-            batch = max(1, len(self.devices) // max(1, self.n_splits))
+            batch = max(1, len(self.devices))
             todo = n_new
             while todo > 0:
                 vals = [_sample_space(rng, self._ranges, n_cov) for _ in range(min(batch, todo))]
