@@ -11,14 +11,19 @@ One "step" is one full-batch MU iteration (W update, B updates, H update, loss t
 * ``value``    : iterations/s with X, Y, W, H, B resident in HBM; K timed steps between barrier+synchronize,
                  CUDA events on the launch stream, max over ranks.  At N > 1 the SAME 20k x 100k problem is
                  sharded by cells over the ranks ("scaling": "strong") with one NCCL all-reduce per iteration.
-* ``e2e``      : the same metric through the public API (``ALPINE.fit`` on host numpy buffers): one fit of K
-                 iterations including validation, host->device upload of X / Y, initialisation, the loop, the loss
-                 read-back and the device->host copy of W / H / B, divided by K.
+* ``e2e``      : the same metric through the public API (``ALPINE.fit`` on host numpy buffers whose rows are
+                 page-locked): one fit of K iterations including validation, host->device upload of X / Y,
+                 initialisation, the loop, the loss read-back and the device->host copy of W / H / B, divided by K;
+                 after one untimed warm-up fit.
 * ``roofline`` : the contraction kernel (two launches per step), timed with CUDA events around each launch
                  inside the timed region; 3xTF32 tensor work against measured bf16 peak / 2.
 * ``cpu_baseline`` : the reference's step restated with its own torch-CPU operators (oracle/torch_port.py: its 7
-                 GEMMs, randperm gather and G x n temporaries) on a bounded column sample of the same workload, all
-                 host cores, extrapolated linearly in cells.
+                 GEMMs, randperm gather and G x n temporaries), measured on the full workload with all host cores
+                 (a leading block of cells only when host memory or the time budget would be exceeded).
+* ``gpu_torch_baseline`` : the same restatement on device="cuda" (fp32 cuBLAS, TF32 off): the reference's own GPU path
+                 on this B200.
+* ``cfg4`` / ``cfg5`` / ``parity_vs_n1`` : BASELINE configs[3] (CSR scaling workload) on the same ranks, configs[4]
+                 (hyper-parameter search, at 8 GPUs) and the sharded == single-GPU self-check (N > 1).
 """
 from __future__ import annotations
 
@@ -64,8 +69,8 @@ def load_peaks():
 
 
 def load_traffic(key):
-    """Measured DRAM bytes per launch of the contraction kernel (ncu --set full), profiles/r1_traffic.json."""
-    path = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    """Measured DRAM bytes per launch of the contraction kernel (ncu --set full), profiles/r2_traffic.json."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
     try:
         with open(path) as f:
             d = json.load(f).get(key)
