@@ -160,6 +160,10 @@ struct GemmOperands {
   bool z_slots = false;   // partial sums go to the second slot buffer (they are consumed together with another plan's)
   int chunk_log2 = kChunkLog2;  // TMEM accumulation chain between two fp32 flushes, in k-blocks (log2)
   int group = 0;          // component group of this launch (K > 128 runs as two launches per contraction)
+  // ORIENT_WX: one more super-tile taken from this [extra_rows][cols] matrix (pitch ldE): its Gram-type product with
+  // the plan's B operand comes out of the same launch (W^T W out of W^T X)
+  const float* extra = nullptr;
+  long long ldE = 0, extra_rows = 0;
   // sparse X: tile lists instead of Xmem (csr_tiles.cuh)
   const long long* sp_ofs = nullptr;
   const uint2* sp_ent = nullptr;
@@ -174,7 +178,8 @@ struct GemmPlan {
   GemmOperands op;
   int* d_slot_ofs = nullptr;  // device copies of the reduce kernel's slot lists
   int* d_slots = nullptr;
-  CUtensorMap tmX, tmBhi, tmBlo;
+  CUtensorMap tmX, tmBhi, tmBlo, tmX2;
+  int extra_tile = -1;
   GemmParams p{};
   ReduceParams r{};
   int grid = 0;
@@ -255,6 +260,9 @@ struct alpine_ctx {
   int n_groups = 1;
   int gk0[2] = {0, 0}, gK[2] = {0, 0};
   int split() const { return n_groups > 1 ? gk0[1] : 0x3fffffff; }
+  // W^T W comes out of the W^T X launch as one more super-tile (dense X that needs its lo half: the count-matrix
+  // variant drops the lo half of the streamed operand, which W^T needs; the sparse producer has no TMA path)
+  bool gram_w_fused() const { return !sparse && !x_exact; }
   float* own_reduce = nullptr;
   float* reduce = nullptr;  // [Pt K*ldG | S K*K | hsum K | Q q_total]
 
@@ -453,7 +461,7 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
 #define ALPINE_GEMM_CASE(NC)                                                                     \
   case NC:                                                                                       \
     PDL_LAUNCH(mu_gemm_kernel<ORIENT, NC, EXACT>, dim3(pl.grid), dim3(kGemmThreads), pl.smem, st, pl.tmX, pl.tmBhi,  \
-               pl.tmBlo, pl.p);                                                                  \
+               pl.tmBlo, pl.tmX2, pl.p);                                                         \
     break;
     ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
     ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
@@ -518,6 +526,8 @@ size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p,
   p.K = Kop;
   p.Kp = static_cast<int>(round_up(Kop, 16));
   p.ws.num_tiles = ceil_div(M, rows);
+  p.extra_tile = -1;
+  if (op.extra != nullptr && op.orient == ORIENT_WX) p.extra_tile = p.ws.num_tiles++;
   p.ws.kb_per_tile = ceil_div(R, kBK);
   // pieces of the reduction axis: the live window of the B operand (one piece of its hi + lo copies, two around
   // a piece boundary) stays in L2 (evict-last) while X streams through with evict-first
@@ -559,6 +569,11 @@ int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long lo
   const float* b_hi = op.Bsplit + static_cast<size_t>(op.k0) * op.ldS;
   AL_TRY(make_map(&pl->tmBhi, b_hi, R, Kop, op.ldS, kBK, p.Kp, true));
   AL_TRY(make_map(&pl->tmBlo, b_hi + static_cast<size_t>(c->K) * op.ldS, R, Kop, op.ldS, kBK, p.Kp, true));
+  pl->extra_tile = p.extra_tile;
+  if (p.extra_tile >= 0)
+    AL_TRY(make_map(&pl->tmX2, op.extra, op.cols, op.extra_rows, op.ldE, kBK, rows, true));
+  else
+    pl->tmX2 = pl->tmBhi;  // (unused; any valid descriptor)
   ReduceParams& r = pl->r;
   r.partial = p.partial;
   r.rows = rows;
@@ -599,6 +614,7 @@ GemmOperands plan_operands(const alpine_ctx* c, int which, int group = 0) {
       op.orient = ORIENT_WX, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
       op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.profiled = true;
       if (c->sparse) op.Xmem = nullptr, op.sp_ofs = c->sp_ofs[ORIENT_WX], op.sp_ent = c->sp_ent[ORIENT_WX];
+      if (c->gram_w_fused()) op.extra = c->WT, op.ldE = c->ldG, op.extra_rows = c->K;
       break;
     case PLAN_GRAM_H:  // S[b][a] = sum_j H[a][j] H[b][j]            (H H^T of main.py:599 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
@@ -626,6 +642,7 @@ GemmOperands plan_operands(const alpine_ctx* c, int which, int group = 0) {
     default: {         // A[k][j] = sum_g X[j][g] W^T[k][g] for the rows k of one component block     (main.py:567)
       op = plan_operands(c, PLAN_WX);
       op.k0 = 0;
+      op.extra = nullptr;
       const int b = which - PLAN_WX_BLOCK;
       for (int i = 0; i < b; ++i) op.k0 += c->kblk[i];
       op.Kop = c->kblk[b];
@@ -1158,6 +1175,10 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
     int h_inexact = 1;  // one 4-byte read-back per fit selects the 2-MMA kernel variant for count matrices
     CU_TRY(cudaMemcpyAsync(&h_inexact, c->flags, sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    if (c->x_exact != (h_inexact == 0)) {  // the kernel variant (and what rides along with W^T X) depends on it
+      for (auto& kind : c->plans)
+        for (auto& pl : kind) pl.valid = false;
+    }
     c->x_exact = (h_inexact == 0);
   }
   // W^T master copy for the gene-side kernels
@@ -1281,12 +1302,16 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   }
   c->w_stale = true;
-  // ---- T = W^T W of the new W (tcgen05 Gram plan; its slots are summed by the finish kernel, which also writes the
-  //      hi / lo copies Z_H needs) and the B updates (main.py:615-628)
-  AL_TRY(run_gemm(c, PLAN_GRAM_W, nullptr, 0, st));
+  // ---- A = W^T X (main.py:653), left in its slots; T = W^T W of the new W rides along as one more super-tile of the
+  //      same launch (dense fp32 X), otherwise it is a Gram plan of its own.  The finish kernel sums T's slots, writes
+  //      the hi / lo copies Z_H needs and applies the B updates (main.py:615-628).
+  const bool fused_t = c->gram_w_fused();
+  if (!fused_t) AL_TRY(run_gemm(c, PLAN_GRAM_W, nullptr, 0, st));
+  AL_TRY(run_gemm(c, PLAN_WX, nullptr, 0, st));
   {
     WFinishParams wf{};
-    wf.gram.src = src_slots(c, PLAN_GRAM_W);
+    wf.gram.src = src_slots(c, fused_t ? PLAN_WX : PLAN_GRAM_W);
+    wf.gram.tile = fused_t ? c->plans[PLAN_WX][0].extra_tile : 0;
     wf.gram.K = c->K;
     wf.gram.out = c->T;
     wf.gram.ld = c->K;
@@ -1303,8 +1328,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     wf.eps = static_cast<float>(c->eps);
     PDL_LAUNCH(w_finish_kernel, dim3(wf.gram_blocks + (c->n_cov > 0 ? 1 : 0)), dim3(256), ckmax * sizeof(float), st, wf);
   }
-  // ---- A = W^T X (main.py:653) and Z_H = (W^T W) H, both left in their slots
-  AL_TRY(run_gemm(c, PLAN_WX, nullptr, 0, st));
+  // ---- Z_H = (W^T W) H, left in its slots
   AL_TRY(run_gemm(c, PLAN_ZH, nullptr, 0, st));
   // ---- H update (main.py:631-663) with the guided terms of (old H, new B), statistics of (new H, new B)
   HUpdParams h{};

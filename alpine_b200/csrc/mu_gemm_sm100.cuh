@@ -138,6 +138,9 @@ struct GemmParams {
   int sx;           // X ring depth
   int sb;           // B ring depth
   int max_segs;     // partial slots per CTA
+  int extra_tile;   // ORIENT_WX only: index of one additional super-tile whose rows come from a second matrix with the
+                    // same reduction axis (tmX2; its first 256 rows), or -1.  Used to get W^T W out of the W^T X launch:
+                    // W^T [K][G] has exactly the layout of a 256-row block of X (rows x genes).
   int chunk_log2;   // k-blocks (2^chunk_log2) accumulated in TMEM between two round-to-nearest flushes: every MMA
                     // adds into the accumulator with round-toward-zero, so shorter chains mean less bias (the small
                     // K x K-deep plans use 1 or 2 k-blocks: their flushes cost nothing next to their launch)
@@ -258,7 +261,7 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int Kp, int sx, int s
 template <int ORIENT, int NC, bool EXACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
-               const __grid_constant__ CUtensorMap tmBlo, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmX2, const GemmParams p) {
   constexpr int Kp = 16 * NC;
   constexpr int kWarpXProd = kConvWarps, kWarpBProd = kConvWarps + 1, kWarpMma = kConvWarps + 2;  // + kMT MMA warps
   constexpr int b_tile_bytes = Kp * kBK * 4;
@@ -310,7 +313,10 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     ptx::fence_barrier_init();
   }
   const bool tiles = p.sp_ofs != nullptr;  // SRC_TILES
-  if (!tiles && warp == kWarpXProd && lane == 0) ptx::prefetch_tensormap(&tmX);
+  if (!tiles && warp == kWarpXProd && lane == 0) {
+    ptx::prefetch_tensormap(&tmX);
+    if (ORIENT == ORIENT_WX && p.extra_tile >= 0) ptx::prefetch_tensormap(&tmX2);
+  }
   if (tiles) {  // the sparse producer only scatters nonzeros: stages start zeroed and are re-zeroed by their readers
     const uint32_t base = ptx::smem_u32(smem_x);
     for (int i = threadIdx.x; i < SX * (kXTileBytes / 16); i += kGemmThreads) ptx::sts_zero_v4(base + i * 16);
@@ -430,6 +436,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           ptx::mbar_arrive_expect_tx(&xfull_bar[s], kXTileBytes);
           if (ORIENT == ORIENT_XH)  // box {256 genes, 32 cells} at (gene0, cell0): smem [32 cells][256 genes]
             ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], tile * kRows, kb * kBK, ptx::kEvictFirst);
+          else if (tile == p.extra_tile)  // the additional super-tile: rows [0, 256) of the second matrix
+            ptx::tma_load_2d(dst, &tmX2, &xfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
           else  // box {32 genes, 256 cells} at (gene0, cell0): smem [256 cells][32 genes], 128B swizzle
             ptx::tma_load_2d(dst, &tmX, &xfull_bar[s], kb * kBK, tile * kRows, ptx::kEvictFirst);
         }

@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
 // tree, so that the many small loads overlap.  Also writes the tf32 hi / lo copies (B operand of the next Z plan).
 struct GramFromSlots {
   SlotSrc2 src;      // slots [K][256] of the Gram plan (rows r < K are meaningful), per component group
+  int tile;          // super-tile of the plan that holds the Gram (0 for a Gram plan; the additional tile of W^T X)
   int K;
   float* out;        // [K][ld]
   int ld;
@@ -560,7 +561,7 @@ __device__ __forceinline__ void gram_from_slots_block(const GramFromSlots& g, in
   const int gi = k >= g.src.split;
   const SlotSrc& src = g.src.g[gi];
   const int kl = k - gi * g.src.split;
-  const int s0 = __ldg(src.slot_ofs), s1 = __ldg(src.slot_ofs + 1);
+  const int s0 = __ldg(src.slot_ofs + g.tile), s1 = __ldg(src.slot_ofs + g.tile + 1);
   float a = 0.f;
   if (r < g.K)
     for (int q = s0 + w; q < s1; q += 8)

@@ -705,7 +705,8 @@ class ALPINE:
                             indptr = torch.cat([indptr, indptr[-1:].expand(size - cnt)])
                         s.bind_csr(indptr.contiguous(), indices, values)
                     else:
-                        Xb[:cnt].copy_(m.X_cells_major.index_select(0, loc))
+                        # one gather pass straight into the batch buffer (rows of the cells-major X are contiguous)
+                        torch.index_select(m.X_cells_major, 0, loc, out=Xb[:cnt])
                         Xb[cnt:].zero_()
                     Hb[:, :cnt].copy_(m.H.index_select(1, loc))
                     Hb[:, cnt:].zero_()
