@@ -1306,8 +1306,8 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   //      same launch (dense fp32 X), otherwise it is a Gram plan of its own.  The finish kernel sums T's slots, writes
   //      the hi / lo copies Z_H needs and applies the B updates (main.py:615-628).
   const bool fused_t = c->gram_w_fused();
-  if (!fused_t) AL_TRY(run_gemm(c, PLAN_GRAM_W, nullptr, 0, st));
-  AL_TRY(run_gemm(c, PLAN_WX, nullptr, 0, st));
+  // (the Gram plan shares the slot buffer with W^T X: unfused, its slots are consumed before W^T X runs)
+  AL_TRY(run_gemm(c, fused_t ? PLAN_WX : PLAN_GRAM_W, nullptr, 0, st));
   {
     WFinishParams wf{};
     wf.gram.src = src_slots(c, fused_t ? PLAN_WX : PLAN_GRAM_W);
@@ -1328,6 +1328,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
     wf.eps = static_cast<float>(c->eps);
     PDL_LAUNCH(w_finish_kernel, dim3(wf.gram_blocks + (c->n_cov > 0 ? 1 : 0)), dim3(256), ckmax * sizeof(float), st, wf);
   }
+  if (!fused_t) AL_TRY(run_gemm(c, PLAN_WX, nullptr, 0, st));
   // ---- Z_H = (W^T W) H, left in its slots
   AL_TRY(run_gemm(c, PLAN_ZH, nullptr, 0, st));
   // ---- H update (main.py:631-663) with the guided terms of (old H, new B), statistics of (new H, new B)

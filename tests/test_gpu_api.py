@@ -354,3 +354,25 @@ def test_max_iter_zero_and_limits_are_handled_on_the_host():
     assert len(model.loss_history) == 0 and list(model.loss_history.columns)[:2] == ["total loss", "reconstruction loss"]
     with pytest.raises(ValueError, match="at least one component per covariate"):
         ALPINE(n_components=4, n_covariate_components=[0], lam=[1.0], device="cuda").fit(ad, ["cov0"], max_iter=2)
+
+
+def test_fit_without_covariates_matches_oracle():
+    """Plain NMF through the same kernels: no guided blocks, no B, no prediction terms (n_covariate_components=[])."""
+    ad = _adata(n=700, G=450, cats=(3,), nan_fraction=0.0)
+    kw = dict(n_components=12, n_covariate_components=[], lam=[], orth_W=0.1, alpha_W=0.2, l1_ratio_W=0.5)
+    model = ALPINE(device="cuda:0", **kw)
+    model.covariate_keys, model.sampling_method, model.verbose = [], "random", False
+    X = np.ascontiguousarray(ad.X, dtype=np.float32).T
+    model.batch_size, model.max_iter = X.shape[1], 8
+    m = model._initialize_matrices(X, [])
+    st = orc.State(m.W.cpu().numpy().copy(), m.H.cpu().numpy().copy(), [], [12])
+    hp = orc.HyperParams(**kw)
+    model._fit(m)
+    orc.fit_loop(X, [], st, hp, 8)
+    assert rel_fro(m.W.cpu().numpy(), st.W) < 2e-5 and rel_fro(m.H.cpu().numpy(), st.H) < 2e-5
+    ref64 = orc.compute_loss(X, [], st, hp, dtype=np.float64)
+    lh = model.loss_history
+    assert list(lh.columns) == ["total loss", "reconstruction loss"]
+    assert abs(lh["reconstruction loss"].iloc[-1] - ref64[1]) / ref64[1] < 1e-4
+    out = ALPINE(device="cuda", **kw).fit(ad, [], max_iter=4)
+    assert len(out.loss_history) == 4 and out.get_covariate_gene_scores() == {}
