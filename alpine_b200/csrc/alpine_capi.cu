@@ -170,8 +170,11 @@ struct GemmOperands {
 };
 // PLAN_WX_BLOCK + b: W_b^T X of component block b alone (block Gauss-Seidel sweep, main.py:567)
 // PLAN_ZW / PLAN_ZH: the K x K-deep products of the Gram reformulation, Z_W = (H H^T) W^T and Z_H = (W^T W) H
-enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_ZW = 4, PLAN_ZH = 5, PLAN_WX_BLOCK = 6,
-       PLAN_COUNT = 6 + kMaxCov + 1 };
+// PLAN_WXG: W^T X with W^T W riding along as one more super-tile (the iteration's launch for dense fp32 X); PLAN_WX
+// stays the plain contraction (alpine_wx_product, transform, block-wise sweep: same work split as the CSR plan, so
+// dense and sparse products stay bit-identical)
+enum { PLAN_XH = 0, PLAN_WX = 1, PLAN_GRAM_H = 2, PLAN_GRAM_W = 3, PLAN_ZW = 4, PLAN_ZH = 5, PLAN_WXG = 6,
+       PLAN_WX_BLOCK = 7, PLAN_COUNT = 7 + kMaxCov + 1 };
 
 struct GemmPlan {
   bool valid = false;
@@ -527,6 +530,7 @@ size_t plan_geometry(const alpine_ctx* c, const GemmOperands& op, GemmParams& p,
   p.Kp = static_cast<int>(round_up(Kop, 16));
   p.ws.num_tiles = ceil_div(M, rows);
   p.extra_tile = -1;
+  p.extra_chunk_log2 = 1;  // (as the Gram plans: the result feeds a denominator through Z_H)
   if (op.extra != nullptr && op.orient == ORIENT_WX) p.extra_tile = p.ws.num_tiles++;
   p.ws.kb_per_tile = ceil_div(R, kBK);
   // pieces of the reduction axis: the live window of the B operand (one piece of its hi + lo copies, two around
@@ -614,8 +618,11 @@ GemmOperands plan_operands(const alpine_ctx* c, int which, int group = 0) {
       op.orient = ORIENT_WX, op.Xmem = c->X, op.ldX = c->ldX, op.rows = c->n, op.cols = c->G;
       op.Bsplit = c->Wsplit, op.ldS = c->ldG, op.profiled = true;
       if (c->sparse) op.Xmem = nullptr, op.sp_ofs = c->sp_ofs[ORIENT_WX], op.sp_ent = c->sp_ent[ORIENT_WX];
-      if (c->gram_w_fused()) op.extra = c->WT, op.ldE = c->ldG, op.extra_rows = c->K;
       break;
+    case PLAN_WXG:
+      op = plan_operands(c, PLAN_WX, group);
+      if (c->gram_w_fused()) op.extra = c->WT, op.ldE = c->ldG, op.extra_rows = c->K;
+      return op;
     case PLAN_GRAM_H:  // S[b][a] = sum_j H[a][j] H[b][j]            (H H^T of main.py:599 after the reformulation)
       op.orient = ORIENT_WX, op.Xmem = c->H, op.ldX = c->ldH, op.rows = c->K, op.cols = c->n;
       op.Bsplit = c->Hsplit, op.ldS = c->ldN, op.chunk_log2 = 1;
@@ -642,7 +649,6 @@ GemmOperands plan_operands(const alpine_ctx* c, int which, int group = 0) {
     default: {         // A[k][j] = sum_g X[j][g] W^T[k][g] for the rows k of one component block     (main.py:567)
       op = plan_operands(c, PLAN_WX);
       op.k0 = 0;
-      op.extra = nullptr;
       const int b = which - PLAN_WX_BLOCK;
       for (int i = 0; i < b; ++i) op.k0 += c->kblk[i];
       op.Kop = c->kblk[b];
@@ -1307,11 +1313,11 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   //      the hi / lo copies Z_H needs and applies the B updates (main.py:615-628).
   const bool fused_t = c->gram_w_fused();
   // (the Gram plan shares the slot buffer with W^T X: unfused, its slots are consumed before W^T X runs)
-  AL_TRY(run_gemm(c, fused_t ? PLAN_WX : PLAN_GRAM_W, nullptr, 0, st));
+  AL_TRY(run_gemm(c, fused_t ? PLAN_WXG : PLAN_GRAM_W, nullptr, 0, st));
   {
     WFinishParams wf{};
-    wf.gram.src = src_slots(c, fused_t ? PLAN_WX : PLAN_GRAM_W);
-    wf.gram.tile = fused_t ? c->plans[PLAN_WX][0].extra_tile : 0;
+    wf.gram.src = src_slots(c, fused_t ? PLAN_WXG : PLAN_GRAM_W);
+    wf.gram.tile = fused_t ? c->plans[PLAN_WXG][0].extra_tile : 0;
     wf.gram.K = c->K;
     wf.gram.out = c->T;
     wf.gram.ld = c->K;
@@ -1337,7 +1343,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   h.ldH = c->ldH;
   h.K = c->K;
   h.n = c->n;
-  h.num = src_slots(c, PLAN_WX);
+  h.num = src_slots(c, fused_t ? PLAN_WXG : PLAN_WX);
   h.z = src_slots(c, PLAN_ZH);
   h.eps = static_cast<float>(c->eps);
   h.cov = tab;

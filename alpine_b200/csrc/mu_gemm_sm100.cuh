@@ -141,6 +141,7 @@ struct GemmParams {
   int extra_tile;   // ORIENT_WX only: index of one additional super-tile whose rows come from a second matrix with the
                     // same reduction axis (tmX2; its first 256 rows), or -1.  Used to get W^T W out of the W^T X launch:
                     // W^T [K][G] has exactly the layout of a 256-row block of X (rows x genes).
+  int extra_chunk_log2;  // flush interval (log2 k-blocks) of the additional super-tile
   int chunk_log2;   // k-blocks (2^chunk_log2) accumulated in TMEM between two round-to-nearest flushes: every MMA
                     // adds into the accumulator with round-toward-zero, so shorter chains mean less bias (the small
                     // K x K-deep plans use 1 or 2 k-blocks: their flushes cost nothing next to their launch)
@@ -273,7 +274,6 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int SX = p.sx, SB = p.sb;
-  const int CL = p.chunk_log2, C = 1 << CL, CM = C - 1;
   const GemmSmemLayout lay = gemm_smem_layout(Kp, SX, SB);
   uint8_t* smem_x = smem + lay.x_off;
   uint8_t* smem_b = smem + lay.b_off;
@@ -494,6 +494,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       int run, tile, kb0, len;
       ws.decode(pos, run, tile, kb0, len);
       if (len > range_end - pos) len = static_cast<int>(range_end - pos);
+      const int CM = (1 << ((ORIENT == ORIENT_WX && tile == p.extra_tile) ? p.extra_chunk_log2 : p.chunk_log2)) - 1;
       for (int li = 0; li < len; ++li, ++it, rb.advance(SB)) {
         const int t = it % kAStages;
         const int sbi = rb.s;
@@ -579,6 +580,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
       int run, tile, kb0, len;
       ws.decode(pos, run, tile, kb0, len);
       if (len > range_end - pos) len = static_cast<int>(range_end - pos);
+      const int CL = (ORIENT == ORIENT_WX && tile == p.extra_tile) ? p.extra_chunk_log2 : p.chunk_log2;
+      const int C = 1 << CL, CM = C - 1;
       for (int li = 0; li < len; ++li, ++it, rx.advance(SX)) {
         const int s = rx.s;
         const int t = it % kAStages;
