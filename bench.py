@@ -430,7 +430,11 @@ def measure_resident(args, wl, sparse, dev, world, rank, local_rank, steps, warm
         exchange = ("NVLink peer memory inside the W-update kernels (reduce-scatter + update + all-gather)" if peer
                     else "NCCL all-reduce of the packed buffer")
     engine = MUEngine(solver, wl["lam"], use_als=args.use_als)
-    total = warmup + steps
+    # the K timed steps run without per-launch events (the events sit between the kernels and take the programmatic
+    # dependent launch away from the contractions); a second pass of `steps_prof` steps right behind them, same
+    # process and thermal state, carries the CUDA events that time every contraction launch for the roofline
+    steps_prof = min(steps, 20)
+    total = warmup + steps + steps_prof
     engine.begin(total)
     for it in range(warmup):
         engine.step(it)
@@ -445,23 +449,27 @@ def measure_resident(args, wl, sparse, dev, world, rank, local_rank, steps, warm
     sampler = ClockSampler(local_rank)
     if rank == 0 and sample_clocks:
         sampler.start()
-    solver.profile(True)
     launches0 = _native.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
     e0.record()
-    for it in range(warmup, total):
+    for it in range(warmup, warmup + steps):
         engine.step(it)
     e1.record()
+    launches = _native.launch_count() - launches0
+    solver.profile(True)
+    for it in range(warmup + steps, total):
+        engine.step(it)
+    e2.record()
     fence()
     ms = e0.elapsed_time(e1)
-    launches = _native.launch_count() - launches0
+    ms_prof = e1.elapsed_time(e2) / steps_prof
     solver.profile(False)
     gemm_ms, gemm_n = solver.profile_read()
     clocks = sampler.stop() if (rank == 0 and sample_clocks) else None
-    t = torch.tensor([ms, gemm_ms / max(gemm_n, 1)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms, gemm_ms / max(gemm_n, 1), ms_prof], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, gemm_ms_avg = float(t[0]), float(t[1])
+    ms, gemm_ms_avg, ms_prof = float(t[0]), float(t[1]), float(t[2])
     hist = engine.collect_losses(total)  # also checks the kernels' error flag
     value = steps / (ms / 1000.0)
 
@@ -493,6 +501,8 @@ def measure_resident(args, wl, sparse, dev, world, rank, local_rank, steps, warm
         "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (no TF32 figure in MEASURED_PEAKS.json; the "
                        f"kernel is timed inside the step loop)",
         "avg_launch_ms": gemm_ms_avg, "launches_timed": gemm_n,
+        "timed_in": f"{steps_prof} further steps right after the {steps} timed ones, with CUDA events around every "
+                    f"contraction launch ({ms_prof:.3f} ms per step there)",
         # the same launch against SURVEY.md 8 d3's HBM bound (dense: 4 B per X element; CSR: 8 B per nonzero)
         "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved_gbs / peaks["hbm_gbs"], "bound_ms_per_launch": hbm_ms},
