@@ -95,9 +95,9 @@ int alpine_batch_begin(alpine_ctx* ctx, void* stream);
 int alpine_mu_partials(alpine_ctx* ctx, void* stream);
 /* Second half, after the (optional) all-reduce of the reduce buffer: W update (main.py:597-612), B updates
  * (main.py:615-628), H update (main.py:631-663), loss terms of iteration `iter` (main.py:666, 726-753) and
- * the statistics for the next iteration.  Six kernel launches per iteration on one GPU together with
- * alpine_mu_partials: two contractions, the two fused update kernels and their two finish kernels
- * (csrc/mu_update_kernels.cuh).                                                                           */
+ * the statistics for the next iteration.  Nine kernel launches per iteration on one GPU together with
+ * alpine_mu_partials: the two sweeps of X (W^T W rides along with W^T X), three small tcgen05 plans for the K-deep
+ * products, the two fused update kernels and their two finish kernels (csrc/mu_update_kernels.cuh).                                                                           */
 int alpine_mu_apply(alpine_ctx* ctx, int iter, void* stream);
 /* The updates keep W as W^T inside the context and refresh the caller's row-major W only on demand: by
  * alpine_fit_losses, alpine_scale, alpine_transform, the next alpine_fit_begin / alpine_batch_begin -- or explicitly
