@@ -59,6 +59,7 @@ SIGNATURES = {
     "alpine_als_finish": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_fit_losses": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]),
+    "alpine_eval_loss": (ctypes.c_int, [_c_ctx, ctypes.POINTER(ctypes.c_double), ctypes.c_void_p]),
     "alpine_scale": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_transform": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_xh_product": (ctypes.c_int, [_c_ctx, _f32p, ctypes.c_int64, ctypes.c_void_p]),
@@ -342,6 +343,15 @@ class Solver:
                                                     rows.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
                                                     self._stream()))
         return float(xn.value), rows[:n_iter]
+
+    def eval_loss(self):
+        """[tr(W^T X H^T), tr(W^T W H H^T), pred_0, ...] of the bound factors on this shard (fp64); synchronises."""
+        import numpy as np
+
+        terms = np.zeros(2 + self.n_cov, dtype=np.float64)
+        _check(self.lib, self.lib.alpine_eval_loss(self._ctx, terms.ctypes.data_as(ctypes.POINTER(ctypes.c_double)),
+                                                   self._stream()))
+        return terms
 
     def scale(self) -> None:
         _check(self.lib, self.lib.alpine_scale(self._ctx, self._stream()))

@@ -253,6 +253,7 @@ struct alpine_ctx {
   bool w_stale = false;           // W^T (the master copy) is ahead of the caller's row-major W
   double* xnorm2 = nullptr;
   double* loss_hist = nullptr;
+  double* eval_row = nullptr;  // alpine_eval_loss
   int loss_cap = 0;
   int* err = nullptr;
   // partial-sum slot buffers, by class = 2 * (Z plan) + component group: a Z plan's slots are consumed together
@@ -873,7 +874,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 9; }
+int alpine_abi_version(void) { return 10; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -958,7 +959,7 @@ int alpine_destroy(alpine_ctx* c) {
   ws_free(c, c->sum_small);
   ws_free(c, c->sum_P);
   void* ptrs[] = {c->WT, c->Hsplit, c->Wsplit, c->A, c->numG, c->denG, c->T, c->colsum, c->q_partial,
-                  c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->err, c->pbuf[0], c->pbuf[1], c->pbuf[2], c->pbuf[3],
+                  c->pred_partial, c->t1_partial, c->hsum_partial, c->sumsq_partial, c->xnorm2, c->loss_hist, c->eval_row, c->err, c->pbuf[0], c->pbuf[1], c->pbuf[2], c->pbuf[3],
                   c->own_reduce, c->sp_ofs[0], c->sp_ofs[1], c->sp_ent[0], c->sp_ent[1], c->sp_xnorm2, c->flags,
                   c->Ssplit, c->Tsplit, c->hsum_part, c->q_part, c->pred_part, c->t1_part, c->finish_counter};
   for (void* p : ptrs) ws_free(c, p);
@@ -1547,6 +1548,29 @@ int alpine_als_finish(alpine_ctx* c, int iter, void* stream) {
   dot_partial_kernel<<<c->sl_blocks_n, 256, 0, st>>>(c->A, c->ldN, c->H, c->ldH, c->K, c->n, c->t1_partial);
   LAUNCH_CHECK();
   return run_stats(c, c->loss_hist + static_cast<size_t>(iter) * (2 + c->n_cov), true, st);
+}
+
+int alpine_eval_loss(alpine_ctx* c, double* terms, void* stream) {
+  AL_TRY(check_bound(c, true));
+  if (terms == nullptr) return fail(ALPINE_ERR_ARG, "null argument");
+  DEVICE_SCOPE(c);
+  AL_TRY(ensure_workspace(c, static_cast<cudaStream_t>(stream)));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AL_TRY(ws_alloc(c, &c->eval_row, static_cast<size_t>(2 + c->n_cov)));
+  AL_TRY(export_w(c, st));
+  transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
+                                                                                       c->WT, c->ldG);
+  LAUNCH_CHECK();
+  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+  AL_TRY(run_gemm(c, PLAN_GRAM_W, c->T, c->K, st));  // T = W^T W
+  AL_TRY(run_gemm(c, PLAN_WX, c->A, c->ldN, st));    // A = W^T X
+  dot_partial_kernel<<<c->sl_blocks_n, 256, 0, st>>>(c->A, c->ldN, c->H, c->ldH, c->K, c->n, c->t1_partial);  // t1
+  LAUNCH_CHECK();
+  AL_TRY(run_stats(c, c->eval_row, false, st));      // S = H H^T, t2 = sum T .* S, prediction terms of (B, H)
+  AL_TRY(run_split_small(c, c->red_S(), c->K, c->Ssplit, st));  // (keeps the context consistent for a following step)
+  CU_TRY(cudaMemcpyAsync(terms, c->eval_row, sizeof(double) * (2 + c->n_cov), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return check_kernel_error(c);
 }
 
 int alpine_fit_losses(alpine_ctx* c, int n_iter, double* xnorm2, double* rows, void* stream) {

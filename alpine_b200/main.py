@@ -745,9 +745,10 @@ class ALPINE:
     def _compute_loss(self, m: AlpineMatrices, solver=None, xnorm2: Optional[float] = None) -> List[float]:
         """[total, reconstruction, prediction...] of the factors as they are (main.py:726-753).
 
-        Not on the hot path (the loop gets its loss terms from the update kernels): the reconstruction term uses
-        the same trace identity, ||X||^2 - 2 tr(W^T X H^T) + tr(W^T W H H^T), with W^T X from the tcgen05
-        contraction and fp64 traces; the prediction terms are evaluated with torch on the device.
+        Not on the hot path of a full-batch fit (the loop gets its loss terms from the update kernels); mini-batch fits
+        call it once per epoch.  Everything runs in the library (``alpine_eval_loss``): the reconstruction term by the
+        same trace identity, ||X||^2 - 2 tr(W^T X H^T) + tr(W^T W H H^T), with W^T X, W^T W and H H^T from the tcgen05
+        contraction and fp64 traces; the prediction terms by the statistics kernel.
         """
         own = solver is None
         if own:
@@ -756,29 +757,18 @@ class ALPINE:
             if xnorm2 is None:
                 solver.fit_begin(1)  # ||X||^2 by the library's fp64 reduction (no fp64 copy of X)
                 xnorm2 = solver.losses(0)[0]
-            A = solver.wx_product().double()
+            terms = solver.eval_loss()
         finally:
             if own:
                 solver.close()
-        H, W = m.H.double(), m.W.double()
-        terms = [torch.tensor(float(xnorm2), dtype=torch.float64, device=H.device), (A * H).sum(),
-                 ((W.T @ W) * (H @ H.T)).sum()]
-        row = 0
-        for i, B in enumerate(m.Bs):
-            k = B.shape[1]
-            y, y_hat = m.Ys[i], B @ m.H[row:row + k]
-            row += k
-            if self.loss_type == "kl-divergence":
-                y_hat = torch.clamp(y_hat, min=self.eps)
-                terms.append(torch.sum(y * torch.log(torch.clamp(y / y_hat, min=self.eps)) - y + y_hat).double())
-            else:
-                terms.append((torch.norm(y - y_hat, p="fro") ** 2).double())
-        vals = torch.stack(terms)
+        vals = np.concatenate([[float(xnorm2)], terms])
         if dist_info()[1] > 1:
             import torch.distributed as dist
 
-            dist.all_reduce(vals)
-        vals = vals.cpu().tolist()
+            t = torch.from_numpy(vals).to(m.W.device)
+            dist.all_reduce(t)
+            vals = t.cpu().numpy()
+        vals = vals.tolist()
         recon = vals[0] - 2.0 * vals[1] + vals[2]
         preds = vals[3:]
         return [recon + sum(self.lam[i] * p for i, p in enumerate(preds)), recon] + preds

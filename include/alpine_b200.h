@@ -130,6 +130,12 @@ int alpine_als_finish(alpine_ctx* ctx, int iter, void* stream);
  * recon = xnorm2 - 2*t1 + t2 (the trace identity that replaces main.py:736).  Also reports kernel faults. */
 int alpine_fit_losses(alpine_ctx* ctx, int n_iter, double* xnorm2, double* rows, void* stream);
 
+/* The loss terms of the factors AS THEY ARE (_compute_loss, main.py:726-753, without materialising W H): terms[0] =
+ * tr(W^T X H^T), terms[1] = tr(W^T W H H^T), terms[2 + i] = prediction loss of covariate i, all of THIS shard and
+ * additive across shards; recon = ||X||^2 - 2 terms[0] + terms[1] with ||X||^2 from alpine_fit_losses.  One sweep of X
+ * on the tcgen05 kernel, fp64 accumulation; synchronises the stream.  Used for the per-epoch loss of mini-batch fits. */
+int alpine_eval_loss(alpine_ctx* ctx, double* terms, void* stream);
+
 /* Post-fit scaling (_scale_matrices, main.py:772-781). */
 int alpine_scale(alpine_ctx* ctx, void* stream);
 
