@@ -67,14 +67,21 @@ class AlpineMatrices:
         else:
             raise RuntimeError("sparse AlpineMatrices without a host copy of X")
         Ys = self.Ys_host if self.Ys_host is not None else [y.cpu().numpy().astype(np.float32) for y in self.Ys]
-        return {
-            "X": X,
-            "Ys": Ys,
-            "Ws": [w.cpu().numpy().astype(np.float32, copy=False) for w in self.Ws],
-            "Hs": [h.cpu().numpy().astype(np.float32, copy=False)
-                   for h in _gather_cells(self.Hs, self.shard, self.n_total)],
-            "Bs": [b.cpu().numpy().astype(np.float32, copy=False) for b in self.Bs],
-        }
+        if self.W is not None and self.H is not None:
+            # one device -> host copy per packed factor (and one gather of the cell blocks under sharding); the blocks
+            # are cut out on the host
+            W = self.W.cpu().numpy()
+            H = _gather_cells([self.H], self.shard, self.n_total)[0].cpu().numpy()
+            cuts_w = np.cumsum([0] + [w.shape[1] for w in self.Ws])
+            cuts_h = np.cumsum([0] + [h.shape[0] for h in self.Hs])
+            Ws = [np.ascontiguousarray(W[:, cuts_w[i]:cuts_w[i + 1]]) for i in range(len(self.Ws))]
+            Hs = [H[cuts_h[i]:cuts_h[i + 1]] for i in range(len(self.Hs))]
+        else:
+            Ws = [w.cpu().numpy().astype(np.float32, copy=False) for w in self.Ws]
+            Hs = [h.cpu().numpy().astype(np.float32, copy=False)
+                  for h in _gather_cells(self.Hs, self.shard, self.n_total)]
+        return {"X": X, "Ys": Ys, "Ws": Ws, "Hs": Hs,
+                "Bs": [b.cpu().numpy().astype(np.float32, copy=False) for b in self.Bs]}
 
 
 def _as_csr_f32(X):

@@ -376,3 +376,18 @@ def test_fit_without_covariates_matches_oracle():
     assert abs(lh["reconstruction loss"].iloc[-1] - ref64[1]) / ref64[1] < 1e-4
     out = ALPINE(device="cuda", **kw).fit(ad, [], max_iter=4)
     assert len(out.loss_history) == 4 and out.get_covariate_gene_scores() == {}
+
+
+def test_fit_on_a_side_stream_equals_the_default_stream():
+    """The library launches on the caller's current stream and orders its own initialisation on it: a fit
+    under a non-blocking side stream gives the same factors as on the default stream."""
+    ad = _adata(n=900, G=500, cats=(3, 4), nan_fraction=0.02)
+    keys = ["cov0", "cov1"]
+    ref = ALPINE(device="cuda:0", **KW).fit(ad, keys, max_iter=6).get_decomposed_matrices()
+    side = torch.cuda.Stream(device="cuda:0")
+    side.wait_stream(torch.cuda.current_stream("cuda:0"))
+    with torch.cuda.stream(side):
+        got = ALPINE(device="cuda:0", **KW).fit(ad, keys, max_iter=6).get_decomposed_matrices()
+    side.synchronize()
+    for a, b in zip(got["Ws"] + got["Hs"] + got["Bs"], ref["Ws"] + ref["Hs"] + ref["Bs"]):
+        np.testing.assert_array_equal(a, b)
