@@ -1305,8 +1305,9 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
       w.wt_peer[q] = (q == c->peer_rank) ? nullptr : c->peer_base[q] + c->xchg_wt_off();
     w.split_hi = w.split_lo = nullptr;  // taken from the gathered W^T below
     AL_TRY(launch_w_update(c, w, st));
-    PDL_LAUNCH(peer_signal_wait_kernel, dim3(1), dim3(32), 0, st, pt, 1, epoch, c->err);  // every slice of the new W^T is in every block
-    AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+    // close of the exchange (every slice of the new W^T is in every block) fused with the split of the gathered W^T
+    PDL_LAUNCH(peer_close_and_split_kernel, dim3(2 * c->num_sms), dim3(256), 0, st, pt, 1, epoch, c->err, c->WT, c->ldG,
+               c->K, c->G, c->Wsplit, c->Wsplit + static_cast<size_t>(c->K) * c->ldG, c->ldG);
   }
   c->w_stale = true;
   // ---- A = W^T X (main.py:653), left in its slots; T = W^T W of the new W rides along as one more super-tile of the

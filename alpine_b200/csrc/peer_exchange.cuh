@@ -7,9 +7,10 @@
 //   2. peer_gather_reduce_kernel: system-scope fence, ready[r] = epoch in every peer's block; wait until
 //      ready[q] == epoch for all q; then sum over the ranks (rank order), with loads straight from peer memory,
 //      the small statistics and THIS RANK'S GENE SLICE of the numerator ("reduce-scatter")
-//   3. sym_long_kernel<EPI_W> on the gene slice: the updated columns of W^T are stored locally and into every
-//      peer's W^T ("all-gather" by peer stores; with step 2: 2 x 7/8 x 8 MB per GPU over NVLink, the update between)
-//   4. peer_signal_wait_kernel: done[r] = epoch everywhere, wait for done[q] == epoch for all q
+//   3. the Z_W plan and w_update_kernel on the gene slice: the updated columns of W^T are stored locally and into
+//      every peer's W^T ("all-gather" by peer stores; with step 2: 2 x 7/8 x 8 MB per GPU over NVLink)
+//   4. peer_close_and_split_kernel: done[r] = epoch everywhere, wait for done[q] == epoch for all q, then the tf32
+//      split of the gathered W^T
 // after which W^T is complete on every rank, bit-identical (same summation order everywhere).  A rank overwrites its
 // partials only after step 4 of the same iteration, i.e. after every peer has finished reading them.
 // All waits are bounded and report through the context's error flag instead of hanging the GPU.
@@ -26,15 +27,6 @@ struct PeerTable {
   int* flags[kMaxPeers];          // every rank's flag array (this rank's own included)
   const float* small[kMaxPeers];  // every rank's [S | hsum | Q] partials
 };
-
-__global__ void peer_signal_kernel(const PeerTable t, int which, int epoch) {
-  __threadfence_system();
-  if (threadIdx.x < t.world) {
-    volatile int* f = t.flags[threadIdx.x] + which * kMaxPeers + t.rank;
-    *f = epoch;
-  }
-  __threadfence_system();
-}
 
 __device__ __forceinline__ bool peer_wait_all(const PeerTable& t, int which, int epoch, int* err) {
   __shared__ int bad;
@@ -58,17 +50,40 @@ __device__ __forceinline__ bool peer_wait_all(const PeerTable& t, int which, int
   return bad == 0;
 }
 
-// done[r] = epoch on every rank, then wait until every rank has said so: one launch between the W-update kernel
-// (whose stores into the peers' W^T precede the fence in stream order) and the first consumer of the gathered W^T
-__global__ void __launch_bounds__(32) peer_signal_wait_kernel(const PeerTable t, int which, int epoch, int* err) {
+// The close of the exchange, fused with the first consumer of the gathered W^T: block 0 publishes done[r] = epoch
+// to every rank (the W-update kernel, whose stores into the peers' W^T precede this one in the stream, is complete),
+// every block waits until all ranks have said so, and then splits W^T [K][cols] into its tf32 hi / lo copies (the
+// B operand of W^T W and W^T X).
+__global__ void __launch_bounds__(256) peer_close_and_split_kernel(const PeerTable t, int which, int epoch, int* err,
+                                                                   const float* __restrict__ src, long long ld_src,
+                                                                   int rows, long long cols, float* __restrict__ hi,
+                                                                   float* __restrict__ lo, long long ld_dst) {
   ptx::pdl_enter();
-  __threadfence_system();
-  if (threadIdx.x < t.world) {
-    volatile int* f = t.flags[threadIdx.x] + which * kMaxPeers + t.rank;
-    *f = epoch;
+  if (blockIdx.x == 0) {
+    __threadfence_system();
+    if (threadIdx.x < t.world) {
+      volatile int* f = t.flags[threadIdx.x] + which * kMaxPeers + t.rank;
+      *f = epoch;
+    }
+    __threadfence_system();
   }
-  __threadfence_system();
-  peer_wait_all(t, which, epoch, err);
+  peer_wait_all(t, which, epoch, err);  // every block polls this rank's own flag array (local memory)
+  const long long c4n = (cols + 3) >> 2;
+  const long long total = static_cast<long long>(rows) * c4n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / c4n, c = (i - r * c4n) << 2;
+    const float4 v = ld_sys_v4(src + r * ld_src + c);  // written by the peers a moment ago: not from a stale L1 line
+    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
+    ptx::split_tf32(v.x, h0, l0);
+    ptx::split_tf32(v.y, h1, l1);
+    ptx::split_tf32(v.z, h2, l2);
+    ptx::split_tf32(v.w, h3, l3);
+    *reinterpret_cast<float4*>(hi + r * ld_dst + c) =
+        make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
+    *reinterpret_cast<float4*>(lo + r * ld_dst + c) =
+        make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+  }
 }
 
 // "Reduce-scatter" by peer loads: block 0 first publishes ready[r] = epoch (this rank's partials are complete: the
