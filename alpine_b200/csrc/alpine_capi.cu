@@ -1198,6 +1198,7 @@ int alpine_fit_begin(alpine_ctx* c, int max_iter, void* stream) {
   AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_stats(c, nullptr, false, st));
   AL_TRY(run_split_small(c, c->red_S(), c->K, c->Ssplit, st));  // (re-done after the exchange under cell sharding)
+  CU_TRY(cudaMemsetAsync(c->finish_counter, 0, 4 * sizeof(unsigned int), st));  // (a faulted launch may have left it set)
   c->fit_active = true;
   return ALPINE_OK;
 }
@@ -1220,6 +1221,7 @@ int alpine_batch_begin(alpine_ctx* c, void* stream) {
   AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
   AL_TRY(run_stats(c, nullptr, false, st));
   AL_TRY(run_split_small(c, c->red_S(), c->K, c->Ssplit, st));
+  CU_TRY(cudaMemsetAsync(c->finish_counter, 0, 4 * sizeof(unsigned int), st));
   c->fit_active = true;
   return ALPINE_OK;
 }
