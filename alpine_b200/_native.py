@@ -47,6 +47,11 @@ SIGNATURES = {
                                        ctypes.c_void_p]),
     "alpine_fit_begin": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_batch_begin": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
+    "alpine_batch_gather": (ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p]),
+    "alpine_batch_scatter": (ctypes.c_int, [_c_ctx, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
+                                            ctypes.c_int64, ctypes.c_void_p]),
     "alpine_mu_partials": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
     "alpine_mu_apply": (ctypes.c_int, [_c_ctx, ctypes.c_int, ctypes.c_void_p]),
     "alpine_sync_w": (ctypes.c_int, [_c_ctx, ctypes.c_void_p]),
@@ -305,6 +310,38 @@ class Solver:
 
     def batch_begin(self) -> None:
         _check(self.lib, self.lib.alpine_batch_begin(self._ctx, self._stream()))
+
+    def batch_gather(self, X_all: Optional[torch.Tensor], H_all: torch.Tensor, Ys_all: List[torch.Tensor],
+                     idx: torch.Tensor) -> None:
+        """Cells ``idx`` of the full-data arrays into the bound batch arrays, the rest of the context zero-filled
+        (one launch; main.py:593-595).  ``X_all``: cells-major (n_all, n_genes), None for a CSR context."""
+        n_all = H_all.shape[1]
+        assert idx.is_cuda and idx.dtype == torch.int64 and idx.dim() == 1 and idx.is_contiguous() and len(idx) <= self.n
+        assert H_all.is_cuda and H_all.dtype == torch.float32 and H_all.shape[0] == self.K and H_all.stride(1) == 1
+        assert len(Ys_all) == self.n_cov
+        for i, Y in enumerate(Ys_all):
+            assert Y.is_cuda and Y.dtype == torch.float32 and Y.shape == (self.c_cov[i], n_all) and Y.is_contiguous()
+        Xb = self._keep.get("X")
+        if Xb is not None:
+            assert X_all is not None and X_all.is_cuda and X_all.dtype == torch.float32 and X_all.stride(1) == 1
+            assert X_all.shape == (n_all, self.G)
+        ya = (ctypes.c_void_p * max(1, self.n_cov))(*([Y.data_ptr() for Y in Ys_all] or [None]))
+        yb = (ctypes.c_void_p * max(1, self.n_cov))(*([Y.data_ptr() for Y in self._keep.get("Ys", [])] or [None]))
+        ldH = H_all.stride(0) if self.K > 1 else max(H_all.stride(0), n_all)
+        _check(self.lib, self.lib.alpine_batch_gather(
+            self._ctx, X_all.data_ptr() if Xb is not None else None,
+            (X_all.stride(0) if n_all > 1 else max(X_all.stride(0), self.G)) if Xb is not None else 0,
+            Xb.data_ptr() if Xb is not None else None, H_all.data_ptr(), ldH, ya, yb, n_all, idx.data_ptr(), len(idx),
+            self._stream()))
+
+    def batch_scatter(self, H_all: torch.Tensor, idx: torch.Tensor) -> None:
+        """``H_all[:, idx] = H_batch[:, :len(idx)]`` (main.py:662), one launch."""
+        n_all = H_all.shape[1]
+        assert idx.is_cuda and idx.dtype == torch.int64 and idx.dim() == 1 and idx.is_contiguous() and len(idx) <= self.n
+        assert H_all.is_cuda and H_all.dtype == torch.float32 and H_all.shape[0] == self.K and H_all.stride(1) == 1
+        ldH = H_all.stride(0) if self.K > 1 else max(H_all.stride(0), n_all)
+        _check(self.lib, self.lib.alpine_batch_scatter(self._ctx, H_all.data_ptr(), ldH, n_all, idx.data_ptr(), len(idx),
+                                                       self._stream()))
 
     def mu_partials(self) -> None:
         _check(self.lib, self.lib.alpine_mu_partials(self._ctx, self._stream()))

@@ -15,6 +15,7 @@
 #include "mu_small_kernels.cuh"
 #include "mu_update_kernels.cuh"
 #include "csr_tiles.cuh"
+#include "batch_kernels.cuh"
 #include "peer_exchange.cuh"
 #include "host_upload.cuh"
 
@@ -864,6 +865,10 @@ int check_kernel_error(alpine_ctx* c) {
   CU_TRY(cudaMemcpy(h, c->err, sizeof(h), cudaMemcpyDeviceToHost));
   if (h[0] != 0) {
     cudaMemset(c->err, 0, sizeof(h));
+    if (h[0] == ERR_BATCH_INDEX)
+      return fail(ALPINE_ERR_ARG, "alpine_batch_gather: idx[%d] = %d is not a cell number of the full-data arrays", h[1], h[2]);
+    if (h[0] == ERR_PEER_TIMEOUT)
+      return fail(ALPINE_ERR_KERNEL, "peer exchange: rank %d waited too long for rank %d (flag set %d, epoch %d)", h[1], h[2], h[3], h[4]);
     return fail(ALPINE_ERR_KERNEL, "contraction kernel pipeline timeout: code %d block %d thread %d aux %d %d", h[0],
                 h[1], h[2], h[3], h[4]);
   }
@@ -874,7 +879,7 @@ int check_kernel_error(alpine_ctx* c) {
 
 extern "C" {
 
-int alpine_abi_version(void) { return 10; }
+int alpine_abi_version(void) { return 11; }
 const char* alpine_last_error(void) { return g_last_error.c_str(); }
 long long alpine_launch_count(void) { return g_launches.load(); }
 
@@ -1212,17 +1217,75 @@ int alpine_batch_begin(alpine_ctx* c, void* stream) {
     AL_TRY(ws_alloc(c, &c->loss_hist, static_cast<size_t>(2 + c->n_cov)));
     c->loss_cap = 1;
   }
-  AL_TRY(export_w(c, st));
-  transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G, c->K,
-                                                                                       c->WT, c->ldG);
-  LAUNCH_CHECK();
-  // split copies of the whole W^T: the simultaneous update rewrites all of them before their first use, the
-  // block-wise sweep (alpine_als_block) only the rows of the block it has just updated
-  AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+  if (!c->w_stale) {
+    // the bound row-major W is the truth (first batch, or another context has updated it since): take W^T and its split
+    // copies from it.  Otherwise this context's own update wrote both a moment ago and nobody has asked for W since
+    // (no alpine_sync_w): consecutive batches of one context skip three G x K passes.
+    transpose_kernel<<<dim3(ceil_div(c->K, 32), ceil_div(c->G, 32)), dim3(32, 8), 0, st>>>(c->W, c->ldW, (int)c->G,
+                                                                                         c->K, c->WT, c->ldG);
+    LAUNCH_CHECK();
+    // split copies of the whole W^T: the simultaneous update rewrites all of them before their first use, the
+    // block-wise sweep (alpine_als_block) only the rows of the block it has just updated
+    AL_TRY(run_split(c, c->WT, c->ldG, c->G, c->Wsplit, c->ldG, st));
+  }
   AL_TRY(run_stats(c, nullptr, false, st));
   AL_TRY(run_split_small(c, c->red_S(), c->K, c->Ssplit, st));
   CU_TRY(cudaMemsetAsync(c->finish_counter, 0, 4 * sizeof(unsigned int), st));
   c->fit_active = true;
+  return ALPINE_OK;
+}
+
+int alpine_batch_gather(alpine_ctx* c, const float* X_all, int64_t ldX_all, float* X_batch, const float* H_all,
+                        int64_t ldH_all, const float* const* Y_all, float* const* Y_batch, int64_t n_all,
+                        const int64_t* idx, int64_t cnt, void* stream) {
+  AL_TRY(check_bound(c, true));
+  if (H_all == nullptr || idx == nullptr || n_all <= 0 || cnt < 0 || cnt > c->n || ldH_all < n_all)
+    return fail(ALPINE_ERR_ARG, "bad batch: %lld of %lld cells into a context of %lld", (long long)cnt, (long long)n_all, (long long)c->n);
+  if (!c->sparse && (X_all == nullptr || X_batch != c->X || ldX_all < c->G))
+    return fail(ALPINE_ERR_ARG, "X_batch must be the array bound with alpine_bind_dense and X_all cells-major with ldX_all >= n_genes");
+  if (c->n_cov > 0 && (Y_all == nullptr || Y_batch == nullptr)) return fail(ALPINE_ERR_ARG, "null label arrays");
+  DEVICE_SCOPE(c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  AL_TRY(ensure_workspace(c, st));
+  BatchGatherParams p{};
+  p.idx = reinterpret_cast<const long long*>(idx);
+  p.cnt = cnt, p.n = c->n, p.n_all = n_all;
+  p.X_all = c->sparse ? nullptr : X_all;
+  p.ldX_all = ldX_all;
+  p.X = c->sparse ? nullptr : X_batch;
+  p.ldX = c->ldX, p.G = c->G;
+  p.vec4 = !c->sparse && ((reinterpret_cast<uintptr_t>(X_all) | reinterpret_cast<uintptr_t>(X_batch)) & 15) == 0 &&
+           ((ldX_all | c->ldX) & 3) == 0;
+  p.H_all = H_all, p.ldH_all = ldH_all, p.H = c->H, p.ldH = c->ldH, p.K = c->K;
+  p.n_cov = c->n_cov;
+  long long rows = c->K;
+  for (int i = 0; i < c->n_cov; ++i) {
+    if (Y_all[i] == nullptr || Y_batch[i] != c->Y[i])
+      return fail(ALPINE_ERR_ARG, "Y_batch[%d] must be the array bound with alpine_bind_labels", i);
+    p.Y_all[i] = Y_all[i], p.Y[i] = Y_batch[i], p.c[i] = c->ccov[i];
+    rows += c->ccov[i];
+  }
+  p.err = c->err;
+  // one row of X per warp and pass: enough blocks to keep every SM's load queues full, no more than there are rows
+  p.x_blocks = c->sparse ? 0 : static_cast<int>(std::min<long long>(ceil_div(c->n, 8), 8ll * c->num_sms));
+  const int hy_blocks = static_cast<int>(std::min<long long>(ceil_div(rows * c->n, 256), 2ll * c->num_sms));
+  batch_gather_kernel<<<p.x_blocks + hy_blocks, 256, 0, st>>>(p);
+  LAUNCH_CHECK();
+  return ALPINE_OK;
+}
+
+int alpine_batch_scatter(alpine_ctx* c, float* H_all, int64_t ldH_all, int64_t n_all, const int64_t* idx, int64_t cnt,
+                         void* stream) {
+  if (c == nullptr || c->H == nullptr) return fail(ALPINE_ERR_STATE, "alpine_bind_factors has not been called");
+  if (H_all == nullptr || idx == nullptr || n_all <= 0 || cnt < 0 || cnt > c->n || ldH_all < n_all)
+    return fail(ALPINE_ERR_ARG, "bad batch");
+  if (cnt == 0) return ALPINE_OK;
+  DEVICE_SCOPE(c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int blocks = static_cast<int>(std::min<long long>(ceil_div(static_cast<long long>(c->K) * cnt, 256), 4ll * c->num_sms));
+  batch_scatter_kernel<<<blocks, 256, 0, st>>>(c->H, c->ldH, c->K, reinterpret_cast<const long long*>(idx), cnt, n_all,
+                                               H_all, ldH_all);
+  LAUNCH_CHECK();
   return ALPINE_OK;
 }
 

@@ -625,9 +625,9 @@ class ALPINE:
         device generator after the W / H / B draws; the weighted sampler's ``multinomial`` on the CPU generator).
 
         Per batch the cells ``idx`` are gathered into contiguous buffers (rows of the cells-major X -- or of the CSR
-        matrix --, columns of H and Y), one MU step runs on them with the same kernels as the full-batch path, and the H
-        columns are scattered back (``Hs[j][:, idx] = ...``, main.py:662; duplicate indices of the weighted sampler
-        resolve as torch's ``index_put`` does).  The loss of every epoch is evaluated on the full data (main.py:666).
+        matrix --, columns of H and Y: one launch, ``alpine_batch_gather``), one MU step runs on them with the same
+        kernels as the full-batch path, and the H columns are scattered back (``Hs[j][:, idx] = ...``, main.py:662,
+        ``alpine_batch_scatter``; duplicate indices of the weighted sampler carry identical columns).  The loss of every epoch is evaluated on the full data (main.py:666).
         Under cell sharding every rank draws the same epoch indices, takes the batch's cells that fall into its own
         column block and the batch's partial sums are all-reduced exactly like a full-batch iteration's.
         """
@@ -681,6 +681,7 @@ class ALPINE:
         # tests replay the reference's recorded sampler output through this hook (one index vector per epoch)
         stream = getattr(self, "_epoch_index_stream", None)
         full = self._make_solver(m)  # full-data context for the per-epoch loss (main.py:666)
+        owner = None  # the batch context whose W^T master copy is ahead of m.W (consecutive batches of one size stay in it)
         try:
             full.fit_begin(1)
             xnorm2 = full.losses(0)[0]
@@ -706,20 +707,17 @@ class ALPINE:
                     else:
                         loc, cnt, size = idx, len(idx), len(idx)
                     s, Xb, Hb, Yb = batch_solver(size)
+                    if owner is not None and owner is not s:
+                        owner.sync_w()  # another context takes over: it reads the shared row-major W
+                        owner = None
+                    loc = loc.contiguous()
                     if sparse:  # the batch's cells as their own CSR matrix -> tile lists (once per batch)
                         indptr, indices, values = _csr_take_rows(m.X_csr, loc)
                         if cnt < size:
                             indptr = torch.cat([indptr, indptr[-1:].expand(size - cnt)])
                         s.bind_csr(indptr.contiguous(), indices, values)
-                    else:
-                        # one gather pass straight into the batch buffer (rows of the cells-major X are contiguous)
-                        torch.index_select(m.X_cells_major, 0, loc, out=Xb[:cnt])
-                        Xb[cnt:].zero_()
-                    Hb[:, :cnt].copy_(m.H.index_select(1, loc))
-                    Hb[:, cnt:].zero_()
-                    for yb, y in zip(Yb, m.Ys):
-                        yb[:, :cnt].copy_(y.index_select(1, loc))
-                        yb[:, cnt:].zero_()
+                    # one launch: rows of the cells-major X (contiguous), columns of H and of every Y, zero padding
+                    s.batch_gather(None if sparse else m.X_cells_major, m.H, m.Ys, loc)
                     s.batch_begin()
                     s.mu_partials()
                     if sharded:
@@ -732,8 +730,11 @@ class ALPINE:
                         s.als_finish(0)
                     else:
                         s.mu_apply(0)
-                        s.sync_w()  # the next batch's context (and the per-epoch loss) read the shared row-major W
-                    m.H[:, loc] = Hb[:, :cnt]  # main.py:662; duplicates of the weighted sampler carry identical columns
+                        owner = s  # its W^T is now ahead of the shared row-major W
+                    s.batch_scatter(m.H, loc)  # main.py:662; duplicates of the weighted sampler carry identical columns
+                if owner is not None:
+                    owner.sync_w()  # the per-epoch loss (and the caller) read the shared row-major W
+                    owner = None
                 history.append(self._compute_loss(m, solver=full, xnorm2=xnorm2))
                 if pbar is not None:
                     pbar.set_postfix({"objective loss": history[-1][0]})

@@ -86,8 +86,23 @@ int alpine_bind_reduce_buffer(alpine_ctx* ctx, float* buf);
 /* Start a fit: ||X||_F^2, tf32 split of the initial H, initial statistics (H H^T, B statistics).
  * max_iter sizes the device-side loss history.  Replaces the head of _fit (main.py:486-498).              */
 int alpine_fit_begin(alpine_ctx* ctx, int max_iter, void* stream);
+/* The cells of one mini-batch into this context's bound arrays, one launch (replaces the advanced-indexing gathers
+ * X[idx], Hs[j][:, idx], Ys[i][:, idx] of main.py:593-595): rows idx[0..cnt) of the cells-major X_all (n_all x n_genes,
+ * pitch ldX_all) -> X_batch (the array bound with alpine_bind_dense; pass NULL / NULL for a CSR context, whose batch
+ * rows the caller binds with alpine_bind_csr), columns idx of H_all (K x n_all, pitch ldH_all) -> the bound H, columns idx of
+ * every Y_all[i] (c_i x n_all, contiguous) -> Y_batch[i] (the arrays bound with alpine_bind_labels).  Cells [cnt, n_cells)
+ * of the context are zero-filled (an all-zero cell contributes nothing and stays zero), so one context serves every
+ * batch of at most n_cells cells.  idx: device array of int64 cell numbers in [0, n_all); a number outside raises
+ * ALPINE_ERR_ARG at the next alpine_fit_losses.                                                                   */
+int alpine_batch_gather(alpine_ctx* ctx, const float* X_all, int64_t ldX_all, float* X_batch, const float* H_all,
+                        int64_t ldH_all, const float* const* Y_all, float* const* Y_batch, int64_t n_all,
+                        const int64_t* idx, int64_t cnt, void* stream);
+/* H_all[:, idx[j]] = H[:, j] for j < cnt after the step (main.py:662).  Duplicate cell numbers carry identical columns. */
+int alpine_batch_scatter(alpine_ctx* ctx, float* H_all, int64_t ldH_all, int64_t n_all, const int64_t* idx, int64_t cnt,
+                         void* stream);
 /* Start a mini-batch step on freshly gathered batch data (main.py:509-521): refreshes the W^T copy from the bound W
- * (another context may have updated it) and the statistics of the bound H / B, without the ||X||^2 pass.  Follow
+ * (another context may have updated it; skipped when this context's own W^T is still ahead of the bound W, i.e. no
+ * alpine_sync_w since its last update) and the statistics of the bound H / B, without the ||X||^2 pass.  Follow
  * with alpine_mu_partials + alpine_mu_apply(ctx, 0, ...); the loss terms of a batch step are not meaningful.     */
 int alpine_batch_begin(alpine_ctx* ctx, void* stream);
 /* First half of one full-batch iteration: numerator X H^T of the W update (main.py:596) into the reduce
