@@ -94,7 +94,8 @@ def default_scorer(val_adata, covariate_keys: List[str], random_state: int) -> f
 
         n_joint = len(val_adata.obs[covariate_keys].astype(str).drop_duplicates())  # distinct joint labels
         k = int(max(2, min(n_joint, len(emb) - 1)))
-        clusters = KMeans(n_clusters=k, n_init=4, random_state=random_state).fit_predict(emb)
+        # (fp64 input: scikit-learn's distance kernels otherwise upcast fp32 chunk by chunk, thousands of small copies)
+        clusters = KMeans(n_clusters=k, n_init=4, random_state=random_state).fit_predict(emb.astype(np.float64))
     score = 0.0
     for key in covariate_keys:
         keep = ~val_adata.obs[key].isna().to_numpy()

@@ -28,6 +28,22 @@ def visible_devices(device: str = "cuda") -> List[str]:
     return [device]
 
 
+def _pool_limits(n_workers: int):
+    """Context manager capping the native thread pools at cores / n_workers (no-op without threadpoolctl)."""
+    import os
+    from contextlib import nullcontext
+
+    try:
+        from threadpoolctl import threadpool_limits
+    except ImportError:  # pragma: no cover
+        return nullcontext()
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        cores = os.cpu_count() or 1
+    return threadpool_limits(limits=max(1, cores // max(1, n_workers)))
+
+
 class DeviceScheduler:
     """Run ``fn(job, device)`` for every job, at most one job per device at a time."""
 
@@ -70,10 +86,13 @@ class DeviceScheduler:
             worker(self.devices[0])
         else:
             threads = [threading.Thread(target=worker, args=(d,), daemon=True) for d in self.devices[:n_workers]]
-            for t in threads:
-                t.start()
-            for t in threads:
-                t.join()
+            # the host-side parts of concurrent jobs (BLAS / OpenMP pools of numpy and scikit-learn inside the scorer)
+            # would each start one thread per core: give every worker its share of the cores instead
+            with _pool_limits(n_workers):
+                for t in threads:
+                    t.start()
+                for t in threads:
+                    t.join()
         if errors:
             raise errors[0]
         return results
