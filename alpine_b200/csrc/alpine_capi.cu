@@ -144,6 +144,24 @@ int make_map(CUtensorMap* m, const float* base, uint64_t inner, uint64_t outer, 
   return ALPINE_OK;
 }
 
+// 2-D bf16 tensor map over 16-bit data: dims {inner, outer}, row pitch ld16 (16-bit elements), box {32, box_outer}
+// (64-byte rows in shared memory, SWIZZLE_64B)
+int make_map_bf16(CUtensorMap* m, const void* base, uint64_t inner, uint64_t outer, uint64_t ld16, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (fn == nullptr) return fail(ALPINE_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0 || (ld16 & 7) != 0)
+    return fail(ALPINE_ERR_ARG, "bf16 TMA operand must be 16-byte aligned with a leading dimension divisible by 8");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld16 * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBK), box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(ALPINE_ERR_CUDA, "cuTensorMapEncodeTiled (bf16) failed with CUresult %d", (int)r);
+  return ALPINE_OK;
+}
+
 inline long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
 inline int ceil_div(long long a, long long b) { return static_cast<int>((a + b - 1) / b); }
 
@@ -182,7 +200,7 @@ struct GemmPlan {
   GemmOperands op;
   int* d_slot_ofs = nullptr;  // device copies of the reduce kernel's slot lists
   int* d_slots = nullptr;
-  CUtensorMap tmX, tmBhi, tmBlo, tmX2;
+  CUtensorMap tmX, tmBhi, tmBh16, tmBl16, tmX2;
   int extra_tile = -1;
   GemmParams p{};
   ReduceParams r{};
@@ -400,7 +418,7 @@ int ensure_workspace(alpine_ctx* c, cudaStream_t st) {
   {
     const int tiles_h = ceil_div(c->n, kUpdCols);
     c->upd_grid_h = tiles_h < 3 * c->num_sms ? tiles_h : 3 * c->num_sms;
-    c->ldK = round_up(c->K, 4);
+    c->ldK = round_up(c->K, 8);
     AL_TRY(ws_alloc(c, &c->Ssplit, 2 * K * c->ldK));
     AL_TRY(ws_alloc(c, &c->Tsplit, 2 * K * c->ldK));
     CU_TRY(cudaMemsetAsync(c->Ssplit, 0, 2 * K * c->ldK * sizeof(float), st));
@@ -466,7 +484,7 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
 #define ALPINE_GEMM_CASE(NC)                                                                     \
   case NC:                                                                                       \
     PDL_LAUNCH(mu_gemm_kernel<ORIENT, NC, EXACT>, dim3(pl.grid), dim3(kGemmThreads), pl.smem, st, pl.tmX, pl.tmBhi,  \
-               pl.tmBlo, pl.tmX2, pl.p);                                                         \
+               pl.tmBh16, pl.tmBl16, pl.tmX2, pl.p);                                             \
     break;
     ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
     ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
@@ -574,7 +592,11 @@ int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long lo
     AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, kBK, rows, true));
   const float* b_hi = op.Bsplit + static_cast<size_t>(op.k0) * op.ldS;
   AL_TRY(make_map(&pl->tmBhi, b_hi, R, Kop, op.ldS, kBK, p.Kp, true));
-  AL_TRY(make_map(&pl->tmBlo, b_hi + static_cast<size_t>(c->K) * op.ldS, R, Kop, op.ldS, kBK, p.Kp, true));
+  // plane 1 of the split copies, read as 16-bit [K][2][ldS]: row k = bf16(hi)[ldS] then bf16(lo)[ldS]
+  const uint16_t* b_16 = reinterpret_cast<const uint16_t*>(op.Bsplit + static_cast<size_t>(c->K) * op.ldS) +
+                         static_cast<size_t>(op.k0) * 2 * op.ldS;
+  AL_TRY(make_map_bf16(&pl->tmBh16, b_16, R, Kop, 2 * op.ldS, p.Kp));
+  AL_TRY(make_map_bf16(&pl->tmBl16, b_16 + op.ldS, R, Kop, 2 * op.ldS, p.Kp));
   pl->extra_tile = p.extra_tile;
   if (p.extra_tile >= 0)
     AL_TRY(make_map(&pl->tmX2, op.extra, op.cols, op.extra_rows, op.ldE, kBK, rows, true));
@@ -946,8 +968,8 @@ int alpine_create(alpine_ctx** out, int device, int64_t n_genes, int64_t n_cells
 #ifdef ALPINE_B200_DEBUG_SIMT
   if (const char* e = getenv("ALPINE_B200_GEMM")) c->simt = (strcmp(e, "simt") == 0);
 #endif
-  c->ldG = round_up(n_genes, 4);
-  c->ldN = round_up(n_cells, 4);
+  c->ldG = round_up(n_genes, 8);  // (8: the bf16 halves of the split copies start on 16-byte boundaries)
+  c->ldN = round_up(n_cells, 8);
   *out = c;
   return ALPINE_OK;
 }

@@ -49,6 +49,7 @@ namespace alpine {
 constexpr int kBM = 128;         // rows per MMA tile == TMEM lanes
 constexpr int kBK = 32;          // reduction elements per pipeline stage (128 bytes of fp32)
 constexpr int kUmmaK = 8;        // tf32: 32 bytes per MMA k-step
+constexpr int kUmmaK16 = 16;     // bf16: 32 bytes per MMA k-step
 constexpr int kTmemCols = 512;
 constexpr int kTmemAOff = 256;   // A staging starts here; accumulators occupy [0, 256)
 constexpr int kMaxXStages = 8;
@@ -241,7 +242,7 @@ constexpr int kRows = kMT * kBM;
 constexpr int kConvWarps = 4 * kMT;
 constexpr int kGemmThreads = (kConvWarps + 4) * 32;  // + X producer, B producer, one MMA issuer per tile
 constexpr int kXTileBytes = kRows * kBK * 4;
-constexpr int kAStageCols = kMT * 64;   // per MMA tile: 32 hi + 32 lo columns
+constexpr int kAStageCols = kMT * 64;   // per MMA tile: 32 tf32 hi columns + 16 bf16(hi) + 16 bf16(lo) columns
 constexpr int kAStages = (kTmemCols - kTmemAOff) / kAStageCols;
 constexpr int kAccStride = kTmemAOff / kMT;  // column distance between the two accumulators (=> Kp <= 128)
 
@@ -262,10 +263,15 @@ __host__ __device__ inline GemmSmemLayout gemm_smem_layout(int Kp, int sx, int s
 template <int ORIENT, int NC, bool EXACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
-               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmX2, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmBh16, const __grid_constant__ CUtensorMap tmBl16,
+               const __grid_constant__ CUtensorMap tmX2, const GemmParams p) {
   constexpr int Kp = 16 * NC;
   constexpr int kWarpXProd = kConvWarps, kWarpBProd = kConvWarps + 1, kWarpMma = kConvWarps + 2;  // + kMT MMA warps
-  constexpr int b_tile_bytes = Kp * kBK * 4;
+  // one B stage: tf32 hi tile [Kp][32] (128-byte rows, SWIZZLE_128B), then the bf16 images of hi and of lo
+  // [Kp][32] each (64-byte rows, SWIZZLE_64B)
+  constexpr int b_hi_bytes = Kp * kBK * 4;
+  constexpr int b_16_bytes = Kp * kBK * 2;
+  constexpr int b_stage_bytes = b_hi_bytes + 2 * b_16_bytes;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -323,7 +329,8 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
   if (warp == kWarpBProd && lane == 0) {
     ptx::prefetch_tensormap(&tmBhi);
-    ptx::prefetch_tensormap(&tmBlo);
+    ptx::prefetch_tensormap(&tmBh16);
+    ptx::prefetch_tensormap(&tmBl16);
   }
   if (warp == kWarpMma) {  // the first MMA warp owns the TMEM allocation
     ptx::tmem_alloc(tmem_slot, kTmemCols);
@@ -465,10 +472,11 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             ok = false;
             break;
           }
-          uint8_t* dst = smem_b + static_cast<size_t>(s) * 2 * b_tile_bytes;
-          ptx::mbar_arrive_expect_tx(&bfull_bar[s], 2 * b_tile_bytes);
+          uint8_t* dst = smem_b + static_cast<size_t>(s) * b_stage_bytes;
+          ptx::mbar_arrive_expect_tx(&bfull_bar[s], b_stage_bytes);
           ptx::tma_load_2d(dst, &tmBhi, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
-          ptx::tma_load_2d(dst + b_tile_bytes, &tmBlo, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+          ptx::tma_load_2d(dst + b_hi_bytes, &tmBh16, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+          ptx::tma_load_2d(dst + b_hi_bytes + b_16_bytes, &tmBl16, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
         }
         pos += len;
       }
@@ -483,6 +491,7 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base, 0);
     const uint32_t smem_b_u32 = __shfl_sync(0xffffffffu, ptx::smem_u32(smem_b), 0);
     const uint32_t idesc = ptx::make_idesc_tf32(kBM, Kp);
+    const uint32_t idesc16 = ptx::make_idesc_bf16(kBM, Kp);
     const uint32_t d_acc = tb + mt * kAccStride;
     uint32_t it = 0, mc = 0;  // k-block counter, chunk counter
     bool ok = true;
@@ -512,21 +521,24 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           }
         }
         ptx::tc_fence_after();
-        const uint32_t sb_addr = smem_b_u32 + static_cast<uint32_t>(sbi) * 2 * b_tile_bytes;
+        const uint32_t sb_addr = smem_b_u32 + static_cast<uint32_t>(sbi) * b_stage_bytes;
         const uint64_t dhi = ptx::make_kmajor_sw128_desc(sb_addr);
-        const uint64_t dlo = ptx::make_kmajor_sw128_desc(sb_addr + b_tile_bytes);
+        const uint64_t dh16 = ptx::make_kmajor_sw64_desc(sb_addr + b_hi_bytes);
+        const uint64_t dl16 = ptx::make_kmajor_sw64_desc(sb_addr + b_hi_bytes + b_16_bytes);
         const uint32_t a_hi = tb + kTmemAOff + t * kAStageCols + mt * 64;
-        const uint32_t a_lo = a_hi + 32;
+        const uint32_t a_h16 = a_hi + 32, a_l16 = a_hi + 48;
+        // the small terms first: lo * hi and hi * lo as bf16 MMAs (16 reduction elements = 32 bytes = 8 TMEM
+        // columns per step), then hi * hi as tf32 MMAs (8 elements per step)
 #pragma unroll
-        for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
-          // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
-          const uint64_t bh = dhi + static_cast<uint64_t>(2 * ks);
-          const uint64_t bl = dlo + static_cast<uint64_t>(2 * ks);
+        for (int ks = 0; ks < kBK / kUmmaK16; ++ks) {
+          // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
           const uint32_t fresh = (c_first && ks == 0) ? 0u : 1u;
-          if (!EXACT) ptx::mma_tf32_ts_if(leader, d_acc, a_lo + ks * kUmmaK, bh, idesc, fresh);
-          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bl, idesc, EXACT ? fresh : 1u);
-          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, bh, idesc, 1u);
+          if (!EXACT) ptx::mma_bf16_ts_if(leader, d_acc, a_l16 + 8 * ks, dh16 + static_cast<uint64_t>(2 * ks), idesc16, fresh);
+          ptx::mma_bf16_ts_if(leader, d_acc, a_h16 + 8 * ks, dl16 + static_cast<uint64_t>(2 * ks), idesc16, EXACT ? fresh : 1u);
         }
+#pragma unroll
+        for (int ks = 0; ks < kBK / kUmmaK; ++ks)
+          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, dhi + static_cast<uint64_t>(2 * ks), idesc, 1u);
         if (c_last) {
           ptx::tc_commit_if(leader, &accfull_bar[mt]);
           ++mc;
@@ -625,7 +637,15 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
           ptx::tmem_st_x8(a_addr + 8 * h, hi);
-          if (!EXACT) ptx::tmem_st_x8(a_addr + 32 + 8 * h, lo);
+          // bf16 images for the correction terms, two reduction elements per column (even element in the low half)
+          uint32_t h16[4], l16[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            h16[q] = ptx::pack_bf16x2(__uint_as_float(hi[2 * q]), __uint_as_float(hi[2 * q + 1]));
+            l16[q] = ptx::pack_bf16x2(__uint_as_float(lo[2 * q]), __uint_as_float(lo[2 * q + 1]));
+          }
+          ptx::tmem_st_x4(a_addr + 32 + 4 * h, h16);
+          if (!EXACT) ptx::tmem_st_x4(a_addr + 48 + 4 * h, l16);
         }
         ptx::tc_wait_st();
         ptx::tc_fence_before();

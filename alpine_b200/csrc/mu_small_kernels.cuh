@@ -237,8 +237,9 @@ __global__ void scale_b_kernel(const CovTable tab, const float* __restrict__ s) 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// 3xTF32 operand split of the small (K x R) operand of a contraction: hi / lo copies with the same pitch.
-// Pitches are multiples of 4 floats and bases 16-byte aligned, so whole float4 groups are always in bounds.
+// Operand split of the small (K x R) operand of a contraction: plane `hi` = tf32 hi values, plane `lo` = the bf16
+// images of hi and of the remainder (ptx::store_split4).  Pitches are multiples of 8 floats and bases 16-byte
+// aligned, so whole groups of four are always in bounds.
 __global__ void split_operand_kernel(const float* __restrict__ src, long long ld_src, int rows, long long cols,
                                      float* __restrict__ hi, float* __restrict__ lo, long long ld_dst) {
   ptx::pdl_enter();
@@ -247,16 +248,7 @@ __global__ void split_operand_kernel(const float* __restrict__ src, long long ld
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / c4n, c = (i - r * c4n) << 2;
-    const float4 v = *reinterpret_cast<const float4*>(src + r * ld_src + c);
-    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-    ptx::split_tf32(v.x, h0, l0);
-    ptx::split_tf32(v.y, h1, l1);
-    ptx::split_tf32(v.z, h2, l2);
-    ptx::split_tf32(v.w, h3, l3);
-    *reinterpret_cast<float4*>(hi + r * ld_dst + c) =
-        make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-    *reinterpret_cast<float4*>(lo + r * ld_dst + c) =
-        make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+    ptx::store_split4(*reinterpret_cast<const float4*>(src + r * ld_src + c), hi, lo, r, c, ld_dst);
   }
 }
 
@@ -267,10 +259,7 @@ __global__ void split_small_kernel(const float* __restrict__ src, int ld_src, in
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= K * K) return;
   const int r = e / K, c = e - r * K;
-  uint32_t h, l;
-  ptx::split_tf32(src[r * ld_src + c], h, l);
-  hi[r * ld_dst + c] = __uint_as_float(h);
-  lo[r * ld_dst + c] = __uint_as_float(l);
+  ptx::store_split1(src[r * ld_src + c], hi, lo, r, c, ld_dst);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -473,14 +462,9 @@ __global__ void __launch_bounds__(256) sym_long_kernel(const SymLongParams p) {
     }
     if (EPI != EPI_TRANSFORM && p.split_hi != nullptr) {
       // pitches are multiples of 4 and the pad columns are never read unmasked, so whole float4 groups are written
-      uint32_t h[4], l[4];
-#pragma unroll
-      for (int x = 0; x < 4; ++x) ptx::split_tf32((col + x < p.L) ? outv[x] : 0.f, h[x], l[x]);
-      const long long o = static_cast<long long>(k) * p.ld_split + col;
-      *reinterpret_cast<float4*>(p.split_hi + o) =
-          make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
-      *reinterpret_cast<float4*>(p.split_lo + o) =
-          make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+      ptx::store_split4(make_float4((col + 0 < p.L) ? outv[0] : 0.f, (col + 1 < p.L) ? outv[1] : 0.f,
+                                    (col + 2 < p.L) ? outv[2] : 0.f, (col + 3 < p.L) ? outv[3] : 0.f),
+                        p.split_hi, p.split_lo, k, col, p.ld_split);
     }
     if (EPI == EPI_H && p.rowsum_partial != nullptr) {
       float v = 0.f;

@@ -154,16 +154,7 @@ __device__ __forceinline__ void store4(float4 v, int k, long long col, long long
         if (col + x < L) pd[x] = vv[x];
     }
   }
-  if (split_hi != nullptr) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int x = 0; x < 4; ++x) ptx::split_tf32(vv[x], h[x], l[x]);
-    const long long o = static_cast<long long>(k) * ld_split + col;
-    *reinterpret_cast<float4*>(split_hi + o) =
-        make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
-    *reinterpret_cast<float4*>(split_lo + o) =
-        make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
-  }
+  if (split_hi != nullptr) ptx::store_split4(v, split_hi, split_lo, k, col, ld_split);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -574,10 +565,7 @@ __device__ __forceinline__ void gram_from_slots_block(const GramFromSlots& g, in
     for (int i = 1; i < 8; ++i) t += red[i][lane];
     g.out[k * g.ld + r] = t;
     if (g.split_hi != nullptr) {
-      uint32_t h, l;
-      ptx::split_tf32(t, h, l);
-      g.split_hi[k * g.ld_split + r] = __uint_as_float(h);
-      g.split_lo[k * g.ld_split + r] = __uint_as_float(l);
+      ptx::store_split1(t, g.split_hi, g.split_lo, k, r, g.ld_split);
     }
   }
 }

@@ -74,15 +74,7 @@ __global__ void __launch_bounds__(256) peer_close_and_split_kernel(const PeerTab
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const long long r = i / c4n, c = (i - r * c4n) << 2;
     const float4 v = ld_sys_v4(src + r * ld_src + c);  // written by the peers a moment ago: not from a stale L1 line
-    uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-    ptx::split_tf32(v.x, h0, l0);
-    ptx::split_tf32(v.y, h1, l1);
-    ptx::split_tf32(v.z, h2, l2);
-    ptx::split_tf32(v.w, h3, l3);
-    *reinterpret_cast<float4*>(hi + r * ld_dst + c) =
-        make_float4(__uint_as_float(h0), __uint_as_float(h1), __uint_as_float(h2), __uint_as_float(h3));
-    *reinterpret_cast<float4*>(lo + r * ld_dst + c) =
-        make_float4(__uint_as_float(l0), __uint_as_float(l1), __uint_as_float(l2), __uint_as_float(l3));
+    ptx::store_split4(v, hi, lo, r, c, ld_dst);
   }
 }
 
@@ -121,10 +113,7 @@ __global__ void __launch_bounds__(256) peer_gather_reduce_kernel(const PeerTable
     if (s_hi != nullptr && e < static_cast<long long>(K) * K) {
       // the first K * K entries are the summed H H^T: its tf32 hi / lo copies are the B operand of (H H^T) W^T
       const int r = static_cast<int>(e / K), c = static_cast<int>(e - static_cast<long long>(r) * K);
-      uint32_t h, l;
-      ptx::split_tf32(acc, h, l);
-      s_hi[r * ld_split + c] = __uint_as_float(h);
-      s_lo[r * ld_split + c] = __uint_as_float(l);
+      ptx::store_split1(acc, s_hi, s_lo, r, c, ld_split);
     }
   }
   const long long w4 = (g1 - g0 + 3) >> 2;  // g0 is a multiple of 64 and ldG of 4: whole float4 groups stay in the pitch

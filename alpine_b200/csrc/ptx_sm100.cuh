@@ -149,6 +149,20 @@ __device__ __forceinline__ void mma_tf32_ts_if(uint32_t leader, uint32_t d_tmem,
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
       : "memory");
 }
+// same for kind::f16 with bf16 operands (A: two elements per 32-bit TMEM column, B: shared-memory descriptor), fp32 D
+__device__ __forceinline__ void mma_bf16_ts_if(uint32_t leader, uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}"
+      ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(leader)
+      : "memory");
+}
 __device__ __forceinline__ void tc_commit_if(uint32_t leader, uint64_t* bar) {
   asm volatile(
       "{\n\t"
@@ -187,6 +201,11 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t (&v)[
       "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
       "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st_x4(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]),
+               "r"(v[2]), "r"(v[3])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&v)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
@@ -229,6 +248,53 @@ __device__ __forceinline__ void split_tf32_fast(float x, uint32_t& hi, uint32_t&
   lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
+// The two correction products of the split (hi * lo and lo * hi, each ~2^-11 of the main product) run as bf16 MMAs at
+// twice the tf32 rate: their operands are the round-to-nearest-even bf16 values of hi and of the exact remainder
+// lo = x - hi.  The rounding is unbiased and contributes ~2^-9 * 2^-11 = 2^-20 relative per product term with a random
+// sign, which averages out over the reduction exactly like the 2^-22 of the plain 3xTF32 split (measured on the golden
+// trajectories: same deviation from the reference).
+// {even element -> low half, odd element -> high half}: the order of two adjacent K elements in a 32-bit word
+__device__ __forceinline__ uint32_t pack_bf16x2(float even, float odd) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(odd), "f"(even));
+  return r;
+}
+__device__ __forceinline__ uint16_t bf16_bits(float x) {
+  const uint32_t b = __float_as_uint(x);
+  return static_cast<uint16_t>((b + 0x7FFFu + ((b >> 16) & 1u)) >> 16);
+}
+// B-operand copies of a value: tf32 hi (fp32 container) and the bf16 images of hi and of the remainder
+__device__ __forceinline__ void split_b_operand(float x, uint32_t& hi, uint16_t& hi16, uint16_t& lo16) {
+  hi = round_tf32(x);
+  hi16 = bf16_bits(__uint_as_float(hi));
+  lo16 = bf16_bits(x - __uint_as_float(hi));
+}
+// The split copies of a [K][ld] operand live in two planes of K * ld floats each: plane 0 holds the tf32 hi values,
+// plane 1 is read as 16-bit [K][2][ld]: row k = bf16(hi)[ld] followed by bf16(lo)[ld]  (ld % 8 == 0).
+__device__ __forceinline__ void store_split1(float x, float* plane0, float* plane1, long long k, long long col, long long ld) {
+  uint32_t hi;
+  uint16_t h16, l16;
+  split_b_operand(x, hi, h16, l16);
+  plane0[k * ld + col] = __uint_as_float(hi);
+  uint16_t* p1 = reinterpret_cast<uint16_t*>(plane1) + 2 * k * ld + col;
+  p1[0] = h16;
+  p1[ld] = l16;
+}
+// four adjacent columns (col % 4 == 0)
+__device__ __forceinline__ void store_split4(float4 v, float* plane0, float* plane1, long long k, long long col, long long ld) {
+  const float x[4] = {v.x, v.y, v.z, v.w};
+  float h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = __uint_as_float(round_tf32(x[i]));
+    l[i] = x[i] - h[i];
+  }
+  *reinterpret_cast<float4*>(plane0 + k * ld + col) = make_float4(h[0], h[1], h[2], h[3]);
+  uint16_t* p1 = reinterpret_cast<uint16_t*>(plane1) + 2 * k * ld + col;
+  *reinterpret_cast<uint2*>(p1) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+  *reinterpret_cast<uint2*>(p1 + ld) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+}
+
 // ---------------------------------------------------------------- descriptors
 // UMMA shared-memory descriptor: K-major operand, SWIZZLE_128B, rows of 128 bytes, 8-row groups 1024 B apart.
 // (layout of cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
@@ -242,11 +308,27 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(2) << 61;             // SWIZZLE_128B
   return d;
 }
+// Same for 64-byte rows (32 bf16 reduction elements per row): SWIZZLE_64B (layout_type 4), 8-row groups 512 B apart.
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
 // UMMA instruction descriptor for kind::tf32, fp32 accumulate, A and B K-major.
 // (cute::UMMA::InstrDescriptor: c_format [4,6)=1 F32, a_format [7,10)=2 TF32, b_format [10,13)=2 TF32,
 //  a_major bit 15, b_major bit 16, n_dim [17,23) = N>>3, m_dim [24,29) = M>>4)
 __host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
   return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+         (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// kind::f16 with bf16 A and B (format 1), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
          (static_cast<uint32_t>(M >> 4) << 24);
 }
 
