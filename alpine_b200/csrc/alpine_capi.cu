@@ -200,7 +200,7 @@ struct GemmPlan {
   GemmOperands op;
   int* d_slot_ofs = nullptr;  // device copies of the reduce kernel's slot lists
   int* d_slots = nullptr;
-  CUtensorMap tmX, tmBhi, tmBh16, tmBl16, tmX2;
+  CUtensorMap tmX, tmBhi, tmBh16, tmBl16, tmBlo, tmX2;
   int extra_tile = -1;
   GemmParams p{};
   ReduceParams r{};
@@ -244,8 +244,8 @@ struct alpine_ctx {
   // workspaces (device)
   long long ldG = 0, ldN = 0;
   float* WT = nullptr;     // [K][ldG]
-  float* Hsplit = nullptr; // [2][K][ldN]  tf32 hi / lo copies of H   (B operand of X H^T)
-  float* Wsplit = nullptr; // [2][K][ldG]  tf32 hi / lo copies of W^T (B operand of W^T X)
+  float* Hsplit = nullptr; // [3][K][ldN]  split copies of H (ptx::store_split4): tf32 hi plane, then [K][2 ldN]: bf16(hi), bf16(lo) | tf32(lo)  (B operand of X H^T)
+  float* Wsplit = nullptr; // [3][K][ldG]  split copies of W^T, same layout (B operand of W^T X)
   float* A = nullptr;      // [K][ldN]   W^T X
   float* numG = nullptr;   // [Kg][ldN]
   float* denG = nullptr;
@@ -261,8 +261,8 @@ struct alpine_ctx {
   // fused update kernels (csrc/mu_update_kernels.cuh): per-CTA partials, summed by the finish kernels
   int upd_grid_h = 0;
   long long ldK = 0;
-  float* Ssplit = nullptr;        // [2][K][ldK]  tf32 hi / lo of the complete H H^T (B operand of Z_W)
-  float* Tsplit = nullptr;        // [2][K][ldK]  tf32 hi / lo of W^T W             (B operand of Z_H)
+  float* Ssplit = nullptr;        // [3][K][ldK]  split copies of the complete H H^T (B operand of Z_W)
+  float* Tsplit = nullptr;        // [3][K][ldK]  split copies of W^T W             (B operand of Z_H)
   float* hsum_part = nullptr;     // [upd_grid_h][K]
   float* q_part = nullptr;        // [upd_grid_h][q_total]
   double* pred_part = nullptr;    // [upd_grid_h][n_cov]
@@ -400,10 +400,10 @@ int ensure_workspace(alpine_ctx* c, cudaStream_t st) {
   const size_t K = c->K;
   AL_TRY(ws_alloc(c, &c->WT, K * c->ldG));
   AL_TRY(ws_alloc(c, &c->A, K * c->ldN));
-  AL_TRY(ws_alloc(c, &c->Hsplit, 2 * K * c->ldN));
-  AL_TRY(ws_alloc(c, &c->Wsplit, 2 * K * c->ldG));
-  CU_TRY(cudaMemsetAsync(c->Hsplit, 0, 2 * K * c->ldN * sizeof(float), st));
-  CU_TRY(cudaMemsetAsync(c->Wsplit, 0, 2 * K * c->ldG * sizeof(float), st));
+  AL_TRY(ws_alloc(c, &c->Hsplit, 3 * K * c->ldN));
+  AL_TRY(ws_alloc(c, &c->Wsplit, 3 * K * c->ldG));
+  CU_TRY(cudaMemsetAsync(c->Hsplit, 0, 3 * K * c->ldN * sizeof(float), st));
+  CU_TRY(cudaMemsetAsync(c->Wsplit, 0, 3 * K * c->ldG * sizeof(float), st));
   AL_TRY(ws_alloc(c, &c->numG, static_cast<size_t>(c->Kg) * c->ldN));
   AL_TRY(ws_alloc(c, &c->denG, static_cast<size_t>(c->Kg) * c->ldN));
   AL_TRY(ws_alloc(c, &c->T, K * K));
@@ -419,10 +419,10 @@ int ensure_workspace(alpine_ctx* c, cudaStream_t st) {
     const int tiles_h = ceil_div(c->n, kUpdCols);
     c->upd_grid_h = tiles_h < 3 * c->num_sms ? tiles_h : 3 * c->num_sms;
     c->ldK = round_up(c->K, 8);
-    AL_TRY(ws_alloc(c, &c->Ssplit, 2 * K * c->ldK));
-    AL_TRY(ws_alloc(c, &c->Tsplit, 2 * K * c->ldK));
-    CU_TRY(cudaMemsetAsync(c->Ssplit, 0, 2 * K * c->ldK * sizeof(float), st));
-    CU_TRY(cudaMemsetAsync(c->Tsplit, 0, 2 * K * c->ldK * sizeof(float), st));
+    AL_TRY(ws_alloc(c, &c->Ssplit, 3 * K * c->ldK));
+    AL_TRY(ws_alloc(c, &c->Tsplit, 3 * K * c->ldK));
+    CU_TRY(cudaMemsetAsync(c->Ssplit, 0, 3 * K * c->ldK * sizeof(float), st));
+    CU_TRY(cudaMemsetAsync(c->Tsplit, 0, 3 * K * c->ldK * sizeof(float), st));
     AL_TRY(ws_alloc(c, &c->hsum_part, K * c->upd_grid_h));
     AL_TRY(ws_alloc(c, &c->q_part, static_cast<size_t>(c->q_total > 0 ? c->q_total : 1) * c->upd_grid_h));
     AL_TRY(ws_alloc(c, &c->pred_part, static_cast<size_t>(c->n_cov > 0 ? c->n_cov : 1) * c->upd_grid_h));
@@ -484,7 +484,7 @@ int launch_gemm_t(const GemmPlan& pl, cudaStream_t st) {
 #define ALPINE_GEMM_CASE(NC)                                                                     \
   case NC:                                                                                       \
     PDL_LAUNCH(mu_gemm_kernel<ORIENT, NC, EXACT>, dim3(pl.grid), dim3(kGemmThreads), pl.smem, st, pl.tmX, pl.tmBhi,  \
-               pl.tmBh16, pl.tmBl16, pl.tmX2, pl.p);                                             \
+               pl.tmBh16, pl.tmBl16, pl.tmBlo, pl.tmX2, pl.p);                                   \
     break;
     ALPINE_GEMM_CASE(1) ALPINE_GEMM_CASE(2) ALPINE_GEMM_CASE(3) ALPINE_GEMM_CASE(4)
     ALPINE_GEMM_CASE(5) ALPINE_GEMM_CASE(6) ALPINE_GEMM_CASE(7) ALPINE_GEMM_CASE(8)
@@ -592,11 +592,12 @@ int build_plan_tail(alpine_ctx* c, GemmPlan* pl, const GemmOperands& op, long lo
     AL_TRY(make_map(&pl->tmX, op.Xmem, op.cols, op.rows, op.ldX, kBK, rows, true));
   const float* b_hi = op.Bsplit + static_cast<size_t>(op.k0) * op.ldS;
   AL_TRY(make_map(&pl->tmBhi, b_hi, R, Kop, op.ldS, kBK, p.Kp, true));
-  // plane 1 of the split copies, read as 16-bit [K][2][ldS]: row k = bf16(hi)[ldS] then bf16(lo)[ldS]
-  const uint16_t* b_16 = reinterpret_cast<const uint16_t*>(op.Bsplit + static_cast<size_t>(c->K) * op.ldS) +
-                         static_cast<size_t>(op.k0) * 2 * op.ldS;
-  AL_TRY(make_map_bf16(&pl->tmBh16, b_16, R, Kop, 2 * op.ldS, p.Kp));
-  AL_TRY(make_map_bf16(&pl->tmBl16, b_16 + op.ldS, R, Kop, 2 * op.ldS, p.Kp));
+  // plane 1 of the split copies, [K][2 * ldS] floats: row k = 16-bit bf16(hi)[ldS], bf16(lo)[ldS], then tf32(lo)[ldS]
+  const float* b_p1 = op.Bsplit + static_cast<size_t>(c->K) * op.ldS + static_cast<size_t>(op.k0) * 2 * op.ldS;
+  const uint16_t* b_16 = reinterpret_cast<const uint16_t*>(b_p1);
+  AL_TRY(make_map_bf16(&pl->tmBh16, b_16, R, Kop, 4 * op.ldS, p.Kp));
+  AL_TRY(make_map_bf16(&pl->tmBl16, b_16 + op.ldS, R, Kop, 4 * op.ldS, p.Kp));
+  AL_TRY(make_map(&pl->tmBlo, b_p1 + op.ldS, R, Kop, 2 * op.ldS, kBK, p.Kp, true));
   pl->extra_tile = p.extra_tile;
   if (p.extra_tile >= 0)
     AL_TRY(make_map(&pl->tmX2, op.extra, op.cols, op.extra_rows, op.ldE, kBK, rows, true));
@@ -687,7 +688,7 @@ GemmOperands plan_operands(const alpine_ctx* c, int which, int group = 0) {
   return op;
 }
 
-// tf32 hi / lo copies of a small operand [K][R]
+// split copies (ptx::store_split4) of a small operand [K][R]
 int run_split(alpine_ctx* c, const float* src, long long ld_src, long long R, float* dst, long long ldS,
               cudaStream_t st) {
   PDL_LAUNCH(split_operand_kernel, dim3(2 * c->num_sms), dim3(256), 0, st, src, ld_src, c->K, R, dst,
@@ -852,7 +853,7 @@ int launch_h_update(alpine_ctx* c, const HUpdParams& p, cudaStream_t st) {
   return ALPINE_OK;
 }
 
-// tf32 hi / lo copies of a K x K matrix (pitch ld_src, any alignment) into a [2][K][ldK] operand buffer
+// split copies of a K x K matrix (pitch ld_src, any alignment) into a [3][K][ldK] operand buffer
 int run_split_small(alpine_ctx* c, const float* src, int ld_src, float* dst, cudaStream_t st) {
   PDL_LAUNCH(split_small_kernel, dim3(ceil_div(static_cast<long long>(c->K) * c->K, 256)), dim3(256), 0, st, src, ld_src,
              c->K, dst, dst + static_cast<size_t>(c->K) * c->ldK, static_cast<int>(c->ldK));
@@ -1005,7 +1006,7 @@ int64_t alpine_workspace_bytes(const alpine_ctx* c) {
   const size_t K = c->K, f = sizeof(float);
   size_t b = 0;
   b += ws_bytes(K * c->ldG, f) + ws_bytes(K * c->ldN, f);                  // W^T, A
-  b += ws_bytes(2 * K * c->ldN, f) + ws_bytes(2 * K * c->ldG, f);          // split copies
+  b += ws_bytes(3 * K * c->ldN, f) + ws_bytes(3 * K * c->ldG, f);          // split copies
   b += 2 * ws_bytes(static_cast<size_t>(c->Kg) * c->ldN, f);              // guided terms
   b += ws_bytes(K * K, f) + ws_bytes(K, f);
   const size_t stat_blocks = ceil_div(c->n, kStatCells), sl_blocks = ceil_div(c->n, kSLCols);
@@ -1014,7 +1015,7 @@ int64_t alpine_workspace_bytes(const alpine_ctx* c) {
   b += ws_bytes(static_cast<size_t>(c->reduce_floats()), f);
   {
     const size_t gh = ceil_div(c->n, kUpdCols) < 3 * c->num_sms ? ceil_div(c->n, kUpdCols) : 3 * c->num_sms;
-    b += 2 * ws_bytes(2 * K * round_up(c->K, 4), f) + ws_bytes(K * gh, f);
+    b += 2 * ws_bytes(3 * K * round_up(c->K, 8), f) + ws_bytes(K * gh, f);
     b += ws_bytes((c->q_total > 0 ? c->q_total : 1) * gh, f) + ws_bytes((c->n_cov > 0 ? c->n_cov : 1) * gh, 8);
     b += ws_bytes(gh, 8) + kWsAlign;
   }

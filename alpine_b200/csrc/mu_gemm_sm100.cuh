@@ -1,5 +1,5 @@
 // The two dense contractions of ALPINE's multiplicative-update step over the gene x cell matrix X, as one
-// warp-specialised, persistent, stream-K tcgen05 kernel for sm_100a (3xTF32 split precision, fp32 accumulate):
+// warp-specialised, persistent, stream-K tcgen05 kernel for sm_100a (split-precision products, fp32 accumulate):
 //
 //   ORIENT_XH:  D[g][k] = sum_j X[g][j] * H[k][j]     (reference main.py:596,  (2*X_batch) @ H^T)
 //   ORIENT_WX:  D[j][k] = sum_g X[g][j] * W[g][k]     (reference main.py:653,  (2*W^T) @ X_batch)
@@ -9,22 +9,32 @@
 // cells (WX), the N side is the K components (padded to a multiple of 16), the reduction runs over the other
 // axis of X in blocks of 32.
 //
+//  * Precision: every fp32 value is split into hi = tf32(x) and the exact remainder lo = x - hi (|lo| <= 2^-11 |x|);
+//    x * y = hi * hi' + hi * lo' + lo * hi' + O(2^-22).  The main term runs as tf32 MMAs, the two correction terms
+//    as bf16 MMAs (kind::f16) on the round-to-nearest bf16 images of hi and lo, at twice the tf32 rate: 2 instead of 3
+//    tf32-MMA equivalents per product, which moves the dense sweep from the tensor roofline to the HBM roofline.
+//    The bf16 rounding of a correction operand is unbiased and costs ~2^-9 of a term that is itself 2^-11 of the
+//    product; over the long reductions of this workload it averages out like the 2^-22 of plain 3xTF32 (the golden
+//    trajectories deviate from the reference by the same amount with either scheme, tests/test_split_precision.py).
 //  * A operand (X super-tile, 256 rows x 32 reduction elements, fp32): TMA -> shared memory ring -> 8
-//    converter warps split every value into tf32 hi + lo and write both to TENSOR MEMORY (tcgen05.st), so the
-//    tensor core reads A from TMEM and the memory orientation of X does not matter (XH reads the tile
-//    transposed out of shared memory, WX reads 128B-swizzled rows).
-//  * B operand (H or W^T, [K][R] K-major, pre-split into tf32 hi / lo copies by split_operand_kernel; 90 MB at
-//    most, L2 resident): two TMA loads (SWIZZLE_128B, rows >= K zero-filled) -> shared memory ring -> UMMA
-//    shared-memory descriptors.  One B tile pair serves 256 rows of X, which keeps L2->SM traffic of the small
-//    operand below that of X itself.
-//  * D accumulates in TMEM (fp32, 2 accumulators of Kp columns): per 8-deep k-step three MMAs
-//    Alo*Bhi + Ahi*Blo + Ahi*Bhi (small terms first).  The tensor core accumulates with round-toward-zero, so
-//    after every `chunk` k-blocks the accumulator is drained into an fp32 master sum held in the registers of
-//    the epilogue threads (round-to-nearest adds); the drain of one tile overlaps the MMAs of the other.
+//    converter warps split every value and write tf32 hi (32 columns per MMA tile), bf16(hi) and bf16(lo) (two
+//    reduction elements per 32-bit column, 16 columns each) to TENSOR MEMORY (tcgen05.st), so the tensor core reads
+//    A from TMEM and the memory orientation of X does not matter (XH reads the tile transposed out of shared
+//    memory, WX reads 128B-swizzled rows).
+//  * B operand (H or W^T, [K][R] K-major, pre-split by the kernels that produce it -- ptx::store_split4: a tf32 hi
+//    plane and a 16-bit plane with the bf16 images of hi and lo; 90 MB at most, L2 resident): three TMA loads
+//    (SWIZZLE_128B for the fp32 tile, SWIZZLE_64B for the two bf16 tiles, rows >= K zero-filled) -> shared memory
+//    ring -> UMMA shared-memory descriptors.  One B stage serves 256 rows of X, which keeps L2->SM traffic of the
+//    small operand below that of X itself.
+//  * D accumulates in TMEM (fp32, 2 accumulators of Kp columns): per 32-deep k-block two 16-deep bf16 steps of
+//    lo*hi' and hi*lo' (small terms first), then four 8-deep tf32 steps of hi*hi'.  The tensor core accumulates with
+//    round-toward-zero, so after every `chunk` k-blocks the accumulator is drained into an fp32 master sum held in
+//    the registers of the epilogue threads (round-to-nearest adds); the drain of one tile overlaps the MMAs of the
+//    other.
 //  * Work split (stream-K inside pieces): the reduction axis is cut into pieces whose B-operand window fits L2;
 //    the (super-tile, k-block) units of every piece are cut into gridDim.x equal contiguous ranges, so all CTAs
 //    move through the pieces together and the small operand is read from HBM about once.  Every contiguous
-//    run inside one tile ("segment") is stored to a partial-sum slot; the reduce kernels add the slots of a
+//    run inside one tile ("segment") is stored to a partial-sum slot; the consumers add the slots of a
 //    tile in a fixed order, so results are deterministic and no CTA ever waits for another.
 //  * One MMA-issuing warp per 128-row tile: a 128x112x8 tf32 MMA lasts only ~56 cycles, so a single issuing
 //    thread (and any per-instruction register shuffling) would leave the tensor pipe idle.
@@ -34,11 +44,14 @@
 //    per nonzero while everything downstream (split, TMEM staging, MMAs, drains) is unchanged.  The tile is
 //    row-major + swizzled for both orientations (the lists carry ready-made offsets), and every converter
 //    thread clears the 128 bytes it has just read, so a stage returns to the producer already zeroed: no
-//    zero-fill traffic through L2 (the L2->SM path, ~43 B/cycle/SM, is what bounds this kernel) and no
-//    single-warp memset.
+//    zero-fill traffic through L2 and no single-warp memset.
 //  * Count matrices (EXACT): when every X value is exactly representable in tf32 (integers < 2048, detected by
-//    the pass that computes ||X||^2), the lo half of A is zero and the Alo*Bhi products are skipped (2 instead
-//    of 3 MMAs per k-step).
+//    the pass that computes ||X||^2), the lo half of A is zero: the converters write hi only and the one remaining
+//    correction term hi*lo' stays a tf32 MMA on a tf32 copy of lo' (two tf32 MMAs per k-step; the sparse path is
+//    bound by the converters, so the bf16 packing would cost it more than the cheaper MMA saves -- measured).
+//  * Measured (round 2, probe on one B200): the sweep is no longer bound by one resource.  Dropping the bf16 MMAs
+//    gives -13 %, dropping all converter arithmetic -8 %, halving / removing the B-operand loads -2 % / -6.5 % (so a
+//    cta_group::2 variant, whose point is to halve them, would gain ~2 %), deeper X rings nothing.
 #pragma once
 #include <vector>
 
@@ -264,11 +277,12 @@ template <int ORIENT, int NC, bool EXACT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmBhi,
                const __grid_constant__ CUtensorMap tmBh16, const __grid_constant__ CUtensorMap tmBl16,
-               const __grid_constant__ CUtensorMap tmX2, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmX2,
+               const GemmParams p) {
   constexpr int Kp = 16 * NC;
   constexpr int kWarpXProd = kConvWarps, kWarpBProd = kConvWarps + 1, kWarpMma = kConvWarps + 2;  // + kMT MMA warps
   // one B stage: tf32 hi tile [Kp][32] (128-byte rows, SWIZZLE_128B), then the bf16 images of hi and of lo
-  // [Kp][32] each (64-byte rows, SWIZZLE_64B)
+  // [Kp][32] each (64-byte rows, SWIZZLE_64B) -- or, for the count-matrix variant (EXACT), the tf32 lo tile
   constexpr int b_hi_bytes = Kp * kBK * 4;
   constexpr int b_16_bytes = Kp * kBK * 2;
   constexpr int b_stage_bytes = b_hi_bytes + 2 * b_16_bytes;
@@ -329,8 +343,12 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
   }
   if (warp == kWarpBProd && lane == 0) {
     ptx::prefetch_tensormap(&tmBhi);
-    ptx::prefetch_tensormap(&tmBh16);
-    ptx::prefetch_tensormap(&tmBl16);
+    if (EXACT) {
+      ptx::prefetch_tensormap(&tmBlo);
+    } else {
+      ptx::prefetch_tensormap(&tmBh16);
+      ptx::prefetch_tensormap(&tmBl16);
+    }
   }
   if (warp == kWarpMma) {  // the first MMA warp owns the TMEM allocation
     ptx::tmem_alloc(tmem_slot, kTmemCols);
@@ -475,8 +493,12 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
           uint8_t* dst = smem_b + static_cast<size_t>(s) * b_stage_bytes;
           ptx::mbar_arrive_expect_tx(&bfull_bar[s], b_stage_bytes);
           ptx::tma_load_2d(dst, &tmBhi, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
-          ptx::tma_load_2d(dst + b_hi_bytes, &tmBh16, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
-          ptx::tma_load_2d(dst + b_hi_bytes + b_16_bytes, &tmBl16, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+          if (EXACT) {
+            ptx::tma_load_2d(dst + b_hi_bytes, &tmBlo, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+          } else {
+            ptx::tma_load_2d(dst + b_hi_bytes, &tmBh16, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+            ptx::tma_load_2d(dst + b_hi_bytes + b_16_bytes, &tmBl16, &bfull_bar[s], kb * kBK, 0, ptx::kEvictLast);
+          }
         }
         pos += len;
       }
@@ -523,22 +545,34 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         ptx::tc_fence_after();
         const uint32_t sb_addr = smem_b_u32 + static_cast<uint32_t>(sbi) * b_stage_bytes;
         const uint64_t dhi = ptx::make_kmajor_sw128_desc(sb_addr);
-        const uint64_t dh16 = ptx::make_kmajor_sw64_desc(sb_addr + b_hi_bytes);
-        const uint64_t dl16 = ptx::make_kmajor_sw64_desc(sb_addr + b_hi_bytes + b_16_bytes);
         const uint32_t a_hi = tb + kTmemAOff + t * kAStageCols + mt * 64;
-        const uint32_t a_h16 = a_hi + 32, a_l16 = a_hi + 48;
-        // the small terms first: lo * hi and hi * lo as bf16 MMAs (16 reduction elements = 32 bytes = 8 TMEM
-        // columns per step), then hi * hi as tf32 MMAs (8 elements per step)
+        if (EXACT) {
+          // count matrix: A has no lo half; hi * lo' stays a tf32 MMA on the tf32 lo tile (small term first)
+          const uint64_t dlo = ptx::make_kmajor_sw128_desc(sb_addr + b_hi_bytes);
 #pragma unroll
-        for (int ks = 0; ks < kBK / kUmmaK16; ++ks) {
-          // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          const uint32_t fresh = (c_first && ks == 0) ? 0u : 1u;
-          if (!EXACT) ptx::mma_bf16_ts_if(leader, d_acc, a_l16 + 8 * ks, dh16 + static_cast<uint64_t>(2 * ks), idesc16, fresh);
-          ptx::mma_bf16_ts_if(leader, d_acc, a_h16 + 8 * ks, dl16 + static_cast<uint64_t>(2 * ks), idesc16, EXACT ? fresh : 1u);
+          for (int ks = 0; ks < kBK / kUmmaK; ++ks) {
+            // advance 32 bytes along K inside the 128B swizzle atom: +2 in the (addr >> 4) field
+            const uint32_t fresh = (c_first && ks == 0) ? 0u : 1u;
+            ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, dlo + static_cast<uint64_t>(2 * ks), idesc, fresh);
+            ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, dhi + static_cast<uint64_t>(2 * ks), idesc, 1u);
+          }
+        } else {
+          const uint64_t dh16 = ptx::make_kmajor_sw64_desc(sb_addr + b_hi_bytes);
+          const uint64_t dl16 = ptx::make_kmajor_sw64_desc(sb_addr + b_hi_bytes + b_16_bytes);
+          const uint32_t a_h16 = a_hi + 32, a_l16 = a_hi + 48;
+          // the small terms first: lo * hi' and hi * lo' as bf16 MMAs (16 reduction elements = 32 bytes = 8 TMEM
+          // columns per step), then hi * hi' as tf32 MMAs (8 elements per step)
+#pragma unroll
+          for (int ks = 0; ks < kBK / kUmmaK16; ++ks) {
+            // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            const uint32_t fresh = (c_first && ks == 0) ? 0u : 1u;
+            ptx::mma_bf16_ts_if(leader, d_acc, a_l16 + 8 * ks, dh16 + static_cast<uint64_t>(2 * ks), idesc16, fresh);
+            ptx::mma_bf16_ts_if(leader, d_acc, a_h16 + 8 * ks, dl16 + static_cast<uint64_t>(2 * ks), idesc16, 1u);
+          }
+#pragma unroll
+          for (int ks = 0; ks < kBK / kUmmaK; ++ks)
+            ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, dhi + static_cast<uint64_t>(2 * ks), idesc, 1u);
         }
-#pragma unroll
-        for (int ks = 0; ks < kBK / kUmmaK; ++ks)
-          ptx::mma_tf32_ts_if(leader, d_acc, a_hi + ks * kUmmaK, dhi + static_cast<uint64_t>(2 * ks), idesc, 1u);
         if (c_last) {
           ptx::tc_commit_if(leader, &accfull_bar[mt]);
           ++mc;
@@ -637,15 +671,17 @@ mu_gemm_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             }
           }
           ptx::tmem_st_x8(a_addr + 8 * h, hi);
-          // bf16 images for the correction terms, two reduction elements per column (even element in the low half)
-          uint32_t h16[4], l16[4];
+          if (!EXACT) {
+            // bf16 images for the correction terms, two reduction elements per column (even element in the low half)
+            uint32_t h16[4], l16[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            h16[q] = ptx::pack_bf16x2(__uint_as_float(hi[2 * q]), __uint_as_float(hi[2 * q + 1]));
-            l16[q] = ptx::pack_bf16x2(__uint_as_float(lo[2 * q]), __uint_as_float(lo[2 * q + 1]));
+            for (int q = 0; q < 4; ++q) {
+              h16[q] = ptx::pack_bf16x2(__uint_as_float(hi[2 * q]), __uint_as_float(hi[2 * q + 1]));
+              l16[q] = ptx::pack_bf16x2(__uint_as_float(lo[2 * q]), __uint_as_float(lo[2 * q + 1]));
+            }
+            ptx::tmem_st_x4(a_addr + 32 + 4 * h, h16);
+            ptx::tmem_st_x4(a_addr + 48 + 4 * h, l16);
           }
-          ptx::tmem_st_x4(a_addr + 32 + 4 * h, h16);
-          if (!EXACT) ptx::tmem_st_x4(a_addr + 48 + 4 * h, l16);
         }
         ptx::tc_wait_st();
         ptx::tc_fence_before();

@@ -1,4 +1,4 @@
-// Element-wise and reduction kernels around the tcgen05 contractions: 3xTF32 operand splitting, the W / B
+// Element-wise and reduction kernels around the tcgen05 contractions: operand splitting, the W / B
 // multiplicative updates, guided (covariate) terms of the H update, per-iteration statistics and loss terms,
 // post-fit scaling and the transform update.  All are HBM-bound streaming kernels: coalesced along the
 // contiguous dimension, fp64 only in the loss accumulators, partial sums reduced in a fixed order.
@@ -40,7 +40,7 @@ struct CovTable {
 // ---------------------------------------------------------------------------------------------------------
 // sum of squares of a pitched matrix in fp64 (||X||_F^2), two-stage deterministic reduction
 // also raises *inexact when some value is not exactly representable in tf32 (low 13 mantissa bits set): only
-// then does the contraction kernel need the lo half of the 3xTF32 split of X
+// then does the contraction kernel need the lo half of the split of X
 __global__ void sumsq_partial_kernel(const float* __restrict__ X, long long ld, long long rows, int cols,
                                      double* __restrict__ partial, int* __restrict__ inexact) {
   double acc = 0.0;
@@ -306,7 +306,7 @@ struct SymLongParams {
   float c1, c2, orth, eps;
   double* t1_partial;   // EPI_H: [gridDim.x]  sum A .* Hnew
   float* rowsum_partial;  // EPI_H: [gridDim.x][K] row sums of the new H over this block's columns, or nullptr
-  float* split_hi;      // EPI_W / EPI_H: tf32 hi / lo copies of the updated matrix (B operand of the next
+  float* split_hi;      // EPI_W / EPI_H: split copies (tf32 hi plane, bf16 plane) of the updated matrix (B operand of the next
   float* split_lo;      //                contraction), pitch ld_split; nullptr to skip
   long long ld_split;
   // Peer mode (EPI_W under cell sharding, csrc/peer_exchange.cuh): the block handles columns col0 + 64 * blockIdx.x

@@ -130,7 +130,7 @@ __device__ __forceinline__ void load_tile_async(float* tile, const float* __rest
   cp_async_commit();
 }
 
-// one float4 of new values -> Mat (masked at L), its tf32 hi / lo copies (whole float4 groups: pitches are
+// one float4 of new values -> Mat (masked at L), its split copies for the next contraction (ptx::store_split4; whole groups of four: pitches are
 // multiples of 4 and the values at columns >= L are zero) and the peers' copies of Mat
 __device__ __forceinline__ void store4(float4 v, int k, long long col, long long L, float* __restrict__ Mat, long long ld,
                                        float* __restrict__ split_hi, float* __restrict__ split_lo, long long ld_split,
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
 // Finish kernels
 // K x K Gram matrix from the slots of its contraction (one super-tile: rows = components): out[k][r] = sum over the
 // slots, in list order.  32 lanes share an output element's slots (strided) and are combined by a fixed shuffle
-// tree, so that the many small loads overlap.  Also writes the tf32 hi / lo copies (B operand of the next Z plan).
+// tree, so that the many small loads overlap.  Also writes the split copies (B operand of the next Z plan).
 struct GramFromSlots {
   SlotSrc2 src;      // slots [K][256] of the Gram plan (rows r < K are meaningful), per component group
   int tile;          // super-tile of the plan that holds the Gram (0 for a Gram plan; the additional tile of W^T X)

@@ -52,7 +52,7 @@ __device__ __forceinline__ bool peer_wait_all(const PeerTable& t, int which, int
 
 // The close of the exchange, fused with the first consumer of the gathered W^T: block 0 publishes done[r] = epoch
 // to every rank (the W-update kernel, whose stores into the peers' W^T precede this one in the stream, is complete),
-// every block waits until all ranks have said so, and then splits W^T [K][cols] into its tf32 hi / lo copies (the
+// every block waits until all ranks have said so, and then splits W^T [K][cols] into its tf32 / bf16 operand copies (the
 // B operand of W^T W and W^T X).
 __global__ void __launch_bounds__(256) peer_close_and_split_kernel(const PeerTable t, int which, int epoch, int* err,
                                                                    const float* __restrict__ src, long long ld_src,
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(256) peer_close_and_split_kernel(const PeerTab
 
 // "Reduce-scatter" by peer loads: block 0 first publishes ready[r] = epoch (this rank's partials are complete: the
 // kernels that wrote them precede this one in the stream); every block then waits for all ranks and sums, in rank
-// order,  (a) the small statistics [S | hsum | Q] of all ranks -> small_out (and the tf32 hi / lo copies of the summed
+// order,  (a) the small statistics [S | hsum | Q] of all ranks -> small_out (and the operand copies of the summed
 // S)  and  (b) the columns [g0, g1) of the
 // partial numerators (K x ldG at the head of every exchange block) -> p_out (same pitch).  One thread per float4,
 // all peers' loads in flight together, so the NVLink latency is paid once, not per peer.
@@ -111,7 +111,7 @@ __global__ void __launch_bounds__(256) peer_gather_reduce_kernel(const PeerTable
     for (int q = 0; q < kMaxPeers; ++q) acc += v[q];
     small_out[e] = acc;
     if (s_hi != nullptr && e < static_cast<long long>(K) * K) {
-      // the first K * K entries are the summed H H^T: its tf32 hi / lo copies are the B operand of (H H^T) W^T
+      // the first K * K entries are the summed H H^T: its split copies are the B operand of (H H^T) W^T
       const int r = static_cast<int>(e / K), c = static_cast<int>(e - static_cast<long long>(r) * K);
       ptx::store_split1(acc, s_hi, s_lo, r, c, ld_split);
     }

@@ -231,7 +231,7 @@ __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
       : "memory");
 }
 
-// 3xTF32 operand split of a FINITE fp32 value: hi = x rounded to nearest (ties away) to tf32's 10 explicit
+// Operand split of a FINITE fp32 value: hi = x rounded to nearest (ties away) to tf32's 10 explicit
 // mantissa bits, lo = (x - hi) (exact in fp32, |lo| <= 2^-11 |x|) rounded the same way, both with the low 13
 // bits zero so the result does not depend on how the tensor core treats them.  |x - hi - lo| <= 2^-22 |x|.
 // (cvt.rna.tf32.f32 compiles to the same add/mask plus an Inf/NaN guard; X, W, H are finite by contract.)
@@ -263,22 +263,19 @@ __device__ __forceinline__ uint16_t bf16_bits(float x) {
   const uint32_t b = __float_as_uint(x);
   return static_cast<uint16_t>((b + 0x7FFFu + ((b >> 16) & 1u)) >> 16);
 }
-// B-operand copies of a value: tf32 hi (fp32 container) and the bf16 images of hi and of the remainder
-__device__ __forceinline__ void split_b_operand(float x, uint32_t& hi, uint16_t& hi16, uint16_t& lo16) {
-  hi = round_tf32(x);
-  hi16 = bf16_bits(__uint_as_float(hi));
-  lo16 = bf16_bits(x - __uint_as_float(hi));
-}
-// The split copies of a [K][ld] operand live in two planes of K * ld floats each: plane 0 holds the tf32 hi values,
-// plane 1 is read as 16-bit [K][2][ld]: row k = bf16(hi)[ld] followed by bf16(lo)[ld]  (ld % 8 == 0).
+// The split copies of a [K][ld] operand: plane 0 = [K][ld] tf32 hi values; plane 1 = [K][2 * ld] floats, row k =
+//   [ ld floats read as 16-bit: bf16(hi)[ld] followed by bf16(lo)[ld] | ld floats: tf32(lo) ]
+// (ld % 8 == 0).  The bf16 images feed the correction MMAs of the general kernel, the tf32 lo copy the count-matrix
+// variant, whose streamed operand has no lo half and whose correction term stays a tf32 MMA.
 __device__ __forceinline__ void store_split1(float x, float* plane0, float* plane1, long long k, long long col, long long ld) {
-  uint32_t hi;
-  uint16_t h16, l16;
-  split_b_operand(x, hi, h16, l16);
+  const uint32_t hi = round_tf32(x);
+  const float lo = x - __uint_as_float(hi);
   plane0[k * ld + col] = __uint_as_float(hi);
-  uint16_t* p1 = reinterpret_cast<uint16_t*>(plane1) + 2 * k * ld + col;
-  p1[0] = h16;
-  p1[ld] = l16;
+  float* row1 = plane1 + 2 * k * ld;
+  uint16_t* p16 = reinterpret_cast<uint16_t*>(row1) + col;
+  p16[0] = bf16_bits(__uint_as_float(hi));
+  p16[ld] = bf16_bits(lo);
+  row1[ld + col] = __uint_as_float(round_tf32(lo));
 }
 // four adjacent columns (col % 4 == 0)
 __device__ __forceinline__ void store_split4(float4 v, float* plane0, float* plane1, long long k, long long col, long long ld) {
@@ -290,9 +287,13 @@ __device__ __forceinline__ void store_split4(float4 v, float* plane0, float* pla
     l[i] = x[i] - h[i];
   }
   *reinterpret_cast<float4*>(plane0 + k * ld + col) = make_float4(h[0], h[1], h[2], h[3]);
-  uint16_t* p1 = reinterpret_cast<uint16_t*>(plane1) + 2 * k * ld + col;
-  *reinterpret_cast<uint2*>(p1) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-  *reinterpret_cast<uint2*>(p1 + ld) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+  float* row1 = plane1 + 2 * k * ld;
+  uint16_t* p16 = reinterpret_cast<uint16_t*>(row1) + col;
+  *reinterpret_cast<uint2*>(p16) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+  *reinterpret_cast<uint2*>(p16 + ld) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+  *reinterpret_cast<float4*>(row1 + ld + col) =
+      make_float4(__uint_as_float(round_tf32(l[0])), __uint_as_float(round_tf32(l[1])),
+                  __uint_as_float(round_tf32(l[2])), __uint_as_float(round_tf32(l[3])));
 }
 
 // ---------------------------------------------------------------- descriptors

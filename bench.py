@@ -16,7 +16,8 @@ One "step" is one full-batch MU iteration (W update, B updates, H update, loss t
                  initialisation, the loop, the loss read-back and the device->host copy of W / H / B, divided by K;
                  after one untimed warm-up fit.
 * ``roofline`` : the contraction kernel (two launches per step), timed with CUDA events around each launch
-                 inside the timed region; 3xTF32 tensor work against measured bf16 peak / 2.
+                 inside the timed region; HBM bytes of X against the measured HBM peak (tensor work: tf32-MMA equivalents against
+                 measured bf16 peak / 2).
 * ``cpu_baseline`` : the reference's step restated with its own torch-CPU operators (oracle/torch_port.py: its 7
                  GEMMs, randperm gather and G x n temporaries), measured on the full workload with all host cores
                  (a leading block of cells only when host memory or the time budget would be exceeded).
@@ -477,36 +478,49 @@ def measure_resident(args, wl, sparse, dev, world, rank, local_rank, steps, warm
     peaks = load_peaks()
     K = sum(blocks)
     n_loc = hi - lo
-    # 3xTF32: three tf32 MMAs per fp32 product; tf32-exact integer counts (the CSR workload): two
-    mma_per_product = 2.0 if sparse else 3.0
+    # Split-precision product: one tf32 MMA (hi * hi) + two bf16 MMAs at twice the rate (hi * lo, lo * hi) = 2 tf32-MMA
+    # equivalents of tensor time per fp32 product; tf32-exact integer counts (the CSR workload) need no lo * hi and keep
+    # hi * lo as a tf32 MMA: also 2
+    mma_per_product = 2.0
     flops = mma_per_product * 2.0 * G * n_loc * K
     tf32_peak = peaks["bf16_tflops_sustained"] / 2.0
     achieved = flops / (gemm_ms_avg * 1e-3) / 1e12 if gemm_ms_avg > 0 else 0.0
     x_bytes = 8.0 * nnz if sparse else 4.0 * G * n_loc
     hbm_ms = x_bytes / (peaks["hbm_gbs"] * 1e9) * 1e3
+    tensor_ms = flops / (tf32_peak * 1e12) * 1e3
     achieved_gbs = x_bytes / (gemm_ms_avg * 1e-3) / 1e9 if gemm_ms_avg > 0 else 0.0
     traffic, traffic_src = (None, None)
     if world == 1 and not args.cells and not args.genes:
         traffic, traffic_src = load_traffic("cfg3_n1" if not sparse else "cfg4_n1")
-    step_bound_ms = 2.0 * max(flops / (tf32_peak * 1e12), x_bytes / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    step_bound_ms = 2.0 * max(tensor_ms, hbm_ms)
+    tensor_block = {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / tf32_peak, "bound_ms_per_launch": tensor_ms,
+                    "what": "tf32-MMA equivalents: hi*hi as tf32 + the correction terms as bf16 MMAs at twice the rate"}
+    # the same launch against SURVEY.md 8 d3's HBM bound (dense: 4 B per X element; CSR: 8 B per nonzero)
+    hbm_block = {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                 "frac": achieved_gbs / peaks["hbm_gbs"], "bound_ms_per_launch": hbm_ms}
+    binding = hbm_block if hbm_ms >= tensor_ms else tensor_block  # the roofline that bounds this launch
     roofline = {
-        "kernel": "mu_gemm_kernel (X H^T and W^T X, %s tcgen05)" % ("2xTF32 on tf32-exact counts, CSR tile lists expanded on chip" if sparse else "3xTF32"),
-        "bound": "tensor",
-        "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s", "frac": achieved / tf32_peak,
+        "kernel": "mu_gemm_kernel (X H^T and W^T X, %s, tcgen05)" % (
+            "2 tf32 MMAs per product on tf32-exact counts, CSR tile lists expanded on chip" if sparse
+            else "tf32 hi*hi + bf16 hi*lo, lo*hi"),
+        "bound": binding["bound"],
+        "achieved": binding["achieved"], "peak": binding["peak"], "unit": binding["unit"], "frac": binding["frac"],
         "traffic": traffic, "traffic_source": traffic_src,
         "iteration": {"what": "whole MU iteration against the slower of (two contractions at the tensor peak, two "
                               "sweeps of X at HBM bandwidth) -- BASELINE north_star's roofline",
                       "bound_ms": step_bound_ms, "measured_ms": ms / steps,
                       "frac": step_bound_ms / (ms / steps)},
-        "peak_source": f"{peaks['source']} bf16_tflops_sustained / 2 (no TF32 figure in MEASURED_PEAKS.json; the "
-                       f"kernel is timed inside the step loop)",
+        "peak_source": f"{peaks['source']} hbm_gbs; tensor: bf16_tflops_sustained / 2 (no TF32 figure in "
+                       f"MEASURED_PEAKS.json; the kernel is timed inside the step loop)",
         "avg_launch_ms": gemm_ms_avg, "launches_timed": gemm_n,
         "timed_in": f"{steps_prof} further steps right after the {steps} timed ones, with CUDA events around every "
                     f"contraction launch ({ms_prof:.3f} ms per step there)",
-        # the same launch against SURVEY.md 8 d3's HBM bound (dense: 4 B per X element; CSR: 8 B per nonzero)
-        "hbm": {"bound": "hbm", "achieved": achieved_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved_gbs / peaks["hbm_gbs"], "bound_ms_per_launch": hbm_ms},
-        "algorithmic": {"tf32_flop_per_launch": flops, "tf32_mma_per_fp32_product": mma_per_product,
+        "hbm": hbm_block, "tensor": tensor_block,
+        # the roofline of the previous build (three tf32 MMAs per product, tensor bound), for comparison across rounds
+        "vs_3xtf32_tensor_roofline": 3.0 * 2.0 * G * n_loc * K / (gemm_ms_avg * 1e-3) / 1e12 / tf32_peak
+        if gemm_ms_avg > 0 and not sparse else None,
+        "algorithmic": {"tf32_equiv_flop_per_launch": flops, "tf32_equiv_mma_per_fp32_product": mma_per_product,
                         "x_bytes_per_launch": x_bytes},
     }
     out = None
@@ -553,7 +567,7 @@ def run_gpu_arm(args):
         line = {"metric": METRIC if not sparse else "MU iterations/sec at 30k genes x 1M cells CSR, k=100",
                 "value": res["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+                "dtype": "f32 (split-precision tensor-core products: tf32 hi*hi + bf16 correction terms, fp32 accumulate)", "data": "synthetic",
                 "config": res["config"], "clocks": res["clocks"], "gpu_launches": res["gpu_launches"],
                 "roofline": res["roofline"], "final_loss": res["final_loss"]}
     if sparse:  # the sparse scaling workload has no host-API / CPU legs (the reference rejects sparse input)
@@ -593,7 +607,7 @@ def run_gpu_arm(args):
                 c4 = {"metric": "MU iterations/sec at 30k genes x 1M cells CSR (5% density), k=100", "value": r4["value"],
                       "unit": UNIT, "ms_per_step": r4["ms_per_step"], "steps": 30, "warmup": 3, "scaling": "strong",
                       "config": r4["config"], "gpu_launches": r4["gpu_launches"], "final_loss": r4["final_loss"],
-                      "roofline": {"tensor": {k: r4["roofline"][k] for k in ("bound", "achieved", "peak", "unit", "frac")},
+                      "roofline": {"tensor": r4["roofline"]["tensor"],
                                    "hbm": r4["roofline"]["hbm"], "avg_launch_ms": r4["roofline"]["avg_launch_ms"],
                                    "algorithmic": r4["roofline"]["algorithmic"]}}
         if rank == 0:
@@ -607,7 +621,7 @@ def run_gpu_arm(args):
         # after every timed region, so that its heat does not touch them
         tf = cublas_tf32_peak(dev)
         line["roofline"]["cublas_tf32_tflops"] = tf
-        line["roofline"]["frac_of_cublas_tf32_sustained"] = line["roofline"]["achieved"] / tf["sustained"]
+        line["roofline"]["tensor"]["frac_of_cublas_tf32_sustained"] = line["roofline"]["tensor"]["achieved"] / tf["sustained"]
     if rank == 0 and world == 1 and not args.no_gpu_torch:
         line["gpu_torch_baseline"] = gpu_torch_baseline(wl, dev)
     if rank == 0 and world == 1 and not args.no_cpu:
