@@ -58,7 +58,7 @@ class AlpineMatrices:
     n_total: int = 0
     solver: Optional[object] = field(default=None, repr=False)  # native context kept between _fit and _scale_matrices
 
-    def to_numpy(self) -> Dict[str, Union[Float32Array, List[Float32Array]]]:
+    def to_numpy(self, bufs: Optional["_HostBuffers"] = None) -> Dict[str, Union[Float32Array, List[Float32Array]]]:
         # the reference copies X back from the device (main.py:38); the host copy it came from is identical
         if self.X_host is not None:
             X = self.X_host
@@ -70,11 +70,21 @@ class AlpineMatrices:
         if self.W is not None and self.H is not None:
             # one device -> host copy per packed factor (and one gather of the cell blocks under sharding); the blocks
             # are cut out on the host
-            W = self.W.cpu().numpy()
-            H = _gather_cells([self.H], self.shard, self.n_total)[0].cpu().numpy()
+            take = (lambda name, shape: bufs.take(name, shape)) if bufs is not None else (lambda name, shape: None)
+            W = _to_host(self.W, take("W", tuple(self.W.shape)))
+            Hd = _gather_cells([self.H], self.shard, self.n_total)[0]
+            H = _to_host(Hd, take("H", tuple(Hd.shape)))
             cuts_w = np.cumsum([0] + [w.shape[1] for w in self.Ws])
             cuts_h = np.cumsum([0] + [h.shape[0] for h in self.Hs])
-            Ws = [np.ascontiguousarray(W[:, cuts_w[i]:cuts_w[i + 1]]) for i in range(len(self.Ws))]
+            Ws = []
+            for i in range(len(self.Ws)):
+                blk = W[:, cuts_w[i]:cuts_w[i + 1]]
+                dst = take(f"W{i}", blk.shape)
+                if dst is None:
+                    Ws.append(np.ascontiguousarray(blk))
+                else:
+                    np.copyto(dst, blk)
+                    Ws.append(dst)
             Hs = [H[cuts_h[i]:cuts_h[i + 1]] for i in range(len(self.Hs))]
         else:
             Ws = [w.cpu().numpy().astype(np.float32, copy=False) for w in self.Ws]
@@ -138,6 +148,42 @@ class _Background:
         if self._exc is not None:
             raise self._exc
         return self._out
+
+
+class _HostBuffers:
+    """Host arrays for the results of a fit, allocated and touched on a background thread while the upload and the
+    loop run: a fresh 40 MB numpy array costs about as much in page faults as in the copy that fills it, and the
+    faults would otherwise sit between the last iteration and the return of ``fit``.  ``take`` hands a buffer out once
+    (``None`` if the shape was not prepared); the arrays are ordinary numpy arrays owned by whoever takes them."""
+
+    def __init__(self, specs: Dict[str, tuple]):
+        import ctypes
+
+        def work():
+            out = {}
+            for name, shape in specs.items():
+                a = np.empty(shape, dtype=np.float32)
+                if a.nbytes:
+                    ctypes.memset(a.ctypes.data, 0, a.nbytes)  # touches every page; ctypes releases the GIL
+                out[name] = a
+            return out
+
+        self._job = _Background(work)
+        self._bufs: Optional[dict] = None
+
+    def take(self, name: str, shape: tuple) -> Optional[np.ndarray]:
+        if self._bufs is None:
+            self._bufs = self._job.result()
+        a = self._bufs.pop(name, None)
+        return a if a is not None and a.shape == tuple(shape) else None
+
+
+def _to_host(t: torch.Tensor, out: Optional[np.ndarray]) -> np.ndarray:
+    """Device tensor -> numpy array, into ``out`` when a prepared buffer of the right shape is at hand."""
+    if out is None:
+        return t.cpu().numpy()
+    torch.from_numpy(out).copy_(t)
+    return out
 
 
 def _gather_cells(Hs: List[torch.Tensor], shard, n_total: int) -> List[torch.Tensor]:
@@ -234,6 +280,14 @@ class ALPINE:
         else:
             X = np.ascontiguousarray(adata.X, dtype=np.float32).T
         n_sample = X.shape[1]
+        # result arrays (W, H, their per-block copies for the AnnData slots) are allocated and touched in the background
+        ks = list(self.n_all_components)
+        specs = {"W": (self.n_features, sum(ks)), "H": (sum(ks), n_sample)}
+        for i, k in enumerate(ks):
+            specs[f"W{i}"] = (self.n_features, k)
+            specs[f"varm{i}"] = (self.n_features, k)
+            specs[f"obsm{i}"] = (k, n_sample)
+        bufs = _HostBuffers(specs)
         # the upload of this rank's cells starts now, on host threads of the library, and overlaps the label encoding
         # and the factor draws; a warm-up fit and the main fit share the one device copy of X (it is never written)
         Xdev = self._start_upload(X)
@@ -267,10 +321,10 @@ class ALPINE:
             if m.solver is not None:
                 m.solver.close()
                 m.solver = None
-        self.matrices = m.to_numpy()
+        self.matrices = m.to_numpy(bufs)
         self._rng_publish()
         lap("scale_download")
-        self.store_embeddings(adata, _dummy_matrices=Y)  # the encoders were fitted on this adata a moment ago
+        self.store_embeddings(adata, _dummy_matrices=Y, _bufs=bufs)  # the encoders were fitted on this adata a moment ago
         lap("store_embeddings")
         return self
 
@@ -401,17 +455,27 @@ class ALPINE:
         scale = np.where(totals > 0, totals / target, 1.0).astype(np.float32)
         adata.layers["normalized_expression"] = Xn / scale[:, None]
 
-    def store_embeddings(self, adata: AnnData, _dummy_matrices=None) -> None:
-        """Write embeddings / weights into the AnnData slots of main.py:303-320."""
+    def store_embeddings(self, adata: AnnData, _dummy_matrices=None, _bufs=None) -> None:
+        """Write embeddings / weights into the AnnData slots of main.py:303-320 (copies, as in the reference)."""
         validation.check_trained(self)
         validation.check_adata(adata)
-        adata.obsm["ALPINE_embedding"] = copy(self.matrices["Hs"][-1].T)
-        adata.varm["ALPINE_weights"] = copy(self.matrices["Ws"][-1])
+
+        def dup(a: np.ndarray, name: str, transposed: bool) -> np.ndarray:
+            # copy(a.T) keeps a's memory order: a (k, n) C-ordered block becomes an (n, k) F-ordered array
+            dst = _bufs.take(name, a.shape) if _bufs is not None else None
+            if dst is None:
+                return copy(a.T) if transposed else copy(a)
+            np.copyto(dst, a)
+            return dst.T if transposed else dst
+
+        last = len(self.matrices["Hs"]) - 1
+        adata.obsm["ALPINE_embedding"] = dup(self.matrices["Hs"][-1], f"obsm{last}", True)
+        adata.varm["ALPINE_weights"] = dup(self.matrices["Ws"][-1], f"varm{last}", False)
         dummy_matrices = _dummy_matrices if _dummy_matrices is not None else self.fe.transform(adata.obs)
         for i, covariate in enumerate(self.covariate_keys):
-            adata.obsm[covariate] = copy(self.matrices["Hs"][i].T)
+            adata.obsm[covariate] = dup(self.matrices["Hs"][i], f"obsm{i}", True)
             adata.obsm[f"{covariate}_dummy_matrix"] = dummy_matrices[i]
-            adata.varm[covariate] = copy(self.matrices["Ws"][i])
+            adata.varm[covariate] = dup(self.matrices["Ws"][i], f"varm{i}", False)
 
     # ------------------------------------------------------------------------------------- device helpers
     def _cuda_device(self) -> torch.device:

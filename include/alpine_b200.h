@@ -83,7 +83,7 @@ int alpine_set_hparams(alpine_ctx* ctx, const double* lam, double alpha_W, doubl
 int64_t alpine_reduce_buffer_size(const alpine_ctx* ctx);
 int alpine_bind_reduce_buffer(alpine_ctx* ctx, float* buf);
 
-/* Start a fit: ||X||_F^2, tf32 split of the initial H, initial statistics (H H^T, B statistics).
+/* Start a fit: ||X||_F^2, operand split (tf32 hi + bf16 images) of the initial H, initial statistics (H H^T, B statistics).
  * max_iter sizes the device-side loss history.  Replaces the head of _fit (main.py:486-498).              */
 int alpine_fit_begin(alpine_ctx* ctx, int max_iter, void* stream);
 /* The cells of one mini-batch into this context's bound arrays, one launch (replaces the advanced-indexing gathers
