@@ -174,3 +174,39 @@ def test_csr_row_gather_matches_scipy():
         ip, ii, vv = _csr_take_rows(csr, torch.from_numpy(idx.astype(np.int64)))
         got = sp.csr_matrix((vv.numpy(), ii.numpy(), ip.numpy()), shape=(len(idx), 37)).toarray()
         np.testing.assert_array_equal(got, M[idx].toarray())
+
+
+def test_result_buffers_give_the_arrays_the_reference_stores():
+    """fit() pre-allocates its result arrays on a background thread (main._HostBuffers); store_embeddings fills them
+    instead of calling copy(): same values, same memory order as the reference's copy(H.T) / copy(W) (main.py:303-320),
+    independent of the model's own matrices."""
+    from copy import copy
+
+    from alpine_b200.main import _HostBuffers
+
+    rng = np.random.default_rng(0)
+    G, n, ks = 7, 11, [2, 3]
+    W = rng.random((G, sum(ks)), dtype=np.float32)
+    H = rng.random((sum(ks), n), dtype=np.float32)
+    model = ALPINE(n_components=3, n_covariate_components=[2], lam=[1.0])
+    model.covariate_keys = ["c"]
+    model.matrices = {"Ws": [np.ascontiguousarray(W[:, :2]), np.ascontiguousarray(W[:, 2:])], "Hs": [H[:2], H[2:]]}
+    obs = pd.DataFrame({"c": ["a", "b"] * 5 + ["a"]})
+    Y = [np.zeros((n, 2), dtype=np.float32)]
+
+    plain = AnnData(np.zeros((n, G), dtype=np.float32), obs=obs.copy())
+    model.store_embeddings(plain, _dummy_matrices=Y)
+    bufs = _HostBuffers({f"{kind}{i}": shape for i, k in enumerate(ks)
+                         for kind, shape in (("obsm", (k, n)), ("varm", (G, k)))})
+    fast = AnnData(np.zeros((n, G), dtype=np.float32), obs=obs.copy())
+    model.store_embeddings(fast, _dummy_matrices=Y, _bufs=bufs)
+    for slot in ("ALPINE_embedding", "c"):
+        a, b = plain.obsm[slot], fast.obsm[slot]
+        assert a.shape == b.shape and a.strides == b.strides and np.array_equal(a, b)
+        assert np.array_equal(a, copy(model.matrices["Hs"][-1 if slot == "ALPINE_embedding" else 0].T))
+        assert not np.shares_memory(b, H)
+    for slot in ("ALPINE_weights", "c"):
+        a, b = plain.varm[slot], fast.varm[slot]
+        assert a.shape == b.shape and a.strides == b.strides and np.array_equal(a, b)
+    assert bufs.take("obsm0", (2, n)) is None          # handed out once
+    assert _HostBuffers({"x": (3, 4)}).take("x", (4, 3)) is None  # a shape that was not prepared: caller allocates
