@@ -50,7 +50,7 @@ def main():
         gbs = 4.0 * G * n / ms / 1e6
         tf = 2.0 * G * n * K / ms / 1e9
         print(f"{name}: best {ms:.3f} ms  median {sorted(ts)[len(ts)//2]:.3f} ms  X-stream {gbs:.0f} GB/s  "
-              f"{tf:.1f} fp32-equiv TFLOP/s ({3*tf:.1f} tf32 issued)  {s.query()}")
+              f"{tf:.1f} fp32-equiv TFLOP/s ({2*tf:.1f} tf32-MMA equivalents: tf32 hi*hi + two bf16 corrections)  {s.query()}")
         # accuracy on a subset against fp64
         r = a.check_rows
         if name == "xh":
