@@ -514,6 +514,10 @@ def measure_resident(args, wl, sparse, dev, world, rank, local_rank, steps, warm
         "peak_source": f"{peaks['source']} hbm_gbs; tensor: bf16_tflops_sustained / 2 (no TF32 figure in "
                        f"MEASURED_PEAKS.json; the kernel is timed inside the step loop)",
         "avg_launch_ms": gemm_ms_avg, "launches_timed": gemm_n,
+        # the pass the launches were timed in is a little slower per step than the timed region (an event pair sits
+        # around every contraction launch): compare the kernel's share of the step within that pass
+        "step_ms_in_timing_pass": ms_prof,
+        "share_of_step": (2.0 * gemm_ms_avg / ms_prof) if ms_prof > 0 else None,
         "timed_in": f"{steps_prof} further steps right after the {steps} timed ones, with CUDA events around every "
                     f"contraction launch ({ms_prof:.3f} ms per step there)",
         "hbm": hbm_block, "tensor": tensor_block,
