@@ -44,7 +44,8 @@ PRODUCT_SHAPES = [
 
 @pytest.mark.parametrize("shape", PRODUCT_SHAPES)
 def test_contractions_match_fp64(shape):
-    """X H^T (main.py:596) and W^T X (main.py:653) as 3xTF32 tcgen05 GEMMs vs float64 matmul."""
+    """X H^T (main.py:596) and W^T X (main.py:653) as split-precision tcgen05 GEMMs (tf32 hi*hi + bf16 correction
+    terms) vs float64 matmul."""
     gu = _gpu_utils()
     n, G, K = shape
     rng = np.random.default_rng(n + G + K)
@@ -60,6 +61,27 @@ def test_contractions_match_fp64(shape):
     assert rel_fro(xh, ref_xh) < PRODUCT_TOL
     assert rel_fro(wx, ref_wx) < PRODUCT_TOL
     # element-wise too: every output is a sum of non-negative terms, so relative error is well defined
+    assert np.max(np.abs(xh - ref_xh) / ref_xh) < 2e-5
+    assert np.max(np.abs(wx - ref_wx) / ref_wx) < 2e-5
+
+
+def test_contractions_keep_fp32_range_and_precision_on_wide_data():
+    """Operands spanning 25 decades (factor entries from 1e-20 to 1e3, X from 1e-6 to 1e5, plus exact zeros): the
+    bf16 images of the correction terms share fp32's exponent range, so nothing over- or underflows and every output
+    keeps fp32-level relative accuracy (sums of non-negative terms)."""
+    gu = _gpu_utils()
+    n, G, K = 1500, 700, 48
+    rng = np.random.default_rng(77)
+    X = (10.0 ** rng.uniform(-6, 5, size=(n, G))).astype(np.float32)
+    X[rng.random((n, G)) < 0.3] = 0.0
+    W = (10.0 ** rng.uniform(-20, 3, size=(G, K))).astype(np.float32)
+    H = (10.0 ** rng.uniform(-20, 3, size=(K, n))).astype(np.float32)
+    prob = gu.DeviceProblem(X, [], W, H, [], [K], {})
+    xh = prob.solver.xh_product().cpu().numpy().astype(np.float64)
+    wx = prob.solver.wx_product().cpu().numpy().astype(np.float64)
+    Xd, Wd, Hd = X.astype(np.float64), W.astype(np.float64), H.astype(np.float64)
+    ref_xh, ref_wx = Hd @ Xd, Wd.T @ Xd.T
+    assert np.isfinite(xh).all() and np.isfinite(wx).all()
     assert np.max(np.abs(xh - ref_xh) / ref_xh) < 2e-5
     assert np.max(np.abs(wx - ref_wx) / ref_wx) < 2e-5
 
