@@ -460,8 +460,10 @@ int set_kernel_attrs() {
   CU_TRY(cudaFuncSetAttribute(sym_long_kernel<kSLKI, EPI_TRANSFORM>, cudaFuncAttributeMaxDynamicSharedMemorySize, sl));
   const int upd = big - 2048;  // (these kernels also hold a little static shared memory)
   CU_TRY(cudaFuncSetAttribute(w_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
-  CU_TRY(cudaFuncSetAttribute(h_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
-  CU_TRY(cudaFuncSetAttribute(h_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
+  CU_TRY(cudaFuncSetAttribute(h_update_kernel<false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, upd));
   CU_TRY(cudaFuncSetAttribute(cov_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   CU_TRY(cudaFuncSetAttribute(guided_terms_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   return ALPINE_OK;
@@ -849,7 +851,12 @@ int launch_h_update(alpine_ctx* c, const HUpdParams& p, cudaStream_t st) {
   const size_t smem = h_update_smem_bytes(c->K, p.Kg, p.c_total, p.q_total);
   if (smem > 225 * 1024)
     return fail(ALPINE_ERR_ARG, "covariate blocks too large for the H update kernel (%zu bytes of shared memory)", smem);
-  PDL_LAUNCH(h_update_kernel<FIT>, dim3(grid), dim3(kUpdThreads), smem, st, p);
+  // small shards: the W^T X plan cuts every 256-cell super-tile into three or four pieces (fewer super-tiles than SMs),
+  // and there are fewer H tiles than two waves of CTAs anyway: the variant that keeps four slots per operand in flight
+  if (ceil_div(c->n, kUpdCols) <= 2 * c->num_sms)
+    PDL_LAUNCH((h_update_kernel<FIT, 4>), dim3(grid), dim3(kUpdThreads), smem, st, p);
+  else
+    PDL_LAUNCH((h_update_kernel<FIT, 2>), dim3(grid), dim3(kUpdThreads), smem, st, p);
   return ALPINE_OK;
 }
 

@@ -33,6 +33,9 @@ constexpr int kUpdThreads = 256;
 __device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc, int src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
 }
+__device__ __forceinline__ void cp_async4(uint32_t smem_dst, const void* gsrc, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -113,6 +116,36 @@ __device__ __forceinline__ SlotPair slot_load_pair(const SlotSrc& s, int k, long
 }
 __device__ __forceinline__ float4 pair_sum(const SlotPair& p) {
   return make_float4(p.a.x + p.b.x, p.a.y + p.b.y, p.a.z + p.b.z, p.a.w + p.b.w);
+}
+
+// The same for up to S slots (small shards: a super-tile of the W^T X plan is shared by three or four CTAs): all
+// loads are issued before any is consumed; the sum adds them in list order, exactly like slot_load4.
+template <int S>
+struct SlotSet {
+  float4 v[S];
+};
+template <int S>
+__device__ __forceinline__ SlotSet<S> slot_load_set(const SlotSrc& s, int k, long long col, const int* ids, int n) {
+  SlotSet<S> r;
+#pragma unroll
+  for (int u = 0; u < S; ++u) r.v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s.direct != nullptr) {
+    r.v[0] = __ldg(reinterpret_cast<const float4*>(s.direct + static_cast<long long>(k) * s.ld + col));
+    return r;
+  }
+  const float* base = s.partial + static_cast<size_t>(k) * 256 + static_cast<int>((col - s.origin) & 255);
+  const size_t stride = static_cast<size_t>(s.K) * 256;
+#pragma unroll
+  for (int u = 0; u < S; ++u)
+    if (u < n) r.v[u] = __ldcg(reinterpret_cast<const float4*>(base + ids[u] * stride));
+  return r;
+}
+template <int S>
+__device__ __forceinline__ float4 set_sum(const SlotSet<S>& r) {
+  float4 acc = r.v[0];
+#pragma unroll
+  for (int u = 1; u < S; ++u) acc.x += r.v[u].x, acc.y += r.v[u].y, acc.z += r.v[u].z, acc.w += r.v[u].w;
+  return acc;
 }
 
 // rows [0, K) x 64 columns [c0, c0 + 64) of Mat [K][ld] -> tile [K][68]; columns >= L arrive as zeros
@@ -288,13 +321,15 @@ struct HUpdParams {
 inline size_t h_update_smem_bytes(int K, int Kg, int c_total, int q_total) {
   const size_t q_pad = (static_cast<size_t>(q_total) + 3) & ~size_t(3);
   size_t f = static_cast<size_t>(2) * K * kUpdPitch;
-  f += q_pad * 2 + 2 * static_cast<size_t>(c_total) * kUpdCols + ((Kg + 3) & ~3) + ((K + 3) & ~3);  // Bs, qacc, rn, rd, dcol, hacc
+  f += q_pad * 2 + 4 * static_cast<size_t>(c_total) * kUpdCols + ((Kg + 3) & ~3) + ((K + 3) & ~3);  // Bs, qacc, rn, rd, ys[2], dcol, hacc
   return f * sizeof(float) + (kUpdThreads / 32) * sizeof(double) + static_cast<size_t>(Kg + 1 + kMaxCov) * sizeof(int) + 32;
 }
 
 // FIT: the full update with statistics; otherwise the transform update H *= 2A / max(2 T H, eps) (main.py:705-709)
-template <bool FIT>
-__global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdParams p) {
+// SLOTS: how many partial-sum slots per operand the two-elements-in-flight path handles (2: three CTAs per SM; 4, for
+// small shards whose super-tiles are cut into more pieces: two CTAs per SM, twice the registers)
+template <bool FIT, int SLOTS = 2>
+__global__ void __launch_bounds__(kUpdThreads, SLOTS == 2 ? 3 : 2) h_update_kernel(const HUpdParams p) {
   extern __shared__ __align__(16) uint8_t upd_smem[];
   __shared__ int ids_num[2][kMaxTileSlots], ids_z[2][kMaxTileSlots];
   ptx::pdl_enter();
@@ -305,7 +340,8 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
   float* qacc = Bs + q_pad;                         // [q_total]  running Q partial of this CTA
   float* rn = qacc + q_pad;                         // [c_total][64]  per-cell numerator ratios (rho / Y)
   float* rd = rn + static_cast<size_t>(p.c_total) * kUpdCols;  // [c_total][64]  Frobenius: B H_i
-  float* dcol = rd + static_cast<size_t>(p.c_total) * kUpdCols;  // [Kg]  KL: lam * colsum(B) per guided row
+  float* ys = rd + static_cast<size_t>(p.c_total) * kUpdCols;    // [2][c_total][64]  the tile's labels (with the H tile)
+  float* dcol = ys + 2 * static_cast<size_t>(p.c_total) * kUpdCols;  // [Kg]  KL: lam * colsum(B) per guided row
   float* hacc = dcol + ((p.Kg + 3) & ~3);           // [K]  running row sums of the new H
   double* red = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(hacc + ((K + 3) & ~3)) + 7) & ~uintptr_t(7));  // [8]
   int* rowcov = reinterpret_cast<int*>(red + kUpdThreads / 32);  // [Kg]  covariate of guided row k
@@ -335,11 +371,32 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
   }
   double t1 = 0.0, pl0 = 0.0, pl1 = 0.0;  // pred loss of covariates (tid / 64) and (tid / 64 + 4)
 
+  // the labels of a tile travel with its H tile (same cp.async group): no global-memory latency inside the two
+  // per-cell phases; cells >= n arrive as zeros
+  auto load_labels_async = [&](float* dst, long long col0) {
+    if (!FIT) return;
+    const uint32_t base = ptx::smem_u32(dst);
+    int coff = 0;
+    for (int i = 0; i < p.cov.n_cov; ++i) {
+      const CovDesc d = p.cov.d[i];
+      for (int e = tid; e < d.c * kUpdCols; e += kUpdThreads) {
+        const int c = e >> 6, j = e & 63;
+        const bool live = col0 + j < p.n;
+        cp_async4(base + ((coff + c) * kUpdCols + j) * 4, live ? d.Y + static_cast<long long>(c) * p.n + col0 + j : d.Y,
+                  live ? 4 : 0);
+      }
+      coff += d.c;
+    }
+  };
   long long tile_i = blockIdx.x;
   int buf = 0;
-  if (tile_i < n_tiles) load_tile_async(tiles, p.H, p.ldH, K, tile_i * kUpdCols, p.n);
+  if (tile_i < n_tiles) {
+    load_labels_async(ys, tile_i * kUpdCols);
+    load_tile_async(tiles, p.H, p.ldH, K, tile_i * kUpdCols, p.n);
+  }
   for (; tile_i < n_tiles; tile_i += gridDim.x, buf ^= 1) {
     float* tile = tiles + buf * K * kUpdPitch;
+    const float* ys_cur = ys + buf * static_cast<size_t>(p.c_total) * kUpdCols;
     const long long c0 = tile_i * kUpdCols;
     cp_async_wait_all();
     __syncthreads();  // the tile has landed (also orders the set-up above); everybody is done with the other buffer
@@ -351,21 +408,23 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
       nn[gi] = (gi == 0 || p.num.split < K) ? stage_slot_ids(p.num.g[gi], c0, ids_num[gi], &idn[gi]) : 0;
       nz[gi] = (gi == 0 || p.z.split < K) ? stage_slot_ids(p.z.g[gi], c0, ids_z[gi], &idz[gi]) : 0;
     }
-    const bool few_slots = nn[0] <= 2 && nn[1] <= 2 && nz[0] <= 2 && nz[1] <= 2;
+    const bool few_slots = nn[0] <= SLOTS && nn[1] <= SLOTS && nz[0] <= SLOTS && nz[1] <= SLOTS;
     if (!FIT) __syncthreads();  // (FIT: the barrier after the guided terms publishes the ids)
     const long long next = tile_i + gridDim.x;
-    if (next < n_tiles) load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.H, p.ldH, K, next * kUpdCols, p.n);
+    if (next < n_tiles) {
+      load_labels_async(ys + (buf ^ 1) * static_cast<size_t>(p.c_total) * kUpdCols, next * kUpdCols);
+      load_tile_async(tiles + (buf ^ 1) * K * kUpdPitch, p.H, p.ldH, K, next * kUpdCols, p.n);
+    }
     if (FIT) {
       // guided terms of the OLD H with the NEW B, per cell (main.py:637-650): thread (i, j) = (tid / 64 [+4], tid % 64)
       const int j = tid & 63;
-      const bool live = c0 + j < p.n;
       for (int i = tid >> 6; i < p.cov.n_cov; i += 4) {
         const CovDesc d = p.cov.d[i];
         const int cbase = rowc0[i];
         for (int c = 0; c < d.c; ++c) {
           float yhat = 0.f;
           for (int k = 0; k < d.k; ++k) yhat += Bs[d.q_off + c * d.k + k] * tile[(d.row0 + k) * kUpdPitch + j];
-          const float y = live ? __ldg(d.Y + static_cast<long long>(c) * p.n + c0 + j) : 0.f;
+          const float y = ys_cur[(cbase + c) * kUpdCols + j];
           rn[(cbase + c) * kUpdCols + j] = (p.loss_type == LOSS_KL) ? y / fmaxf(yhat, p.eps) : y;
           rd[(cbase + c) * kUpdCols + j] = yhat;
         }
@@ -413,19 +472,19 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
       for (int e = tid; e < n_items; e += 2 * kUpdThreads) {
         const int e2 = e + kUpdThreads;
         const bool v1 = c0 + 4 * (e & 15) < p.n, v2 = e2 < n_items && c0 + 4 * (e2 & 15) < p.n;
-        SlotPair n1{}, z1{}, n2{}, z2{};
+        SlotSet<SLOTS> n1{}, z1{}, n2{}, z2{};
         if (v1) {
           const int k = e >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
-          n1 = slot_load_pair(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e & 15), idn[gn], nn[gn]);
-          z1 = slot_load_pair(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e & 15), idz[gz], nz[gz]);
+          n1 = slot_load_set<SLOTS>(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e & 15), idn[gn], nn[gn]);
+          z1 = slot_load_set<SLOTS>(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e & 15), idz[gz], nz[gz]);
         }
         if (v2) {
           const int k = e2 >> 4, gn = k >= p.num.split, gz = k >= p.z.split;
-          n2 = slot_load_pair(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e2 & 15), idn[gn], nn[gn]);
-          z2 = slot_load_pair(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e2 & 15), idz[gz], nz[gz]);
+          n2 = slot_load_set<SLOTS>(p.num.g[gn], k - gn * p.num.split, c0 + 4 * (e2 & 15), idn[gn], nn[gn]);
+          z2 = slot_load_set<SLOTS>(p.z.g[gz], k - gz * p.z.split, c0 + 4 * (e2 & 15), idz[gz], nz[gz]);
         }
-        if (v1) update(e, pair_sum(n1), pair_sum(z1));
-        if (v2) update(e2, pair_sum(n2), pair_sum(z2));
+        if (v1) update(e, set_sum<SLOTS>(n1), set_sum<SLOTS>(z1));
+        if (v2) update(e2, set_sum<SLOTS>(n2), set_sum<SLOTS>(z2));
       }
     } else {
       for (int e = tid; e < n_items; e += kUpdThreads) {
@@ -448,7 +507,7 @@ __global__ void __launch_bounds__(kUpdThreads, 3) h_update_kernel(const HUpdPara
         for (int c = 0; c < d.c; ++c) {
           float yhat = 0.f;
           for (int k = 0; k < d.k; ++k) yhat += Bs[d.q_off + c * d.k + k] * tile[(d.row0 + k) * kUpdPitch + j];
-          const float y = live ? __ldg(d.Y + static_cast<long long>(c) * p.n + c0 + j) : 0.f;
+          const float y = ys_cur[(cbase + c) * kUpdCols + j];
           float r;
           if (p.loss_type == LOSS_KL) {
             const float yh = fmaxf(yhat, p.eps);
