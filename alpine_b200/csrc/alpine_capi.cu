@@ -1407,7 +1407,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   c->w_stale = true;
   // ---- A = W^T X (main.py:653), left in its slots; T = W^T W of the new W rides along as one more super-tile of the
   //      same launch (dense fp32 X), otherwise it is a Gram plan of its own.  The finish kernel sums T's slots, writes
-  //      the hi / lo copies Z_H needs and applies the B updates (main.py:615-628).
+  //      the split copies Z_H needs and applies the B updates (main.py:615-628).
   const bool fused_t = c->gram_w_fused();
   // (the Gram plan shares the slot buffer with W^T X: unfused, its slots are consumed before W^T X runs)
   AL_TRY(run_gemm(c, fused_t ? PLAN_WXG : PLAN_GRAM_W, nullptr, 0, st));
@@ -1464,7 +1464,7 @@ int mu_apply_impl(alpine_ctx* c, int iter, void* stream, bool peer) {
   hf.gram.K = c->K;
   hf.gram.out = c->red_S();
   hf.gram.ld = c->K;
-  if (single) {  // S stays this GPU's own: its hi / lo copies can be written right away
+  if (single) {  // S stays this GPU's own: its split copies can be written right away
     hf.gram.split_hi = c->Ssplit;
     hf.gram.split_lo = c->Ssplit + static_cast<size_t>(c->K) * c->ldK;
     hf.gram.ld_split = static_cast<int>(c->ldK);
